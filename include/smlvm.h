@@ -1,0 +1,214 @@
+/*
+ * smlvm.h -- C ABI of the B200-native sparse-marginalization hot path.
+ *
+ * One shared library (libsmlvm.so, built by `nvcc -gencode
+ * arch=compute_100a,code=sm_100a`) exports exactly the entry points below.
+ * They are what the reference's FFI for this path binds today through Cython /
+ * torch / lpsmap; each declaration cites the reference interface it replaces
+ * (paths relative to the reference repo deep-spin/sparse-marginalization-lvm).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *  - all buffers are allocated and owned by the caller (the torch tensors of
+ *    the Python side); the library never allocates, never synchronises the
+ *    device and never keeps a pointer after the call returns
+ *    (same ownership contract as the Cython memoryviews,
+ *    lvmhelpers/pbinary_topk.pyx:23-25);
+ *  - `stream` is a `cudaStream_t` passed as `void*` (0 = legacy default stream);
+ *    launches are asynchronous on it;
+ *  - return value: 0 = OK; <0 = argument error (SMLVM_ERR_*); >0 = the
+ *    `cudaError_t` of a failed launch.  Nothing throws across the ABI;
+ *  - matrices are row-major, contiguous, fp32 unless stated.
+ */
+#ifndef SMLVM_H_
+#define SMLVM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMLVM_ABI_VERSION 1
+
+#define SMLVM_OK 0
+#define SMLVM_ERR_ARG (-1)         /* null pointer, negative size, bad enum        */
+#define SMLVM_ERR_UNSUPPORTED (-2) /* shape outside what the kernels are built for */
+#define SMLVM_ERR_WORKSPACE (-3)   /* caller-provided workspace too small          */
+
+/* limits (checked; SMLVM_ERR_UNSUPPORTED beyond them) */
+#define SMLVM_SPARSEMAX_MAX_COLS 8192 /* register path <=1024, shared-memory path beyond */
+#define SMLVM_TOPK_MAX_BITS 512       /* = CODE_MAX_SIZE, lvmhelpers/binary_topk.h:13    */
+#define SMLVM_TOPK_MAX_K 32
+#define SMLVM_SPARSEMAP_MAX_BITS 128  /* (n+1)^2 fp64 inverse must fit 227 KB smem       */
+
+/* factor kinds of the SparseMAP solver */
+#define SMLVM_FACTOR_BERNOULLI 0       /* lvmhelpers/bernoulli.h  (PFactorBernoulli)      */
+#define SMLVM_FACTOR_BUDGET 1          /* lvmhelpers/budget.h     (PFactorBudget)         */
+#define SMLVM_FACTOR_SEQUENCE_BINARY 2 /* lvmhelpers/sequence_binary.h (PFactorSequenceBinary) */
+
+/* per-sample solver status written by smlvm_sparsemap_fwd */
+#define SMLVM_SOLVE_CONVERGED 0
+#define SMLVM_SOLVE_MAX_ITER 1
+#define SMLVM_SOLVE_REPEATED_CONFIG 2
+#define SMLVM_SOLVE_SINGULAR 3
+
+int smlvm_version(void);
+/* Static description of an error code returned by this library (never NULL). */
+const char* smlvm_error_string(int code);
+
+/* ------------------------------------------------------------------------- *
+ * (1) batched sparsemax
+ * replaces: entmax.sparsemax(X, dim=-1) as called at lvmhelpers/marg.py:51 and
+ *           lvmhelpers/structmarg.py:48 (SparsemaxFunction.forward/backward),
+ *           fused with what the callers do to its output row by row:
+ *           entropy(p) lvmhelpers/marg.py:6-28 and scores.argmax(-1) marg.py:53.
+ * ------------------------------------------------------------------------- */
+
+/* x[rows,cols] -> p[rows,cols]; optional per-row outputs (NULL to skip):
+ *   supp_size[rows]  int32  entmax's support size k (count of rho*S_rho > cumsum_rho - 1)
+ *   nnz[rows]        int32  number of p > 0 (what the compaction will emit)
+ *   entropy[rows]    fp32   -sum_{p>0} clamp(p,eps,1-eps) log clamp(p,eps,1-eps)
+ *   argmax[rows]     int64  first index of the row maximum of x                          */
+int smlvm_sparsemax_fwd(const float* x, float* p, int32_t* supp_size, int32_t* nnz,
+                        float* entropy, int64_t* argmax, int64_t rows, int32_t cols,
+                        void* stream);
+
+/* Jacobian-vector product over the support, fused with the gradient sources the
+ * callers feed it.  Effective upstream gradient per element
+ *     g = dp + loss_scale * loss + dent[row] * d entropy / d p
+ * where each of dp[rows,cols], loss[rows,cols], dent[rows] may be NULL (term absent);
+ * loss_scale_dev is a device scalar (fp32) or NULL (=1).
+ *     dx = where(p != 0, g - sum_{p != 0} g / supp_size, 0)
+ * replaces: SparsemaxFunction.backward (entmax) + the autograd of
+ *           `encoder_probs.unsqueeze(1).bmm(losses.unsqueeze(-1))` marg.py:125 and of
+ *           entropy() marg.py:6-28 w.r.t. p.                                              */
+int smlvm_sparsemax_bwd(const float* p, const int32_t* supp_size, const float* dp,
+                        const float* loss, const float* loss_scale_dev, float loss_scale_host,
+                        const float* dent, float* dx, int64_t rows, int32_t cols, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * (2) support compaction
+ * replaces: `mask = p.view(-1) > 0; t[mask]` lvmhelpers/structmarg.py:116-126 and the
+ *           column test of lvmhelpers/marg.py:87.  Order = torch.nonzero(p > 0), i.e.
+ *           row-major.
+ * ------------------------------------------------------------------------- */
+
+/* counts[rows] int32 -> offsets[rows+1] int64 (exclusive prefix sum, offsets[rows] = total).
+ * Single pass (decoupled look-back).  workspace: smlvm_scan_workspace_bytes(rows) bytes.   */
+size_t smlvm_scan_workspace_bytes(int64_t rows);
+int smlvm_scan_counts(const int32_t* counts, int64_t* offsets, int64_t rows, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/* counts[rows] = number of p[row,:] > 0 (only needed when smlvm_sparsemax_fwd did not
+ * already write `nnz`).                                                                   */
+int smlvm_compact_count(const float* p, int32_t* counts, int64_t rows, int32_t cols, void* stream);
+
+/* Emits, for every p[r,c] > 0 in row-major order at position offsets[r] + rank:
+ *   vals (fp32), row_idx (int32), col_idx (int32); each output may be NULL.               */
+int smlvm_compact_fill(const float* p, const int64_t* offsets, float* vals, int32_t* row_idx,
+                       int32_t* col_idx, int64_t rows, int32_t cols, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * (3a) k-best bit-vectors
+ * replaces: lvmhelpers.pbinary_topk.batched_topk(scores, configs, k)
+ *           lvmhelpers/pbinary_topk.pyx:23-34 -> topk()/merge_branch()
+ *           lvmhelpers/binary_topk.h:57-129.
+ * ------------------------------------------------------------------------- */
+
+/* x[rows,n] -> any of (NULL to skip):
+ *   configs[rows,k,n] fp32 in {0,1}      (the reference's in-place output)
+ *   bits[rows,k,ceil(n/32)] uint32       (bit i of a config = bit i%32 of word i/32)
+ *   dp_scores[rows,k] fp32               (the search's own fp32 scores, descending)
+ * Requires 2 <= k <= min(2^n, SMLVM_TOPK_MAX_K), 1 <= n <= SMLVM_TOPK_MAX_BITS.            */
+int smlvm_topk_bits(const float* x, float* configs, uint32_t* bits, float* dp_scores,
+                    int64_t rows, int32_t n, int32_t k, void* stream);
+
+/* scores_k[rows,k] = sum_j bits[r,k,j] * x[r,j]   (fp64 accumulate, fp32 out)
+ * replaces: torch.einsum("bkj,bj->bk", bit_vector_z, scores) lvmhelpers/structmarg.py:47    */
+int smlvm_bits_score_fwd(const uint32_t* bits, const float* x, float* scores_k, int64_t rows,
+                         int32_t n, int32_t k, void* stream);
+/* dx[rows,n] = sum_k dscores_k[r,k] * bits[r,k,j]  (autograd of the einsum w.r.t. scores)   */
+int smlvm_bits_score_bwd(const uint32_t* bits, const float* dscores_k, float* dx, int64_t rows,
+                         int32_t n, int32_t k, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * (3b) SparseMAP active-set solver, one CTA per sample
+ * replaces: SparseMAP.run_sparsemap lvmhelpers/sparsemap.py:13-36 (factor graph
+ *           construction, init_active_set_from_scores, solve_qp, get_sparse_solution)
+ *           for PFactorBernoulli / PFactorBudget / PFactorSequenceBinary
+ *           (lvmhelpers/pbernoulli.pyx:10-22, pbudget.pyx:10-22, psequence.pyx:25-37),
+ *           i.e. libad3 GenericFactor::SolveQP with the MAP oracles of
+ *           lvmhelpers/bernoulli.h:14-35, budget.h:24-85, sequence.h:74-151.
+ * ------------------------------------------------------------------------- */
+
+/* Capacity (vertices per sample) the padded outputs must have: n + 1.                     */
+int32_t smlvm_sparsemap_capacity(int32_t n);
+
+/* x[rows,n] on-scores (off-scores are 0, sparsemap.py:22);
+ * t[rows,n-1] 1->1 transition scores (sequence-binary only, else NULL);
+ * init_scores[rows,2n] fp64: the uniform draws of sparsemap.py:26 (NULL = init=False).
+ * Padded outputs, cap = smlvm_sparsemap_capacity(n):
+ *   p_pad[rows,cap]            fp32   distribution (float(double), as torch.tensor(p))
+ *   aset_bits[rows,cap,W]      uint32 W = ceil(n/32); active vertices in solver order
+ *   counts[rows]               int32  |A|
+ *   kept[rows]                 int32  number of p_pad > 0 (NULL to skip)
+ *   iters[rows], status[rows]  int32  (NULL to skip)
+ *   S_pad[rows,cap*cap]        fp64   inverse_A[1:,1:], packed with row stride |A|
+ *                                     (NULL to skip; needed by smlvm_sparsemap_bwd)       */
+int smlvm_sparsemap_fwd(const float* x, const float* t, const double* init_scores, int32_t kind,
+                        int32_t budget, int32_t max_iter, int64_t rows, int32_t n, float* p_pad,
+                        uint32_t* aset_bits, int32_t* counts, int32_t* kept, int32_t* iters,
+                        int32_t* status, double* S_pad, void* stream);
+
+/* Ragged expansion in sample order (structmarg.py:181-198): for every kept vertex
+ * (all of them if only_positive == 0, those with p_pad > 0 otherwise) at
+ * offsets[r] + rank:  p_out (fp32), aset_out[.,n] (fp32 {0,1}), idx_out (int32 sample id). */
+int smlvm_sparsemap_expand(const float* p_pad, const uint32_t* aset_bits, const int32_t* counts,
+                           const int64_t* offsets, int32_t only_positive, float* p_out,
+                           float* aset_out, int32_t* idx_out, int64_t rows, int32_t n,
+                           void* stream);
+
+/* Backward: dx[r,:] = (M S dp)[:n], dt[r,:] = N S dp (sequence-binary; else NULL).
+ * dp is ragged in the same layout smlvm_sparsemap_expand produced (same offsets,
+ * same only_positive); dropped vertices get dp = 0.
+ * replaces: SparseMAP.jv / dist_jacobian_vec lvmhelpers/sparsemap.py:38-44,80-87          */
+int smlvm_sparsemap_bwd(const float* dp, const int64_t* offsets, int32_t only_positive,
+                        const float* p_pad, const uint32_t* aset_bits, const int32_t* counts,
+                        const double* S_pad, float* dx, float* dt, int64_t rows, int32_t n,
+                        void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * (4) probability-weighted loss, fused segmented reduce
+ * replaces: marg.py:125 (bmm), structmarg.py:140,242 ((p @ loss) / B) and the
+ *           structured entropy -p.log p / B structmarg.py:51-58,200-202.
+ * ------------------------------------------------------------------------- */
+
+/* Dense: row_loss[r] = sum_c p[r,c]*loss[r,c] (NULL to skip); total[0] (fp32 device scalar,
+ * NULL to skip) = scale * sum_r row_loss[r], accumulated in fp64 in a fixed order.
+ * workspace: smlvm_reduce_workspace_bytes() bytes.                                          */
+size_t smlvm_reduce_workspace_bytes(void);
+int smlvm_wloss_dense_fwd(const float* p, const float* loss, float* row_loss, float* total,
+                          float scale, int64_t rows, int32_t cols, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
+/* Ragged: offsets[rows+1] segments over p[N], loss[N].
+ *   row_loss[r] = sum_{j in seg r} p_j*loss_j      (NULL to skip; offsets may then be NULL)
+ *   total[0]    = scale * sum_j p_j*loss_j          (NULL to skip)
+ *   neg_plogp[0]= -scale * sum_j p_j*log(p_j)        (NULL to skip; structured entropy)     */
+int smlvm_wloss_ragged_fwd(const float* p, const float* loss, const int64_t* offsets,
+                           float* row_loss, float* total, float* neg_plogp, float scale,
+                           int64_t rows, int64_t n_items, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
+/* dp_j = g*scale*loss_j - gent*scale*(log p_j + 1),  dloss_j = g*scale*p_j;
+ * g, gent: fp32 device scalars (upstream gradients of total / neg_plogp; NULL = 0).
+ * dp / dloss may be NULL.                                                                  */
+int smlvm_wloss_ragged_bwd(const float* p, const float* loss, const float* g, const float* gent,
+                           float scale, float* dp, float* dloss, int64_t n_items, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMLVM_H_ */

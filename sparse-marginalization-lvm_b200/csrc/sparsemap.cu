@@ -1,0 +1,723 @@
+// SparseMAP active-set solver for sm_100a: one CTA per sample.
+//
+// replaces, per sample, SparseMAP.run_sparsemap (lvmhelpers/sparsemap.py:13-36): building a
+// factor graph with 2n binary variables, `init_active_set_from_scores`, `solve_qp` (libad3
+// GenericFactor::SolveQP) and `get_sparse_solution`, for the factors of
+// lvmhelpers/bernoulli.h, budget.h and sequence_binary.h; and SparseMAP.jv
+// (sparsemap.py:38-44, dist_jacobian_vec) for the backward.
+//
+// The algorithm is AD3's active-set method, followed step by step so that pivots, tie rules
+// and hence (p, aset) agree with it:
+//   state  A (active vertices, ordered), p (distribution), inv = inverse of [[0,1'],[1,M'M]]
+//   loop   if A changed: b = [1, score(y_j)],  [tau; z] = inv b; line search p -> z, first
+//          blocking constraint leaves A (block down-date of inv);
+//          else: u = M z, y^ = MAP(eta - u); stop if value <= tau + 1e-9; else y^ joins A
+//          (block update of inv, Schur complement s = <y^,y^> - r' inv r).
+// Everything lives in shared memory in fp64: inv as a dense (n+2)^2 matrix addressed through a
+// slot indirection (perm: solver order -> slot) so that removals do not move data, vertices as
+// bitmasks (Gram entries are n - popc(a ^ b)), MAP oracles as block-wide primitives
+// (ballot for Bernoulli, rank-select for the budget, 2-state Viterbi for the sequence).
+// No FMA contraction in the inverse updates: the pivoting sequence is sensitive to last bits.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace smlvm {
+
+struct SolverSmem {
+    double* inv;    // [LD*LD]  physical index 0 = constraint row, slot s -> s + 1
+    double* score;  // [cap]    by slot: score(y_slot) under eta
+    double* p;      // [cap]    by slot
+    double* z;      // [cap]    by slot
+    double* d;      // [LD]     by physical index
+    double* r;      // [LD]
+    double* eta;    // [n]      on-scores (off-scores are 0)
+    double* t;      // [n]      transition scores (n-1 used)
+    double* son;    // [n]      oracle input, "on" half
+    double* soff;   // [n]      oracle input, "off" half
+    double* red;    // [40]     reduction scratch
+    int* perm;      // [cap]    solver order -> slot
+    int* freestk;   // [cap]    free slots (stack)
+    uint32_t* bits; // [cap*W]  by slot
+    uint32_t* ynew; // [W]
+    unsigned char* bp;  // [2*n] Viterbi back-pointers
+    int* misc;      // [8]
+};
+
+__host__ __device__ inline size_t solver_smem_bytes(int n)
+{
+    const int cap = n + 1, LD = (n + 2) | 1, W = (n + 31) / 32;
+    size_t dbl = (size_t)LD * LD + 3 * cap + 2 * LD + 4 * n + 40;
+    size_t b = dbl * sizeof(double);
+    b += (size_t)(2 * cap + 8) * sizeof(int);
+    b += (size_t)(cap * W + W) * sizeof(uint32_t);
+    b += (size_t)2 * n + 16;
+    return (b + 15) & ~(size_t)15;
+}
+
+__device__ inline SolverSmem carve(unsigned char* raw, int n)
+{
+    const int cap = n + 1, LD = (n + 2) | 1, W = (n + 31) / 32;
+    SolverSmem s;
+    double* d = reinterpret_cast<double*>(raw);
+    s.inv = d; d += (size_t)LD * LD;
+    s.score = d; d += cap;
+    s.p = d; d += cap;
+    s.z = d; d += cap;
+    s.d = d; d += LD;
+    s.r = d; d += LD;
+    s.eta = d; d += n;
+    s.t = d; d += n;
+    s.son = d; d += n;
+    s.soff = d; d += n;
+    s.red = d; d += 40;
+    int* ip = reinterpret_cast<int*>(d);
+    s.perm = ip; ip += cap;
+    s.freestk = ip; ip += cap;
+    s.misc = ip; ip += 8;
+    uint32_t* up = reinterpret_cast<uint32_t*>(ip);
+    s.bits = up; up += cap * W;
+    s.ynew = up; up += W;
+    s.bp = reinterpret_cast<unsigned char*>(up);
+    return s;
+}
+
+__device__ __forceinline__ int block_sum_int(int v, double* red)
+{
+    return (int)(block_sum((double)v, red) + 0.5);
+}
+
+// ---- factor MAP oracles: read (son, soff[, t]), write the vertex to sm.ynew, return value ----
+
+// lvmhelpers/bernoulli.h:14-35
+__device__ double map_bernoulli(const SolverSmem& sm, int n)
+{
+    const int lane = threadIdx.x & 31;
+    const int n32 = (n + 31) & ~31;
+    double part = 0.0;
+    for (int i = threadIdx.x; i < n32; i += blockDim.x) {
+        const bool valid = i < n;
+        const double on = valid ? sm.son[i] : 0.0, off = valid ? sm.soff[i] : 0.0;
+        const bool y = valid && (on > off);
+        if (valid) part += y ? on : off;
+        const unsigned b = __ballot_sync(kFull, y);
+        if (lane == 0) sm.ynew[i >> 5] = b;
+    }
+    return block_sum(part, sm.red);
+}
+
+// lvmhelpers/budget.h:24-85.  Uses sm.d as the gain vector.
+__device__ double map_budget(const SolverSmem& sm, int n, int budget)
+{
+    const int lane = threadIdx.x & 31;
+    const int n32 = (n + 31) & ~31;
+    double base = 0.0, sum = 0.0;
+    int cnt = 0;
+    for (int i = threadIdx.x; i < n32; i += blockDim.x) {
+        const bool valid = i < n;
+        const double gain = valid ? __dsub_rn(sm.son[i], sm.soff[i]) : -1.0;
+        if (valid) {
+            sm.d[i] = gain;
+            base += sm.soff[i];
+        }
+        const bool y = valid && gain > 0.0;
+        if (y) { sum += gain; ++cnt; }
+        const unsigned b = __ballot_sync(kFull, y);
+        if (lane == 0) sm.ynew[i >> 5] = b;
+    }
+    const int active = block_sum_int(cnt, sm.red);  // also orders the sm.d / sm.ynew writes
+    if (active > budget) {
+        // keep the `budget` largest gains, ties towards the lower index (sort of (-gain, i))
+        sum = 0.0;
+        for (int i = threadIdx.x; i < n32; i += blockDim.x) {
+            const bool valid = i < n;
+            bool y = false;
+            if (valid) {
+                const double gi = sm.d[i];
+                int rank = 0;
+                for (int j = 0; j < n; ++j) {
+                    const double gj = sm.d[j];
+                    rank += (gj > gi || (gj == gi && j < i)) ? 1 : 0;
+                }
+                y = rank < budget && !(gi < 0.0);
+                if (y) sum += gi;
+            }
+            const unsigned b = __ballot_sync(kFull, y);
+            if (lane == 0) sm.ynew[i >> 5] = b;
+        }
+    }
+    const double tot = block_sum(base + sum, sm.red);
+    return tot;
+}
+
+// lvmhelpers/sequence.h:74-151 with the scores of lvmhelpers/sequence_binary.h:10-37.
+// `edge` == nullptr means all transition scores are 0 (init_active_set_from_scores).
+__device__ double map_sequence(const SolverSmem& sm, int n, const double* edge)
+{
+    const int W = (n + 31) / 32;
+    if (threadIdx.x == 0) {
+        double v0 = sm.soff[0], v1 = sm.son[0];
+        for (int i = 0; i + 1 < n; ++i) {
+            const double e = edge ? edge[i] : 0.0;
+            // into state 0: l=0 gives v0, l=1 gives v1 (edge 0); into state 1: v0, v1 + e
+            const int b0 = (v1 > v0) ? 1 : 0;
+            const double c1 = __dadd_rn(v1, e);
+            const int b1 = (c1 > v0) ? 1 : 0;
+            const double n0 = __dadd_rn(b0 ? v1 : v0, sm.soff[i + 1]);
+            const double n1 = __dadd_rn(b1 ? c1 : v0, sm.son[i + 1]);
+            sm.bp[2 * (i + 1)] = (unsigned char)b0;
+            sm.bp[2 * (i + 1) + 1] = (unsigned char)b1;
+            v0 = n0;
+            v1 = n1;
+        }
+        int state = (v1 > v0) ? 1 : 0;
+        sm.red[39] = state ? v1 : v0;
+        for (int q = 0; q < W; ++q) sm.ynew[q] = 0u;
+        for (int i = n - 1; i >= 0; --i) {
+            if (state) sm.ynew[i >> 5] |= 1u << (i & 31);
+            if (i > 0) state = sm.bp[2 * i + state];
+        }
+    }
+    __syncthreads();
+    const double v = sm.red[39];
+    __syncthreads();
+    return v;
+}
+
+template <int KIND>
+__device__ __forceinline__ double factor_map(const SolverSmem& sm, int n, int budget,
+                                             const double* edge)
+{
+    if (KIND == SMLVM_FACTOR_BERNOULLI) return map_bernoulli(sm, n);
+    if (KIND == SMLVM_FACTOR_BUDGET) return map_budget(sm, n, budget);
+    return map_sequence(sm, n, edge);
+}
+
+// ---- order-sensitive sums, done the way libad3 does them -------------------------------------
+// At every oracle call the reduced scores of all coordinates that are already "solved" tie to
+// within rounding, so WHICH vertex the MAP oracle returns is decided by the last bits of z.  To
+// follow the reference's pivoting the sums that feed z must be rounded in its order.  Row-wise
+// sums (z, tau, d, u) are sequential per thread anyway; the two whole-matrix / whole-vector sums
+// below are chains: warp 0 forms 32 terms at a time in parallel and folds them in sequence.
+
+// score of the vertex in sm.ynew under (eta, 0[, t]): bernoulli.h:38-54 / sequence.h:154-179.
+// Call with all lanes of warp 0; returns the score on every lane.
+template <int KIND>
+__device__ double evaluate_chain(const SolverSmem& sm, int n)
+{
+    const int lane = threadIdx.x & 31;
+    double acc = 0.0;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + lane;
+        double node = 0.0, edge = 0.0;
+        if (i < n && ((sm.ynew[i >> 5] >> (i & 31)) & 1u)) {
+            node = sm.eta[i];
+            if (KIND == SMLVM_FACTOR_SEQUENCE_BINARY && i > 0 &&
+                ((sm.ynew[(i - 1) >> 5] >> ((i - 1) & 31)) & 1u))
+                edge = sm.t[i - 1];
+        }
+        const int valid = min(32, n - i0);
+        for (int c = 0; c < valid; ++c) {
+            acc = __dadd_rn(acc, __shfl_sync(kFull, node, c));
+            if (KIND == SMLVM_FACTOR_SEQUENCE_BINARY) acc = __dadd_rn(acc, __shfl_sync(kFull, edge, c));
+        }
+    }
+    return acc;
+}
+
+// Schur complement s = r0 - sum_{i<=j} c_ij r_i r_j inv_ij in libad3's order (rows in solver
+// order, c_ii = 1, c_ij = 2).  Call with all lanes of warp 0.
+__device__ double schur_chain(const SolverSmem& sm, int m, int LD, double r0)
+{
+    const int lane = threadIdx.x & 31;
+    double s = r0;
+    for (int a = 0; a <= m; ++a) {
+        const int ip = (a == 0) ? 0 : sm.perm[a - 1] + 1;
+        const double ri = sm.r[ip];
+        if (ri == 0.0) continue;
+        for (int b0 = a; b0 <= m; b0 += 32) {
+            const int b = b0 + lane;
+            double term = 0.0;
+            if (b <= m) {
+                const int jp = (b == 0) ? 0 : sm.perm[b - 1] + 1;
+                const double v = sm.inv[ip * LD + jp];
+                term = (b == a) ? __dmul_rn(__dmul_rn(ri, ri), v)
+                                : __dmul_rn(__dmul_rn(__dmul_rn(2.0, ri), sm.r[jp]), v);
+            }
+            const int valid = min(32, m + 1 - b0);
+            for (int c = 0; c < valid; ++c) s = __dsub_rn(s, __shfl_sync(kFull, term, c));
+        }
+    }
+    return s;
+}
+
+__device__ __forceinline__ int common_values(const uint32_t* a, const uint32_t* b, int W, int n)
+{
+    int diff = 0;
+    for (int q = 0; q < W; ++q) diff += __popc(a[q] ^ b[q]);
+    return n - diff;
+}
+
+template <int KIND>
+__global__ void sparsemap_fwd_kernel(const float* __restrict__ x, const float* __restrict__ t,
+                                     const double* __restrict__ init_scores, int budget,
+                                     int max_iter, int64_t rows, int n, float* __restrict__ p_pad,
+                                     uint32_t* __restrict__ aset_bits, int32_t* __restrict__ counts,
+                                     int32_t* __restrict__ kept, int32_t* __restrict__ iters,
+                                     int32_t* __restrict__ status, double* __restrict__ S_pad)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int cap = n + 1, LD = (n + 2) | 1, W = (n + 31) / 32;  // odd LD: row-wise reads spread over banks
+    const SolverSmem sm = carve(smem_raw, n);
+    const int tid = threadIdx.x, T = blockDim.x;
+
+    for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+        __syncthreads();
+        // ---- load the sample -----------------------------------------------------------
+        for (int i = tid; i < n; i += T) {
+            sm.eta[i] = (double)x[row * n + i];
+            sm.t[i] = (KIND == SMLVM_FACTOR_SEQUENCE_BINARY && t != nullptr && i + 1 < n)
+                          ? (double)t[row * (int64_t)(n - 1) + i] : 0.0;
+            if (init_scores != nullptr) {
+                sm.son[i] = init_scores[row * 2 * (int64_t)n + i];
+                sm.soff[i] = init_scores[row * 2 * (int64_t)n + n + i];
+            } else {
+                sm.son[i] = (double)x[row * n + i];
+                sm.soff[i] = 0.0;
+            }
+        }
+        for (int i = tid; i < LD * LD; i += T) sm.inv[i] = 0.0;
+        for (int i = tid; i < cap; i += T) sm.freestk[i] = cap - 1 - i;  // pop order 0,1,2,...
+        __syncthreads();
+
+        // ---- seed: single MAP vertex, weight 1, inv = [[-n, 1], [1, 0]] ---------------------
+        // (init_active_set_from_scores, sparsemap.py:25-27, or the LP solution under eta)
+        factor_map<KIND>(sm, n, budget, init_scores != nullptr ? nullptr : sm.t);
+        __syncthreads();
+        {
+            double sc0 = 0.0;
+            if (tid < 32) sc0 = evaluate_chain<KIND>(sm, n);
+            if (tid == 0) {
+                sm.perm[0] = 0;
+                sm.score[0] = sc0;
+                sm.p[0] = 1.0;
+                sm.z[0] = 1.0;
+                sm.inv[0] = -(double)n;
+                sm.inv[1] = 1.0;
+                sm.inv[LD] = 1.0;
+                sm.inv[LD + 1] = 0.0;
+            }
+            for (int q = tid; q < W; q += T) sm.bits[q] = sm.ynew[q];
+        }
+        int m = 1;          // |A|
+        int nfree = cap - 1; // free-stack height (slot 0 popped)
+        int hw = 2;          // physical indices < hw have been touched
+        bool changed = true;
+        double tau = 0.0;
+        int st = SMLVM_SOLVE_MAX_ITER;
+        int it = 0;
+        __syncthreads();
+
+        for (it = 0; it < max_iter; ++it) {
+            if (changed) {
+                // ---- [tau; z] = inv * [1; score], rows in solver order ---------------------
+                for (int a = tid; a <= m; a += T) {
+                    const int rp = (a == 0) ? 0 : sm.perm[a - 1] + 1;
+                    double acc = sm.inv[rp * LD];  // column 0 times b_0 = 1
+                    for (int j = 1; j <= m; ++j) {
+                        const int sj = sm.perm[j - 1];
+                        acc = __dadd_rn(acc, __dmul_rn(sm.inv[rp * LD + sj + 1], sm.score[sj]));
+                    }
+                    if (a == 0) sm.red[38] = acc; else sm.z[sm.perm[a - 1]] = acc;
+                }
+                __syncthreads();
+                tau = sm.red[38];
+
+                // ---- line search: first minimal ratio p/(p-z) over z < p -----------------
+                if (tid < 32) {
+                    double best = CUDART_INF;
+                    int besti = 0x7fffffff;
+                    int anyneg = 0;
+                    for (int a = tid; a < m; a += 32) {
+                        const int s = sm.perm[a];
+                        const double zz = sm.z[s], pp = sm.p[s];
+                        if (zz >= pp) continue;
+                        if (zz < 0.0) anyneg = 1;
+                        const double ratio = __ddiv_rn(pp, __dsub_rn(pp, zz));
+                        if (ratio < best) { best = ratio; besti = a; }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const double ob = __shfl_xor_sync(kFull, best, o);
+                        const int oi = __shfl_xor_sync(kFull, besti, o);
+                        anyneg |= __shfl_xor_sync(kFull, anyneg, o);
+                        if (oi != 0x7fffffff &&
+                            (besti == 0x7fffffff || ob < best || (ob == best && oi < besti))) {
+                            best = ob;
+                            besti = oi;
+                        }
+                    }
+                    if (tid == 0) {
+                        sm.misc[0] = anyneg;
+                        sm.misc[1] = besti;
+                        sm.red[37] = best;
+                    }
+                }
+                __syncthreads();
+                const bool exist_blocking = sm.misc[0] != 0;
+                if (!exist_blocking) {
+                    for (int a = tid; a < m; a += T) {
+                        const int s = sm.perm[a];
+                        sm.p[s] = sm.z[s];
+                    }
+                    changed = false;
+                    __syncthreads();
+                } else {
+                    const int blocking = sm.misc[1];
+                    double alpha = sm.red[37];
+                    if (alpha > 1.0) alpha = 1.0;
+                    const int srem = sm.perm[blocking];
+                    const int rem = srem + 1;
+                    for (int a = tid; a < m; a += T) {
+                        const int s = sm.perm[a];
+                        if (alpha == 1.0) {
+                            sm.p[s] = sm.z[s];
+                        } else {
+                            const double v = __dadd_rn(__dmul_rn(__dsub_rn(1.0, alpha), sm.p[s]),
+                                                       __dmul_rn(alpha, sm.z[s]));
+                            sm.z[s] = v;
+                            sm.p[s] = v;
+                        }
+                    }
+                    // ---- down-date inv: d = -(1/inv_rr) inv[r,:],  inv -= inv_rr d d' ---------
+                    const double invs = sm.inv[rem * LD + rem];
+                    const double sval = __ddiv_rn(1.0, invs);
+                    for (int i = tid; i < hw; i += T)
+                        sm.d[i] = (i == rem) ? 0.0 : __dmul_rn(-sval, sm.inv[rem * LD + i]);
+                    __syncthreads();
+                    for (int e = tid; e < hw * hw; e += T) {
+                        const int i = e / hw, j = e - i * hw;
+                        const double upd = __dmul_rn(__dmul_rn(invs, sm.d[i]), sm.d[j]);
+                        sm.inv[i * LD + j] = __dsub_rn(sm.inv[i * LD + j], upd);
+                    }
+                    __syncthreads();
+                    // clear the freed row/column, drop it from the order, recycle the slot
+                    for (int i = tid; i < hw; i += T) {
+                        sm.inv[rem * LD + i] = 0.0;
+                        sm.inv[i * LD + rem] = 0.0;
+                    }
+                    __syncthreads();
+                    if (tid == 0) {
+                        for (int a = blocking; a + 1 < m; ++a) sm.perm[a] = sm.perm[a + 1];
+                        sm.freestk[nfree] = srem;
+                    }
+                    ++nfree;
+                    --m;
+                    changed = true;
+                    __syncthreads();
+                }
+            } else {
+                // ---- u = M z (solver order), oracle scores eta - u ---------------------------
+                for (int i = tid; i < n; i += T) {
+                    double uon = 0.0, uoff = 0.0;
+                    for (int a = 0; a < m; ++a) {
+                        const int s = sm.perm[a];
+                        const double zz = sm.z[s];
+                        if ((sm.bits[s * W + (i >> 5)] >> (i & 31)) & 1u) uon = __dadd_rn(uon, zz);
+                        else uoff = __dadd_rn(uoff, zz);
+                    }
+                    sm.son[i] = __dsub_rn(sm.eta[i], uon);
+                    sm.soff[i] = __dsub_rn(0.0, uoff);
+                }
+                __syncthreads();
+                const double value = factor_map<KIND>(sm, n, budget, sm.t);
+                __syncthreads();
+                if (value <= tau + 1e-9) {
+                    st = SMLVM_SOLVE_CONVERGED;
+                    ++it;
+                    break;
+                }
+                // already active?  (libad3 clears its cache here; we keep the solution)
+                int same = 0;
+                for (int a = tid; a < m; a += T) {
+                    const uint32_t* ya = sm.bits + sm.perm[a] * W;
+                    bool eq = true;
+                    for (int q = 0; q < W; ++q) eq = eq && (ya[q] == sm.ynew[q]);
+                    same |= eq ? 1 : 0;
+                }
+                same = block_sum_int(same, sm.red);
+                if (same > 0) {
+                    st = SMLVM_SOLVE_REPEATED_CONFIG;
+                    ++it;
+                    break;
+                }
+                // ---- insertion: r = [1, common(y_j, y^)], d = inv r, s = n - r'd -------------
+                for (int i = tid; i < hw; i += T) sm.r[i] = 0.0;
+                __syncthreads();
+                if (tid == 0) sm.r[0] = 1.0;
+                for (int a = tid; a < m; a += T) {
+                    const int s = sm.perm[a];
+                    sm.r[s + 1] = (double)common_values(sm.bits + s * W, sm.ynew, W, n);
+                }
+                __syncthreads();
+                // warp 0: the two order-sensitive chains; meanwhile the other warps (reverse
+                // thread mapping) form d_j = sum_i inv[i][j] r_i, i in solver order
+                if (tid < 32) {
+                    const double sv = schur_chain(sm, m, LD, (double)n);
+                    const double scn = evaluate_chain<KIND>(sm, n);
+                    if (tid == 0) { sm.red[36] = sv; sm.red[35] = scn; }
+                }
+                for (int a = T - 1 - tid; a <= m; a += T) {
+                    const int jp = (a == 0) ? 0 : sm.perm[a - 1] + 1;
+                    double acc = __dmul_rn(sm.inv[jp], sm.r[0]);
+                    for (int b = 1; b <= m; ++b) {
+                        const int ip = sm.perm[b - 1] + 1;
+                        const double ri = sm.r[ip];
+                        if (ri != 0.0) acc = __dadd_rn(acc, __dmul_rn(sm.inv[ip * LD + jp], ri));
+                    }
+                    sm.d[jp] = acc;
+                }
+                __syncthreads();
+                const double sval = sm.red[36];
+                if (sval > -1e-9 && sval < 1e-9) {
+                    st = SMLVM_SOLVE_SINGULAR;
+                    ++it;
+                    break;
+                }
+                const double invs = __ddiv_rn(1.0, sval);
+                const int snew = sm.freestk[nfree - 1];
+                const int pn = snew + 1;
+                const int hw_new = max(hw, pn + 1);
+                // zero d on inactive indices (r is zero there, but d was only written for active)
+                // -> use r as the activity mask: r[0] = 1 and r[slot+1] >= 0 ... common can be 0,
+                //    so mark activity explicitly through a pass over perm.
+                for (int i = tid; i < hw_new; i += T) sm.r[i] = 0.0;  // reuse r as activity flags
+                __syncthreads();
+                if (tid == 0) sm.r[0] = 1.0;
+                for (int a = tid; a < m; a += T) sm.r[sm.perm[a] + 1] = 1.0;
+                __syncthreads();
+                for (int e = tid; e < hw * hw; e += T) {
+                    const int i = e / hw, j = e - i * hw;
+                    if (sm.r[i] != 0.0 && sm.r[j] != 0.0) {
+                        const double upd = __dmul_rn(__dmul_rn(invs, sm.d[i]), sm.d[j]);
+                        sm.inv[i * LD + j] = __dadd_rn(sm.inv[i * LD + j], upd);
+                    }
+                }
+                __syncthreads();
+                for (int i = tid; i < hw_new; i += T) {
+                    if (i == pn) continue;
+                    const double v = (sm.r[i] != 0.0) ? __dmul_rn(-invs, sm.d[i]) : 0.0;
+                    sm.inv[i * LD + pn] = v;
+                    sm.inv[pn * LD + i] = v;
+                }
+                if (tid == 0) sm.inv[pn * LD + pn] = invs;
+                for (int q = tid; q < W; q += T) sm.bits[snew * W + q] = sm.ynew[q];
+                __syncthreads();
+                const double scn = sm.red[35];
+                if (tid == 0) {
+                    sm.perm[m] = snew;
+                    sm.score[snew] = scn;
+                    sm.p[snew] = 0.0;
+                    sm.z[snew] = 0.0;
+                }
+                --nfree;
+                ++m;
+                hw = hw_new;
+                changed = true;
+                __syncthreads();
+            }
+        }
+        if (it > max_iter) it = max_iter;
+
+        // ---- outputs (solver order) -----------------------------------------------------
+        __syncthreads();
+        int kp = 0;
+        for (int a = tid; a < cap; a += T) {
+            float pf = 0.f;
+            if (a < m) {
+                pf = (float)sm.p[sm.perm[a]];
+                kp += pf > 0.f ? 1 : 0;
+            }
+            p_pad[row * cap + a] = pf;
+        }
+        for (int e = tid; e < cap * W; e += T) {
+            const int a = e / W, q = e - a * W;
+            aset_bits[(row * cap + a) * W + q] = (a < m) ? sm.bits[sm.perm[a] * W + q] : 0u;
+        }
+        if (S_pad != nullptr) {
+            double* S = S_pad + row * (int64_t)cap * cap;
+            for (int e = tid; e < m * m; e += T) {
+                const int a = e / m, c = e - a * m;
+                S[e] = sm.inv[(sm.perm[a] + 1) * LD + sm.perm[c] + 1];
+            }
+        }
+        if (kept != nullptr) {
+            const int tot = block_sum_int(kp, sm.red);
+            if (tid == 0) kept[row] = tot;
+        }
+        if (tid == 0) {
+            counts[row] = m;
+            if (iters != nullptr) iters[row] = it;
+            if (status != nullptr) status[row] = st;
+        }
+    }
+}
+
+// Ragged expansion: one warp per sample.
+__global__ void __launch_bounds__(256)
+sparsemap_expand_kernel(const float* __restrict__ p_pad, const uint32_t* __restrict__ aset_bits,
+                        const int32_t* __restrict__ counts, const int64_t* __restrict__ offsets,
+                        int only_positive, float* __restrict__ p_out, float* __restrict__ aset_out,
+                        int32_t* __restrict__ idx_out, int64_t rows, int n)
+{
+    const int cap = n + 1, W = (n + 31) / 32;
+    const int lane = threadIdx.x & 31;
+    const int64_t warps_total = (int64_t)gridDim.x * 8;
+    for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += warps_total) {
+        const int m = __ldg(counts + row);
+        int64_t out = __ldg(offsets + row);
+        for (int a = 0; a < m; ++a) {
+            const float pa = __ldg(p_pad + row * cap + a);
+            if (only_positive && !(pa > 0.f)) continue;
+            if (lane == 0) {
+                if (p_out != nullptr) p_out[out] = pa;
+                if (idx_out != nullptr) idx_out[out] = (int32_t)row;
+            }
+            if (aset_out != nullptr) {
+                const uint32_t* bw = aset_bits + (row * cap + a) * W;
+                for (int i = lane; i < n; i += 32)
+                    stg_stream(aset_out + out * n + i, (float)((__ldg(bw + (i >> 5)) >> (i & 31)) & 1u));
+            }
+            ++out;
+        }
+    }
+}
+
+// Backward: w = S dp (dp scattered to solver order, 0 for dropped vertices), dx = M_on w,
+// dt_i = sum_a w_a [y_a,i = y_a,i+1 = 1].  One CTA (128 threads) per sample.
+__global__ void __launch_bounds__(128)
+sparsemap_bwd_kernel(const float* __restrict__ dp, const int64_t* __restrict__ offsets,
+                     int only_positive, const float* __restrict__ p_pad,
+                     const uint32_t* __restrict__ aset_bits, const int32_t* __restrict__ counts,
+                     const double* __restrict__ S_pad, float* __restrict__ dx,
+                     float* __restrict__ dt, int64_t rows, int n)
+{
+    extern __shared__ double sh[];
+    const int cap = n + 1, W = (n + 31) / 32;
+    double* g = sh;        // [cap] upstream gradient in solver order
+    double* wv = sh + cap; // [cap]
+    const int tid = threadIdx.x, T = blockDim.x;
+    for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int m = __ldg(counts + row);
+        const int64_t base = __ldg(offsets + row);
+        __syncthreads();
+        if (tid == 0) {
+            int rank = 0;
+            for (int a = 0; a < m; ++a) {
+                const bool keep = !only_positive || (__ldg(p_pad + row * cap + a) > 0.f);
+                g[a] = keep ? (double)__ldg(dp + base + rank) : 0.0;
+                rank += keep ? 1 : 0;
+            }
+        }
+        __syncthreads();
+        const double* S = S_pad + row * (int64_t)cap * cap;
+        for (int a = tid; a < m; a += T) {
+            double acc = 0.0;
+            for (int c = 0; c < m; ++c) acc += S[(int64_t)c * m + a] * g[c];  // S symmetric
+            wv[a] = acc;
+        }
+        __syncthreads();
+        for (int i = tid; i < n; i += T) {
+            double on = 0.0, edge = 0.0;
+            for (int a = 0; a < m; ++a) {
+                const uint32_t* bw = aset_bits + (row * cap + a) * W;
+                const bool yi = (__ldg(bw + (i >> 5)) >> (i & 31)) & 1u;
+                if (yi) {
+                    on += wv[a];
+                    if (dt != nullptr && i + 1 < n &&
+                        ((__ldg(bw + ((i + 1) >> 5)) >> ((i + 1) & 31)) & 1u))
+                        edge += wv[a];
+                }
+            }
+            dx[row * n + i] = (float)on;
+            if (dt != nullptr && i + 1 < n) dt[row * (int64_t)(n - 1) + i] = (float)edge;
+        }
+    }
+}
+
+}  // namespace smlvm
+
+using namespace smlvm;
+
+extern "C" int32_t smlvm_sparsemap_capacity(int32_t n) { return n + 1; }
+
+extern "C" int smlvm_sparsemap_fwd(const float* x, const float* t, const double* init_scores,
+                                   int32_t kind, int32_t budget, int32_t max_iter, int64_t rows,
+                                   int32_t n, float* p_pad, uint32_t* aset_bits, int32_t* counts,
+                                   int32_t* kept, int32_t* iters, int32_t* status, double* S_pad,
+                                   void* stream)
+{
+    if (rows < 0 || n < 1 || max_iter < 0 || budget < 0) return SMLVM_ERR_ARG;
+    if (kind < SMLVM_FACTOR_BERNOULLI || kind > SMLVM_FACTOR_SEQUENCE_BINARY) return SMLVM_ERR_ARG;
+    if (n > SMLVM_SPARSEMAP_MAX_BITS) return SMLVM_ERR_UNSUPPORTED;
+    if (rows == 0) return SMLVM_OK;
+    if (x == nullptr || p_pad == nullptr || aset_bits == nullptr || counts == nullptr)
+        return SMLVM_ERR_ARG;
+    const size_t smem = solver_smem_bytes(n);
+    const int threads = n <= 32 ? 64 : (n <= 64 ? 128 : 256);
+    int64_t cap_grid = (int64_t)device_sm_count() * 64;
+    const int grid = (int)(rows < cap_grid ? rows : cap_grid);
+    cudaStream_t st = as_stream(stream);
+#define SMLVM_SMAP_LAUNCH(K)                                                                       \
+    do {                                                                                           \
+        cudaError_t e =                                                                            \
+            cudaFuncSetAttribute(sparsemap_fwd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 (int)smem);                                                       \
+        if (e != cudaSuccess) return (int)e;                                                       \
+        sparsemap_fwd_kernel<K><<<grid, threads, smem, st>>>(x, t, init_scores, budget, max_iter,  \
+                                                             rows, n, p_pad, aset_bits, counts,    \
+                                                             kept, iters, status, S_pad);          \
+    } while (0)
+    if (kind == SMLVM_FACTOR_BERNOULLI) SMLVM_SMAP_LAUNCH(SMLVM_FACTOR_BERNOULLI);
+    else if (kind == SMLVM_FACTOR_BUDGET) SMLVM_SMAP_LAUNCH(SMLVM_FACTOR_BUDGET);
+    else SMLVM_SMAP_LAUNCH(SMLVM_FACTOR_SEQUENCE_BINARY);
+#undef SMLVM_SMAP_LAUNCH
+    SMLVM_LAUNCH_CHECK();
+    return SMLVM_OK;
+}
+
+extern "C" int smlvm_sparsemap_expand(const float* p_pad, const uint32_t* aset_bits,
+                                      const int32_t* counts, const int64_t* offsets,
+                                      int32_t only_positive, float* p_out, float* aset_out,
+                                      int32_t* idx_out, int64_t rows, int32_t n, void* stream)
+{
+    if (rows < 0 || n < 1) return SMLVM_ERR_ARG;
+    if (rows == 0) return SMLVM_OK;
+    if (p_pad == nullptr || aset_bits == nullptr || counts == nullptr || offsets == nullptr)
+        return SMLVM_ERR_ARG;
+    int64_t need = (rows + 7) / 8;
+    int64_t cap = (int64_t)device_sm_count() * 16;
+    sparsemap_expand_kernel<<<(int)(need < cap ? need : cap), 256, 0, as_stream(stream)>>>(
+        p_pad, aset_bits, counts, offsets, only_positive, p_out, aset_out, idx_out, rows, n);
+    SMLVM_LAUNCH_CHECK();
+    return SMLVM_OK;
+}
+
+extern "C" int smlvm_sparsemap_bwd(const float* dp, const int64_t* offsets, int32_t only_positive,
+                                   const float* p_pad, const uint32_t* aset_bits,
+                                   const int32_t* counts, const double* S_pad, float* dx, float* dt,
+                                   int64_t rows, int32_t n, void* stream)
+{
+    if (rows < 0 || n < 1) return SMLVM_ERR_ARG;
+    if (rows == 0) return SMLVM_OK;
+    if (dp == nullptr || offsets == nullptr || p_pad == nullptr || aset_bits == nullptr ||
+        counts == nullptr || S_pad == nullptr || dx == nullptr)
+        return SMLVM_ERR_ARG;
+    if (n > SMLVM_SPARSEMAP_MAX_BITS) return SMLVM_ERR_UNSUPPORTED;
+    const size_t smem = 2 * (size_t)(n + 1) * sizeof(double);
+    int64_t cap = (int64_t)device_sm_count() * 32;
+    sparsemap_bwd_kernel<<<(int)(rows < cap ? rows : cap), 128, smem, as_stream(stream)>>>(
+        dp, offsets, only_positive, p_pad, aset_bits, counts, S_pad, dx, dt, rows, n);
+    SMLVM_LAUNCH_CHECK();
+    return SMLVM_OK;
+}

@@ -1,0 +1,599 @@
+// Batched sparsemax forward / backward for sm_100a.
+//
+// Semantics follow entmax.sparsemax as the reference calls it
+// (lvmhelpers/marg.py:51, lvmhelpers/structmarg.py:48) evaluated with torch CPU
+// ops, because support sets must be bit-exact against that path:
+//   X' = X - max(X)                      (fp32)
+//   S  = sort(X', descending)
+//   C_r = fl32(fl32(sum_{j<=r} S_j in fp64) - 1)      (torch CPU cumsum accumulates fp64)
+//   k  = #{ r : fl32(r * S_r) > C_r }    (strict)
+//   tau = C_k / k                        (fp32 divide)
+//   P  = max(X' - tau, 0)
+// Backward (SparsemaxFunction.backward):
+//   g <- dP with g = 0 where P == 0;  dX = where(P != 0, g - sum(g)/k, 0)
+//
+// Layout: a row of K fp32 lives in the registers of a G-lane sub-warp group
+// (E values per lane, E*G >= K), so a warp handles 32/G rows at once; the sort
+// is a bitonic network whose strides < E are register-local and whose strides
+// >= E are shuffles.  Rows wider than 1024 go through a shared-memory path
+// (one CTA per row).  Every row is read once and written once (HBM-bound
+// design point: 8K B/row forward, 12K B/row backward).
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace smlvm {
+
+constexpr int kThreads = 256;
+
+// ---- register path ---------------------------------------------------------
+
+// Column held by slot e of lane l.  VEC: 128-bit chunks interleaved across the
+// group (coalesced float4 accesses); scalar: plain striping.
+template <int E, int G, bool VEC>
+__device__ __forceinline__ int col_of(int e, int l)
+{
+    if (VEC) return 4 * ((e >> 2) * G + l) + (e & 3);
+    return e * G + l;
+}
+
+template <int E, int G, bool VEC>
+__device__ __forceinline__ void load_row(const float* __restrict__ base, int K, int l, float fill,
+                                         float (&v)[E])
+{
+    if (VEC) {
+#pragma unroll
+        for (int c = 0; c < E / 4; ++c) {
+            int col = 4 * (c * G + l);
+            float4 q = make_float4(fill, fill, fill, fill);
+            if (col < K) q = ldg_stream4(base + col);
+            v[4 * c + 0] = q.x; v[4 * c + 1] = q.y; v[4 * c + 2] = q.z; v[4 * c + 3] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            int col = e * G + l;
+            v[e] = (col < K) ? ldg_stream(base + col) : fill;
+        }
+    }
+}
+
+template <int E, int G, bool VEC>
+__device__ __forceinline__ void store_row(float* __restrict__ base, int K, int l,
+                                          const float (&v)[E])
+{
+    if (VEC) {
+#pragma unroll
+        for (int c = 0; c < E / 4; ++c) {
+            int col = 4 * (c * G + l);
+            if (col < K)
+                stg_stream4(base + col, make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            int col = e * G + l;
+            if (col < K) stg_stream(base + col, v[e]);
+        }
+    }
+}
+
+// Descending bitonic sort of the E*G values of a group; sorted position of
+// slot e in lane l is l*E + e.
+template <int E, int G>
+__device__ __forceinline__ void group_sort_desc(float (&s)[E], int l)
+{
+    constexpr int N = E * G;
+#pragma unroll
+    for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= E) {
+                const int lj = j / E;  // lane stride
+                const bool lower = (l & lj) == 0;
+                // every slot of a lane shares (pos & k) when k >= E... k > j >= E
+                const bool desc = ((l * E) & k) == 0;
+                const bool keep_max = (lower == desc);
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    float o = __shfl_xor_sync(kFull, s[e], lj, G);
+                    s[e] = keep_max ? fmaxf(s[e], o) : fminf(s[e], o);
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    if ((e & j) == 0) {
+                        const int f = e | j;
+                        // direction of the block containing pos = l*E + e
+                        const bool desc = (((l * E + e) & k) == 0);
+                        float hi = fmaxf(s[e], s[f]), lo = fminf(s[e], s[f]);
+                        s[e] = desc ? hi : lo;
+                        s[f] = desc ? lo : hi;
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int E, int G, bool VEC>
+__global__ void __launch_bounds__(kThreads)
+sparsemax_fwd_reg(const float* __restrict__ x, float* __restrict__ p, int32_t* __restrict__ supp,
+                  int32_t* __restrict__ nnz, float* __restrict__ ent, int64_t* __restrict__ amax,
+                  int64_t rows, int K)
+{
+    constexpr int RPW = kWarp / G;  // rows per warp
+    const int lane = threadIdx.x & 31;
+    const int l = lane % G;
+    const int g = lane / G;
+    const int64_t warps_total = (int64_t)gridDim.x * (kThreads / kWarp);
+    int64_t w = (int64_t)blockIdx.x * (kThreads / kWarp) + (threadIdx.x >> 5);
+
+    for (; w * RPW < rows; w += warps_total) {
+        const int64_t row = w * RPW + g;
+        const bool live = row < rows;
+        const int Kr = live ? K : 0;  // dead groups see an empty row (all -inf)
+        const float* xr = x + (live ? row : 0) * (int64_t)K;
+
+        float v[E];
+        load_row<E, G, VEC>(xr, Kr, l, -CUDART_INF_F, v);
+
+        // row max and its first index
+        float m = v[0];
+#pragma unroll
+        for (int e = 1; e < E; ++e) m = fmaxf(m, v[e]);
+        m = group_max<G>(m);
+
+        if (amax != nullptr) {
+            int first = 0x7fffffff;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                int col = col_of<E, G, VEC>(e, l);
+                if (col < Kr && v[e] == m) first = min(first, col);
+            }
+            first = group_reduce<G>(first, [](int a, int b) { return min(a, b); });
+            if (live && l == 0) amax[row] = first;
+        }
+
+        float s[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            v[e] = __fsub_rn(v[e], m);  // X' (padding stays -inf)
+            s[e] = v[e];
+        }
+        group_sort_desc<E, G>(s, l);
+
+        // fp64 inclusive prefix sums in sorted order
+        double cs[E];
+        double run = 0.0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            run += (double)s[e];
+            cs[e] = run;
+        }
+        double incl = run;  // lane totals -> exclusive offset of this lane
+#pragma unroll
+        for (int o = 1; o < G; o <<= 1) {
+            double t = __shfl_up_sync(kFull, incl, o, G);
+            if (l >= o) incl += t;
+        }
+        // (not incl - run: a lane holding -inf padding would turn that into NaN)
+        double excl = __shfl_up_sync(kFull, incl, 1, G);
+        if (l == 0) excl = 0.0;
+
+        float C[E];
+        int cnt = 0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int pos = l * E + e;
+            C[e] = __fsub_rn((float)(excl + cs[e]), 1.0f);
+            const float lhs = __fmul_rn((float)(pos + 1), s[e]);
+            cnt += (pos < Kr && lhs > C[e]) ? 1 : 0;
+        }
+        int k = group_sum<G>(cnt);
+        k = max(k, 1);
+
+        // tau = C[k-1] / k : fetch slot (k-1) % E of lane (k-1) / E
+        float ck = C[0];
+#pragma unroll
+        for (int e = 1; e < E; ++e) ck = (((k - 1) % E) == e) ? C[e] : ck;
+        ck = __shfl_sync(kFull, ck, (k - 1) / E, G);
+        const float tau = __fdiv_rn(ck, (float)k);
+
+        int nz = 0;
+        float h = 0.f;
+        const float eps = 1.1920928955078125e-07f;  // torch.finfo(float32).eps
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            float pe = fmaxf(__fsub_rn(v[e], tau), 0.f);
+            v[e] = pe;
+            if (pe > 0.f) {
+                ++nz;
+                if (ent != nullptr) {
+                    float ps = fminf(fmaxf(pe, eps), 1.f - eps);
+                    h = fmaf(ps, logf(ps), h);
+                }
+            }
+        }
+        if (live) store_row<E, G, VEC>(p + row * (int64_t)K, K, l, v);
+        if (nnz != nullptr) {
+            nz = group_sum<G>(nz);
+            if (live && l == 0) nnz[row] = nz;
+        }
+        if (ent != nullptr) {
+            h = group_sum<G>(h);
+            if (live && l == 0) ent[row] = -h;
+        }
+        if (supp != nullptr && live && l == 0) supp[row] = k;
+    }
+}
+
+// d entropy / d p for entropy() of marg.py:6-28: -(log p~ + 1) where the clamp
+// passes gradient (eps <= p <= 1-eps) and p > 0; 0 elsewhere.
+__device__ __forceinline__ float dent_dp(float p)
+{
+    const float eps = 1.1920928955078125e-07f;
+    return (p >= eps && p <= 1.f - eps) ? -(logf(p) + 1.f) : 0.f;
+}
+
+template <int E, int G, bool VEC>
+__global__ void __launch_bounds__(kThreads)
+sparsemax_bwd_reg(const float* __restrict__ p, const int32_t* __restrict__ supp,
+                  const float* __restrict__ dp, const float* __restrict__ loss,
+                  const float* __restrict__ loss_scale_dev, float loss_scale_host,
+                  const float* __restrict__ dent, float* __restrict__ dx, int64_t rows, int K)
+{
+    constexpr int RPW = kWarp / G;
+    const int lane = threadIdx.x & 31;
+    const int l = lane % G;
+    const int g = lane / G;
+    const int64_t warps_total = (int64_t)gridDim.x * (kThreads / kWarp);
+    int64_t w = (int64_t)blockIdx.x * (kThreads / kWarp) + (threadIdx.x >> 5);
+    float ls = loss_scale_host;
+    if (loss_scale_dev != nullptr) ls *= __ldg(loss_scale_dev);
+
+    for (; w * RPW < rows; w += warps_total) {
+        const int64_t row = w * RPW + g;
+        const bool live = row < rows;
+        const int Kr = live ? K : 0;
+        const int64_t off = (live ? row : 0) * (int64_t)K;
+
+        float pv[E], gv[E];
+        load_row<E, G, VEC>(p + off, Kr, l, 0.f, pv);
+        if (dp != nullptr) {
+            load_row<E, G, VEC>(dp + off, Kr, l, 0.f, gv);
+        } else {
+#pragma unroll
+            for (int e = 0; e < E; ++e) gv[e] = 0.f;
+        }
+        if (loss != nullptr) {
+            float lv[E];
+            load_row<E, G, VEC>(loss + off, Kr, l, 0.f, lv);
+#pragma unroll
+            for (int e = 0; e < E; ++e) gv[e] = fmaf(ls, lv[e], gv[e]);
+        }
+        if (dent != nullptr) {
+            const float de = live ? __ldg(dent + row) : 0.f;
+#pragma unroll
+            for (int e = 0; e < E; ++e) gv[e] = fmaf(de, dent_dp(pv[e]), gv[e]);
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            gv[e] = (pv[e] != 0.f) ? gv[e] : 0.f;
+            sum += gv[e];
+        }
+        sum = group_sum<G>(sum);
+        const int k = live ? __ldg(supp + row) : 1;
+        const float vhat = __fdiv_rn(sum, (float)k);
+#pragma unroll
+        for (int e = 0; e < E; ++e) gv[e] = (pv[e] != 0.f) ? __fsub_rn(gv[e], vhat) : 0.f;
+        if (live) store_row<E, G, VEC>(dx + off, K, l, gv);
+    }
+}
+
+// ---- shared-memory path (1024 < K <= 8192): one CTA per row -------------------
+
+constexpr int kWideThreads = 256;
+
+__global__ void __launch_bounds__(kWideThreads)
+sparsemax_fwd_wide(const float* __restrict__ x, float* __restrict__ p, int32_t* __restrict__ supp,
+                   int32_t* __restrict__ nnz, float* __restrict__ ent, int64_t* __restrict__ amax,
+                   int64_t rows, int K, int N /* pow2 >= K */)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* xs = reinterpret_cast<float*>(smem_raw);  // [N] shifted row
+    float* ss = xs + N;                              // [N] sorted copy
+    double* red = reinterpret_cast<double*>(ss + N); // [kWideThreads + 32]
+    __shared__ float s_f[2];
+    __shared__ int s_i[2];
+    const int tid = threadIdx.x;
+
+    for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+        const float* xr = x + row * (int64_t)K;
+        float m = -CUDART_INF_F;
+        for (int c = tid; c < N; c += kWideThreads) {
+            float val = (c < K) ? ldg_stream(xr + c) : -CUDART_INF_F;
+            xs[c] = val;
+            m = fmaxf(m, val);
+        }
+        m = group_max<32>(m);
+        float* redf = reinterpret_cast<float*>(red);
+        __syncthreads();
+        if ((tid & 31) == 0) redf[tid >> 5] = m;
+        __syncthreads();
+        m = redf[0];
+        for (int i = 1; i < kWideThreads / 32; ++i) m = fmaxf(m, redf[i]);
+        __syncthreads();
+        int first = 0x7fffffff;
+        for (int c = tid; c < N; c += kWideThreads) {
+            if (c < K && xs[c] == m) first = min(first, c);
+            float sh = __fsub_rn(xs[c], m);
+            xs[c] = sh;
+            ss[c] = sh;
+        }
+        if (amax != nullptr) {
+            first = group_reduce<32>(first, [](int a, int b) { return min(a, b); });
+            int* redi = reinterpret_cast<int*>(red);
+            if ((tid & 31) == 0) redi[tid >> 5] = first;
+            __syncthreads();
+            if (tid == 0) {
+                int f = redi[0];
+                for (int i = 1; i < kWideThreads / 32; ++i) f = min(f, redi[i]);
+                amax[row] = f;
+            }
+        }
+        __syncthreads();
+        // bitonic sort, descending
+        for (int k = 2; k <= N; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < N; i += kWideThreads) {
+                    int q = i ^ j;
+                    if (q > i) {
+                        bool desc = (i & k) == 0;
+                        float a = ss[i], b = ss[q];
+                        float hi = fmaxf(a, b), lo = fminf(a, b);
+                        ss[i] = desc ? hi : lo;
+                        ss[q] = desc ? lo : hi;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        // fp64 prefix sums: contiguous chunk per thread, then scan of chunk totals
+        const int chunk = N / kWideThreads;  // N >= 2048 > kWideThreads
+        const int beg = tid * chunk;
+        double run = 0.0;
+        for (int i = 0; i < chunk; ++i) run += (double)ss[beg + i];
+        red[tid] = run;
+        __syncthreads();
+        if (tid == 0) {
+            double acc = 0.0;
+            for (int i = 0; i < kWideThreads; ++i) {
+                double t = red[i];
+                red[i] = acc;
+                acc += t;
+            }
+        }
+        __syncthreads();
+        const double excl = red[tid];
+        run = 0.0;
+        int cnt = 0;
+        for (int i = 0; i < chunk; ++i) {
+            const int pos = beg + i;
+            run += (double)ss[pos];
+            float C = __fsub_rn((float)(excl + run), 1.0f);
+            float lhs = __fmul_rn((float)(pos + 1), ss[pos]);
+            cnt += (pos < K && lhs > C) ? 1 : 0;
+        }
+        cnt = group_sum<32>(cnt);
+        __syncthreads();
+        int* redi = reinterpret_cast<int*>(red);
+        const double excl_keep = excl;
+        if ((tid & 31) == 0) redi[tid >> 5] = cnt;
+        __syncthreads();
+        if (tid == 0) {
+            int kk = 0;
+            for (int i = 0; i < kWideThreads / 32; ++i) kk += redi[i];
+            s_i[0] = max(kk, 1);
+        }
+        __syncthreads();
+        const int k = s_i[0];
+        if ((k - 1) / chunk == tid) {
+            double r2 = 0.0;
+            for (int i = 0; i <= (k - 1) - beg; ++i) r2 += (double)ss[beg + i];
+            float C = __fsub_rn((float)(excl_keep + r2), 1.0f);
+            s_f[0] = __fdiv_rn(C, (float)k);
+        }
+        __syncthreads();
+        const float tau = s_f[0];
+        const float eps = 1.1920928955078125e-07f;
+        int nz = 0;
+        float h = 0.f;
+        float* pr = p + row * (int64_t)K;
+        for (int c = tid; c < K; c += kWideThreads) {
+            float pe = fmaxf(__fsub_rn(xs[c], tau), 0.f);
+            stg_stream(pr + c, pe);
+            if (pe > 0.f) {
+                ++nz;
+                float ps = fminf(fmaxf(pe, eps), 1.f - eps);
+                h = fmaf(ps, logf(ps), h);
+            }
+        }
+        double tot_h = block_sum((double)h, red);
+        double tot_nz = block_sum((double)nz, red);
+        if (tid == 0) {
+            if (supp != nullptr) supp[row] = k;
+            if (nnz != nullptr) nnz[row] = (int)tot_nz;
+            if (ent != nullptr) ent[row] = -(float)tot_h;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kWideThreads)
+sparsemax_bwd_wide(const float* __restrict__ p, const int32_t* __restrict__ supp,
+                   const float* __restrict__ dp, const float* __restrict__ loss,
+                   const float* __restrict__ loss_scale_dev, float loss_scale_host,
+                   const float* __restrict__ dent, float* __restrict__ dx, int64_t rows, int K)
+{
+    __shared__ double red[kWideThreads / 32 + 1];
+    const int tid = threadIdx.x;
+    float ls = loss_scale_host;
+    if (loss_scale_dev != nullptr) ls *= __ldg(loss_scale_dev);
+    for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int64_t off = row * (int64_t)K;
+        const float de = dent != nullptr ? __ldg(dent + row) : 0.f;
+        float sum = 0.f;
+        for (int c = tid; c < K; c += kWideThreads) {
+            float pe = p[off + c];
+            if (pe != 0.f) {
+                float g = dp != nullptr ? dp[off + c] : 0.f;
+                if (loss != nullptr) g = fmaf(ls, loss[off + c], g);
+                if (dent != nullptr) g = fmaf(de, dent_dp(pe), g);
+                sum += g;
+            }
+        }
+        const float tot = (float)block_sum((double)sum, red);
+        const float vhat = __fdiv_rn(tot, (float)__ldg(supp + row));
+        for (int c = tid; c < K; c += kWideThreads) {
+            float pe = p[off + c];
+            float o = 0.f;
+            if (pe != 0.f) {
+                float g = dp != nullptr ? dp[off + c] : 0.f;
+                if (loss != nullptr) g = fmaf(ls, loss[off + c], g);
+                if (dent != nullptr) g = fmaf(de, dent_dp(pe), g);
+                o = __fsub_rn(g, vhat);
+            }
+            stg_stream(dx + off + c, o);
+        }
+        __syncthreads();
+    }
+}
+
+// ---- host dispatch ----------------------------------------------------------------
+
+struct RegShape {
+    int E, G;
+};
+
+// Smallest (E, G) tile with E*G >= K; E = 4 (one float4 per lane) up to K = 128.
+static RegShape pick_shape(int K)
+{
+    if (K <= 4) return {4, 1};
+    if (K <= 8) return {4, 2};
+    if (K <= 16) return {4, 4};
+    if (K <= 32) return {4, 8};
+    if (K <= 64) return {4, 16};
+    if (K <= 128) return {4, 32};
+    if (K <= 256) return {8, 32};
+    if (K <= 512) return {16, 32};
+    return {32, 32};
+}
+
+static int grid_for(int64_t rows, int G)
+{
+    const int rows_per_cta = (kThreads / kWarp) * (kWarp / G);
+    int64_t need = (rows + rows_per_cta - 1) / rows_per_cta;
+    int64_t cap = (int64_t)device_sm_count() * 16;  // resident waves; grid-stride beyond
+    return (int)(need < cap ? (need > 0 ? need : 1) : cap);
+}
+
+template <int E, int G>
+static void launch_fwd(bool vec, int grid, cudaStream_t st, const float* x, float* p, int32_t* supp,
+                       int32_t* nnz, float* ent, int64_t* amax, int64_t rows, int K)
+{
+    if (vec)
+        sparsemax_fwd_reg<E, G, true><<<grid, kThreads, 0, st>>>(x, p, supp, nnz, ent, amax, rows, K);
+    else
+        sparsemax_fwd_reg<E, G, false><<<grid, kThreads, 0, st>>>(x, p, supp, nnz, ent, amax, rows, K);
+}
+template <int E, int G>
+static void launch_bwd(bool vec, int grid, cudaStream_t st, const float* p, const int32_t* supp,
+                       const float* dp, const float* loss, const float* lsd, float lsh,
+                       const float* dent, float* dx, int64_t rows, int K)
+{
+    if (vec)
+        sparsemax_bwd_reg<E, G, true><<<grid, kThreads, 0, st>>>(p, supp, dp, loss, lsd, lsh, dent, dx, rows, K);
+    else
+        sparsemax_bwd_reg<E, G, false><<<grid, kThreads, 0, st>>>(p, supp, dp, loss, lsd, lsh, dent, dx, rows, K);
+}
+
+#define SMLVM_DISPATCH_SHAPE(FN, ...)                                   \
+    switch (sh.E * 100 + sh.G) {                                        \
+        case 401: FN<4, 1>(__VA_ARGS__); break;                         \
+        case 402: FN<4, 2>(__VA_ARGS__); break;                         \
+        case 404: FN<4, 4>(__VA_ARGS__); break;                         \
+        case 408: FN<4, 8>(__VA_ARGS__); break;                         \
+        case 416: FN<4, 16>(__VA_ARGS__); break;                        \
+        case 432: FN<4, 32>(__VA_ARGS__); break;                        \
+        case 832: FN<8, 32>(__VA_ARGS__); break;                        \
+        case 1632: FN<16, 32>(__VA_ARGS__); break;                      \
+        default: FN<32, 32>(__VA_ARGS__); break;                        \
+    }
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace smlvm
+
+using namespace smlvm;
+
+extern "C" int smlvm_sparsemax_fwd(const float* x, float* p, int32_t* supp_size, int32_t* nnz,
+                                   float* entropy, int64_t* argmax, int64_t rows, int32_t cols,
+                                   void* stream)
+{
+    if (rows < 0 || cols < 1) return SMLVM_ERR_ARG;
+    if (rows == 0) return SMLVM_OK;
+    if (x == nullptr || p == nullptr) return SMLVM_ERR_ARG;
+    if (cols > SMLVM_SPARSEMAX_MAX_COLS) return SMLVM_ERR_UNSUPPORTED;
+    cudaStream_t st = as_stream(stream);
+    if (cols <= 1024) {
+        RegShape sh = pick_shape(cols);
+        const bool vec = (cols % 4 == 0) && aligned16(x) && aligned16(p);
+        const int grid = grid_for(rows, sh.G);
+        SMLVM_DISPATCH_SHAPE(launch_fwd, vec, grid, st, x, p, supp_size, nnz, entropy, argmax, rows, cols);
+    } else {
+        int N = 2048;
+        while (N < cols) N <<= 1;
+        size_t smem = (size_t)N * 8 + (kWideThreads + 32) * sizeof(double);
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(sparsemax_fwd_wide, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 8192 * 8 + (kWideThreads + 32) * (int)sizeof(double));
+            attr_set = true;
+        }
+        int64_t cap = (int64_t)device_sm_count() * 8;
+        int grid = (int)(rows < cap ? rows : cap);
+        sparsemax_fwd_wide<<<grid, kWideThreads, smem, st>>>(x, p, supp_size, nnz, entropy, argmax,
+                                                             rows, cols, N);
+    }
+    SMLVM_LAUNCH_CHECK();
+    return SMLVM_OK;
+}
+
+extern "C" int smlvm_sparsemax_bwd(const float* p, const int32_t* supp_size, const float* dp,
+                                   const float* loss, const float* loss_scale_dev,
+                                   float loss_scale_host, const float* dent, float* dx, int64_t rows,
+                                   int32_t cols, void* stream)
+{
+    if (rows < 0 || cols < 1) return SMLVM_ERR_ARG;
+    if (rows == 0) return SMLVM_OK;
+    if (p == nullptr || supp_size == nullptr || dx == nullptr) return SMLVM_ERR_ARG;
+    if (cols > SMLVM_SPARSEMAX_MAX_COLS) return SMLVM_ERR_UNSUPPORTED;
+    cudaStream_t st = as_stream(stream);
+    if (cols <= 1024) {
+        RegShape sh = pick_shape(cols);
+        const bool vec = (cols % 4 == 0) && aligned16(p) && aligned16(dx) &&
+                         (dp == nullptr || aligned16(dp)) && (loss == nullptr || aligned16(loss));
+        const int grid = grid_for(rows, sh.G);
+        SMLVM_DISPATCH_SHAPE(launch_bwd, vec, grid, st, p, supp_size, dp, loss, loss_scale_dev,
+                             loss_scale_host, dent, dx, rows, cols);
+    } else {
+        int64_t cap = (int64_t)device_sm_count() * 8;
+        int grid = (int)(rows < cap ? rows : cap);
+        sparsemax_bwd_wide<<<grid, kWideThreads, 0, st>>>(p, supp_size, dp, loss, loss_scale_dev,
+                                                          loss_scale_host, dent, dx, rows, cols);
+    }
+    SMLVM_LAUNCH_CHECK();
+    return SMLVM_OK;
+}

@@ -1,0 +1,236 @@
+// k-best bit-vectors of n independent bits for sm_100a.
+//
+// replaces lvmhelpers.pbinary_topk.batched_topk (lvmhelpers/pbinary_topk.pyx:23-34) ->
+// topk()/merge_branch() (lvmhelpers/binary_topk.h:57-129).  Results are bit-exact with the
+// reference: same list initialisation (x0 >= 0, :110), same fp32 score accumulation in bit
+// order (:27-29), same merge tie rule ("bit on" only if STRICTLY greater, :72), same
+// truncation to k after every bit.
+//
+// Mapping: one G-lane group per row (G = 8/16/32 >= k), lane r owns list slot r: its fp32
+// score and its configuration as W 32-bit words in registers.  The sequential list merge of
+// the reference becomes a merge-path search: output slot r finds by binary search (shuffles
+// inside the group) how many "bit off" items precede it, then gathers score and words from
+// the source lane.  n steps of O(log k) shuffles per row; the scores row is staged in
+// shared memory; the fp32 {0,1} output (4*k*n B/row, the API's format) is written coalesced.
+#include "common.cuh"
+
+namespace smlvm {
+
+constexpr int kThreads = 256;
+
+template <int G, int W>
+__global__ void __launch_bounds__(kThreads)
+topk_bits_kernel(const float* __restrict__ x, float* __restrict__ configs,
+                 uint32_t* __restrict__ bits, float* __restrict__ dp_scores, int64_t rows, int n,
+                 int k, int n_pad)
+{
+    extern __shared__ float xs_all[];
+    constexpr int GPW = kWarp / G;
+    const int lane = threadIdx.x & 31;
+    const int l = lane % G;
+    const int g = lane / G;
+    float* xs = xs_all + ((threadIdx.x >> 5) * GPW + g) * n_pad;
+    const int words_n = (n + 31) >> 5;
+    const int64_t warps_total = (int64_t)gridDim.x * (kThreads / kWarp);
+    int64_t w = (int64_t)blockIdx.x * (kThreads / kWarp) + (threadIdx.x >> 5);
+
+    for (; w * GPW < rows; w += warps_total) {
+        const int64_t row = w * GPW + g;
+        const bool live = row < rows;
+        const float* xr = x + (live ? row : 0) * (int64_t)n;
+        __syncwarp();
+        for (int c = l; c < n; c += G) xs[c] = live ? ldg_stream(xr + c) : 0.f;
+        __syncwarp();
+
+        // list = [(x0,{0}), (0,{})] ordered by x0 >= 0        (binary_topk.h:104-116)
+        const float x0 = xs[0];
+        const bool on_first = x0 >= 0.f;
+        float sc = 0.f;
+        uint32_t cfg[W];
+#pragma unroll
+        for (int i = 0; i < W; ++i) cfg[i] = 0u;
+        if (l == 0) { sc = on_first ? x0 : 0.f; cfg[0] = on_first ? 1u : 0u; }
+        if (l == 1) { sc = on_first ? 0.f : x0; cfg[0] = on_first ? 0u : 1u; }
+        int len = 2;
+
+        for (int i = 1; i < n; ++i) {
+            const float v = xs[i];
+            const int outlen = min(k, 2 * len);
+            const int r = min(l, 2 * len - 1);
+            int lo = max(0, r - len), hi = min(r, len);
+            // merge path: a = number of "off" items among the first r outputs
+            for (int s = 0; (1 << s) <= len; ++s) {
+                const int mid = (lo + hi) >> 1;
+                const float am = __shfl_sync(kFull, sc, min(mid, len - 1), G);
+                const float bm = __fadd_rn(__shfl_sync(kFull, sc, max(r - mid - 1, 0), G), v);
+                if (lo < hi) {
+                    if (am >= bm) lo = mid + 1; else hi = mid;
+                }
+            }
+            const int a = lo, b = r - lo;
+            const float Aa = __shfl_sync(kFull, sc, min(a, len - 1), G);
+            const float Bb = __fadd_rn(__shfl_sync(kFull, sc, min(b, len - 1), G), v);
+            const bool takeA = (a < len) && (b >= len || Aa >= Bb);
+            const int src = takeA ? a : b;
+            sc = takeA ? Aa : Bb;
+            const int wi = i >> 5;
+            const uint32_t bit = takeA ? 0u : (1u << (i & 31));
+#pragma unroll
+            for (int q = 0; q < W; ++q) {
+                if (q <= wi) {  // words above the current bit are still all zero
+                    uint32_t t = __shfl_sync(kFull, cfg[q], src, G);
+                    cfg[q] = t | (q == wi ? bit : 0u);
+                }
+            }
+            len = outlen;
+        }
+
+        if (live) {
+            if (dp_scores != nullptr && l < k) dp_scores[row * k + l] = sc;
+            if (bits != nullptr && l < k) {
+#pragma unroll
+                for (int q = 0; q < W; ++q)
+                    if (q < words_n) bits[(row * k + l) * words_n + q] = cfg[q];
+            }
+        }
+        if (configs != nullptr) {
+            for (int j = 0; j < k; ++j) {
+                float* out = configs + ((live ? row : 0) * k + j) * (int64_t)n;
+#pragma unroll
+                for (int q = 0; q < W; ++q) {
+                    const uint32_t word = __shfl_sync(kFull, cfg[q], j, G);
+                    if (live && q < words_n) {
+                        const int hi_c = min(n, q * 32 + 32);
+                        for (int c = q * 32 + l; c < hi_c; c += G)
+                            stg_stream(out + c, (float)((word >> (c & 31)) & 1u));
+                    }
+                }
+            }
+        }
+    }
+}
+
+// scores_k[r,j] = sum_i bit(r,j,i) * x[r,i]; one thread per (row, j); fp64 accumulate.
+__global__ void __launch_bounds__(kThreads)
+bits_score_fwd_kernel(const uint32_t* __restrict__ bits, const float* __restrict__ x,
+                      float* __restrict__ scores_k, int64_t rows, int n, int k)
+{
+    const int words_n = (n + 31) >> 5;
+    const int64_t total = rows * k;
+    for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * kThreads) {
+        const int64_t r = t / k;
+        const uint32_t* b = bits + t * words_n;
+        const float* xr = x + r * (int64_t)n;
+        double acc = 0.0;
+        for (int q = 0; q < words_n; ++q) {
+            uint32_t word = __ldg(b + q);
+            while (word) {
+                const int i = __ffs(word) - 1;
+                word &= word - 1;
+                acc += (double)__ldg(xr + q * 32 + i);
+            }
+        }
+        scores_k[t] = (float)acc;
+    }
+}
+
+// dx[r,i] = sum_j ds[r,j] * bit(r,j,i); one thread per (row, i).
+__global__ void __launch_bounds__(kThreads)
+bits_score_bwd_kernel(const uint32_t* __restrict__ bits, const float* __restrict__ ds,
+                      float* __restrict__ dx, int64_t rows, int n, int k)
+{
+    const int words_n = (n + 31) >> 5;
+    const int64_t total = rows * n;
+    for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * kThreads) {
+        const int64_t r = t / n;
+        const int i = (int)(t - r * n);
+        float acc = 0.f;
+        for (int j = 0; j < k; ++j) {
+            const uint32_t word = __ldg(bits + (r * k + j) * words_n + (i >> 5));
+            if ((word >> (i & 31)) & 1u) acc += __ldg(ds + r * k + j);
+        }
+        dx[t] = acc;
+    }
+}
+
+template <int G>
+static void launch_topk_w(int W, int grid, size_t smem, cudaStream_t st, const float* x,
+                          float* configs, uint32_t* bits, float* dp_scores, int64_t rows, int n,
+                          int k, int n_pad)
+{
+#define SMLVM_TOPK_CASE(WW)                                                                       \
+    case WW:                                                                                      \
+        cudaFuncSetAttribute(topk_bits_kernel<G, WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                             (int)smem);                                                          \
+        topk_bits_kernel<G, WW><<<grid, kThreads, smem, st>>>(x, configs, bits, dp_scores, rows, n, \
+                                                              k, n_pad);                          \
+        break;
+    switch (W) {
+        SMLVM_TOPK_CASE(1)
+        SMLVM_TOPK_CASE(2)
+        SMLVM_TOPK_CASE(4)
+        SMLVM_TOPK_CASE(8)
+        SMLVM_TOPK_CASE(16)
+    }
+#undef SMLVM_TOPK_CASE
+}
+
+}  // namespace smlvm
+
+using namespace smlvm;
+
+extern "C" int smlvm_topk_bits(const float* x, float* configs, uint32_t* bits, float* dp_scores,
+                               int64_t rows, int32_t n, int32_t k, void* stream)
+{
+    if (rows < 0 || n < 1 || k < 2) return SMLVM_ERR_ARG;  // k > 1: binary_topk.h:102
+    if (n < 31 && (1 << n) < k) return SMLVM_ERR_ARG;      // fewer than k bit-vectors exist
+    if (n > SMLVM_TOPK_MAX_BITS || k > SMLVM_TOPK_MAX_K) return SMLVM_ERR_UNSUPPORTED;
+    if (rows == 0) return SMLVM_OK;
+    if (x == nullptr) return SMLVM_ERR_ARG;
+    const int G = k <= 8 ? 8 : (k <= 16 ? 16 : 32);
+    const int words_n = (n + 31) >> 5;
+    int W = 1;
+    while (W < words_n) W <<= 1;
+    const int n_pad = (n + 3) & ~3;
+    const int groups_per_cta = (kThreads / kWarp) * (kWarp / G);
+    const size_t smem = (size_t)groups_per_cta * n_pad * sizeof(float);
+    int64_t need = (rows + groups_per_cta - 1) / groups_per_cta;
+    int64_t cap = (int64_t)device_sm_count() * 8;
+    const int grid = (int)(need < cap ? need : cap);
+    cudaStream_t st = as_stream(stream);
+    if (G == 8) launch_topk_w<8>(W, grid, smem, st, x, configs, bits, dp_scores, rows, n, k, n_pad);
+    else if (G == 16) launch_topk_w<16>(W, grid, smem, st, x, configs, bits, dp_scores, rows, n, k, n_pad);
+    else launch_topk_w<32>(W, grid, smem, st, x, configs, bits, dp_scores, rows, n, k, n_pad);
+    SMLVM_LAUNCH_CHECK();
+    return SMLVM_OK;
+}
+
+extern "C" int smlvm_bits_score_fwd(const uint32_t* bits, const float* x, float* scores_k,
+                                    int64_t rows, int32_t n, int32_t k, void* stream)
+{
+    if (rows < 0 || n < 1 || k < 1) return SMLVM_ERR_ARG;
+    if (rows == 0) return SMLVM_OK;
+    if (bits == nullptr || x == nullptr || scores_k == nullptr) return SMLVM_ERR_ARG;
+    int64_t need = (rows * k + kThreads - 1) / kThreads;
+    int64_t cap = (int64_t)device_sm_count() * 16;
+    bits_score_fwd_kernel<<<(int)(need < cap ? need : cap), kThreads, 0, as_stream(stream)>>>(
+        bits, x, scores_k, rows, n, k);
+    SMLVM_LAUNCH_CHECK();
+    return SMLVM_OK;
+}
+
+extern "C" int smlvm_bits_score_bwd(const uint32_t* bits, const float* dscores_k, float* dx,
+                                    int64_t rows, int32_t n, int32_t k, void* stream)
+{
+    if (rows < 0 || n < 1 || k < 1) return SMLVM_ERR_ARG;
+    if (rows == 0) return SMLVM_OK;
+    if (bits == nullptr || dscores_k == nullptr || dx == nullptr) return SMLVM_ERR_ARG;
+    int64_t need = (rows * n + kThreads - 1) / kThreads;
+    int64_t cap = (int64_t)device_sm_count() * 16;
+    bits_score_bwd_kernel<<<(int)(need < cap ? need : cap), kThreads, 0, as_stream(stream)>>>(
+        bits, dscores_k, dx, rows, n, k);
+    SMLVM_LAUNCH_CHECK();
+    return SMLVM_OK;
+}

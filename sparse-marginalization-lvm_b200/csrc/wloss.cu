@@ -1,0 +1,231 @@
+// Probability-weighted loss for sm_100a: fused (segmented) reduce.
+//
+// replaces
+//   dense : encoder_probs.unsqueeze(1).bmm(losses.unsqueeze(-1)) + .mean()  lvmhelpers/marg.py:125-126
+//   ragged: (p @ loss_components) / batch_size                              lvmhelpers/structmarg.py:140,242
+//           -p . log p / batch_size  (structured entropy)                   lvmhelpers/structmarg.py:51-58,200-202
+//
+// Totals are accumulated in fp64 and finished by the last CTA in a fixed order, so the
+// scalar is run-to-run deterministic.  Streaming kernels: 8 B per (p, loss) pair forward,
+// 8 B read + 8 B written backward.
+#include "common.cuh"
+
+namespace smlvm {
+
+constexpr int kThreads = 256;
+constexpr int kMaxCtas = 2048;
+
+// workspace layout: [0] uint32 arrival counter (self-resetting), [64..] double partials[3][kMaxCtas]
+struct ReduceWs {
+    unsigned int* counter;
+    double* part;  // [3 * kMaxCtas]
+};
+__host__ __device__ inline ReduceWs ws_view(void* ws)
+{
+    ReduceWs r;
+    r.counter = reinterpret_cast<unsigned int*>(ws);
+    r.part = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(ws) + 64);
+    return r;
+}
+
+// Every CTA deposits up to 3 partial sums; the last CTA to arrive adds them up in CTA order.
+__device__ __forceinline__ void finish_totals(ReduceWs ws, double a, double b, float scale,
+                                              float* out_a, float* out_b, double* smem)
+{
+    a = block_sum(a, smem);
+    b = block_sum(b, smem);
+    __shared__ bool s_last;
+    if (threadIdx.x == 0) {
+        ws.part[blockIdx.x] = a;
+        ws.part[kMaxCtas + blockIdx.x] = b;
+        __threadfence();
+        unsigned int t = atomicAdd(ws.counter, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        double sa = 0.0, sb = 0.0;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+            sa += __ldcg(ws.part + i);
+            sb += __ldcg(ws.part + kMaxCtas + i);
+        }
+        sa = block_sum(sa, smem);
+        sb = block_sum(sb, smem);
+        if (threadIdx.x == 0) {
+            if (out_a != nullptr) *out_a = (float)((double)scale * sa);
+            if (out_b != nullptr) *out_b = (float)((double)scale * sb);
+            *ws.counter = 0u;  // leave the workspace ready for the next call
+        }
+    }
+}
+
+template <int G>
+__global__ void __launch_bounds__(kThreads)
+wloss_dense_kernel(const float* __restrict__ p, const float* __restrict__ loss,
+                   float* __restrict__ row_loss, float* __restrict__ total, float scale,
+                   int64_t rows, int K, bool vec, ReduceWs ws)
+{
+    __shared__ double smem[kThreads / 32 + 1];
+    constexpr int RPW = kWarp / G;
+    const int lane = threadIdx.x & 31;
+    const int l = lane % G;
+    const int g = lane / G;
+    const int64_t warps_total = (int64_t)gridDim.x * (kThreads / kWarp);
+    int64_t w = (int64_t)blockIdx.x * (kThreads / kWarp) + (threadIdx.x >> 5);
+    double acc = 0.0;
+    for (; w * RPW < rows; w += warps_total) {
+        const int64_t row = w * RPW + g;
+        const bool live = row < rows;
+        const int64_t off = (live ? row : 0) * (int64_t)K;
+        float s = 0.f;
+        if (live) {
+            if (vec) {
+                for (int c = 4 * l; c < K; c += 4 * G) {
+                    float4 a = ldg_stream4(p + off + c), b = ldg_stream4(loss + off + c);
+                    s = fmaf(a.x, b.x, s); s = fmaf(a.y, b.y, s);
+                    s = fmaf(a.z, b.z, s); s = fmaf(a.w, b.w, s);
+                }
+            } else {
+                for (int c = l; c < K; c += G) s = fmaf(ldg_stream(p + off + c), ldg_stream(loss + off + c), s);
+            }
+        }
+        s = group_sum<G>(s);
+        if (live && l == 0) {
+            if (row_loss != nullptr) row_loss[row] = s;
+            acc += (double)s;
+        }
+    }
+    if (total != nullptr) finish_totals(ws, acc, 0.0, scale, total, nullptr, smem);
+}
+
+__global__ void __launch_bounds__(kThreads)
+wloss_ragged_kernel(const float* __restrict__ p, const float* __restrict__ loss,
+                    const int64_t* __restrict__ offsets, float* __restrict__ row_loss,
+                    float* __restrict__ total, float* __restrict__ neg_plogp, float scale,
+                    int64_t rows, int64_t n_items, ReduceWs ws)
+{
+    __shared__ double smem[kThreads / 32 + 1];
+    const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * kThreads;
+    double acc = 0.0, ent = 0.0;
+    if (total != nullptr || neg_plogp != nullptr) {
+        for (int64_t i = tid; i < n_items; i += nthreads) {
+            const float pi = __ldg(p + i);
+            if (loss != nullptr) acc += (double)(pi * __ldg(loss + i));
+            if (neg_plogp != nullptr) ent -= (double)(pi * logf(pi));
+        }
+    }
+    if (row_loss != nullptr) {
+        // one 8-lane group per segment (supports are short: tens of items)
+        constexpr int G = 8;
+        constexpr int RPW = kWarp / G;
+        const int l = threadIdx.x % G;
+        const int g = (threadIdx.x & 31) / G;
+        // warp-uniform outer loop: the group reduction needs all 32 lanes present
+        for (int64_t r0 = (tid / kWarp) * RPW; r0 < rows; r0 += (nthreads / kWarp) * RPW) {
+            const int64_t r = r0 + g;
+            const bool live = r < rows;
+            const int64_t b = live ? __ldg(offsets + r) : 0, e = live ? __ldg(offsets + r + 1) : 0;
+            float s = 0.f;
+            for (int64_t i = b + l; i < e; i += G) s = fmaf(__ldg(p + i), __ldg(loss + i), s);
+            s = group_sum<G>(s);
+            if (live && l == 0) row_loss[r] = s;
+        }
+    }
+    if (total != nullptr || neg_plogp != nullptr)
+        finish_totals(ws, acc, ent, scale, total, neg_plogp, smem);
+}
+
+__global__ void __launch_bounds__(kThreads)
+wloss_ragged_bwd_kernel(const float* __restrict__ p, const float* __restrict__ loss,
+                        const float* __restrict__ g, const float* __restrict__ gent, float scale,
+                        float* __restrict__ dp, float* __restrict__ dloss, int64_t n_items)
+{
+    const float gs = (g != nullptr ? __ldg(g) : 0.f) * scale;
+    const float ge = (gent != nullptr ? __ldg(gent) : 0.f) * scale;
+    const int64_t nthreads = (int64_t)gridDim.x * kThreads;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n_items; i += nthreads) {
+        const float pi = __ldg(p + i);
+        if (dp != nullptr) {
+            float d = (loss != nullptr) ? gs * __ldg(loss + i) : 0.f;
+            if (gent != nullptr) d -= ge * (logf(pi) + 1.f);
+            dp[i] = d;
+        }
+        if (dloss != nullptr) dloss[i] = gs * pi;
+    }
+}
+
+static int grid_1d(int64_t work_items, int per_cta)
+{
+    int64_t need = (work_items + per_cta - 1) / per_cta;
+    int64_t cap = (int64_t)device_sm_count() * 8;
+    if (cap > kMaxCtas) cap = kMaxCtas;
+    return (int)(need < cap ? (need > 0 ? need : 1) : cap);
+}
+
+}  // namespace smlvm
+
+using namespace smlvm;
+
+extern "C" size_t smlvm_reduce_workspace_bytes(void) { return 64 + 3 * sizeof(double) * kMaxCtas; }
+
+extern "C" int smlvm_wloss_dense_fwd(const float* p, const float* loss, float* row_loss,
+                                     float* total, float scale, int64_t rows, int32_t cols,
+                                     void* workspace, size_t workspace_bytes, void* stream)
+{
+    if (rows < 0 || cols < 1) return SMLVM_ERR_ARG;
+    if (p == nullptr || loss == nullptr) return SMLVM_ERR_ARG;
+    if (total != nullptr && (workspace == nullptr || workspace_bytes < smlvm_reduce_workspace_bytes()))
+        return SMLVM_ERR_WORKSPACE;
+    cudaStream_t st = as_stream(stream);
+    int G = 1;
+    while (G < 32 && G * 4 < cols) G <<= 1;
+    const bool vec = (cols % 4 == 0) && ((reinterpret_cast<uintptr_t>(p) & 15u) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(loss) & 15u) == 0);
+    const int rows_per_cta = (kThreads / kWarp) * (kWarp / G);
+    const int grid = grid_1d(rows, rows_per_cta);
+    ReduceWs ws = ws_view(workspace);
+    switch (G) {
+        case 1: wloss_dense_kernel<1><<<grid, kThreads, 0, st>>>(p, loss, row_loss, total, scale, rows, cols, vec, ws); break;
+        case 2: wloss_dense_kernel<2><<<grid, kThreads, 0, st>>>(p, loss, row_loss, total, scale, rows, cols, vec, ws); break;
+        case 4: wloss_dense_kernel<4><<<grid, kThreads, 0, st>>>(p, loss, row_loss, total, scale, rows, cols, vec, ws); break;
+        case 8: wloss_dense_kernel<8><<<grid, kThreads, 0, st>>>(p, loss, row_loss, total, scale, rows, cols, vec, ws); break;
+        case 16: wloss_dense_kernel<16><<<grid, kThreads, 0, st>>>(p, loss, row_loss, total, scale, rows, cols, vec, ws); break;
+        default: wloss_dense_kernel<32><<<grid, kThreads, 0, st>>>(p, loss, row_loss, total, scale, rows, cols, vec, ws); break;
+    }
+    SMLVM_LAUNCH_CHECK();
+    return SMLVM_OK;
+}
+
+extern "C" int smlvm_wloss_ragged_fwd(const float* p, const float* loss, const int64_t* offsets,
+                                      float* row_loss, float* total, float* neg_plogp, float scale,
+                                      int64_t rows, int64_t n_items, void* workspace,
+                                      size_t workspace_bytes, void* stream)
+{
+    if (rows < 0 || n_items < 0 || p == nullptr) return SMLVM_ERR_ARG;
+    if ((total != nullptr || row_loss != nullptr) && loss == nullptr) return SMLVM_ERR_ARG;
+    if (row_loss != nullptr && offsets == nullptr) return SMLVM_ERR_ARG;
+    if ((total != nullptr || neg_plogp != nullptr) &&
+        (workspace == nullptr || workspace_bytes < smlvm_reduce_workspace_bytes()))
+        return SMLVM_ERR_WORKSPACE;
+    int64_t work = n_items > rows * 8 ? n_items : rows * 8;
+    const int grid = grid_1d(work, kThreads);
+    wloss_ragged_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(
+        p, loss, offsets, row_loss, total, neg_plogp, scale, rows, n_items, ws_view(workspace));
+    SMLVM_LAUNCH_CHECK();
+    return SMLVM_OK;
+}
+
+extern "C" int smlvm_wloss_ragged_bwd(const float* p, const float* loss, const float* g,
+                                      const float* gent, float scale, float* dp, float* dloss,
+                                      int64_t n_items, void* stream)
+{
+    if (n_items < 0 || p == nullptr) return SMLVM_ERR_ARG;
+    if (n_items == 0) return SMLVM_OK;
+    const int grid = grid_1d(n_items, kThreads);
+    wloss_ragged_bwd_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(p, loss, g, gent, scale, dp,
+                                                                      dloss, n_items);
+    SMLVM_LAUNCH_CHECK();
+    return SMLVM_OK;
+}

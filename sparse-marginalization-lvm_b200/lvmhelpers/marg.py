@@ -1,0 +1,160 @@
+"""lvmhelpers.marg counterpart: categorical sparsemax marginalisation.
+
+Reference: lvmhelpers/marg.py.  Same public names, arguments and return
+conventions (``entropy``, ``ExplicitWrapper``, ``Marginalizer``); the sparsemax
+normaliser, its entropy/argmax, the probability-weighted loss and the whole
+backward run as fused sm_100a kernels (``ops.sparsemax_stats``,
+``smlvm_wloss_dense_fwd``, ``smlvm_sparsemax_bwd``).
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+def entropy(p: torch.Tensor):
+    """Shannon entropy of rows with exact zeros (reference marg.py:6-28).
+
+    Kept in torch ops so it stays usable on any tensor; the sparsemax path of
+    ``ExplicitWrapper`` gets the same quantity fused into its forward kernel.
+    """
+    nz = p > 0
+    eps = torch.finfo(p.dtype).eps
+    p_stable = p.clone().clamp(min=eps, max=1 - eps)
+    out = torch.where(nz, p_stable * torch.log(p_stable),
+                      torch.tensor(0., device=p.device, dtype=torch.float))
+    return -(out).sum(-1)
+
+
+class _FusedMarginalObjective(torch.autograd.Function):
+    """mean_b sum_z P[b,z] L[b,z]  -  coeff * mean_b H(P[b,:])   (marg.py:83,125-126).
+
+    Forward: one segmented-reduce launch.  Backward: ONE launch that applies the
+    sparsemax Jacobian to g*L/B + d(-coeff*mean H)/dP without materialising dP, and
+    an elementwise P*g/B for the decoder side.
+    """
+
+    @staticmethod
+    def forward(ctx, scores, losses, p, supp, ent_rows, coeff):
+        rows = p.shape[0]
+        row_loss, total = ops.wloss_dense_fwd(p, losses, scale=1.0 / rows)
+        ctx.save_for_backward(p, supp, losses)
+        ctx.coeff = float(coeff)
+        ctx.mark_non_differentiable(row_loss)
+        full = total - ctx.coeff * ent_rows.mean()
+        return full, total.clone(), row_loss
+
+    @staticmethod
+    def backward(ctx, g_full, g_total, _g_rows):
+        p, supp, losses = ctx.saved_tensors
+        rows = p.shape[0]
+        g = (g_full + g_total).contiguous().float()
+        dscores = dlosses = None
+        if ctx.needs_input_grad[0]:
+            dent = None
+            if ctx.coeff != 0.0:
+                dent = (g_full.float() * (-ctx.coeff / rows)).expand(rows).contiguous()
+            dscores = ops.sparsemax_bwd(p, supp, loss=losses, loss_scale=g,
+                                        loss_scale_host=1.0 / rows, dent=dent)
+        if ctx.needs_input_grad[1]:
+            dlosses = p * (g / rows)
+        return dscores, dlosses, None, None, None, None
+
+
+class ExplicitWrapper(nn.Module):
+    """scores -> (sample, distribution, entropy) (reference marg.py:31-54).
+
+    ``normalizer='sparsemax'`` is the B200-native path (one fused kernel for
+    sparsemax + entropy + argmax).  ``'softmax'`` stays on torch ops.
+    ``'entmax'`` (entmax15) is outside the replaced hot path and raises.
+    """
+
+    def __init__(self, agent, normalizer='entmax'):
+        super().__init__()
+        self.agent = agent
+        if normalizer not in ('softmax', 'sparsemax', 'entmax'):
+            raise KeyError(normalizer)
+        self.normalizer_name = normalizer
+
+    def forward(self, *args, **kwargs):
+        scores = self.agent(*args, **kwargs)
+        if self.normalizer_name == 'sparsemax':
+            shp = scores.shape
+            flat = scores.reshape(-1, shp[-1])
+            distr, entropy_distr, sample, nnz, supp = ops.sparsemax_stats(flat)
+            distr = distr.reshape(shp)
+            # side channel for Marginalizer: lets it fuse loss + entropy gradients into
+            # one backward launch (dP never materialised)
+            distr._smlvm = dict(scores=flat, nnz=nnz, entropy=entropy_distr, supp=supp)
+            return sample.reshape(shp[:-1]), distr, entropy_distr.reshape(shp[:-1])
+        if self.normalizer_name == 'softmax':
+            distr = torch.softmax(scores, dim=-1)
+            return scores.argmax(dim=-1), distr, entropy(distr)
+        raise NotImplementedError(
+            "normalizer='entmax' (entmax15) is not part of the sparse-marginalization hot path "
+            "replaced by this package; use 'sparsemax' or 'softmax'")
+
+
+class Marginalizer(torch.nn.Module):
+    """Marginalise the downstream loss over the support of a categorical latent
+    (reference marg.py:57-132).  Encoder: ``ExplicitWrapper``; decoder:
+    ``utils.DeterministicWrapper``.
+
+    Differences in mechanics only: the K per-column host syncs of marg.py:87 become one
+    read of the column-activity vector, and with a sparsemax encoder the final
+    ``bmm`` + entropy term + their backward run as fused kernels.
+    """
+
+    def __init__(self, encoder, decoder, loss_fun,
+                 encoder_entropy_coeff=0.0, decoder_entropy_coeff=0.0):
+        super().__init__()
+        self.encoder = encoder
+        self.decoder = decoder
+        self.loss = loss_fun
+        self.encoder_entropy_coeff = encoder_entropy_coeff
+        self.decoder_entropy_coeff = decoder_entropy_coeff
+
+    def forward(self, encoder_input, decoder_input, labels):
+        discrete_latent_z, encoder_probs, encoder_entropy = self.encoder(encoder_input)
+        batch_size, latent_size = encoder_probs.shape
+
+        # marg.py:87 -- columns whose total mass is exactly zero are skipped
+        active = (encoder_probs.detach().sum(0) != 0).tolist()
+
+        losses = torch.zeros_like(encoder_probs)
+        logs_global = None
+        logs = {}
+        for z in range(latent_size):
+            if not active[z]:
+                continue
+            z_ = torch.full((batch_size,), z, dtype=torch.long, device=encoder_probs.device)
+            decoder_output = self.decoder(z_, decoder_input)
+            loss_sum_term, logs = self.loss(
+                encoder_input, discrete_latent_z, decoder_input, decoder_output, labels)
+            losses[:, z] += loss_sum_term
+            if not logs_global:
+                logs_global = {k: 0.0 for k in logs.keys()}
+            for k, v in logs.items():
+                if hasattr(v, 'mean'):
+                    # expectation of the per-sample statistic under p(z|x)
+                    logs_global[k] += (encoder_probs[:, z] * v).mean()
+        for k, v in logs.items():
+            if hasattr(v, 'mean'):
+                logs[k] = logs_global[k]
+
+        side = getattr(encoder_probs, "_smlvm", None)
+        if side is not None and encoder_probs.is_cuda:
+            full_loss, loss_mean, _ = _FusedMarginalObjective.apply(
+                side["scores"], losses, encoder_probs.detach(), side["supp"],
+                side["entropy"].detach(), float(self.encoder_entropy_coeff))
+        else:
+            entropy_loss = -(encoder_entropy.mean() * self.encoder_entropy_coeff)
+            loss = (encoder_probs * losses).sum(-1)
+            loss_mean = loss.mean()
+            full_loss = loss_mean + entropy_loss
+
+        logs['loss'] = loss_mean
+        logs['encoder_entropy'] = encoder_entropy.mean()
+        logs['support'] = (encoder_probs != 0).sum(-1).to(torch.float).mean()
+        logs['distr'] = encoder_probs
+        return {'loss': full_loss, 'log': logs}

@@ -1,0 +1,409 @@
+"""Torch-facing operators over the C-ABI kernels (``include/smlvm.h``).
+
+Raw launches (``*_raw`` / plain functions) return tensors and never synchronise;
+``torch.autograd.Function`` subclasses own the forward/backward pairing.  All
+tensors must be CUDA fp32 contiguous; inputs are made contiguous, never copied to
+the CPU.  The only host round trip is the one read of the ragged total in
+``compact`` / ``sparsemap_solve`` (the reference builds Python lists there,
+lvmhelpers/structmarg.py:195-202).
+"""
+import torch
+
+from . import _native as N
+from ._native import lib, check, ptr, stream
+
+
+def _f32c(t, name):
+    N.require_cuda(t, name)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+# --------------------------------------------------------------------------------------
+# (1) sparsemax
+# --------------------------------------------------------------------------------------
+def sparsemax_fwd(x, want_entropy=False, want_argmax=False, want_nnz=True):
+    """x [rows, K] -> dict(p, supp [int32], nnz [int32]|None, entropy|None, argmax [int64]|None).
+
+    entmax.sparsemax forward (lvmhelpers/marg.py:51) fused with entropy() (marg.py:6-28)
+    and scores.argmax(-1) (marg.py:53).
+    """
+    x = _f32c(x, "scores")
+    rows, K = x.shape
+    p = torch.empty_like(x)
+    supp = torch.empty(rows, dtype=torch.int32, device=x.device)
+    nnz = torch.empty(rows, dtype=torch.int32, device=x.device) if want_nnz else None
+    ent = torch.empty(rows, dtype=torch.float32, device=x.device) if want_entropy else None
+    amax = torch.empty(rows, dtype=torch.int64, device=x.device) if want_argmax else None
+    check(lib.smlvm_sparsemax_fwd(ptr(x), ptr(p), ptr(supp), ptr(nnz), ptr(ent), ptr(amax),
+                                  rows, K, stream()), "smlvm_sparsemax_fwd")
+    return dict(p=p, supp=supp, nnz=nnz, entropy=ent, argmax=amax)
+
+
+def sparsemax_bwd(p, supp, dp=None, loss=None, loss_scale=None, loss_scale_host=1.0, dent=None):
+    """Fused Jacobian-vector product; see smlvm_sparsemax_bwd in include/smlvm.h."""
+    rows, K = p.shape
+    dx = torch.empty_like(p)
+    dp = None if dp is None else _f32c(dp, "dp")
+    loss = None if loss is None else _f32c(loss, "loss")
+    dent = None if dent is None else _f32c(dent, "dent")
+    check(lib.smlvm_sparsemax_bwd(ptr(p), ptr(supp), ptr(dp), ptr(loss), ptr(loss_scale),
+                                  float(loss_scale_host), ptr(dent), ptr(dx), rows, K, stream()),
+          "smlvm_sparsemax_bwd")
+    return dx
+
+
+class _Sparsemax(torch.autograd.Function):
+    """P = sparsemax(X) with entmax's saved state (supp_size, P)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        out = sparsemax_fwd(x, want_nnz=False)
+        ctx.save_for_backward(out["supp"], out["p"])
+        return out["p"]
+
+    @staticmethod
+    def backward(ctx, dp):
+        supp, p = ctx.saved_tensors
+        return sparsemax_bwd(p, supp, dp=dp)
+
+
+class _SparsemaxStats(torch.autograd.Function):
+    """(P, entropy, argmax, nnz) in one launch; backward fuses d entropy / d P."""
+
+    @staticmethod
+    def forward(ctx, x):
+        out = sparsemax_fwd(x, want_entropy=True, want_argmax=True, want_nnz=True)
+        ctx.save_for_backward(out["supp"], out["p"])
+        ctx.mark_non_differentiable(out["argmax"], out["nnz"], out["supp"])
+        ctx.set_materialize_grads(False)
+        return out["p"], out["entropy"], out["argmax"], out["nnz"], out["supp"]
+
+    @staticmethod
+    def backward(ctx, dp, dent, _damax, _dnnz, _dsupp):
+        supp, p = ctx.saved_tensors
+        if dp is None and dent is None:
+            return torch.zeros_like(p)
+        return sparsemax_bwd(p, supp, dp=dp, dent=dent)
+
+
+def sparsemax(X, dim=-1):
+    """Drop-in for ``entmax.sparsemax(X, dim=-1)`` on CUDA tensors."""
+    if dim not in (-1, X.dim() - 1):
+        X = X.transpose(dim, -1)
+        return sparsemax(X, -1).transpose(dim, -1)
+    shp = X.shape
+    return _Sparsemax.apply(X.reshape(-1, shp[-1])).reshape(shp)
+
+
+def sparsemax_stats(X):
+    """X [rows, K] -> (P, entropy [rows], argmax [rows] int64, nnz [rows] int32, supp [rows] int32)."""
+    return _SparsemaxStats.apply(X)
+
+
+# --------------------------------------------------------------------------------------
+# (2) compaction
+# --------------------------------------------------------------------------------------
+def scan_counts(counts):
+    """int32 [rows] -> int64 [rows+1] exclusive prefix sum (last entry = total)."""
+    N.require_cuda(counts, "counts")
+    counts = counts.contiguous()
+    rows = counts.numel()
+    offsets = torch.empty(rows + 1, dtype=torch.int64, device=counts.device)
+    ws = N.scan_workspace(counts.device, rows)
+    check(lib.smlvm_scan_counts(ptr(counts), ptr(offsets), rows, ptr(ws), ws.numel(), stream()),
+          "smlvm_scan_counts")
+    return offsets
+
+
+def compact_count(p):
+    p = _f32c(p, "p")
+    rows, K = p.shape
+    counts = torch.empty(rows, dtype=torch.int32, device=p.device)
+    check(lib.smlvm_compact_count(ptr(p), ptr(counts), rows, K, stream()), "smlvm_compact_count")
+    return counts
+
+
+def compact_fill(p, offsets, total, want_vals=True, want_rows=True, want_cols=True):
+    p = _f32c(p, "p")
+    rows, K = p.shape
+    dev = p.device
+    vals = torch.empty(total, dtype=torch.float32, device=dev) if want_vals else None
+    ri = torch.empty(total, dtype=torch.int32, device=dev) if want_rows else None
+    ci = torch.empty(total, dtype=torch.int32, device=dev) if want_cols else None
+    check(lib.smlvm_compact_fill(ptr(p), ptr(offsets), ptr(vals), ptr(ri), ptr(ci), rows, K,
+                                 stream()), "smlvm_compact_fill")
+    return vals, ri, ci
+
+
+def compact(p, nnz=None):
+    """Row-major compaction of p > 0 (== torch.nonzero(p > 0) order).
+
+    Returns dict(offsets [rows+1] int64, total int, vals, rows, cols).  One D2H read (total).
+    """
+    if nnz is None:
+        nnz = compact_count(p)
+    offsets = scan_counts(nnz)
+    total = int(offsets[-1].item())
+    vals, ri, ci = compact_fill(p, offsets, total)
+    return dict(offsets=offsets, total=total, vals=vals, rows=ri, cols=ci)
+
+
+# --------------------------------------------------------------------------------------
+# (4) weighted loss
+# --------------------------------------------------------------------------------------
+def wloss_dense_fwd(p, loss, scale=1.0, want_rows=True, want_total=True):
+    p = _f32c(p, "p")
+    loss = _f32c(loss, "loss")
+    rows, K = p.shape
+    dev = p.device
+    row_loss = torch.empty(rows, dtype=torch.float32, device=dev) if want_rows else None
+    total = torch.empty((), dtype=torch.float32, device=dev) if want_total else None
+    ws = N.reduce_workspace(dev)
+    check(lib.smlvm_wloss_dense_fwd(ptr(p), ptr(loss), ptr(row_loss), ptr(total), float(scale),
+                                    rows, K, ptr(ws), ws.numel(), stream()),
+          "smlvm_wloss_dense_fwd")
+    return row_loss, total
+
+
+def wloss_ragged_fwd(p, loss, offsets=None, scale=1.0, want_rows=False, want_total=True,
+                     want_entropy=False):
+    p = _f32c(p, "p")
+    loss = None if loss is None else _f32c(loss, "loss")
+    n_items = p.numel()
+    dev = p.device
+    rows = 0 if offsets is None else offsets.numel() - 1
+    row_loss = torch.empty(rows, dtype=torch.float32, device=dev) if (want_rows and offsets is not None) else None
+    total = torch.empty((), dtype=torch.float32, device=dev) if want_total else None
+    ent = torch.empty((), dtype=torch.float32, device=dev) if want_entropy else None
+    ws = N.reduce_workspace(dev)
+    check(lib.smlvm_wloss_ragged_fwd(ptr(p), ptr(loss), ptr(offsets), ptr(row_loss), ptr(total),
+                                     ptr(ent), float(scale), rows, n_items, ptr(ws), ws.numel(),
+                                     stream()), "smlvm_wloss_ragged_fwd")
+    return row_loss, total, ent
+
+
+class _MarginalLossDense(torch.autograd.Function):
+    """mean_b sum_z P[b,z] L[b,z] for the categorical Marginalizer (marg.py:125-126).
+
+    ``scores`` is listed as an input only so that autograd routes the fused gradient
+    (sparsemax Jacobian applied to g * L / B, dP never materialised) straight to it;
+    ``p`` must be the detached output of the sparsemax forward on ``scores``.
+    """
+
+    @staticmethod
+    def forward(ctx, scores, p, supp, losses):
+        rows = p.shape[0]
+        row_loss, total = wloss_dense_fwd(p, losses, scale=1.0 / rows)
+        ctx.save_for_backward(p, supp, losses)
+        ctx.mark_non_differentiable(row_loss)
+        return total, row_loss
+
+    @staticmethod
+    def backward(ctx, g, _grow):
+        p, supp, losses = ctx.saved_tensors
+        rows = p.shape[0]
+        g = g.contiguous().float()
+        dscores = None
+        dlosses = None
+        if ctx.needs_input_grad[0]:
+            dscores = sparsemax_bwd(p, supp, loss=losses, loss_scale=g, loss_scale_host=1.0 / rows)
+        if ctx.needs_input_grad[3]:
+            dlosses = p * (g / rows)
+        return dscores, None, None, dlosses
+
+
+class _RaggedLoss(torch.autograd.Function):
+    """scale * (p . loss) over a ragged batch (structmarg.py:140,242)."""
+
+    @staticmethod
+    def forward(ctx, p, loss, scale):
+        _, total, _ = wloss_ragged_fwd(p, loss, scale=scale, want_total=True)
+        ctx.save_for_backward(p, loss)
+        ctx.scale = scale
+        return total
+
+    @staticmethod
+    def backward(ctx, g):
+        p, loss = ctx.saved_tensors
+        dp = torch.empty_like(p) if ctx.needs_input_grad[0] else None
+        dl = torch.empty_like(loss) if ctx.needs_input_grad[1] else None
+        g = g.contiguous().float()
+        check(lib.smlvm_wloss_ragged_bwd(ptr(p), ptr(loss), ptr(g), None, float(ctx.scale),
+                                         ptr(dp), ptr(dl), p.numel(), stream()),
+              "smlvm_wloss_ragged_bwd")
+        return dp, dl, None
+
+
+class _RaggedEntropy(torch.autograd.Function):
+    """-scale * (p . log p) over the (strictly positive) entries of a ragged batch
+    (structmarg.py:51-58,200-202)."""
+
+    @staticmethod
+    def forward(ctx, p, scale):
+        _, _, ent = wloss_ragged_fwd(p, None, scale=scale, want_total=False, want_entropy=True)
+        ctx.save_for_backward(p)
+        ctx.scale = scale
+        return ent
+
+    @staticmethod
+    def backward(ctx, gent):
+        (p,) = ctx.saved_tensors
+        dp = torch.empty_like(p)
+        gent = gent.contiguous().float()
+        check(lib.smlvm_wloss_ragged_bwd(ptr(p), None, None, ptr(gent), float(ctx.scale),
+                                         ptr(dp), None, p.numel(), stream()),
+              "smlvm_wloss_ragged_bwd")
+        return dp, None
+
+
+def ragged_loss(p, loss, scale):
+    return _RaggedLoss.apply(_f32c(p, "p"), _f32c(loss, "loss"), float(scale))
+
+
+def ragged_entropy(p, scale):
+    return _RaggedEntropy.apply(_f32c(p, "p"), float(scale))
+
+
+# --------------------------------------------------------------------------------------
+# (3a) top-k bit-vectors
+# --------------------------------------------------------------------------------------
+def topk_bits(x, k, want_configs=True, want_bits=True, want_scores=False):
+    """x [rows, n] -> (configs [rows,k,n] fp32 | None, bits [rows,k,W] int32 | None,
+    dp_scores [rows,k] | None); lvmhelpers/pbinary_topk.pyx:23-34."""
+    x = _f32c(x, "scores")
+    rows, n = x.shape
+    dev = x.device
+    W = (n + 31) // 32
+    cfg = torch.empty((rows, k, n), dtype=torch.float32, device=dev) if want_configs else None
+    bits = torch.empty((rows, k, W), dtype=torch.int32, device=dev) if want_bits else None
+    sc = torch.empty((rows, k), dtype=torch.float32, device=dev) if want_scores else None
+    check(lib.smlvm_topk_bits(ptr(x), ptr(cfg), ptr(bits), ptr(sc), rows, n, k, stream()),
+          "smlvm_topk_bits")
+    return cfg, bits, sc
+
+
+class _BitsScore(torch.autograd.Function):
+    """scores_k = einsum('bkj,bj->bk', bits, scores) (structmarg.py:47) from packed bits."""
+
+    @staticmethod
+    def forward(ctx, x, bits):
+        rows, n = x.shape
+        k = bits.shape[1]
+        out = torch.empty((rows, k), dtype=torch.float32, device=x.device)
+        check(lib.smlvm_bits_score_fwd(ptr(bits), ptr(x), ptr(out), rows, n, k, stream()),
+              "smlvm_bits_score_fwd")
+        ctx.save_for_backward(bits)
+        ctx.n = n
+        return out
+
+    @staticmethod
+    def backward(ctx, ds):
+        (bits,) = ctx.saved_tensors
+        rows, k = ds.shape
+        ds = ds.contiguous().float()
+        dx = torch.empty((rows, ctx.n), dtype=torch.float32, device=ds.device)
+        check(lib.smlvm_bits_score_bwd(ptr(bits), ptr(ds), ptr(dx), rows, ctx.n, k, stream()),
+              "smlvm_bits_score_bwd")
+        return dx, None
+
+
+def bits_score(x, bits):
+    return _BitsScore.apply(_f32c(x, "scores"), bits)
+
+
+# --------------------------------------------------------------------------------------
+# (3b) SparseMAP
+# --------------------------------------------------------------------------------------
+def sparsemap_solve(x, kind, budget=0, t=None, init_scores=None, max_iter=100, keep_S=True):
+    """Batched active-set solve.  x [rows, n] -> padded solver state (dict), no host sync."""
+    x = _f32c(x, "scores")
+    rows, n = x.shape
+    dev = x.device
+    cap = lib.smlvm_sparsemap_capacity(n)
+    W = (n + 31) // 32
+    t = None if t is None else _f32c(t, "t")
+    if init_scores is not None:
+        init_scores = init_scores.to(device=dev, dtype=torch.float64).contiguous()
+        assert init_scores.shape == (rows, 2 * n)
+    p_pad = torch.empty((rows, cap), dtype=torch.float32, device=dev)
+    bits = torch.empty((rows, cap, W), dtype=torch.int32, device=dev)
+    counts = torch.empty(rows, dtype=torch.int32, device=dev)
+    kept = torch.empty(rows, dtype=torch.int32, device=dev)
+    iters = torch.empty(rows, dtype=torch.int32, device=dev)
+    status = torch.empty(rows, dtype=torch.int32, device=dev)
+    S = torch.empty((rows, cap * cap), dtype=torch.float64, device=dev) if keep_S else None
+    check(lib.smlvm_sparsemap_fwd(ptr(x), ptr(t), ptr(init_scores), kind, budget, max_iter, rows, n,
+                                  ptr(p_pad), ptr(bits), ptr(counts), ptr(kept), ptr(iters),
+                                  ptr(status), ptr(S), stream()), "smlvm_sparsemap_fwd")
+    return dict(p_pad=p_pad, bits=bits, counts=counts, kept=kept, iters=iters, status=status, S=S,
+                n=n, rows=rows, kind=kind)
+
+
+def sparsemap_expand(state, only_positive, offsets, total, want_aset=True, want_idx=True):
+    rows, n = state["rows"], state["n"]
+    dev = state["p_pad"].device
+    p = torch.empty(total, dtype=torch.float32, device=dev)
+    aset = torch.empty((total, n), dtype=torch.float32, device=dev) if want_aset else None
+    idx = torch.empty(total, dtype=torch.int32, device=dev) if want_idx else None
+    check(lib.smlvm_sparsemap_expand(ptr(state["p_pad"]), ptr(state["bits"]), ptr(state["counts"]),
+                                     ptr(offsets), int(only_positive), ptr(p), ptr(aset), ptr(idx),
+                                     rows, n, stream()), "smlvm_sparsemap_expand")
+    return p, aset, idx
+
+
+def sparsemap_bwd(state, dp, offsets, only_positive, want_dt=False):
+    rows, n = state["rows"], state["n"]
+    dev = dp.device
+    dp = dp.contiguous().float()
+    dx = torch.empty((rows, n), dtype=torch.float32, device=dev)
+    dt = torch.empty((rows, max(n - 1, 1)), dtype=torch.float32, device=dev) if want_dt else None
+    check(lib.smlvm_sparsemap_bwd(ptr(dp), ptr(offsets), int(only_positive), ptr(state["p_pad"]),
+                                  ptr(state["bits"]), ptr(state["counts"]), ptr(state["S"]), ptr(dx),
+                                  ptr(dt), rows, n, stream()), "smlvm_sparsemap_bwd")
+    if want_dt:
+        dt = dt[:, :n - 1]
+    return dx, dt
+
+
+class _SparseMAPBatch(torch.autograd.Function):
+    """Batched SparseMAP: scores [rows, n] -> ragged (p [N], aset [N, n]) in sample order.
+
+    One autograd node for the whole batch instead of the reference's one node (and one
+    factor graph) per sample (lvmhelpers/structmarg.py:181-196, sparsemap.py:90-127).
+    """
+
+    @staticmethod
+    def forward(ctx, x, t, kind, budget, max_iter, init_scores, only_positive, aux):
+        state = sparsemap_solve(x, kind, budget=budget, t=t, init_scores=init_scores,
+                                max_iter=max_iter, keep_S=True)
+        sizes = state["kept"] if only_positive else state["counts"]
+        offsets = scan_counts(sizes)
+        host = torch.cat([offsets[-1:], sizes.to(torch.int64)]).cpu()  # the one D2H per batch
+        total = int(host[0])
+        p, aset, idx = sparsemap_expand(state, only_positive, offsets, total)
+        ctx.state = state
+        ctx.offsets = offsets
+        ctx.only_positive = only_positive
+        ctx.has_t = t is not None
+        ctx.mark_non_differentiable(aset)
+        aux["sizes"] = host[1:]
+        aux["idx"] = idx
+        aux["offsets"] = offsets
+        aux["state"] = state
+        return p, aset
+
+    @staticmethod
+    def backward(ctx, dp, _daset):
+        dx, dt = sparsemap_bwd(ctx.state, dp, ctx.offsets, ctx.only_positive, want_dt=ctx.has_t)
+        return dx, dt, None, None, None, None, None, None
+
+
+def sparsemap_batch(x, kind, budget=0, t=None, max_iter=100, init_scores=None, only_positive=True):
+    """Returns (p [N], aset [N, n], aux) with aux = dict(sizes [rows] int64 CPU, idx [N] int32,
+    offsets, state)."""
+    aux = {}
+    p, aset = _SparseMAPBatch.apply(_f32c(x, "scores"), t, kind, int(budget), int(max_iter),
+                                    init_scores, bool(only_positive), aux)
+    return p, aset, aux

@@ -1,0 +1,212 @@
+"""lvmhelpers.structmarg counterpart: bit-vector latents, top-k sparsemax and SparseMAP.
+
+Reference: lvmhelpers/structmarg.py.  Same classes, constructor arguments, return tuples
+and ``log`` keys.  What changed underneath:
+
+* top-k: the k best bit-vectors come from ``smlvm_topk_bits`` on the device (no
+  D2H/H2D round trip, structmarg.py:43-44), the re-scoring einsum, the sparsemax over k,
+  the support compaction (boolean-mask indexing, :116-126) and the weighted loss (:140)
+  are kernels of ``libsmlvm.so``; inputs are gathered by compacted row index instead of
+  being repeated k times and masked (:95-126).
+* SparseMAP: the per-sample Python loop over factor graphs (:181-196) is one batched
+  solver launch (one CTA per sample) + one ragged expansion; ``idxs`` / ``support`` are
+  still Python lists (one D2H of the per-sample sizes).
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._native import FACTOR_BERNOULLI, FACTOR_BUDGET
+from .sparsemap import draw_init_scores
+
+
+def entropy(p):
+    """reference structmarg.py:9-20 (same as marg.entropy)."""
+    nz = p > 0
+    eps = torch.finfo(p.dtype).eps
+    p_stable = p.clone().clamp(min=eps, max=1 - eps)
+    out = torch.where(nz, p_stable * torch.log(p_stable),
+                      torch.tensor(0., device=p.device, dtype=torch.float))
+    return -(out).sum(-1)
+
+
+class _CompactValues(torch.autograd.Function):
+    """p[mask] with mask = p > 0, from the compaction kernel; backward scatters."""
+
+    @staticmethod
+    def forward(ctx, p, comp):
+        ctx.flat_idx = comp["flat_idx"]
+        ctx.shape = p.shape
+        return comp["vals"]
+
+    @staticmethod
+    def backward(ctx, dvals):
+        d = torch.zeros(ctx.shape, dtype=dvals.dtype, device=dvals.device)
+        d.view(-1).index_copy_(0, ctx.flat_idx, dvals)
+        return d, None
+
+
+def _compact_with_flat(p, nnz):
+    comp = ops.compact(p.detach(), nnz)
+    comp["flat_idx"] = comp["rows"].to(torch.int64) * p.shape[-1] + comp["cols"].to(torch.int64)
+    return comp
+
+
+class _IdxList(list):
+    """``idxs`` as the Python list the reference returns (structmarg.py:195,202), carrying
+    the same indices as a device tensor so that gathers need no host round trip."""
+    tensor = None
+
+
+class TopKSparsemaxWrapper(nn.Module):
+    """scores -> (k best bit-vectors [B,k,n], sparsemax over their scores [B,k],
+    entropy / B)  (reference structmarg.py:23-58)."""
+
+    def __init__(self, agent, k=10):
+        super().__init__()
+        self.agent = agent
+        self.k = k
+
+    def forward(self, *args, **kwargs):
+        scores = self.agent(*args, **kwargs)
+        batch_size, latent_size = scores.shape
+        # the top-k bit-vectors (detached, as the numpy round trip of structmarg.py:43)
+        bit_vector_z, bits, _ = ops.topk_bits(scores.detach(), self.k)
+        # rank them: scores_k = einsum("bkj,bj->bk"), differentiable w.r.t. scores (:47)
+        scores_k = ops.bits_score(scores, bits)
+        distr, _, _, nnz, _ = ops.sparsemax_stats(scores_k)
+        # entropy over the support (:51-58)
+        comp = _compact_with_flat(distr, nnz)
+        vals = _CompactValues.apply(distr, comp)
+        entropy_distr = ops.ragged_entropy(vals, 1.0 / batch_size)
+        distr._smlvm_compact = comp
+        distr._smlvm_vals = vals
+        return bit_vector_z, distr, entropy_distr
+
+
+class TopKSparsemaxMarg(torch.nn.Module):
+    """reference structmarg.py:61-153"""
+
+    def __init__(self, encoder, decoder, loss_fun,
+                 encoder_entropy_coeff=0.0, decoder_entropy_coeff=0.0):
+        super().__init__()
+        self.encoder = encoder
+        self.decoder = decoder
+        self.loss = loss_fun
+        self.encoder_entropy_coeff = encoder_entropy_coeff
+        self.decoder_entropy_coeff = decoder_entropy_coeff
+
+    def forward(self, encoder_input, decoder_input, labels):
+        bit_vector_z, encoder_probs, encoder_entropy = self.encoder(encoder_input)
+        batch_size = bit_vector_z.shape[0]
+        latent_size = bit_vector_z.shape[-1]
+
+        entropy_loss = -(encoder_entropy * self.encoder_entropy_coeff)
+
+        # support compaction (:116-126): row-major order of encoder_probs > 0
+        comp = getattr(encoder_probs, "_smlvm_compact", None)
+        if comp is None:
+            comp = _compact_with_flat(encoder_probs, None)
+            encoder_probs_flat = _CompactValues.apply(encoder_probs, comp)
+        else:
+            encoder_probs_flat = encoder_probs._smlvm_vals
+        rows = comp["rows"]
+        # x.unsqueeze(1).repeat(1,k,1).view(B*k,-1)[mask] == x[row of each survivor] (:95-124)
+        encoder_input_rep_flat = encoder_input.index_select(0, rows)
+        decoder_input_rep_flat = decoder_input.index_select(0, rows)
+        labels_rep_flat = labels.index_select(0, rows)
+        bit_vector_z_flat = bit_vector_z.view(-1, latent_size).index_select(0, comp["flat_idx"])
+
+        decoder_output = self.decoder(bit_vector_z_flat, decoder_input)
+
+        loss_components, logs = self.loss(
+            encoder_input_rep_flat, bit_vector_z_flat, decoder_input_rep_flat,
+            decoder_output, labels_rep_flat)
+
+        # (p . loss) / B  (:140)
+        loss = ops.ragged_loss(encoder_probs_flat, loss_components, 1.0 / batch_size)
+        full_loss = loss + entropy_loss
+
+        for k, v in logs.items():
+            if hasattr(v, 'mean'):
+                logs[k] = v.mean()
+
+        logs['loss'] = loss.detach()
+        logs['encoder_entropy'] = encoder_entropy.detach()
+        logs['support'] = (encoder_probs > 0).sum(dim=-1).to(torch.float)
+        logs['distr'] = encoder_probs
+        logs['loss_output'] = loss_components
+        return {'loss': full_loss, 'log': logs}
+
+
+class SparseMAPWrapper(nn.Module):
+    """scores -> (vertices [N,n], distribution [N], entropy / B, idxs, support)
+    (reference structmarg.py:156-202)."""
+
+    def __init__(self, agent, budget=0, init=False, max_iter=300):
+        super().__init__()
+        self.agent = agent
+        self.budget = budget
+        self.init = init
+        self.max_iter = max_iter
+
+    def forward(self, *args, **kwargs):
+        scores = self.agent(*args, **kwargs)
+        batch_size, latent_size = scores.shape
+        kind = FACTOR_BUDGET if self.budget > 0 else FACTOR_BERNOULLI
+        init_scores = draw_init_scores(batch_size, latent_size) if self.init else None
+        distr, sample, aux = ops.sparsemap_batch(
+            scores, kind, budget=self.budget, max_iter=self.max_iter,
+            init_scores=init_scores, only_positive=True)
+        support = aux["sizes"].tolist()
+        assert all(s > 0 for s in support)  # structmarg.py:192
+        idxs = _IdxList(aux["idx"].tolist())
+        idxs.tensor = aux["idx"]
+        entropy_distr = ops.ragged_entropy(distr, 1.0 / batch_size)
+        self.last_solver_state = aux["state"]
+        return sample, distr, entropy_distr, idxs, support
+
+
+class SparseMAPMarg(torch.nn.Module):
+    """reference structmarg.py:205-255"""
+
+    def __init__(self, encoder, decoder, loss_fun,
+                 encoder_entropy_coeff=0.0, decoder_entropy_coeff=0.0):
+        super().__init__()
+        self.encoder = encoder
+        self.decoder = decoder
+        self.loss = loss_fun
+        self.encoder_entropy_coeff = encoder_entropy_coeff
+        self.decoder_entropy_coeff = decoder_entropy_coeff
+
+    def forward(self, encoder_input, decoder_input, labels):
+        bit_vector_z, encoder_probs, encoder_entropy, idxs, support = \
+            self.encoder(encoder_input)
+        batch_size = encoder_input.shape[0]
+
+        entropy_loss = -(encoder_entropy * self.encoder_entropy_coeff)
+
+        decoder_output = self.decoder(bit_vector_z)
+
+        gather = getattr(idxs, "tensor", None)
+        if gather is None:
+            gather = torch.as_tensor(idxs, device=encoder_input.device)
+        loss_components, logs = self.loss(
+            encoder_input.index_select(0, gather), bit_vector_z,
+            decoder_input.index_select(0, gather), decoder_output,
+            labels.index_select(0, gather))
+
+        loss = ops.ragged_loss(encoder_probs, loss_components, 1.0 / batch_size)
+        full_loss = loss + entropy_loss
+
+        for k, v in logs.items():
+            if hasattr(v, 'mean'):
+                logs[k] = v.mean()
+
+        logs['loss'] = loss.detach()
+        logs['encoder_entropy'] = encoder_entropy.detach()
+        logs['support'] = torch.tensor(support).to(torch.float)
+        logs['distr'] = encoder_probs.detach()
+        logs['loss_output'] = loss_components.detach()
+        logs['idxs'] = idxs
+        return {'loss': full_loss, 'log': logs}

@@ -1,0 +1,84 @@
+"""GPU parity: support compaction (bit-exact indices) and the weighted-loss reduce."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("rows,K", [(64, 10), (64, 256), (1, 1), (5, 3), (100, 33), (4097, 128),
+                                    (20000, 12), (3, 1000), (70000, 8)])
+def test_compaction_matches_nonzero(rows, K):
+    from lvmhelpers import ops
+    x = torch.randn(rows, K, generator=torch.Generator().manual_seed(K))
+    out = ops.sparsemax_fwd(x.cuda())
+    P = out["p"]
+    comp = ops.compact(P, out["nnz"])
+    ref = torch.nonzero(P > 0)  # row-major, the order of boolean-mask indexing
+    assert comp["total"] == ref.shape[0]
+    assert torch.equal(comp["rows"].long(), ref[:, 0])
+    assert torch.equal(comp["cols"].long(), ref[:, 1])
+    assert torch.equal(comp["vals"], P[P > 0])
+    # offsets = exclusive scan of the row counts
+    cnt = (P > 0).sum(-1)
+    assert torch.equal(comp["offsets"][1:], cnt.cumsum(0))
+    assert comp["offsets"][0].item() == 0
+    # count kernel alone
+    assert torch.equal(ops.compact_count(P).long(), cnt)
+
+
+def test_compaction_edge_cases():
+    from lvmhelpers import ops
+    # empty rows, full rows, negative and zero entries
+    P = torch.tensor([[0.0, 0.0, 0.0, 0.0], [0.25, 0.25, 0.25, 0.25], [0.0, 1.0, 0.0, 0.0],
+                      [-1.0, 0.0, 0.5, 0.5]], device="cuda")
+    comp = ops.compact(P)
+    ref = torch.nonzero(P > 0)
+    assert torch.equal(comp["rows"].long(), ref[:, 0]) and torch.equal(comp["cols"].long(), ref[:, 1])
+    assert comp["offsets"].tolist() == [0, 0, 4, 5, 7]
+    # all-zero matrix -> empty ragged batch
+    comp = ops.compact(torch.zeros(10, 7, device="cuda"))
+    assert comp["total"] == 0 and comp["vals"].numel() == 0
+
+
+@pytest.mark.parametrize("rows", [1, 7, 2048, 2049, 100000, 1 << 20])
+def test_scan(rows):
+    from lvmhelpers import ops
+    c = torch.randint(0, 130, (rows,), dtype=torch.int32, device="cuda")
+    off = ops.scan_counts(c)
+    ref = torch.cat([torch.zeros(1, dtype=torch.int64, device="cuda"), c.long().cumsum(0)])
+    assert torch.equal(off, ref)
+
+
+@pytest.mark.parametrize("rows,K", [(64, 10), (64, 256), (4097, 128), (3, 7), (50, 1000)])
+def test_dense_weighted_loss(rows, K):
+    from lvmhelpers import ops
+    g = torch.Generator().manual_seed(rows)
+    P = torch.rand(rows, K, generator=g)
+    L = torch.rand(rows, K, generator=g) * 3
+    row_loss, total = ops.wloss_dense_fwd(P.cuda(), L.cuda(), scale=1.0 / rows)
+    ref_rows = P.unsqueeze(1).bmm(L.unsqueeze(-1)).squeeze()  # marg.py:125
+    assert torch.allclose(row_loss.cpu(), ref_rows.reshape(-1), rtol=1e-5, atol=1e-5)
+    assert abs(total.item() - ref_rows.double().mean().item()) <= 1e-5 * abs(ref_rows.mean().item()) + 1e-6
+
+
+def test_ragged_loss_and_entropy_autograd():
+    from lvmhelpers import ops
+    N, B = 1000, 64
+    g = torch.Generator().manual_seed(1)
+    p = (torch.rand(N, generator=g) * 0.1 + 1e-4)
+    l = torch.rand(N, generator=g) * 500 + 1500
+    pr, lr = p.clone().requires_grad_(True), l.clone().requires_grad_(True)
+    ref = (pr @ lr) / B + 0.3 * (-(pr @ torch.log(pr)) / B)     # structmarg.py:140, :54-58
+    ref.backward()
+    pc, lc = p.cuda().requires_grad_(True), l.cuda().requires_grad_(True)
+    out = ops.ragged_loss(pc, lc, 1.0 / B) + 0.3 * ops.ragged_entropy(pc, 1.0 / B)
+    out.backward()
+    assert abs(out.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    assert torch.allclose(pc.grad.cpu(), pr.grad, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(lc.grad.cpu(), lr.grad, rtol=1e-5, atol=1e-8)
+    # segmented row sums
+    offsets = torch.tensor([0, 10, 10, 500, 1000], dtype=torch.int64, device="cuda")
+    rows, _, _ = ops.wloss_ragged_fwd(p.cuda(), l.cuda(), offsets=offsets, want_rows=True, want_total=False)
+    pl = (p * l).double()
+    ref_rows = torch.stack([pl[0:10].sum(), pl[10:10].sum(), pl[10:500].sum(), pl[500:].sum()])
+    assert torch.allclose(rows.cpu().double(), ref_rows, rtol=1e-5)

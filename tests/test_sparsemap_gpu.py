@@ -1,0 +1,190 @@
+"""GPU parity: SparseMAP active-set solver vs the CPU oracle (restated AD3) and vs
+restatement-independent known answers (closed-form marginals, KKT)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BERN, BUDGET, SEQ = 0, 1, 2
+
+
+def _solve_gpu(x, kind, budget=0, t=None, init=None, max_iter=300):
+    from lvmhelpers import ops
+    xs = torch.from_numpy(np.asarray(x, dtype=np.float32)).cuda()
+    tt = None if t is None else torch.from_numpy(np.asarray(t, dtype=np.float32)).cuda()
+    ini = None if init is None else torch.from_numpy(np.asarray(init, dtype=np.float64))
+    st = ops.sparsemap_solve(xs, kind, budget=budget, t=tt, init_scores=ini, max_iter=max_iter)
+    torch.cuda.synchronize()
+    return st
+
+
+def _unpack(st, r):
+    n = st["n"]
+    m = int(st["counts"][r])
+    p = st["p_pad"][r, :m].cpu().numpy()
+    b = st["bits"][r, :m].cpu().numpy().astype(np.uint32)
+    idx = np.arange(n)
+    aset = ((b[:, idx // 32] >> (idx % 32)) & 1).astype(np.int32)
+    return p, aset
+
+
+@pytest.mark.parametrize("n,kind,budget", [(32, BERN, 0), (32, BUDGET, 16), (32, BUDGET, 3), (5, BERN, 0),
+                                           (5, BUDGET, 3), (128, BERN, 0), (128, BUDGET, 64), (1, BERN, 0),
+                                           (33, BERN, 0), (64, BUDGET, 10), (100, BERN, 0)])
+@pytest.mark.parametrize("scale", [0.3, 1.0, 3.0])
+def test_forward_matches_oracle(oracle, n, kind, budget, scale):
+    rows = 24 if n > 64 else 64
+    rng = np.random.default_rng(n * 7 + kind + budget)
+    x = (rng.standard_normal((rows, n)) * scale).astype(np.float32)
+    st = _solve_gpu(x, kind, budget)
+    flagged = 0
+    for r in range(rows):
+        ref = oracle.sparsemap_fwd(x[r], kind, budget, max_iter=300)
+        p, aset = _unpack(st, r)
+        assert int(st["status"][r]) == ref["status"]
+        flagged += ref["status"] >= 2
+        # active sets identical (same vertices, same order), p within 1e-5
+        assert aset.shape == ref["aset"].shape, (r, aset.shape, ref["aset"].shape)
+        assert np.array_equal(aset, ref["aset"])
+        assert np.abs(p - ref["p"]).max() <= 1e-5
+        assert int(st["iters"][r]) == ref["iters"]
+        assert int(st["kept"][r]) == int((ref["p"].astype(np.float32) > 0).sum())
+        # restatement-independent: marginals equal the closed form, p on the simplex
+        u = aset.T.astype(np.float64) @ p.astype(np.float64)
+        cf = oracle.bernoulli_marginals(x[r]) if kind == BERN else oracle.budget_marginals(x[r], budget)
+        if ref["status"] == 0:
+            assert np.abs(u - cf).max() <= 1e-5
+        assert abs(p.sum() - 1) <= 1e-5 and p.min() >= -1e-7
+        if kind == BUDGET:
+            assert aset.sum(1).max() <= budget
+    assert flagged == 0  # repeated-config / singular branches never fire on random inputs
+
+
+@pytest.mark.parametrize("n,kind,budget", [(32, BERN, 0), (32, BUDGET, 16), (128, BUDGET, 64)])
+def test_forward_with_random_init(oracle, n, kind, budget):
+    """init=True: seed vertex = MAP of torch.rand(2n, double) (sparsemap.py:25-27)."""
+    rows = 32
+    torch.manual_seed(42)
+    init = torch.rand(rows, 2 * n, dtype=torch.double).numpy()
+    x = torch.randn(rows, n).numpy()
+    st = _solve_gpu(x, kind, budget, init=init)
+    for r in range(rows):
+        ref = oracle.sparsemap_fwd(x[r], kind, budget, init=init[r], max_iter=300)
+        p, aset = _unpack(st, r)
+        assert np.array_equal(aset, ref["aset"])
+        assert np.abs(p - ref["p"]).max() <= 1e-5
+
+
+def test_sequence_binary_matches_oracle(oracle):
+    rows, n = 48, 24
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((rows, n)).astype(np.float32)
+    t = rng.standard_normal((rows, n - 1)).astype(np.float32)
+    st = _solve_gpu(x, SEQ, t=t, max_iter=100)
+    for r in range(rows):
+        ref = oracle.sparsemap_fwd(x[r], SEQ, t=t[r], max_iter=100)
+        p, aset = _unpack(st, r)
+        assert np.array_equal(aset, ref["aset"])
+        assert np.abs(p - ref["p"]).max() <= 1e-5
+
+
+def test_max_iter_cutoff(oracle):
+    """Small max_iter: same truncated (p, aset), status = max_iter, zeros allowed in p."""
+    rows, n = 32, 32
+    x = np.random.default_rng(11).standard_normal((rows, n)).astype(np.float32)
+    for mi in (1, 2, 5, 10):
+        st = _solve_gpu(x, BERN, max_iter=mi)
+        for r in range(rows):
+            ref = oracle.sparsemap_fwd(x[r], BERN, max_iter=mi)
+            p, aset = _unpack(st, r)
+            assert np.array_equal(aset, ref["aset"]) and np.abs(p - ref["p"]).max() <= 1e-5
+            assert int(st["status"][r]) == ref["status"]
+
+
+@pytest.mark.parametrize("n,kind,budget", [(32, BERN, 0), (32, BUDGET, 16), (128, BERN, 0)])
+def test_backward_matches_oracle(oracle, n, kind, budget):
+    from lvmhelpers import ops
+    rows = 16
+    rng = np.random.default_rng(n + kind)
+    x = rng.standard_normal((rows, n)).astype(np.float32)
+    xs = torch.from_numpy(x).cuda().requires_grad_(True)
+    p, aset, aux = ops.sparsemap_batch(xs, kind, budget=budget, max_iter=300, only_positive=False)
+    w = torch.randn(p.shape[0], generator=torch.Generator().manual_seed(0))
+    (p * w.cuda()).sum().backward()
+    sizes = aux["sizes"].tolist()
+    off = 0
+    for r in range(rows):
+        dx_ref, _ = oracle.sparsemap_bwd(x[r], w[off:off + sizes[r]].numpy(), kind, budget, max_iter=300)
+        off += sizes[r]
+        assert np.abs(xs.grad[r].cpu().numpy() - dx_ref).max() <= 1e-5 * max(1.0, np.abs(dx_ref).max())
+
+
+def test_backward_sequence_and_finite_differences(oracle):
+    from lvmhelpers.sparsemap import sequence_smap, bernoulli_smap
+    n = 12
+    torch.manual_seed(0)
+    x = torch.randn(n, device="cuda", requires_grad=True)
+    t = torch.randn(n - 1, device="cuda", requires_grad=True)
+    p, aset = sequence_smap(x, t, max_iter=100, init=False)
+    w = torch.randn(p.shape[0], device="cuda")
+    (p * w).sum().backward()
+    dx_ref, dt_ref = oracle.sparsemap_bwd(x.detach().cpu().numpy(), w.cpu().numpy(), 2,
+                                          t=t.detach().cpu().numpy(), max_iter=100)
+    assert np.abs(x.grad.cpu().numpy() - dx_ref).max() <= 1e-5
+    assert np.abs(t.grad.cpu().numpy() - dt_ref).max() <= 1e-5
+    # finite differences on the (unique) marginals u = aset' p for the Bernoulli factor
+    x0 = torch.randn(8, dtype=torch.float32)
+    xg = x0.cuda().requires_grad_(True)
+    p, aset = bernoulli_smap(xg, max_iter=100, init=False)
+    c = torch.randn(8, device="cuda")
+    ((aset.t() @ p) * c).sum().backward()
+    inside = (x0.abs() < 1).float()  # du_i/dx_i = 1/2 strictly inside the box, 0 when clipped
+    assert torch.allclose(xg.grad.cpu(), 0.5 * inside * c.cpu(), atol=1e-5)
+
+
+def test_structured_api_matches_reference_loop(oracle):
+    """SparseMAPWrapper output == the reference's per-sample loop (structmarg.py:181-202)
+    run over the oracle solver: ragged order, p > 0 filter, idxs, support, entropy."""
+    from lvmhelpers.structmarg import SparseMAPWrapper
+    B, n = 64, 32
+    torch.manual_seed(42)
+    x = torch.randn(B, n)
+    for budget, init in [(0, False), (16, False), (0, True), (16, True)]:
+        wrap = SparseMAPWrapper(torch.nn.Identity(), budget=budget, init=init, max_iter=300)
+        torch.manual_seed(7)
+        sample, distr, ent, idxs, support = wrap(x.cuda())
+        torch.manual_seed(7)
+        ref_p, ref_s, ref_idx, ref_supp = [], [], [], []
+        for k in range(B):
+            ini = torch.rand(2 * n, dtype=torch.double).numpy() if init else None
+            r = oracle.sparsemap_fwd(x[k].numpy(), 1 if budget > 0 else 0, budget, init=ini, max_iter=300)
+            pf = r["p"].astype(np.float32)
+            keep = pf > 0
+            ref_p.append(pf[keep]); ref_s.append(r["aset"][keep].astype(np.float32))
+            ref_idx += [k] * int(keep.sum()); ref_supp.append(int(keep.sum()))
+        ref_p = np.concatenate(ref_p); ref_s = np.concatenate(ref_s)
+        assert list(idxs) == ref_idx and support == ref_supp
+        assert np.array_equal(sample.cpu().numpy(), ref_s)
+        assert np.abs(distr.detach().cpu().numpy() - ref_p).max() <= 1e-5
+        ref_ent = -(ref_p.astype(np.float64) @ np.log(ref_p.astype(np.float64))) / B
+        assert abs(ent.item() - ref_ent) <= 1e-5 * abs(ref_ent)
+
+
+def test_demo_vector(oracle):
+    """The reference's print-only smoke demo (sparsemap.py:163-178): seed 42, randn(5)."""
+    from lvmhelpers.sparsemap import bernoulli_smap, budget_smap
+    torch.manual_seed(42)
+    x = torch.randn(5)
+    xg = x.cuda().requires_grad_(True)
+    p, aset = bernoulli_smap(xg, init=False)
+    ref = oracle.sparsemap_fwd(x.numpy(), 0, max_iter=100)
+    assert np.array_equal(aset.cpu().numpy(), ref["aset"].astype(np.float32))
+    assert np.abs(p.detach().cpu().numpy() - ref["p"]).max() <= 1e-5
+    p, aset = budget_smap(xg, budget=3, init=False)
+    ref = oracle.sparsemap_fwd(x.numpy(), 1, 3, max_iter=100)
+    assert np.array_equal(aset.cpu().numpy(), ref["aset"].astype(np.float32))
+    g0 = torch.autograd.grad(p[0], xg, retain_graph=True)[0]
+    e0 = np.zeros(len(ref["p"])); e0[0] = 1
+    dx_ref, _ = oracle.sparsemap_bwd(x.numpy(), e0, 1, 3, max_iter=100)
+    assert np.abs(g0.cpu().numpy() - dx_ref).max() <= 1e-5

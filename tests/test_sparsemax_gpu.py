@@ -1,0 +1,143 @@
+"""GPU parity: batched sparsemax fwd/bwd (through the C ABI) vs the CPU oracle.
+
+Bar (BASELINE.json north_star): supports bit-exact, probabilities within 1e-6.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(64, 10), (64, 256), (64, 128), (1, 1), (3, 2), (7, 5), (33, 17), (5, 33), (130, 100),
+          (9, 255), (9, 257), (6, 500), (5, 1000), (4, 1024), (3, 1500), (2, 4096), (2, 8192),
+          (4097, 128), (1000, 12)]
+
+
+def _inputs(rows, K, scale, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(rows, K, generator=g) * scale
+
+
+@pytest.mark.parametrize("rows,K", SHAPES)
+@pytest.mark.parametrize("scale", [0.1, 1.0, 3.0])
+def test_forward_parity(oracle, rows, K, scale):
+    from lvmhelpers import ops
+    x = _inputs(rows, K, scale, 42 + K)
+    P_ref, k_ref = oracle.sparsemax_fwd(x)
+    out = ops.sparsemax_fwd(x.cuda(), want_entropy=True, want_argmax=True)
+    P = out["p"].cpu()
+    # supports bit-exact
+    assert torch.equal(P > 0, P_ref > 0)
+    assert torch.equal(out["supp"].cpu().long(), k_ref)
+    assert torch.equal(out["nnz"].cpu().long(), (P_ref > 0).sum(-1))
+    # probabilities within 1e-6 (in practice bit-identical: same fp32 operations)
+    assert (P - P_ref).abs().max().item() <= 1e-6
+    assert torch.equal(P, P_ref)
+    # fused extras
+    assert torch.equal(out["argmax"].cpu(), x.argmax(-1))
+    H_ref = oracle.entropy(P_ref)
+    assert torch.allclose(out["entropy"].cpu(), H_ref, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("rows,K", SHAPES)
+def test_backward_parity(oracle, rows, K):
+    from lvmhelpers import ops
+    x = _inputs(rows, K, 1.0, 7 + K)
+    g = _inputs(rows, K, 1.0, 8 + K)
+    P_ref, k_ref = oracle.sparsemax_fwd(x)
+    dx_ref = oracle.sparsemax_bwd(P_ref, k_ref, g)
+    out = ops.sparsemax_fwd(x.cuda())
+    dx = ops.sparsemax_bwd(out["p"], out["supp"], dp=g.cuda()).cpu()
+    assert torch.equal(dx != 0, dx_ref != 0) or (dx - dx_ref).abs().max() <= 1e-6
+    # fp32 sum over the support in a different order: tolerance 1e-6 * max|g| * sqrt(k)
+    tol = 1e-6 * max(1.0, g.abs().max().item()) * max(1.0, float(k_ref.max()) ** 0.5)
+    assert (dx - dx_ref).abs().max().item() <= tol
+
+
+def test_edge_rows(oracle):
+    from lvmhelpers import ops
+    K = 16
+    rows = [
+        torch.zeros(K),                                   # constant row -> uniform
+        torch.full((K,), 5.0),                            # constant, shifted
+        torch.tensor([10.0] + [0.0] * (K - 1)),           # one-hot (gap >= 1)
+        torch.tensor([1.0, 0.0] + [-5.0] * (K - 2)),      # gap exactly 1: second entry at tau
+        torch.tensor([0.0, -1.0] * (K // 2)),             # many entries exactly at the threshold
+        torch.tensor([0.5, 0.5] + [-1.0] * (K - 2)),      # tied maxima
+        torch.tensor([float("-inf")] * (K - 1) + [0.0]),  # masked logits
+        torch.linspace(-1e-3, 1e-3, K),                   # nearly constant
+        torch.tensor([1e4, 1e4 - 0.5] + [0.0] * (K - 2)), # large magnitude
+    ]
+    x = torch.stack(rows)
+    P_ref, k_ref = oracle.sparsemax_fwd(x)
+    out = ops.sparsemax_fwd(x.cuda())
+    assert torch.equal(out["p"].cpu(), P_ref)
+    assert torch.equal(out["supp"].cpu().long(), k_ref)
+    assert torch.allclose(out["p"].sum(-1).cpu(), torch.ones(len(rows)), atol=1e-6)
+
+
+def test_properties_full_size():
+    """BASELINE config-5 size: size-independent properties instead of an oracle run."""
+    from lvmhelpers import ops
+    rows, K = 1 << 18, 128
+    x = torch.randn(rows, K, device="cuda")
+    out = ops.sparsemax_fwd(x)
+    P = out["p"]
+    assert (P >= 0).all()
+    assert (P.sum(-1) - 1).abs().max().item() < 1e-5
+    assert torch.equal(out["nnz"].long(), (P > 0).sum(-1))
+    # shift invariance (exact: the max is subtracted first; shifts by powers of two are exact)
+    out2 = ops.sparsemax_fwd(x + 4.0)
+    assert (out2["p"] - P).abs().max().item() < 1e-5
+    # p_i > 0  <=>  x_i above the threshold: support = the top-k entries of the row
+    kth = torch.topk(x, int(out["nnz"].max()), dim=-1).values
+    thr = kth.gather(1, (out["nnz"].long() - 1).unsqueeze(1))
+    assert torch.equal(P > 0, x >= thr)
+    # backward: gradient sums to zero over the support, is zero elsewhere
+    g = torch.randn_like(x)
+    dx = ops.sparsemax_bwd(P, out["supp"], dp=g)
+    assert (dx[P == 0] == 0).all()
+    assert dx.sum(-1).abs().max().item() < 1e-3
+
+
+def test_autograd_and_dims(oracle):
+    from lvmhelpers import ops
+    x = torch.randn(4, 6, 20)
+    xg = x.cuda().requires_grad_(True)
+    P = ops.sparsemax(xg, dim=-1)
+    w = torch.randn(4, 6, 20)
+    (P * w.cuda()).sum().backward()
+    xr = x.clone().requires_grad_(True)
+    Pr = oracle.sparsemax(xr)
+    (Pr * w).sum().backward()
+    assert torch.equal(P.detach().cpu(), Pr.detach())
+    assert (xg.grad.cpu() - xr.grad).abs().max().item() <= 2e-6
+    # other dim
+    P1 = ops.sparsemax(x.cuda(), dim=1)
+    Pr1 = oracle.sparsemax(x.transpose(1, 2)).transpose(1, 2)
+    assert torch.equal(P1.cpu(), Pr1)
+
+
+def test_fused_entropy_and_loss_backward(oracle):
+    """smlvm_sparsemax_bwd with loss / entropy terms == autograd of the reference expressions."""
+    from lvmhelpers import ops
+    rows, K = 64, 10
+    x = _inputs(rows, K, 1.0, 3)
+    L = torch.rand(rows, K) * 200 + 50
+    coeff = 0.7
+    xr = x.clone().requires_grad_(True)
+    Pr = oracle.sparsemax(xr)
+    obj = (Pr * L).sum(-1).mean() - coeff * oracle.entropy(Pr).mean()
+    obj.backward()
+    out = ops.sparsemax_fwd(x.cuda())
+    dent = torch.full((rows,), -coeff / rows, device="cuda")
+    dx = ops.sparsemax_bwd(out["p"], out["supp"], loss=L.cuda(), loss_scale_host=1.0 / rows, dent=dent)
+    assert (dx.cpu() - xr.grad).abs().max().item() <= 1e-5 * max(1.0, xr.grad.abs().max().item())
+
+
+def test_rejects_bad_arguments():
+    from lvmhelpers import ops
+    from lvmhelpers._native import SmlvmError
+    with pytest.raises(RuntimeError):
+        ops.sparsemax_fwd(torch.randn(2, 3))  # CPU tensor: no CPU path
+    with pytest.raises(SmlvmError):
+        ops.sparsemax_fwd(torch.randn(1, 8193, device="cuda"))

@@ -1,0 +1,83 @@
+"""GPU parity: k-best bit-vectors (bit-exact vs the CPU oracle / the reference build)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("rows,n,k", [(64, 32, 10), (64, 128, 10), (16, 1, 2), (16, 2, 4), (16, 3, 8),
+                                      (50, 5, 4), (40, 12, 16), (30, 33, 17), (20, 64, 32), (10, 200, 7),
+                                      (6, 512, 10), (6, 512, 32), (1000, 40, 3), (5, 31, 2)])
+def test_topk_matches_oracle(oracle, rows, n, k):
+    from lvmhelpers import ops
+    rng = np.random.default_rng(n * 100 + k)
+    s = rng.standard_normal((rows, n)).astype(np.float32)
+    ref, ref_sc = oracle.topk(s, k, return_scores=True)
+    cfg, bits, sc = ops.topk_bits(torch.from_numpy(s).cuda(), k, want_scores=True)
+    assert np.array_equal(cfg.cpu().numpy(), ref)
+    assert np.array_equal(sc.cpu().numpy(), ref_sc)
+    # packed bits agree with the fp32 configs
+    b = bits.cpu().numpy().astype(np.uint32)
+    idx = np.arange(n)
+    unpacked = ((b[:, :, idx // 32] >> (idx % 32)) & 1).astype(np.float32)
+    assert np.array_equal(unpacked, ref)
+    if oracle.have_ref("ref_topk"):
+        assert np.array_equal(cfg.cpu().numpy(), oracle.topk(s, k, which="ref_topk"))
+
+
+def test_topk_ties_and_zeros(oracle):
+    """Quantised scores: many exact ties and exact zeros exercise the strict-> rule."""
+    from lvmhelpers import ops
+    rng = np.random.default_rng(5)
+    for n, k in [(20, 10), (8, 16), (40, 32)]:
+        s = rng.integers(-3, 4, (300, n)).astype(np.float32)
+        ref = oracle.topk(s, k)
+        cfg, _, _ = ops.topk_bits(torch.from_numpy(s).cuda(), k)
+        assert np.array_equal(cfg.cpu().numpy(), ref)
+    s = np.zeros((4, 10), dtype=np.float32)
+    cfg, _, _ = ops.topk_bits(torch.from_numpy(s).cuda(), 5)
+    assert np.array_equal(cfg.cpu().numpy(), oracle.topk(s, 5))
+
+
+def test_topk_bruteforce_small(oracle):
+    from lvmhelpers import ops
+    rng = np.random.default_rng(9)
+    s = rng.standard_normal((20, 10)).astype(np.float32)
+    cfg, _, sc = ops.topk_bits(torch.from_numpy(s).cuda(), 12, want_scores=True)
+    cfg = cfg.cpu().numpy()
+    for r in range(20):
+        best, best_bits = oracle.topk_bruteforce(s[r], 12)
+        assert np.allclose(sc[r].cpu().numpy(), best, atol=1e-5)
+        assert np.array_equal(cfg[r], best_bits.astype(np.float32))
+        assert np.array_equal(cfg[r, 0], (s[r] > 0).astype(np.float32))
+
+
+def test_pbinary_topk_api(oracle):
+    """Drop-in module: in-place fill of a host buffer, returns None (pbinary_topk.pyx:23-34)."""
+    from lvmhelpers.pbinary_topk import batched_topk, binary_topk
+    s = np.random.default_rng(1).standard_normal((8, 32)).astype(np.float32)
+    out = torch.empty((8, 10, 32), dtype=torch.float32)
+    assert batched_topk(s, out.numpy(), 10) is None
+    assert np.array_equal(out.numpy(), oracle.topk(s, 10))
+    res = binary_topk(list(s[0]), 3)
+    assert len(res) == 3 and res[0][1] == [int(v > 0) for v in s[0]]
+    with pytest.raises(ValueError):
+        batched_topk(s, out.numpy(), 1)
+    with pytest.raises(ValueError):
+        batched_topk(s.astype(np.float64), out.numpy(), 10)
+
+
+def test_bits_score_fwd_bwd():
+    from lvmhelpers import ops
+    x = torch.randn(64, 32, device="cuda", requires_grad=True)
+    cfg, bits, _ = ops.topk_bits(x.detach(), 10)
+    sk = ops.bits_score(x, bits)
+    w = torch.randn(64, 10, device="cuda")
+    (sk * w).sum().backward()
+    xr = x.detach().clone().requires_grad_(True)
+    ref = torch.einsum("bkj,bj->bk", cfg.double(), xr.double())  # structmarg.py:47
+    (ref * w.double()).sum().backward()
+    # kernel accumulates in fp64 and rounds once; einsum in fp32 would differ by ~1e-6*|score|
+    assert (sk.double() - ref).abs().max().item() <= 1e-6 * ref.abs().max().item()
+    assert (x.grad.double() - xr.grad.double()).abs().max().item() <= 1e-5
