@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""Benchmark of the sparse-marginalization hot path (BASELINE.json metric:
+"latent-marginalized samples/sec fwd+bwd at 1/2/4/8 B200; % HBM roofline").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our sm_100a path
+  python bench.py --impl reference [--gpus N] [--steps K] ...    the reference's CPU path
+
+Workload (BASELINE.json configs[4], the config the metric is quoted on): synthetic scaling
+sweep, batched sparsemax marginalisation at latent width 128, 1,048,576 rows per GPU
+(weak scaling: every rank owns its own shard, no data-path collective).  One step = one pass
+of the categorical hot path over the batch, forward and backward:
+  sparsemax fwd (+entropy, argmax, nnz) -> scan -> support compaction -> probability-weighted
+  loss -> fused backward (sparsemax Jacobian of the loss + decoder-side gradient).
+Inputs (scores X, per-latent losses L: 512 MiB each, >> the 126 MB L2) are resident in HBM
+for `value`; `e2e` repeats the step with X and L coming from pinned host memory and the
+gradient + loss going back to the host inside the timed region.
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "sparse-marginalization-lvm_b200"))
+
+import torch  # noqa: E402
+
+METRIC = "latent-marginalized samples/sec fwd+bwd"
+UNIT = "samples/s"
+
+
+def measured_hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_inputs(rows, cols, seed):
+    """Scores ~ N(0,1), per-latent losses ~ U(0,3); CPU generator so that
+    the CPU baseline and the GPU path see identical bits."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(rows, cols, generator=g)
+    losses = torch.rand(rows, cols, generator=g) * 3
+    return x, losses
+
+
+# --------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap", 0x80: "hw_power_brake", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.stop_flag, self.ok = [], False, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.max_mhz = None
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self.stop_flag:
+            try:
+                mhz = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+                rs = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((time.time(), mhz, rs))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def summary(self, t0, t1):
+        inside = [s for s in self.samples if t0 <= s[0] <= t1] or self.samples[-3:]
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        mhz = sorted(s[1] for s in inside)
+        bits = 0
+        for s in inside:
+            bits |= s[2]
+        reasons = [name for bit, name in self.REASONS.items() if bits & bit]
+        return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(inside)}
+
+
+def physical_gpu_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# --------------------------------------------------------------------------------------
+# CPU reference path (oracle): what the reference does on host cores for the same step
+# --------------------------------------------------------------------------------------
+def cpu_step(x, losses):
+    """entmax.sparsemax restated with torch CPU ops (marg.py:51) + boolean-mask compaction
+    (structmarg.py:116-126) + weighted loss (marg.py:125-126) + sparsemax backward."""
+    import oracle
+    rows = x.shape[0]
+    P, k = oracle.sparsemax_fwd(x)
+    mask = P > 0
+    vals = P[mask]
+    idx = torch.nonzero(mask)
+    loss = P.unsqueeze(1).bmm(losses.unsqueeze(-1)).squeeze().mean()
+    dx = oracle.sparsemax_bwd(P, k, losses / rows)
+    dl = P / rows
+    return loss, dx, dl, vals, idx
+
+
+def time_cpu(x, losses, steps, warmup):
+    for _ in range(warmup):
+        cpu_step(x, losses)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_step(x, losses)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return x.shape[0] / dt, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = torch.get_num_threads()
+    x, losses = make_inputs(65536, args.cols, 42)
+    rate, _ = time_cpu(x, losses, 1, 1)  # calibrate
+    budget_s = 120.0
+    rows = int(min(args.rows, max(4096, rate * budget_s / max(args.steps + args.warmup, 1))))
+    rows = 1 << (rows.bit_length() - 1)
+    x, losses = make_inputs(rows, args.cols, 42)
+    rate, dt = time_cpu(x, losses, args.steps, args.warmup)
+    sample = "%d of %d rows per step (%d steps, %d warm-up), torch CPU ops, %d threads" % (
+        rows, args.rows, args.steps, args.warmup, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 * (args.rows / rows),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": workload_config(args, world),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "host_cpus": os.cpu_count()},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "entmax is not installable offline; the CPU arm is the oracle's torch-CPU "
+                "restatement of entmax.sparsemax + the reference's own torch expressions",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": "C5a synthetic sweep: sparsemax marginalisation fwd+bwd, latent width %d, "
+                        "%d rows per GPU, scores N(0,1), losses U(0,3)" % (args.cols, args.rows),
+            "rows_per_gpu": args.rows, "cols": args.cols, "global_rows": args.rows * world,
+            "sharding": "rows, %d shard(s), no data-path collective" % world,
+            "l2": "inputs (2 x %d MiB per GPU) exceed the 126 MB L2; no explicit flush"
+                  % (args.rows * args.cols * 4 >> 20)}
+
+
+# --------------------------------------------------------------------------------------
+# our path
+# --------------------------------------------------------------------------------------
+def dist_max(value, world, device):
+    if world == 1:
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(world):
+    if world > 1:
+        torch.distributed.barrier()
+
+
+def timed(fn, steps, warmup, world, device):
+    """warm-up, barrier + sync, K steps between two CUDA events, sync + barrier; max over ranks (ms)."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    barrier(world)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_host0 = time.time()
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    t_host1 = time.time()
+    barrier(world)
+    return dist_max(e0.elapsed_time(e1), world, device), t_host0, t_host1
+
+
+def extra_paths(args, world, device, rank):
+    """The other named shapes of configs[4]: top-k sparsemax and SparseMAP at width 128 (public
+    wrapper API, forward + backward, CUDA events, max over ranks)."""
+    from lvmhelpers import ops
+    from lvmhelpers.structmarg import TopKSparsemaxWrapper
+    out = {}
+    g = torch.Generator().manual_seed(1000 + rank)
+
+    rows = args.path_rows_topk
+    x = torch.randn(rows, 128, generator=g).to(device).requires_grad_(True)
+    wrap = TopKSparsemaxWrapper(torch.nn.Identity(), k=10)
+    cand_loss = (torch.rand(rows * 10, generator=g) * 500 + 1500).to(device)
+
+    def topk_step():
+        x.grad = None
+        bits, distr, ent = wrap(x)
+        vals = distr._smlvm_vals
+        loss = ops.ragged_loss(vals, cand_loss[:vals.numel()], 1.0 / rows) - ent
+        loss.backward()
+
+    ms, _, _ = timed(topk_step, 5, 2, world, device)
+    out["topk_sparsemax_n128_k10"] = {"rows_per_gpu": rows, "ms_per_step": ms / 5,
+                                     "value": rows * world / (ms / 5 * 1e-3), "unit": UNIT}
+
+    for name, kind, budget in (("sparsemap_bernoulli_n128", 0, 0), ("sparsemap_budget64_n128", 1, 64)):
+        rows = args.path_rows_smap
+        xs = torch.randn(rows, 128, generator=g).to(device).requires_grad_(True)
+        stats = {}
+
+        def smap_step():
+            xs.grad = None
+            p, aset, aux = ops.sparsemap_batch(xs, kind, budget=budget, max_iter=300, only_positive=True)
+            w = torch.ones_like(p)
+            loss = ops.ragged_loss(p, w, 1.0 / rows) - ops.ragged_entropy(p, 1.0 / rows)
+            loss.backward()
+            stats["N"] = int(p.numel())
+            stats["st"] = aux["state"]
+
+        ms, _, _ = timed(smap_step, 3, 1, world, device)
+        st = stats["st"]
+        n_items = stats["N"]
+        fwd_bytes = rows * 4 * 128 + n_items * (4 * 128 + 8) + 4 * rows
+        bwd_bytes = 4 * n_items + 4 * 128 * n_items + 4 * 128 * rows
+        out[name] = {"rows_per_gpu": rows, "ms_per_step": ms / 3, "value": rows * world / (ms / 3 * 1e-3),
+                     "unit": UNIT, "mean_support": n_items / rows,
+                     "mean_iterations": float(st["iters"].float().mean()),
+                     "status_hist": torch.bincount(st["status"], minlength=4).tolist(),
+                     "hbm_frac_of_algorithmic_bytes": (fwd_bytes + bwd_bytes) / (ms / 3 * 1e-3) / 1e9
+                     / measured_hbm_peak()[0]}
+    return out
+
+
+def run_native(args, rank, local_rank, world):
+    from lvmhelpers.hotpath import SparsemaxMargStep
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    peak, peak_src = measured_hbm_peak()
+    rows, K = args.rows, args.cols
+
+    x_host, l_host = make_inputs(rows, K, 42 + rank)
+    x_pin, l_pin = x_host.pin_memory(), l_host.pin_memory()
+    x, losses = x_pin.to(device), l_pin.to(device)
+    total_nnz = SparsemaxMargStep.size_capacity(x)
+    step = SparsemaxMargStep(rows, K, device, capacity=total_nnz + 1024, entropy_coeff=1.0)
+
+    # per-kernel CUDA events, recorded on the launching stream inside the timed region
+    marks = []
+
+    def rec(name):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        marks.append((name, ev))
+
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    sampler.start()
+    ms, th0, th1 = timed(lambda: step.run(x, losses, rec), args.steps, args.warmup, world, device)
+    clocks = sampler.summary(th0, th1)
+
+    # kernel durations over the timed steps only (drop the warm-up marks)
+    per_step = len(SparsemaxMargStep.KERNELS) + 1
+    marks = marks[args.warmup * per_step:]
+    dur = {k: 0.0 for k in SparsemaxMargStep.KERNELS}
+    for i in range(len(marks) - 1):
+        name, ev = marks[i]
+        if name is not None:
+            dur[name] += ev.elapsed_time(marks[i + 1][1])
+    dur = {k: v / args.steps for k, v in dur.items()}
+    abytes = step.algorithmic_bytes(total_nnz)
+    kernels = {k: {"ms": dur[k], "algorithmic_bytes": abytes[k],
+                   "gbs": abytes[k] / (dur[k] * 1e-3) / 1e9 if dur[k] > 0 else None,
+                   "frac": abytes[k] / (dur[k] * 1e-3) / 1e9 / peak if dur[k] > 0 else None}
+               for k in dur}
+    top = max(dur, key=dur.get)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(top)
+    step_bytes = sum(abytes.values())
+    ms_per_step = ms / args.steps
+    value = rows * world / (ms_per_step * 1e-3)
+
+    # end to end through host buffers: H2D of X and L, the step, D2H of gradient + loss
+    dx_pin = torch.empty(rows, K).pin_memory()
+    tot_pin = torch.empty(()).pin_memory()
+    e2e_steps = max(3, min(args.steps, 20))
+
+    def e2e_step():
+        x.copy_(x_pin, non_blocking=True)
+        losses.copy_(l_pin, non_blocking=True)
+        step.run(x, losses)
+        dx_pin.copy_(step.dx, non_blocking=True)
+        tot_pin.copy_(step.total, non_blocking=True)
+
+    ms_e2e, _, _ = timed(e2e_step, e2e_steps, 3, world, device)
+    loss_value = float(tot_pin)
+    e2e = {"value": rows * world / (ms_e2e / e2e_steps * 1e-3), "unit": UNIT,
+           "h2d_bytes_per_step": 2 * rows * K * 4, "d2h_bytes_per_step": rows * K * 4 + 4,
+           "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
+           "api": "lvmhelpers.hotpath.SparsemaxMargStep.run over pinned host buffers"}
+
+    paths = extra_paths(args, world, device, rank) if not args.no_paths else None
+    sampler.stop_flag = True
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = torch.get_num_threads()
+        rate, dt = time_cpu(x_host, l_host, 3, 1)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "host_cpus": os.cpu_count(),
+               "sample": "3 timed passes (1 warm-up) over the full %dx%d workload, torch CPU ops" % (rows, K)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, world),
+            "clocks": clocks,
+            "e2e": e2e,
+            "gpu_launches": args.steps * len(SparsemaxMargStep.KERNELS),
+            "roofline": {"bound": "hbm", "kernel": top, "achieved": kernels[top]["gbs"], "peak": peak,
+                         "unit": "GB/s", "frac": kernels[top]["frac"], "traffic": traffic,
+                         "peak_source": peak_src,
+                         "step": {"algorithmic_bytes": step_bytes,
+                                  "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,
+                                  "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak}},
+            "kernels": kernels,
+            "cpu_baseline": cpu,
+            "paths": paths,
+            "check": {"loss": loss_value, "support_mean": total_nnz / rows},
+        }
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", choices=["native", "reference"], default="native")
+    ap.add_argument("--rows", type=int, default=1 << 20, help="rows per GPU")
+    ap.add_argument("--cols", type=int, default=128)
+    ap.add_argument("--path-rows-topk", type=int, default=1 << 18)
+    ap.add_argument("--path-rows-smap", type=int, default=1 << 14)
+    ap.add_argument("--no-paths", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the sm_100a path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_native(args, rank, local_rank, world)
+    finally:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -81,12 +81,15 @@ int smlvm_sparsemax_fwd(const float* x, float* p, int32_t* supp_size, int32_t* n
  * where each of dp[rows,cols], loss[rows,cols], dent[rows] may be NULL (term absent);
  * loss_scale_dev is a device scalar (fp32) or NULL (=1).
  *     dx = where(p != 0, g - sum_{p != 0} g / supp_size, 0)
+ * dloss[rows,cols] (NULL to skip) receives the decoder side of the weighted loss,
+ *     dloss = loss_scale * p    (d/dloss of loss_scale * sum(p * loss)).
  * replaces: SparsemaxFunction.backward (entmax) + the autograd of
  *           `encoder_probs.unsqueeze(1).bmm(losses.unsqueeze(-1))` marg.py:125 and of
  *           entropy() marg.py:6-28 w.r.t. p.                                              */
 int smlvm_sparsemax_bwd(const float* p, const int32_t* supp_size, const float* dp,
                         const float* loss, const float* loss_scale_dev, float loss_scale_host,
-                        const float* dent, float* dx, int64_t rows, int32_t cols, void* stream);
+                        const float* dent, float* dx, float* dloss, int64_t rows, int32_t cols,
+                        void* stream);
 
 /* ------------------------------------------------------------------------- *
  * (2) support compaction

@@ -116,6 +116,33 @@ __device__ __forceinline__ void group_sort_desc(float (&s)[E], int l)
     }
 }
 
+
+// Full-warp groups reduce in one REDUX/CREDUX instruction (sm_100a has the fp32 max form);
+// sub-warp groups fall back to shuffles (a partial-mask redux serialises per mask).
+template <int G>
+__device__ __forceinline__ float gmax_fast(float v)
+{
+    if (G == 32) {
+        float m;
+        asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(v));
+        return m;
+    }
+    return group_max<G>(v);
+}
+template <int G>
+__device__ __forceinline__ int gsum_fast(int v)
+{
+    if (G == 32) return __reduce_add_sync(kFull, v);
+    return group_sum<G>(v);
+}
+template <int G>
+__device__ __forceinline__ int gmin_fast(int v)
+{
+    if (G == 32) return __reduce_min_sync(kFull, v);
+    return group_reduce<G>(v, [](int a, int b) { return min(a, b); });
+}
+constexpr int ilog2_c(int n) { return n <= 1 ? 0 : 1 + ilog2_c(n >> 1); }
+
 template <int E, int G, bool VEC>
 __global__ void __launch_bounds__(kThreads)
 sparsemax_fwd_reg(const float* __restrict__ x, float* __restrict__ p, int32_t* __restrict__ supp,
@@ -142,7 +169,7 @@ sparsemax_fwd_reg(const float* __restrict__ x, float* __restrict__ p, int32_t* _
         float m = v[0];
 #pragma unroll
         for (int e = 1; e < E; ++e) m = fmaxf(m, v[e]);
-        m = group_max<G>(m);
+        m = gmax_fast<G>(m);
 
         if (amax != nullptr) {
             int first = 0x7fffffff;
@@ -151,74 +178,137 @@ sparsemax_fwd_reg(const float* __restrict__ x, float* __restrict__ p, int32_t* _
                 int col = col_of<E, G, VEC>(e, l);
                 if (col < Kr && v[e] == m) first = min(first, col);
             }
-            first = group_reduce<G>(first, [](int a, int b) { return min(a, b); });
+            first = gmin_fast<G>(first);
             if (live && l == 0) amax[row] = first;
         }
-
-        float s[E];
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-            v[e] = __fsub_rn(v[e], m);  // X' (padding stays -inf)
-            s[e] = v[e];
+        for (int e = 0; e < E; ++e) v[e] = __fsub_rn(v[e], m);  // X' (padding stays -inf)
+
+        // ---- fast path: threshold search (Michelot / Newton on sum max(x - tau, 0) = 1) -----
+        // in fixed point with single-instruction warp reductions, then one exact evaluation of the reference's tau on the proposed
+        // support and a check, with rounding margins, that the reference's sort-based support
+        // test yields exactly this support.  Rows that fail the check (an entry within ~1e-6
+        // of the threshold, or a proposal spoilt by the 2^-SHIFT grid) take the sort path below.
+        constexpr int LOGN = ilog2_c(E * G);
+        constexpr int SHIFT = (30 - LOGN) < 24 ? (30 - LOGN) : 24;  // N * 2^SHIFT <= 2^30
+        constexpr int ONE = 1 << SHIFT;
+        int qv[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) qv[e] = __float2int_rn(v[e] * (float)ONE);  // -inf -> INT_MIN
+        int tq = -ONE;  // tau >= max - 1
+        int cprev = -1, C = 0;
+        for (int iter = 0; iter < 64; ++iter) {
+            int sq = 0, c = 0;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const bool in = qv[e] > tq;
+                sq += in ? qv[e] : 0;
+                c += in ? 1 : 0;
+            }
+            const int S = gsum_fast<G>(sq);
+            C = gsum_fast<G>(c);
+            if (__all_sync(kFull, C == cprev)) break;  // supports stopped shrinking in every row
+            cprev = C;
+            const int tn = __float2int_rd(__fdividef((float)(S - ONE), (float)max(C, 1)));
+            tq = max(tq, tn);
         }
-        group_sort_desc<E, G>(s, l);
-
-        // fp64 inclusive prefix sums in sorted order
-        double cs[E];
-        double run = 0.0;
+        int k = max(C, 1);
+        float tau;
+        bool need_sort;
+        {
+            double sd = 0.0;
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-            run += (double)s[e];
-            cs[e] = run;
+            for (int e = 0; e < E; ++e) sd += (qv[e] > tq) ? (double)v[e] : 0.0;
+            sd = group_sum<G>(sd);
+            // the reference's arithmetic: tau = fl32(fl32(fl32(cumsum_k) - 1) / k)
+            const float kf = (float)k;
+            tau = __fdiv_rn(__fsub_rn((float)sd, 1.0f), kf);
+            // margins (sparsemax): inside needs x - tau > 6*2^-24 (+ tau rounding),
+            // outside needs (tau - x) * k > 2^-24 (3.06 K + 1) (+ k * tau rounding); x2 safety
+            const float thr_in = tau + 1e-6f;
+            const float thr_out = tau - __fdividef((3.06f * (float)K + 1.f) * 1.2e-7f, kf) - 3e-7f;
+            bool bad = false;
+#pragma unroll
+            for (int e = 0; e < E; ++e) bad |= (qv[e] > tq) ? !(v[e] > thr_in) : !(v[e] < thr_out);
+            const unsigned gm = (G == 32) ? kFull : (((1u << G) - 1u) << (g * G));
+            // (ballot hoisted: `live && ballot()` would short-circuit the collective away
+            //  from dead lanes and deadlock the warp)
+            const unsigned bal = __ballot_sync(kFull, bad);
+            need_sort = live && ((bal & gm) != 0u);
         }
-        double incl = run;  // lane totals -> exclusive offset of this lane
+
+        if (__any_sync(kFull, need_sort)) {
+            // ---- exact path: the reference's definition, by sorting -----------------------
+            float s[E];
 #pragma unroll
-        for (int o = 1; o < G; o <<= 1) {
-            double t = __shfl_up_sync(kFull, incl, o, G);
-            if (l >= o) incl += t;
+            for (int e = 0; e < E; ++e) s[e] = v[e];
+            group_sort_desc<E, G>(s, l);
+
+            // fp64 inclusive prefix sums in sorted order
+            double cs[E];
+            double run = 0.0;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                run += (double)s[e];
+                cs[e] = run;
+            }
+            double incl = run;  // lane totals -> exclusive offset of this lane
+#pragma unroll
+            for (int o = 1; o < G; o <<= 1) {
+                double t = __shfl_up_sync(kFull, incl, o, G);
+                if (l >= o) incl += t;
+            }
+            // (not incl - run: a lane holding -inf padding would turn that into NaN)
+            double excl = __shfl_up_sync(kFull, incl, 1, G);
+            if (l == 0) excl = 0.0;
+
+            float Cc[E];
+            int cnt = 0;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int pos = l * E + e;
+                Cc[e] = __fsub_rn((float)(excl + cs[e]), 1.0f);
+                const float lhs = __fmul_rn((float)(pos + 1), s[e]);
+                cnt += (pos < Kr && lhs > Cc[e]) ? 1 : 0;
+            }
+            int ks = group_sum<G>(cnt);
+            ks = max(ks, 1);
+
+            // tau = C[k-1] / k : fetch slot (k-1) % E of lane (k-1) / E
+            float ck = Cc[0];
+#pragma unroll
+            for (int e = 1; e < E; ++e) ck = (((ks - 1) % E) == e) ? Cc[e] : ck;
+            ck = __shfl_sync(kFull, ck, (ks - 1) / E, G);
+            if (need_sort) {
+                tau = __fdiv_rn(ck, (float)ks);
+                k = ks;
+            }
         }
-        // (not incl - run: a lane holding -inf padding would turn that into NaN)
-        double excl = __shfl_up_sync(kFull, incl, 1, G);
-        if (l == 0) excl = 0.0;
 
-        float C[E];
-        int cnt = 0;
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-            const int pos = l * E + e;
-            C[e] = __fsub_rn((float)(excl + cs[e]), 1.0f);
-            const float lhs = __fmul_rn((float)(pos + 1), s[e]);
-            cnt += (pos < Kr && lhs > C[e]) ? 1 : 0;
-        }
-        int k = group_sum<G>(cnt);
-        k = max(k, 1);
-
-        // tau = C[k-1] / k : fetch slot (k-1) % E of lane (k-1) / E
-        float ck = C[0];
-#pragma unroll
-        for (int e = 1; e < E; ++e) ck = (((k - 1) % E) == e) ? C[e] : ck;
-        ck = __shfl_sync(kFull, ck, (k - 1) / E, G);
-        const float tau = __fdiv_rn(ck, (float)k);
-
-        int nz = 0;
         float h = 0.f;
+        int nz = 0;
         const float eps = 1.1920928955078125e-07f;  // torch.finfo(float32).eps
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-            float pe = fmaxf(__fsub_rn(v[e], tau), 0.f);
+            const float pe = fmaxf(__fsub_rn(v[e], tau), 0.f);
             v[e] = pe;
             if (pe > 0.f) {
                 ++nz;
                 if (ent != nullptr) {
-                    float ps = fminf(fmaxf(pe, eps), 1.f - eps);
-                    h = fmaf(ps, logf(ps), h);
+                    const float ps = fminf(fmaxf(pe, eps), 1.f - eps);
+                    h = fmaf(ps, __logf(ps), h);  // MUFU.LG2 path: |err| <= 4e-7 on p log p
                 }
             }
         }
         if (live) store_row<E, G, VEC>(p + row * (int64_t)K, K, l, v);
         if (nnz != nullptr) {
-            nz = group_sum<G>(nz);
-            if (live && l == 0) nnz[row] = nz;
+            // on the verified fast path #(p > 0) == k; only sorted rows need the count
+            int nzr = k;
+            if (__any_sync(kFull, need_sort)) {
+                const int cnt = gsum_fast<G>(nz);
+                if (need_sort) nzr = cnt;
+            }
+            if (live && l == 0) nnz[row] = nzr;
         }
         if (ent != nullptr) {
             h = group_sum<G>(h);
@@ -241,7 +331,8 @@ __global__ void __launch_bounds__(kThreads)
 sparsemax_bwd_reg(const float* __restrict__ p, const int32_t* __restrict__ supp,
                   const float* __restrict__ dp, const float* __restrict__ loss,
                   const float* __restrict__ loss_scale_dev, float loss_scale_host,
-                  const float* __restrict__ dent, float* __restrict__ dx, int64_t rows, int K)
+                  const float* __restrict__ dent, float* __restrict__ dx,
+                  float* __restrict__ dloss, int64_t rows, int K)
 {
     constexpr int RPW = kWarp / G;
     const int lane = threadIdx.x & 31;
@@ -260,6 +351,12 @@ sparsemax_bwd_reg(const float* __restrict__ p, const int32_t* __restrict__ supp,
 
         float pv[E], gv[E];
         load_row<E, G, VEC>(p + off, Kr, l, 0.f, pv);
+        if (dloss != nullptr) {  // decoder side of the weighted loss: d/dL sum(P L) * ls = ls * P
+            float dl[E];
+#pragma unroll
+            for (int e = 0; e < E; ++e) dl[e] = ls * pv[e];
+            if (live) store_row<E, G, VEC>(dloss + off, K, l, dl);
+        }
         if (dp != nullptr) {
             load_row<E, G, VEC>(dp + off, Kr, l, 0.f, gv);
         } else {
@@ -435,7 +532,8 @@ __global__ void __launch_bounds__(kWideThreads)
 sparsemax_bwd_wide(const float* __restrict__ p, const int32_t* __restrict__ supp,
                    const float* __restrict__ dp, const float* __restrict__ loss,
                    const float* __restrict__ loss_scale_dev, float loss_scale_host,
-                   const float* __restrict__ dent, float* __restrict__ dx, int64_t rows, int K)
+                   const float* __restrict__ dent, float* __restrict__ dx,
+                   float* __restrict__ dloss, int64_t rows, int K)
 {
     __shared__ double red[kWideThreads / 32 + 1];
     const int tid = threadIdx.x;
@@ -459,6 +557,7 @@ sparsemax_bwd_wide(const float* __restrict__ p, const int32_t* __restrict__ supp
         for (int c = tid; c < K; c += kWideThreads) {
             float pe = p[off + c];
             float o = 0.f;
+            if (dloss != nullptr) stg_stream(dloss + off + c, ls * pe);
             if (pe != 0.f) {
                 float g = dp != nullptr ? dp[off + c] : 0.f;
                 if (loss != nullptr) g = fmaf(ls, loss[off + c], g);
@@ -511,12 +610,12 @@ static void launch_fwd(bool vec, int grid, cudaStream_t st, const float* x, floa
 template <int E, int G>
 static void launch_bwd(bool vec, int grid, cudaStream_t st, const float* p, const int32_t* supp,
                        const float* dp, const float* loss, const float* lsd, float lsh,
-                       const float* dent, float* dx, int64_t rows, int K)
+                       const float* dent, float* dx, float* dloss, int64_t rows, int K)
 {
     if (vec)
-        sparsemax_bwd_reg<E, G, true><<<grid, kThreads, 0, st>>>(p, supp, dp, loss, lsd, lsh, dent, dx, rows, K);
+        sparsemax_bwd_reg<E, G, true><<<grid, kThreads, 0, st>>>(p, supp, dp, loss, lsd, lsh, dent, dx, dloss, rows, K);
     else
-        sparsemax_bwd_reg<E, G, false><<<grid, kThreads, 0, st>>>(p, supp, dp, loss, lsd, lsh, dent, dx, rows, K);
+        sparsemax_bwd_reg<E, G, false><<<grid, kThreads, 0, st>>>(p, supp, dp, loss, lsd, lsh, dent, dx, dloss, rows, K);
 }
 
 #define SMLVM_DISPATCH_SHAPE(FN, ...)                                   \
@@ -573,8 +672,8 @@ extern "C" int smlvm_sparsemax_fwd(const float* x, float* p, int32_t* supp_size,
 
 extern "C" int smlvm_sparsemax_bwd(const float* p, const int32_t* supp_size, const float* dp,
                                    const float* loss, const float* loss_scale_dev,
-                                   float loss_scale_host, const float* dent, float* dx, int64_t rows,
-                                   int32_t cols, void* stream)
+                                   float loss_scale_host, const float* dent, float* dx,
+                                   float* dloss, int64_t rows, int32_t cols, void* stream)
 {
     if (rows < 0 || cols < 1) return SMLVM_ERR_ARG;
     if (rows == 0) return SMLVM_OK;
@@ -584,15 +683,16 @@ extern "C" int smlvm_sparsemax_bwd(const float* p, const int32_t* supp_size, con
     if (cols <= 1024) {
         RegShape sh = pick_shape(cols);
         const bool vec = (cols % 4 == 0) && aligned16(p) && aligned16(dx) &&
-                         (dp == nullptr || aligned16(dp)) && (loss == nullptr || aligned16(loss));
+                         (dp == nullptr || aligned16(dp)) && (loss == nullptr || aligned16(loss)) &&
+                         (dloss == nullptr || aligned16(dloss));
         const int grid = grid_for(rows, sh.G);
         SMLVM_DISPATCH_SHAPE(launch_bwd, vec, grid, st, p, supp_size, dp, loss, loss_scale_dev,
-                             loss_scale_host, dent, dx, rows, cols);
+                             loss_scale_host, dent, dx, dloss, rows, cols);
     } else {
         int64_t cap = (int64_t)device_sm_count() * 8;
         int grid = (int)(rows < cap ? rows : cap);
         sparsemax_bwd_wide<<<grid, kWideThreads, 0, st>>>(p, supp_size, dp, loss, loss_scale_dev,
-                                                          loss_scale_host, dent, dx, rows, cols);
+                                                          loss_scale_host, dent, dx, dloss, rows, cols);
     }
     SMLVM_LAUNCH_CHECK();
     return SMLVM_OK;

@@ -49,15 +49,13 @@ class _FusedMarginalObjective(torch.autograd.Function):
         p, supp, losses = ctx.saved_tensors
         rows = p.shape[0]
         g = (g_full + g_total).contiguous().float()
-        dscores = dlosses = None
-        if ctx.needs_input_grad[0]:
-            dent = None
-            if ctx.coeff != 0.0:
-                dent = (g_full.float() * (-ctx.coeff / rows)).expand(rows).contiguous()
-            dscores = ops.sparsemax_bwd(p, supp, loss=losses, loss_scale=g,
-                                        loss_scale_host=1.0 / rows, dent=dent)
-        if ctx.needs_input_grad[1]:
-            dlosses = p * (g / rows)
+        dent = None
+        if ctx.coeff != 0.0:
+            dent = (g_full.float() * (-ctx.coeff / rows)).expand(rows).contiguous()
+        # one launch: dscores (sparsemax Jacobian of g*L/B + entropy term) and dlosses = g*P/B
+        dscores, dlosses = ops.sparsemax_bwd(p, supp, loss=losses, loss_scale=g,
+                                             loss_scale_host=1.0 / rows, dent=dent,
+                                             want_dloss=True)
         return dscores, dlosses, None, None, None, None
 
 

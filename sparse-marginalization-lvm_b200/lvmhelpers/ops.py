@@ -41,17 +41,22 @@ def sparsemax_fwd(x, want_entropy=False, want_argmax=False, want_nnz=True):
     return dict(p=p, supp=supp, nnz=nnz, entropy=ent, argmax=amax)
 
 
-def sparsemax_bwd(p, supp, dp=None, loss=None, loss_scale=None, loss_scale_host=1.0, dent=None):
-    """Fused Jacobian-vector product; see smlvm_sparsemax_bwd in include/smlvm.h."""
+def sparsemax_bwd(p, supp, dp=None, loss=None, loss_scale=None, loss_scale_host=1.0, dent=None,
+                  want_dloss=False, out=None, out_dloss=None):
+    """Fused Jacobian-vector product; see smlvm_sparsemax_bwd in include/smlvm.h.
+    With want_dloss also returns dloss = loss_scale * p (decoder side of the weighted loss)."""
     rows, K = p.shape
-    dx = torch.empty_like(p)
+    dx = torch.empty_like(p) if out is None else out
+    dloss = None
+    if want_dloss:
+        dloss = torch.empty_like(p) if out_dloss is None else out_dloss
     dp = None if dp is None else _f32c(dp, "dp")
     loss = None if loss is None else _f32c(loss, "loss")
     dent = None if dent is None else _f32c(dent, "dent")
     check(lib.smlvm_sparsemax_bwd(ptr(p), ptr(supp), ptr(dp), ptr(loss), ptr(loss_scale),
-                                  float(loss_scale_host), ptr(dent), ptr(dx), rows, K, stream()),
-          "smlvm_sparsemax_bwd")
-    return dx
+                                  float(loss_scale_host), ptr(dent), ptr(dx), ptr(dloss), rows, K,
+                                  stream()), "smlvm_sparsemax_bwd")
+    return (dx, dloss) if want_dloss else dx
 
 
 class _Sparsemax(torch.autograd.Function):
