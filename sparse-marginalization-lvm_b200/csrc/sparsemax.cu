@@ -19,23 +19,17 @@
 // (one CTA per row).  Every row is read once and written once (HBM-bound
 // design point: 8K B/row forward, 12K B/row backward).
 #include <math_constants.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
+#include "sparsemax_exact.cuh"
 
 namespace smlvm {
 
 constexpr int kThreads = 256;
 
 // ---- register path ---------------------------------------------------------
-
-// Column held by slot e of lane l.  VEC: 128-bit chunks interleaved across the
-// group (coalesced float4 accesses); scalar: plain striping.
-template <int E, int G, bool VEC>
-__device__ __forceinline__ int col_of(int e, int l)
-{
-    if (VEC) return 4 * ((e >> 2) * G + l) + (e & 3);
-    return e * G + l;
-}
 
 template <int E, int G, bool VEC>
 __device__ __forceinline__ void load_row(const float* __restrict__ base, int K, int l, float fill,
@@ -77,71 +71,6 @@ __device__ __forceinline__ void store_row(float* __restrict__ base, int K, int l
         }
     }
 }
-
-// Descending bitonic sort of the E*G values of a group; sorted position of
-// slot e in lane l is l*E + e.
-template <int E, int G>
-__device__ __forceinline__ void group_sort_desc(float (&s)[E], int l)
-{
-    constexpr int N = E * G;
-#pragma unroll
-    for (int k = 2; k <= N; k <<= 1) {
-#pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            if (j >= E) {
-                const int lj = j / E;  // lane stride
-                const bool lower = (l & lj) == 0;
-                // every slot of a lane shares (pos & k) when k >= E... k > j >= E
-                const bool desc = ((l * E) & k) == 0;
-                const bool keep_max = (lower == desc);
-#pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    float o = __shfl_xor_sync(kFull, s[e], lj, G);
-                    s[e] = keep_max ? fmaxf(s[e], o) : fminf(s[e], o);
-                }
-            } else {
-#pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    if ((e & j) == 0) {
-                        const int f = e | j;
-                        // direction of the block containing pos = l*E + e
-                        const bool desc = (((l * E + e) & k) == 0);
-                        float hi = fmaxf(s[e], s[f]), lo = fminf(s[e], s[f]);
-                        s[e] = desc ? hi : lo;
-                        s[f] = desc ? lo : hi;
-                    }
-                }
-            }
-        }
-    }
-}
-
-
-// Full-warp groups reduce in one REDUX/CREDUX instruction (sm_100a has the fp32 max form);
-// sub-warp groups fall back to shuffles (a partial-mask redux serialises per mask).
-template <int G>
-__device__ __forceinline__ float gmax_fast(float v)
-{
-    if (G == 32) {
-        float m;
-        asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(v));
-        return m;
-    }
-    return group_max<G>(v);
-}
-template <int G>
-__device__ __forceinline__ int gsum_fast(int v)
-{
-    if (G == 32) return __reduce_add_sync(kFull, v);
-    return group_sum<G>(v);
-}
-template <int G>
-__device__ __forceinline__ int gmin_fast(int v)
-{
-    if (G == 32) return __reduce_min_sync(kFull, v);
-    return group_reduce<G>(v, [](int a, int b) { return min(a, b); });
-}
-constexpr int ilog2_c(int n) { return n <= 1 ? 0 : 1 + ilog2_c(n >> 1); }
 
 template <int E, int G, bool VEC>
 __global__ void __launch_bounds__(kThreads)
@@ -239,48 +168,11 @@ sparsemax_fwd_reg(const float* __restrict__ x, float* __restrict__ p, int32_t* _
 
         if (__any_sync(kFull, need_sort)) {
             // ---- exact path: the reference's definition, by sorting -----------------------
-            float s[E];
-#pragma unroll
-            for (int e = 0; e < E; ++e) s[e] = v[e];
-            group_sort_desc<E, G>(s, l);
-
-            // fp64 inclusive prefix sums in sorted order
-            double cs[E];
-            double run = 0.0;
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-                run += (double)s[e];
-                cs[e] = run;
-            }
-            double incl = run;  // lane totals -> exclusive offset of this lane
-#pragma unroll
-            for (int o = 1; o < G; o <<= 1) {
-                double t = __shfl_up_sync(kFull, incl, o, G);
-                if (l >= o) incl += t;
-            }
-            // (not incl - run: a lane holding -inf padding would turn that into NaN)
-            double excl = __shfl_up_sync(kFull, incl, 1, G);
-            if (l == 0) excl = 0.0;
-
-            float Cc[E];
-            int cnt = 0;
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-                const int pos = l * E + e;
-                Cc[e] = __fsub_rn((float)(excl + cs[e]), 1.0f);
-                const float lhs = __fmul_rn((float)(pos + 1), s[e]);
-                cnt += (pos < Kr && lhs > Cc[e]) ? 1 : 0;
-            }
-            int ks = group_sum<G>(cnt);
-            ks = max(ks, 1);
-
-            // tau = C[k-1] / k : fetch slot (k-1) % E of lane (k-1) / E
-            float ck = Cc[0];
-#pragma unroll
-            for (int e = 1; e < E; ++e) ck = (((ks - 1) % E) == e) ? Cc[e] : ck;
-            ck = __shfl_sync(kFull, ck, (ks - 1) / E, G);
+            int ks;
+            float taus;
+            exact_threshold_sorted<E, G>(v, l, Kr, ks, taus);
             if (need_sort) {
-                tau = __fdiv_rn(ck, (float)ks);
+                tau = taus;
                 k = ks;
             }
         }
@@ -633,6 +525,25 @@ static void launch_bwd(bool vec, int grid, cudaStream_t st, const float* p, cons
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// sparsemax_tile.cu
+bool sparsemax_tile_supported(int cols);
+int sparsemax_fwd_tile_launch(const float* x, float* p, int32_t* supp, int32_t* nnz, float* ent, int64_t* amax,
+                              int64_t rows, int cols, cudaStream_t st);
+
+// Forward path selection.  The TMA-staged tile kernel wins once there are enough 32-row tiles to
+// occupy the SMs; tiny batches (the B = 64 experiment shapes) are launch-bound and stay on the
+// register kernel.  SMLVM_SPARSEMAX_FWD=reg|tile overrides (tests exercise both on every shape).
+static int fwd_path_override()
+{
+    static int cached = -1;
+    if (cached < 0) {
+        const char* e = getenv("SMLVM_SPARSEMAX_FWD");
+        cached = (e == nullptr) ? 0 : (strcmp(e, "reg") == 0 ? 1 : (strcmp(e, "tile") == 0 ? 2 : 0));
+    }
+    return cached;
+}
+constexpr int64_t kTileMinRows = 4096;
+
 }  // namespace smlvm
 
 using namespace smlvm;
@@ -646,6 +557,10 @@ extern "C" int smlvm_sparsemax_fwd(const float* x, float* p, int32_t* supp_size,
     if (x == nullptr || p == nullptr) return SMLVM_ERR_ARG;
     if (cols > SMLVM_SPARSEMAX_MAX_COLS) return SMLVM_ERR_UNSUPPORTED;
     cudaStream_t st = as_stream(stream);
+    const int ovr = fwd_path_override();
+    if (sparsemax_tile_supported(cols) && aligned16(x) && aligned16(p) && ovr != 1 &&
+        (rows >= kTileMinRows || ovr == 2))
+        return sparsemax_fwd_tile_launch(x, p, supp_size, nnz, entropy, argmax, rows, cols, st);
     if (cols <= 1024) {
         RegShape sh = pick_shape(cols);
         const bool vec = (cols % 4 == 0) && aligned16(x) && aligned16(p);

@@ -1,0 +1,466 @@
+// Batched sparsemax forward, TMA-staged tile kernel for sm_100a (K in {32,64,128,256}).
+//
+// Same semantics as sparsemax.cu (entmax.sparsemax evaluated with torch CPU ops,
+// lvmhelpers/marg.py:51, lvmhelpers/structmarg.py:48) but organised around the observation
+// that the register kernel is ISSUE-bound (ncu r01: 427 warp instructions per row, 79 % issue
+// utilisation, 36 % of the HBM roofline): with one warp per row every element of the row pays
+// for every step of the threshold search.  Here
+//
+//   * a warp owns a tile of 32 consecutive rows (32*K*4 contiguous bytes), fetched by ONE
+//     `cp.async.bulk` (TMA) into shared memory and written back by one bulk store; each warp
+//     runs its own 2-stage mbarrier ring, so there is no CTA-wide synchronisation;
+//   * a THREAD owns a row.  It reads the row from shared memory in 128-bit chunks, rotated
+//     by the lane id so that the 32 rows (stride K words) never collide on a bank;
+//   * pass A finds the row max; pass B builds a bitmask of the candidates X' > thr (X' = X -
+//     max, thr = -1 first: nothing at or below max-1 can be in the support) and their sum,
+//     from which Michelot's bound tau >= (sum - 1) / count tightens thr until at most 32
+//     candidates are left (one pass is enough for peaked rows);
+//   * the candidates -- a superset of the support with a rounding margin -- are insertion-
+//     sorted and the REFERENCE'S OWN definition (fp64 cumulative sums in sorted order,
+//     fl32(r*S_r) > fl32(fl32(cumsum_r) - 1), tau = C_k / k) is evaluated on them: the sorted
+//     candidates are exactly the head of the reference's full sort, and every position behind
+//     them fails the support test by more than the rounding error, so (k, tau)
+//     and hence P are those of the reference;
+//   * rows whose support does not fit 32 candidates (near-uniform rows) are handed to the
+//     whole warp, which evaluates them with the bitonic-sort path of sparsemax_exact.cuh.
+//
+// Work per row drops from ~430 to ~50 warp instructions; HBM traffic stays at the algorithmic
+// 8K bytes per row.
+#include <math_constants.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "sparsemax_exact.cuh"
+
+namespace smlvm {
+
+constexpr int kTileRows = 32;
+constexpr int kCap = 32;        // candidate-list entries per row
+constexpr int kMaxPasses = 24;  // Michelot tightening passes before a row is declared slow
+
+// ---- PTX: mbarrier + bulk async copies -----------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* dst, uint32_t src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// per-warp shared memory of the tile kernel
+template <int K, int S>
+struct TileSmem {
+    static constexpr int kTileFloats = kTileRows * K;
+    static constexpr size_t kWarpBytes = (size_t)S * kTileFloats * 4 + kCap * 32 * 4 + kCap * 32 * 1;
+    static constexpr size_t total(int W) { return W * kWarpBytes + (size_t)W * S * 8; }
+};
+
+// Cooperative (whole-warp) evaluation of one row held in shared memory: the sort-based
+// reference definition.  Overwrites the row with P; returns the per-row scalars to every lane.
+template <int K>
+__device__ __forceinline__ void warp_row_exact(float* srow, int lane, int& k_out, int& nz_out, float& h_out,
+                                               int& first_out)
+{
+    constexpr int E = K / 32;
+    constexpr bool VEC = (E % 4 == 0);
+    float v[E];
+    if (VEC) {
+#pragma unroll
+        for (int c = 0; c < E / 4; ++c) {
+            const float4 q = *reinterpret_cast<const float4*>(srow + 4 * (c * 32 + lane));
+            v[4 * c + 0] = q.x; v[4 * c + 1] = q.y; v[4 * c + 2] = q.z; v[4 * c + 3] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) v[e] = srow[e * 32 + lane];
+    }
+    float m = v[0];
+#pragma unroll
+    for (int e = 1; e < E; ++e) m = fmaxf(m, v[e]);
+    m = gmax_fast<32>(m);
+    int first = 0x7fffffff;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        if (v[e] == m) first = min(first, col_of<E, 32, VEC>(e, lane));
+        v[e] = __fsub_rn(v[e], m);
+    }
+    first_out = gmin_fast<32>(first);
+    int k;
+    float tau;
+    exact_threshold_sorted<E, 32>(v, lane, K, k, tau);
+    const float eps = 1.1920928955078125e-07f;
+    int nz = 0;
+    float h = 0.f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const float pe = fmaxf(__fsub_rn(v[e], tau), 0.f);
+        v[e] = pe;
+        if (pe > 0.f) {
+            ++nz;
+            const float ps = fminf(fmaxf(pe, eps), 1.f - eps);
+            h = fmaf(ps, __logf(ps), h);
+        }
+    }
+    if (VEC) {
+#pragma unroll
+        for (int c = 0; c < E / 4; ++c)
+            *reinterpret_cast<float4*>(srow + 4 * (c * 32 + lane)) =
+                make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) srow[e * 32 + lane] = v[e];
+    }
+    k_out = k;
+    nz_out = gsum_fast<32>(nz);
+    h_out = group_sum<32>(h);
+}
+
+
+// (k, tau) of the reference from the candidate list of one row (thread-private column `lv` of
+// the [slot][lane] shared-memory list, n <= N entries): the candidates are loaded into
+// registers, sorted descending by a bitonic network (compile-time indices, no divergence) and
+// the reference's own support test is evaluated position by position -- fp64 cumulative sum in
+// sorted order, C_r = fl32(fl32(cumsum_r) - 1), support where fl32(r * S_r) > C_r, k = number
+// of such r, tau = C_k / k.  Padding is -inf: it sorts last and fails the test.
+template <int N>
+__device__ __forceinline__ void list_threshold(const float* lv, int n, int& k_out, float& tau_out)
+{
+    float v[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) v[j] = (j < n) ? lv[j * 32] : -CUDART_INF_F;
+#pragma unroll
+    for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const bool desc = (i & k) == 0;
+                    const float hi = fmaxf(v[i], v[l]), lo = fminf(v[i], v[l]);
+                    v[i] = desc ? hi : lo;
+                    v[l] = desc ? lo : hi;
+                }
+            }
+        }
+    }
+    double cs = 0.0;
+    float c_last = -1.f;
+    int kk = 0, last_true = -1;
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+        cs += (double)v[r];
+        const float C = __fsub_rn((float)cs, 1.0f);
+        if (__fmul_rn((float)(r + 1), v[r]) > C) {
+            ++kk;
+            c_last = C;
+            last_true = r;
+        }
+    }
+    if (__any_sync(kFull, last_true + 1 != kk && kk > 0)) {
+        // trues not contiguous (rounding): the reference takes C at index k, not at the last true
+        if (last_true + 1 != kk && kk > 0) {
+            cs = 0.0;
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+                if (r < kk) cs += (double)v[r];
+            c_last = __fsub_rn((float)cs, 1.0f);
+        }
+    }
+    kk = max(kk, 1);
+    k_out = kk;
+    tau_out = __fdiv_rn(c_last, (float)kk);
+}
+
+template <int K, int S, int W>
+__global__ void __launch_bounds__(W * 32, 1)
+sparsemax_fwd_tile(const float* __restrict__ x, float* __restrict__ p, int32_t* __restrict__ supp,
+                   int32_t* __restrict__ nnz, float* __restrict__ ent, int64_t* __restrict__ amax,
+                   int64_t rows)
+{
+    static_assert(S == 1 || S == 2, "1- or 2-stage ring");
+    constexpr int NC = K / 4;   // 128-bit chunks per row
+    constexpr int MW = K / 32;  // candidate-mask words per row
+    constexpr int TILE_F = kTileRows * K;
+    // superset margin: candidates are X' > bound - kMargin; covers the fp32 error of the
+    // Michelot bound (<= 2K ulp) and the rounding slack of the reference's support test behind
+    // the candidates (<= 6K ulp), DESIGN.md §4.1
+    constexpr float kMargin = 32.f * K * 5.9604645e-08f;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* tiles = reinterpret_cast<float*>(smem_raw) + (size_t)warp * S * TILE_F;
+    float* lval = reinterpret_cast<float*>(smem_raw) + (size_t)W * S * TILE_F + warp * (kCap * 32) + lane;
+    uint8_t* lrho = reinterpret_cast<uint8_t*>(reinterpret_cast<float*>(smem_raw) + (size_t)W * S * TILE_F +
+                                               W * (kCap * 32)) + warp * (kCap * 32) + lane;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)W * TileSmem<K, S>::kWarpBytes) + warp * S;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < W * S; ++i)
+            mbar_init(smem_u32(reinterpret_cast<uint64_t*>(smem_raw + (size_t)W * TileSmem<K, S>::kWarpBytes) + i), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int64_t ntiles = (rows + kTileRows - 1) / kTileRows;
+    const int64_t stride = (int64_t)gridDim.x * W;
+    int64_t t = (int64_t)warp * gridDim.x + blockIdx.x;
+
+    auto issue_load = [&](int stage, int64_t tile) {
+        const int64_t r0 = tile * kTileRows;
+        const uint32_t bytes = (uint32_t)min((int64_t)kTileRows, rows - r0) * K * 4u;
+        const uint32_t bar = smem_u32(bars + stage);
+        mbar_expect_tx(bar, bytes);
+        bulk_load(smem_u32(tiles + stage * TILE_F), x + r0 * K, bytes, bar);
+    };
+
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+            if (t + s * stride < ntiles) issue_load(s, t + s * stride);
+    }
+
+    uint32_t parity = 0;  // bit s: phase to wait for on stage s
+    int stage = 0;
+    for (int64_t it = 0; t < ntiles; t += stride, ++it) {
+        mbar_wait(smem_u32(bars + stage), (parity >> stage) & 1u);
+        parity ^= 1u << stage;
+
+        const int64_t row0 = t * kTileRows;
+        const int trows = (int)min((int64_t)kTileRows, rows - row0);
+        const bool live = lane < trows;
+        float* tile = tiles + stage * TILE_F;
+        float* rowp = tile + (live ? lane : 0) * K;
+
+        // ---- pass A: row max --------------------------------------------------------------
+        float m = -CUDART_INF_F;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            const int c = (i + lane) & (NC - 1);
+            const float4 q = *reinterpret_cast<const float4*>(rowp + 4 * c);
+            m = fmaxf(fmaxf(m, fmaxf(q.x, q.y)), fmaxf(q.z, q.w));
+        }
+
+        // refill the other stage: its tile was stored one iteration ago, the store has long
+        // finished reading it (S == 2); the new tile has the rest of this iteration to land
+        if (S == 2 && it > 0 && lane == 0) {
+            bulk_wait_read0();
+            if (t + stride < ntiles) issue_load(stage ^ 1, t + stride);
+        }
+
+        // ---- pass B: candidate mask, tightened with Michelot's bound -------------------------
+        uint32_t mask[MW];
+        float thr = -1.0f - kMargin;
+        bool need = true, slow = false;
+        for (int pass = 0; pass < kMaxPasses; ++pass) {
+            if (need) {
+                float s = 0.f;
+#pragma unroll
+                for (int w = 0; w < MW; ++w) mask[w] = 0u;
+#pragma unroll
+                for (int i = 0; i < NC; ++i) {
+                    const int c = (i + lane) & (NC - 1);
+                    const float4 q = *reinterpret_cast<const float4*>(rowp + 4 * c);
+                    const float xv[4] = {__fsub_rn(q.x, m), __fsub_rn(q.y, m), __fsub_rn(q.z, m), __fsub_rn(q.w, m)};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if (xv[e] > thr) {
+                            mask[(4 * i + e) >> 5] |= 1u << ((4 * i + e) & 31);
+                            s += xv[e];
+                        }
+                    }
+                }
+                int cnt = 0;
+#pragma unroll
+                for (int w = 0; w < MW; ++w) cnt += __popc(mask[w]);
+                if (cnt <= kCap) {
+                    need = false;
+                } else {
+                    const float tn = __fdividef(s - 1.f, (float)cnt) - kMargin;
+                    if (tn > thr) thr = tn;
+                    else { slow = true; need = false; }  // > kCap entries at the bound: wide support
+                }
+            }
+            if (!__any_sync(kFull, need)) break;
+        }
+        if (need) slow = true;
+
+        // ---- candidates -> shared-memory list (value, rotated index), warp-uniform loops ------
+        // (a per-thread `while (mask)` would serialise the 32 rows of the warp: ncu r01 showed
+        //  3.4 active threads per instruction with nested data-dependent loops)
+        int n = 0;
+        int cnt_mine = 0;
+#pragma unroll
+        for (int w = 0; w < MW; ++w) cnt_mine += slow ? 0 : __popc(mask[w]);
+#pragma unroll
+        for (int w = 0; w < MW; ++w) {
+            uint32_t mw = slow ? 0u : mask[w];
+            const int steps = __reduce_max_sync(kFull, __popc(mw));
+            for (int jj = 0; jj < steps; ++jj) {
+                if (mw) {
+                    const int rho = w * 32 + __ffs(mw) - 1;
+                    mw &= mw - 1;
+                    lval[n * 32] = __fsub_rn(rowp[(rho + 4 * lane) & (K - 1)], m);
+                    lrho[n * 32] = (uint8_t)rho;
+                    ++n;
+                }
+            }
+        }
+        const int nmax = __reduce_max_sync(kFull, cnt_mine);
+
+        int k = 1, nz = 0, first = 0x7fffffff;
+        float h = 0.f;
+        float tau = 0.f;
+        if (nmax <= 8) list_threshold<8>(lval, n, k, tau);
+        else if (nmax <= 16) list_threshold<16>(lval, n, k, tau);
+        else list_threshold<32>(lval, n, k, tau);
+
+        // ---- zero-fill the row, then P on the support + entropy + argmax -----------------------
+        if (live && !slow) {
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                const int c = (i + lane) & (NC - 1);
+                *reinterpret_cast<float4*>(rowp + 4 * c) = z4;
+            }
+        }
+        {
+            const float eps = 1.1920928955078125e-07f;
+            for (int j = 0; j < nmax; ++j) {
+                if (j < n) {
+                    const float sv = lval[j * 32];
+                    const float pe = fmaxf(__fsub_rn(sv, tau), 0.f);
+                    if (pe > 0.f) {
+                        const int col = ((int)lrho[j * 32] + 4 * lane) & (K - 1);
+                        if (live) rowp[col] = pe;
+                        ++nz;
+                        const float ps = fminf(fmaxf(pe, eps), 1.f - eps);
+                        h = fmaf(ps, __logf(ps), h);
+                        if (sv == 0.f) first = min(first, col);
+                    }
+                }
+            }
+        }
+
+        // ---- wide-support rows: the whole warp, one row at a time ---------------------------
+        unsigned sm = __ballot_sync(kFull, slow && live);
+        while (sm) {
+            const int r = __ffs(sm) - 1;
+            sm &= sm - 1;
+            int k2, nz2, f2;
+            float h2;
+            warp_row_exact<K>(tile + r * K, lane, k2, nz2, h2, f2);
+            if (lane == r) { k = k2; nz = nz2; h = h2; first = f2; }
+        }
+
+        if (live) {
+            const int64_t row = row0 + lane;
+            if (supp != nullptr) supp[row] = k;
+            if (nnz != nullptr) nnz[row] = nz;
+            if (ent != nullptr) ent[row] = -h;
+            if (amax != nullptr) amax[row] = first;
+        }
+
+        // ---- tile of P back to HBM -----------------------------------------------------------
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            bulk_store(p + row0 * K, smem_u32(tile), (uint32_t)trows * K * 4u);
+            bulk_commit();
+            if (S == 1) {
+                bulk_wait_read0();
+                if (t + stride < ntiles) issue_load(0, t + stride);
+            }
+        }
+        __syncwarp();
+        if (S == 2) stage ^= 1;
+    }
+    if (lane == 0) bulk_wait_read0();
+}
+
+template <int K, int S, int W>
+static int launch_tile(const float* x, float* p, int32_t* supp, int32_t* nnz, float* ent, int64_t* amax,
+                       int64_t rows, cudaStream_t st)
+{
+    auto kern = sparsemax_fwd_tile<K, S, W>;
+    const size_t smem = TileSmem<K, S>::total(W);
+    static bool configured_dev[64] = {false};
+    static int ctas_per_sm = 1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bool& configured = configured_dev[dev & 63];
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, W * 32, smem) != cudaSuccess ||
+            ctas_per_sm < 1)
+            ctas_per_sm = 1;
+        configured = true;
+    }
+    const int64_t ntiles = (rows + kTileRows - 1) / kTileRows;
+    const int64_t need = (ntiles + W - 1) / W;
+    const int64_t cap = (int64_t)device_sm_count() * ctas_per_sm;
+    const int grid = (int)(need < cap ? need : cap);
+    kern<<<grid, W * 32, smem, st>>>(x, p, supp, nnz, ent, amax, rows);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SMLVM_OK : (int)e;
+}
+
+bool sparsemax_tile_supported(int cols) { return cols == 32 || cols == 64 || cols == 128 || cols == 256; }
+
+int sparsemax_fwd_tile_launch(const float* x, float* p, int32_t* supp, int32_t* nnz, float* ent, int64_t* amax,
+                              int64_t rows, int cols, cudaStream_t st)
+{
+    // (stages, warps) per K: as many independent warp pipelines as 227 KB of shared memory hold
+    static int variant = -1;
+    if (variant < 0) {
+        const char* e = getenv("SMLVM_TILE_VARIANT");
+        variant = e ? atoi(e) : 0;
+    }
+    switch (cols) {
+        case 32: return launch_tile<32, 2, 8>(x, p, supp, nnz, ent, amax, rows, st);
+        case 64: return launch_tile<64, 2, 8>(x, p, supp, nnz, ent, amax, rows, st);
+        case 128:
+            if (variant == 1) return launch_tile<128, 1, 10>(x, p, supp, nnz, ent, amax, rows, st);
+            return launch_tile<128, 2, 6>(x, p, supp, nnz, ent, amax, rows, st);
+        case 256:
+            if (variant == 1) return launch_tile<256, 1, 6>(x, p, supp, nnz, ent, amax, rows, st);
+            return launch_tile<256, 2, 3>(x, p, supp, nnz, ent, amax, rows, st);
+        default: return SMLVM_ERR_UNSUPPORTED;
+    }
+}
+
+}  // namespace smlvm

@@ -75,6 +75,44 @@ def test_edge_rows(oracle):
     assert torch.allclose(out["p"].sum(-1).cpu(), torch.ones(len(rows)), atol=1e-6)
 
 
+TILE_SHAPES = [(4096, 32), (4113, 64), (4096 + 31, 128), (8192, 128), (4097, 256), (5000, 512)]
+
+
+@pytest.mark.parametrize("rows,K", TILE_SHAPES)
+@pytest.mark.parametrize("scale", [0.01, 0.1, 0.3, 1.0, 3.0])
+def test_tile_kernel_parity(oracle, rows, K, scale):
+    """rows >= 4096 and K in {32..512}: the TMA-staged tile kernel (sparsemax_tile.cu).  Small
+    scales give supports wider than the 32-entry candidate list (whole-warp path), large scales
+    the per-thread path; a partial last tile is included.  Bit-exact against the oracle."""
+    from lvmhelpers import ops
+    x = _inputs(rows, K, scale, 1000 + K)
+    # structured rows inside the batch: ties, one-hot with gap exactly 1, constants, masked
+    x[5] = 0.0
+    x[6] = torch.tensor([1.0] + [0.0] * (K - 1))
+    x[7] = torch.round(x[7] * 2) / 2
+    x[8, : K // 2] = float("-inf")
+    x[9] = 1e4 * torch.sign(x[9])
+    x[rows - 1] = torch.linspace(-1e-3, 1e-3, K)
+    P_ref, k_ref = oracle.sparsemax_fwd(x)
+    out = ops.sparsemax_fwd(x.cuda(), want_entropy=True, want_argmax=True)
+    P = out["p"].cpu()
+    assert torch.equal(P > 0, P_ref > 0)
+    assert torch.equal(out["supp"].cpu().long(), k_ref)
+    assert torch.equal(out["nnz"].cpu().long(), (P_ref > 0).sum(-1))
+    assert (P - P_ref).abs().max().item() <= 1e-6
+    assert torch.equal(P, P_ref)
+    assert torch.equal(out["argmax"].cpu(), x.argmax(-1))
+    assert torch.allclose(out["entropy"].cpu(), oracle.entropy(P_ref), rtol=1e-5, atol=1e-6)
+
+
+def test_tile_kernel_optional_outputs():
+    from lvmhelpers import ops
+    x = torch.randn(4096, 128, device="cuda")
+    a = ops.sparsemax_fwd(x, want_entropy=True, want_argmax=True)
+    b = ops.sparsemax_fwd(x, want_nnz=False)
+    assert torch.equal(a["p"], b["p"]) and torch.equal(a["supp"], b["supp"]) and b["nnz"] is None
+
+
 def test_properties_full_size():
     """BASELINE config-5 size: size-independent properties instead of an oracle run."""
     from lvmhelpers import ops
