@@ -80,6 +80,51 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+
+// shared-memory accesses by 32-bit shared address (volatile: the row is re-read and overwritten)
+__device__ __forceinline__ float4 lds128(uint32_t a)
+{
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ float lds32(uint32_t a)
+{
+    float r;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float4 v)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t a, float v)
+{
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+
+// Descending bitonic network over a register array (compile-time indices, no divergence).
+template <int N>
+__device__ __forceinline__ void sort_desc_regs(float (&v)[N])
+{
+#pragma unroll
+    for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const bool desc = (i & k) == 0;
+                    const float hi = fmaxf(v[i], v[l]), lo = fminf(v[i], v[l]);
+                    v[i] = desc ? hi : lo;
+                    v[l] = desc ? lo : hi;
+                }
+            }
+        }
+    }
+}
+
 // per-warp shared memory of the tile kernel
 template <int K, int S>
 struct TileSmem {
@@ -161,22 +206,7 @@ __device__ __forceinline__ void list_threshold(const float* lv, int n, int& k_ou
     float v[N];
 #pragma unroll
     for (int j = 0; j < N; ++j) v[j] = (j < n) ? lv[j * 32] : -CUDART_INF_F;
-#pragma unroll
-    for (int k = 2; k <= N; k <<= 1) {
-#pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                const int l = i ^ j;
-                if (l > i) {
-                    const bool desc = (i & k) == 0;
-                    const float hi = fmaxf(v[i], v[l]), lo = fminf(v[i], v[l]);
-                    v[i] = desc ? hi : lo;
-                    v[l] = desc ? lo : hi;
-                }
-            }
-        }
-    }
+    sort_desc_regs<N>(v);
     double cs = 0.0;
     float c_last = -1.f;
     int kk = 0, last_true = -1;
@@ -220,7 +250,7 @@ sparsemax_fwd_tile(const float* __restrict__ x, float* __restrict__ p, int32_t* 
     // the candidates (<= 6K ulp), DESIGN.md §4.1
     constexpr float kMargin = 32.f * K * 5.9604645e-08f;
 
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* tiles = reinterpret_cast<float*>(smem_raw) + (size_t)warp * S * TILE_F;
     float* lval = reinterpret_cast<float*>(smem_raw) + (size_t)W * S * TILE_F + warp * (kCap * 32) + lane;
@@ -263,15 +293,40 @@ sparsemax_fwd_tile(const float* __restrict__ x, float* __restrict__ p, int32_t* 
         const int trows = (int)min((int64_t)kTileRows, rows - row0);
         const bool live = lane < trows;
         float* tile = tiles + stage * TILE_F;
-        float* rowp = tile + (live ? lane : 0) * K;
+        // Row `lane` of the tile, read in 128-bit chunks.  Lane l visits chunk i ^ (l mod NC) at
+        // step i, so the 32 rows (stride K words) never collide on a bank; the row base is
+        // aligned to the row size, hence chunk address = swz ^ (i << 4): one LOP3 per access.
+        const uint32_t rowa = smem_u32(tile + (live ? lane : 0) * K);
+        const uint32_t lsw = (uint32_t)lane & (uint32_t)((NC - 1) & 31);
+        const uint32_t swz = rowa ^ (lsw << 4);
 
-        // ---- pass A: row max --------------------------------------------------------------
-        float m = -CUDART_INF_F;
+        // ---- pass A: 8 class maxima -> row max and a first lower bound on tau ----------------
+        // For ANY subset T of the row, tau >= (sum_T X' - 1) / |T|  (Michelot).  The maxima of 8
+        // disjoint classes (float4 component x chunk parity) are 8 distinct entries; the best
+        // prefix of their sorted order gives the starting bound (>= -1, the bound of {max}).
+        float cm[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cm[j] = -CUDART_INF_F;
 #pragma unroll
         for (int i = 0; i < NC; ++i) {
-            const int c = (i + lane) & (NC - 1);
-            const float4 q = *reinterpret_cast<const float4*>(rowp + 4 * c);
-            m = fmaxf(fmaxf(m, fmaxf(q.x, q.y)), fmaxf(q.z, q.w));
+            const float4 q = lds128(swz ^ (i << 4));
+            const int o = (i & 1) * 4;
+            cm[o + 0] = fmaxf(cm[o + 0], q.x);
+            cm[o + 1] = fmaxf(cm[o + 1], q.y);
+            cm[o + 2] = fmaxf(cm[o + 2], q.z);
+            cm[o + 3] = fmaxf(cm[o + 3], q.w);
+        }
+        sort_desc_regs<8>(cm);
+        const float m = cm[0];
+        float thr = -1.0f;
+        {
+            float run = 0.f;
+#pragma unroll
+            for (int j = 2; j <= 8; ++j) {
+                run += __fsub_rn(cm[j - 1], m);
+                thr = fmaxf(thr, (run - 1.f) * (1.f / (float)j));
+            }
+            thr -= kMargin;
         }
 
         // refill the other stage: its tile was stored one iteration ago, the store has long
@@ -281,50 +336,67 @@ sparsemax_fwd_tile(const float* __restrict__ x, float* __restrict__ p, int32_t* 
             if (t + stride < ntiles) issue_load(stage ^ 1, t + stride);
         }
 
-        // ---- pass B: candidate mask, tightened with Michelot's bound -------------------------
+        // ---- pass B: candidate mask {X > max + thr}, 2 instructions per element ---------------
+        // (compared unshifted against the rounded-DOWN sum, a superset of {fl(X - max) > thr};
+        //  the extraction below applies the exact shifted test)
         uint32_t mask[MW];
-        float thr = -1.0f - kMargin;
-        bool need = true, slow = false;
-        for (int pass = 0; pass < kMaxPasses; ++pass) {
-            if (need) {
-                float s = 0.f;
+        {
+            const float thr_abs = __fadd_rd(m, thr);
 #pragma unroll
-                for (int w = 0; w < MW; ++w) mask[w] = 0u;
+            for (int w = 0; w < MW; ++w) mask[w] = 0u;
 #pragma unroll
-                for (int i = 0; i < NC; ++i) {
-                    const int c = (i + lane) & (NC - 1);
-                    const float4 q = *reinterpret_cast<const float4*>(rowp + 4 * c);
-                    const float xv[4] = {__fsub_rn(q.x, m), __fsub_rn(q.y, m), __fsub_rn(q.z, m), __fsub_rn(q.w, m)};
+            for (int i = 0; i < NC; ++i) {
+                const float4 q = lds128(swz ^ (i << 4));
+                const float xq[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        if (xv[e] > thr) {
-                            mask[(4 * i + e) >> 5] |= 1u << ((4 * i + e) & 31);
-                            s += xv[e];
+                for (int e = 0; e < 4; ++e)
+                    if (xq[e] > thr_abs) mask[(4 * i + e) >> 5] |= 1u << ((4 * i + e) & 31);
+            }
+        }
+        int cnt = 0;
+#pragma unroll
+        for (int w = 0; w < MW; ++w) cnt += __popc(mask[w]);
+        bool need = cnt > kCap, slow = false;
+        // wide rows only: tighten the bound with Michelot passes over the row (mask + sum)
+        if (__any_sync(kFull, need)) {
+            for (int pass = 0; pass < kMaxPasses; ++pass) {
+                if (need) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int w = 0; w < MW; ++w) mask[w] = 0u;
+#pragma unroll
+                    for (int i = 0; i < NC; ++i) {
+                        const float4 q = lds128(swz ^ (i << 4));
+                        const float xv[4] = {__fsub_rn(q.x, m), __fsub_rn(q.y, m), __fsub_rn(q.z, m),
+                                             __fsub_rn(q.w, m)};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            if (xv[e] > thr) {
+                                mask[(4 * i + e) >> 5] |= 1u << ((4 * i + e) & 31);
+                                s += xv[e];
+                            }
                         }
                     }
-                }
-                int cnt = 0;
+                    cnt = 0;
 #pragma unroll
-                for (int w = 0; w < MW; ++w) cnt += __popc(mask[w]);
-                if (cnt <= kCap) {
-                    need = false;
-                } else {
-                    const float tn = __fdividef(s - 1.f, (float)cnt) - kMargin;
-                    if (tn > thr) thr = tn;
-                    else { slow = true; need = false; }  // > kCap entries at the bound: wide support
+                    for (int w = 0; w < MW; ++w) cnt += __popc(mask[w]);
+                    if (cnt <= kCap) {
+                        need = false;
+                    } else {
+                        const float tn = __fdividef(s - 1.f, (float)cnt) - kMargin;
+                        if (tn > thr) thr = tn;
+                        else { slow = true; need = false; }  // > kCap entries at the bound: wide support
+                    }
                 }
+                if (!__any_sync(kFull, need)) break;
             }
-            if (!__any_sync(kFull, need)) break;
+            if (need) slow = true;
         }
-        if (need) slow = true;
 
-        // ---- candidates -> shared-memory list (value, rotated index), warp-uniform loops ------
+        // ---- candidates -> shared-memory list (value, swizzled index), warp-uniform loops -----
         // (a per-thread `while (mask)` would serialise the 32 rows of the warp: ncu r01 showed
         //  3.4 active threads per instruction with nested data-dependent loops)
         int n = 0;
-        int cnt_mine = 0;
-#pragma unroll
-        for (int w = 0; w < MW; ++w) cnt_mine += slow ? 0 : __popc(mask[w]);
 #pragma unroll
         for (int w = 0; w < MW; ++w) {
             uint32_t mw = slow ? 0u : mask[w];
@@ -333,13 +405,16 @@ sparsemax_fwd_tile(const float* __restrict__ x, float* __restrict__ p, int32_t* 
                 if (mw) {
                     const int rho = w * 32 + __ffs(mw) - 1;
                     mw &= mw - 1;
-                    lval[n * 32] = __fsub_rn(rowp[(rho + 4 * lane) & (K - 1)], m);
-                    lrho[n * 32] = (uint8_t)rho;
-                    ++n;
+                    const float xv = __fsub_rn(lds32(rowa + (((uint32_t)rho ^ (lsw << 2)) << 2)), m);
+                    if (xv > thr) {
+                        lval[n * 32] = xv;
+                        lrho[n * 32] = (uint8_t)rho;
+                        ++n;
+                    }
                 }
             }
         }
-        const int nmax = __reduce_max_sync(kFull, cnt_mine);
+        const int nmax = __reduce_max_sync(kFull, n);
 
         int k = 1, nz = 0, first = 0x7fffffff;
         float h = 0.f;
@@ -350,12 +425,8 @@ sparsemax_fwd_tile(const float* __restrict__ x, float* __restrict__ p, int32_t* 
 
         // ---- zero-fill the row, then P on the support + entropy + argmax -----------------------
         if (live && !slow) {
-            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int i = 0; i < NC; ++i) {
-                const int c = (i + lane) & (NC - 1);
-                *reinterpret_cast<float4*>(rowp + 4 * c) = z4;
-            }
+            for (int i = 0; i < NC; ++i) sts128(swz ^ (i << 4), make_float4(0.f, 0.f, 0.f, 0.f));
         }
         {
             const float eps = 1.1920928955078125e-07f;
@@ -364,12 +435,12 @@ sparsemax_fwd_tile(const float* __restrict__ x, float* __restrict__ p, int32_t* 
                     const float sv = lval[j * 32];
                     const float pe = fmaxf(__fsub_rn(sv, tau), 0.f);
                     if (pe > 0.f) {
-                        const int col = ((int)lrho[j * 32] + 4 * lane) & (K - 1);
-                        if (live) rowp[col] = pe;
+                        const uint32_t col = (uint32_t)lrho[j * 32] ^ (lsw << 2);
+                        if (live) sts32(rowa + (col << 2), pe);
                         ++nz;
                         const float ps = fminf(fmaxf(pe, eps), 1.f - eps);
                         h = fmaf(ps, __logf(ps), h);
-                        if (sv == 0.f) first = min(first, col);
+                        if (sv == 0.f) first = min(first, (int)col);
                     }
                 }
             }

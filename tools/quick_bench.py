@@ -36,7 +36,7 @@ def main():
     which = sys.argv[1:] or ["sparsemax", "compact", "wloss", "topk", "smap"]
     if "sparsemax" in which:
         for rows, K, scale in [(1 << 20, 128, 1.0), (1 << 20, 128, 0.3), (1 << 19, 256, 0.1), (1 << 22, 10, 1.0),
-                               (1 << 16, 1024, 1.0)]:
+                               (1 << 16, 1024, 1.0), (1 << 21, 64, 1.0), (1 << 22, 32, 1.0), (1 << 20, 128, 3.0), (1 << 20, 128, 0.1)]:
             x = torch.randn(rows, K, device=dev) * scale
             g = torch.randn(rows, K, device=dev)
             out = ops.sparsemax_fwd(x)
