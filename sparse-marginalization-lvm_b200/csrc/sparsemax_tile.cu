@@ -523,10 +523,12 @@ int sparsemax_fwd_tile_launch(const float* x, float* p, int32_t* supp, int32_t* 
     }
     switch (cols) {
         case 32: return launch_tile<32, 2, 8>(x, p, supp, nnz, ent, amax, rows, st);
-        case 64: return launch_tile<64, 2, 8>(x, p, supp, nnz, ent, amax, rows, st);
+        case 64:
+            if (variant == 1) return launch_tile<64, 1, 12>(x, p, supp, nnz, ent, amax, rows, st);
+            return launch_tile<64, 2, 8>(x, p, supp, nnz, ent, amax, rows, st);
         case 128:
-            if (variant == 1) return launch_tile<128, 1, 10>(x, p, supp, nnz, ent, amax, rows, st);
-            return launch_tile<128, 2, 6>(x, p, supp, nnz, ent, amax, rows, st);
+            if (variant == 1) return launch_tile<128, 2, 6>(x, p, supp, nnz, ent, amax, rows, st);
+            return launch_tile<128, 1, 10>(x, p, supp, nnz, ent, amax, rows, st);
         case 256:
             if (variant == 1) return launch_tile<256, 1, 6>(x, p, supp, nnz, ent, amax, rows, st);
             return launch_tile<256, 2, 3>(x, p, supp, nnz, ent, amax, rows, st);
