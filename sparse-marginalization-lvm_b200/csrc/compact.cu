@@ -11,6 +11,9 @@
 //   fill    G-lane group per row, ballot + popc ranks, coalesced ragged stores
 //
 // Algorithmic bytes per row: 4K (read P) + 4 + 8 (count, offset) + 12 s_b.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace smlvm {
@@ -241,6 +244,23 @@ static int launch_compact(const float* p, const int64_t* offsets, int32_t* count
     return SMLVM_OK;
 }
 
+// compact_tile.cu
+bool compact_tile_supported(int cols);
+int compact_fill_tile_launch(const float* p, const int64_t* offsets, float* vals, int32_t* row_idx,
+                             int32_t* col_idx, int64_t rows, int cols, cudaStream_t st);
+
+// SMLVM_COMPACT=reg|tile overrides the path choice (tests run both).
+static int compact_path_override()
+{
+    static int cached = -1;
+    if (cached < 0) {
+        const char* e = getenv("SMLVM_COMPACT");
+        cached = (e == nullptr) ? 0 : (strcmp(e, "reg") == 0 ? 1 : (strcmp(e, "tile") == 0 ? 2 : 0));
+    }
+    return cached;
+}
+constexpr int64_t kCompactTileMinRows = 4096;
+
 }  // namespace smlvm
 
 using namespace smlvm;
@@ -293,6 +313,10 @@ extern "C" int smlvm_compact_fill(const float* p, const int64_t* offsets, float*
     if (rows < 0 || cols < 1) return SMLVM_ERR_ARG;
     if (rows == 0) return SMLVM_OK;
     if (p == nullptr || offsets == nullptr) return SMLVM_ERR_ARG;
+    const int ovr = compact_path_override();
+    if (compact_tile_supported(cols) && (reinterpret_cast<uintptr_t>(p) & 15u) == 0 && ovr != 1 &&
+        (rows >= kCompactTileMinRows || ovr == 2))
+        return compact_fill_tile_launch(p, offsets, vals, row_idx, col_idx, rows, cols, as_stream(stream));
     return launch_compact<true>(p, offsets, nullptr, vals, row_idx, col_idx, rows, cols,
                                 as_stream(stream));
 }

@@ -1,0 +1,188 @@
+// Support compaction (fill pass), TMA-staged tile kernel for sm_100a (K in {32,64,128,256}).
+//
+// Same output as compact_kernel<FILL> in compact.cu -- (value, row, col) of every p > 0 at
+// offsets[row] + rank, i.e. torch.nonzero(p > 0) order, lvmhelpers/structmarg.py:116-126 --
+// but the group-per-row version is ISSUE-bound (ncu r01: 129 warp instructions per row, 71 %
+// issue utilisation, 52 % of the HBM roofline at 1M x 128): four ballots and their popcounts
+// per 128-bit chunk are paid by every row although only ~3 of 128 entries are non-zero.
+//
+// Here a warp owns a tile of 32 rows (one cp.async.bulk into shared memory, 2-stage mbarrier
+// ring per warp, no CTA-wide synchronisation) and a THREAD owns a row: it scans the row in
+// XOR-swizzled 128-bit chunks (conflict-free across the 32 rows) into a K-bit mask, un-swizzles
+// the mask by a nibble-index butterfly so that set bits are in column order, and emits its
+// entries in a warp-uniform loop.  ~17 warp instructions per row; traffic unchanged (read P
+// once, write 12 B per non-zero).
+#include "common.cuh"
+#include "tile_ptx.cuh"
+
+namespace smlvm {
+
+// bit (4*i + e) of the swizzled mask belongs to column (4*i + e) ^ (lsw << 2): permute the
+// nibbles of the K-bit mask by XOR-ing their index with lsw (one butterfly level per bit).
+template <int MW>
+__device__ __forceinline__ void unswizzle_mask(uint32_t (&m)[MW], uint32_t lsw)
+{
+#pragma unroll
+    for (int w = 0; w < MW; ++w) {
+        uint32_t v = m[w];
+        uint32_t t = ((v & 0xF0F0F0F0u) >> 4) | ((v & 0x0F0F0F0Fu) << 4);
+        v = (lsw & 1u) ? t : v;
+        t = __byte_perm(v, 0, 0x2301);
+        v = (lsw & 2u) ? t : v;
+        t = __byte_perm(v, 0, 0x1032);
+        v = (lsw & 4u) ? t : v;
+        m[w] = v;
+    }
+    if (MW >= 2) {
+#pragma unroll
+        for (int w = 0; w < MW; w += 2) {
+            const uint32_t a = m[w], b = m[w + 1 < MW ? w + 1 : w];
+            const bool sw = (lsw & 8u) != 0;
+            m[w] = sw ? b : a;
+            if (w + 1 < MW) m[w + 1] = sw ? a : b;
+        }
+    }
+    if (MW >= 4) {
+#pragma unroll
+        for (int w = 0; w < MW; ++w) {
+            if ((w & 2) == 0 && w + 2 < MW) {
+                const uint32_t a = m[w], b = m[w + 2];
+                const bool sw = (lsw & 16u) != 0;
+                m[w] = sw ? b : a;
+                m[w + 2] = sw ? a : b;
+            }
+        }
+    }
+}
+
+template <int K, int W>
+__global__ void __launch_bounds__(W * 32, 1)
+compact_fill_tile(const float* __restrict__ p, const int64_t* __restrict__ offsets, float* __restrict__ vals,
+                  int32_t* __restrict__ row_idx, int32_t* __restrict__ col_idx, int64_t rows)
+{
+    constexpr int S = 2;
+    constexpr int NC = K / 4;
+    constexpr int MW = K / 32;
+    constexpr int TILE_F = kTileRows * K;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* tiles = reinterpret_cast<float*>(smem_raw) + (size_t)warp * S * TILE_F;
+    uint64_t* bars_all = reinterpret_cast<uint64_t*>(smem_raw + (size_t)W * S * TILE_F * 4);
+    uint64_t* bars = bars_all + warp * S;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < W * S; ++i) mbar_init(smem_u32(bars_all + i), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int64_t ntiles = (rows + kTileRows - 1) / kTileRows;
+    const int64_t stride = (int64_t)gridDim.x * W;
+    int64_t t = (int64_t)warp * gridDim.x + blockIdx.x;
+    auto issue_load = [&](int stage, int64_t tile) {
+        const int64_t r0 = tile * kTileRows;
+        const uint32_t bytes = (uint32_t)min((int64_t)kTileRows, rows - r0) * K * 4u;
+        const uint32_t bar = smem_u32(bars + stage);
+        mbar_expect_tx(bar, bytes);
+        bulk_load(smem_u32(tiles + stage * TILE_F), p + r0 * K, bytes, bar);
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+            if (t + s * stride < ntiles) issue_load(s, t + s * stride);
+    }
+
+    const uint32_t lsw = (uint32_t)lane & (uint32_t)((NC - 1) & 31);
+    uint32_t parity = 0;
+    int stage = 0;
+    for (; t < ntiles; t += stride) {
+        const int64_t row0 = t * kTileRows;
+        const int trows = (int)min((int64_t)kTileRows, rows - row0);
+        const bool live = lane < trows;
+        const int64_t row = row0 + lane;
+        int64_t out = live ? __ldg(offsets + row) : 0;  // in flight while the tile lands
+
+        mbar_wait(smem_u32(bars + stage), (parity >> stage) & 1u);
+        parity ^= 1u << stage;
+        const uint32_t rowa = smem_u32(tiles + stage * TILE_F + (live ? lane : 0) * K);
+        const uint32_t swz = rowa ^ (lsw << 4);
+
+        uint32_t mask[MW];
+#pragma unroll
+        for (int w = 0; w < MW; ++w) mask[w] = 0u;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            const float4 q = lds128(swz ^ (i << 4));
+            const float xq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (xq[e] > 0.f) mask[(4 * i + e) >> 5] |= 1u << ((4 * i + e) & 31);
+        }
+        unswizzle_mask<MW>(mask, lsw);
+
+        // entries in column order; warp-uniform trip counts (word by word)
+#pragma unroll
+        for (int w = 0; w < MW; ++w) {
+            uint32_t mw = live ? mask[w] : 0u;
+            const int steps = __reduce_max_sync(kFull, __popc(mw));
+            for (int jj = 0; jj < steps; ++jj) {
+                if (mw) {
+                    const int col = w * 32 + __ffs(mw) - 1;
+                    mw &= mw - 1;
+                    if (vals != nullptr) vals[out] = lds32(rowa + (col << 2));
+                    if (row_idx != nullptr) row_idx[out] = (int32_t)row;
+                    if (col_idx != nullptr) col_idx[out] = col;
+                    ++out;
+                }
+            }
+        }
+
+        // this stage is free again: every lane is done reading it
+        __syncwarp();
+        if (lane == 0 && t + S * stride < ntiles) issue_load(stage, t + S * stride);
+        stage ^= 1;
+    }
+}
+
+template <int K, int W>
+static int launch_compact_tile(const float* p, const int64_t* offsets, float* vals, int32_t* row_idx,
+                               int32_t* col_idx, int64_t rows, cudaStream_t st)
+{
+    auto kern = compact_fill_tile<K, W>;
+    const size_t smem = (size_t)W * 2 * kTileRows * K * 4 + (size_t)W * 2 * 8;
+    static bool configured_dev[64] = {false};
+    static int ctas_per_sm = 1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bool& configured = configured_dev[dev & 63];
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, W * 32, smem) != cudaSuccess ||
+            ctas_per_sm < 1)
+            ctas_per_sm = 1;
+        configured = true;
+    }
+    const int64_t ntiles = (rows + kTileRows - 1) / kTileRows;
+    const int64_t need = (ntiles + W - 1) / W;
+    const int64_t cap = (int64_t)device_sm_count() * ctas_per_sm;
+    const int grid = (int)(need < cap ? need : cap);
+    kern<<<grid, W * 32, smem, st>>>(p, offsets, vals, row_idx, col_idx, rows);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SMLVM_OK : (int)e;
+}
+
+bool compact_tile_supported(int cols) { return cols == 32 || cols == 64 || cols == 128 || cols == 256; }
+
+int compact_fill_tile_launch(const float* p, const int64_t* offsets, float* vals, int32_t* row_idx,
+                             int32_t* col_idx, int64_t rows, int cols, cudaStream_t st)
+{
+    switch (cols) {
+        case 32: return launch_compact_tile<32, 8>(p, offsets, vals, row_idx, col_idx, rows, st);
+        case 64: return launch_compact_tile<64, 8>(p, offsets, vals, row_idx, col_idx, rows, st);
+        case 128: return launch_compact_tile<128, 7>(p, offsets, vals, row_idx, col_idx, rows, st);
+        case 256: return launch_compact_tile<256, 3>(p, offsets, vals, row_idx, col_idx, rows, st);
+        default: return SMLVM_ERR_UNSUPPORTED;
+    }
+}
+
+}  // namespace smlvm

@@ -26,6 +26,28 @@ def test_compaction_matches_nonzero(rows, K):
     assert torch.equal(ops.compact_count(P).long(), cnt)
 
 
+@pytest.mark.parametrize("rows,K", [(4096, 32), (4100, 64), (4096 + 31, 128), (9000, 128), (4097, 256)])
+@pytest.mark.parametrize("density", [0.0, 0.03, 0.3, 1.0])
+def test_compaction_tile_kernel(rows, K, density):
+    """rows >= 4096, K in {32..256}: the TMA-staged tile kernel (compact_tile.cu), arbitrary
+    non-negative matrices including empty and fully dense rows and a partial last tile."""
+    from lvmhelpers import ops
+    g = torch.Generator().manual_seed(rows + K)
+    P = torch.rand(rows, K, generator=g)
+    P = torch.where(torch.rand(rows, K, generator=g) < density, P, torch.zeros(()))
+    P[3] = 0.0
+    P[4] = 1.0 / K
+    P[rows - 1, K - 1] = 0.5
+    P[rows - 1, 0] = -1.0     # negative entries are not part of the support
+    P = P.cuda()
+    comp = ops.compact(P)
+    ref = torch.nonzero(P > 0)
+    assert comp["total"] == ref.shape[0]
+    assert torch.equal(comp["rows"].long(), ref[:, 0])
+    assert torch.equal(comp["cols"].long(), ref[:, 1])
+    assert torch.equal(comp["vals"], P[P > 0])
+
+
 def test_compaction_edge_cases():
     from lvmhelpers import ops
     # empty rows, full rows, negative and zero entries
