@@ -36,6 +36,7 @@ struct SolverSmem {
     double* son;    // [n]      oracle input, "on" half
     double* soff;   // [n]      oracle input, "off" half
     double* red;    // [40]     reduction scratch
+    double* terms;  // [(cap+1)(cap+2)/2] Schur-complement terms in libad3's summation order
     int* perm;      // [cap]    solver order -> slot
     int* freestk;   // [cap]    free slots (stack)
     uint32_t* bits; // [cap*W]  by slot
@@ -47,7 +48,7 @@ struct SolverSmem {
 __host__ __device__ inline size_t solver_smem_bytes(int n)
 {
     const int cap = n + 1, LD = (n + 2) | 1, W = (n + 31) / 32;
-    size_t dbl = (size_t)LD * LD + 3 * cap + 2 * LD + 4 * n + 40;
+    size_t dbl = (size_t)LD * LD + 3 * cap + 2 * LD + 4 * n + 40 + (size_t)(cap + 1) * (cap + 2) / 2;
     size_t b = dbl * sizeof(double);
     b += (size_t)(2 * cap + 8) * sizeof(int);
     b += (size_t)(cap * W + W) * sizeof(uint32_t);
@@ -71,6 +72,7 @@ __device__ inline SolverSmem carve(unsigned char* raw, int n)
     s.son = d; d += n;
     s.soff = d; d += n;
     s.red = d; d += 40;
+    s.terms = d; d += (size_t)(cap + 1) * (cap + 2) / 2;
     int* ip = reinterpret_cast<int*>(d);
     s.perm = ip; ip += cap;
     s.freestk = ip; ip += cap;
@@ -201,53 +203,57 @@ __device__ __forceinline__ double factor_map(const SolverSmem& sm, int n, int bu
 // below are chains: warp 0 forms 32 terms at a time in parallel and folds them in sequence.
 
 // score of the vertex in sm.ynew under (eta, 0[, t]): bernoulli.h:38-54 / sequence.h:154-179.
-// Call with all lanes of warp 0; returns the score on every lane.
+// ONE thread, sequential fp64 adds in bit order (adding 0.0 for a clear bit is exact).
 template <int KIND>
-__device__ double evaluate_chain(const SolverSmem& sm, int n)
+__device__ double evaluate_serial(const SolverSmem& sm, int n)
 {
-    const int lane = threadIdx.x & 31;
     double acc = 0.0;
-    for (int i0 = 0; i0 < n; i0 += 32) {
-        const int i = i0 + lane;
-        double node = 0.0, edge = 0.0;
-        if (i < n && ((sm.ynew[i >> 5] >> (i & 31)) & 1u)) {
-            node = sm.eta[i];
-            if (KIND == SMLVM_FACTOR_SEQUENCE_BINARY && i > 0 &&
-                ((sm.ynew[(i - 1) >> 5] >> ((i - 1) & 31)) & 1u))
-                edge = sm.t[i - 1];
-        }
-        const int valid = min(32, n - i0);
-        for (int c = 0; c < valid; ++c) {
-            acc = __dadd_rn(acc, __shfl_sync(kFull, node, c));
-            if (KIND == SMLVM_FACTOR_SEQUENCE_BINARY) acc = __dadd_rn(acc, __shfl_sync(kFull, edge, c));
+    uint32_t prev = 0u;
+    for (int i = 0; i < n; ++i) {
+        const uint32_t bit = (sm.ynew[i >> 5] >> (i & 31)) & 1u;
+        acc = __dadd_rn(acc, bit ? sm.eta[i] : 0.0);
+        if (KIND == SMLVM_FACTOR_SEQUENCE_BINARY) {
+            acc = __dadd_rn(acc, (bit & prev) ? sm.t[i - 1] : 0.0);
+            prev = bit;
         }
     }
     return acc;
 }
 
 // Schur complement s = r0 - sum_{i<=j} c_ij r_i r_j inv_ij in libad3's order (rows in solver
-// order, c_ii = 1, c_ij = 2).  Call with all lanes of warp 0.
-__device__ double schur_chain(const SolverSmem& sm, int m, int LD, double r0)
+// order, c_ii = 1, c_ij = 2; libad3 skips r_i == 0 / r_j == 0, whose terms are exact zeros).
+// Two steps: every thread of the CTA forms terms into sm.terms (row-major upper triangle), then
+// ONE thread folds them in sequence -- the fold is a pure DSUB dependency chain fed by
+// independent 64-bit shared loads (ncu r01: the shuffle-fed version cost ~45 cycles per term and
+// kept the other 7 warps at the barrier 60 % of the time).
+__device__ __forceinline__ void schur_terms_fill(const SolverSmem& sm, int m, int LD)
 {
-    const int lane = threadIdx.x & 31;
-    double s = r0;
-    for (int a = 0; a <= m; ++a) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int a = warp; a <= m; a += nw) {
         const int ip = (a == 0) ? 0 : sm.perm[a - 1] + 1;
         const double ri = sm.r[ip];
-        if (ri == 0.0) continue;
-        for (int b0 = a; b0 <= m; b0 += 32) {
-            const int b = b0 + lane;
-            double term = 0.0;
-            if (b <= m) {
-                const int jp = (b == 0) ? 0 : sm.perm[b - 1] + 1;
-                const double v = sm.inv[ip * LD + jp];
-                term = (b == a) ? __dmul_rn(__dmul_rn(ri, ri), v)
-                                : __dmul_rn(__dmul_rn(__dmul_rn(2.0, ri), sm.r[jp]), v);
-            }
-            const int valid = min(32, m + 1 - b0);
-            for (int c = 0; c < valid; ++c) s = __dsub_rn(s, __shfl_sync(kFull, term, c));
+        double* out = sm.terms + (a * (m + 1) - (a * (a - 1)) / 2) - a;  // + b
+        for (int b = a + lane; b <= m; b += 32) {
+            const int jp = (b == 0) ? 0 : sm.perm[b - 1] + 1;
+            const double v = sm.inv[ip * LD + jp];
+            out[b] = (b == a) ? __dmul_rn(__dmul_rn(ri, ri), v)
+                              : __dmul_rn(__dmul_rn(__dmul_rn(2.0, ri), sm.r[jp]), v);
         }
     }
+}
+__device__ __forceinline__ double schur_fold(const SolverSmem& sm, int m, double r0)
+{
+    const int total = ((m + 1) * (m + 2)) / 2;
+    double s = r0;
+    int e = 0;
+    for (; e + 8 <= total; e += 8) {
+        double t[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t[q] = sm.terms[e + q];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s = __dsub_rn(s, t[q]);
+    }
+    for (; e < total; ++e) s = __dsub_rn(s, sm.terms[e]);
     return s;
 }
 
@@ -296,7 +302,7 @@ __global__ void sparsemap_fwd_kernel(const float* __restrict__ x, const float* _
         __syncthreads();
         {
             double sc0 = 0.0;
-            if (tid < 32) sc0 = evaluate_chain<KIND>(sm, n);
+            if (tid == 0) sc0 = evaluate_serial<KIND>(sm, n);
             if (tid == 0) {
                 sm.perm[0] = 0;
                 sm.score[0] = sc0;
@@ -460,13 +466,13 @@ __global__ void sparsemap_fwd_kernel(const float* __restrict__ x, const float* _
                     sm.r[s + 1] = (double)common_values(sm.bits + s * W, sm.ynew, W, n);
                 }
                 __syncthreads();
-                // warp 0: the two order-sensitive chains; meanwhile the other warps (reverse
-                // thread mapping) form d_j = sum_i inv[i][j] r_i, i in solver order
-                if (tid < 32) {
-                    const double sv = schur_chain(sm, m, LD, (double)n);
-                    const double scn = evaluate_chain<KIND>(sm, n);
-                    if (tid == 0) { sm.red[36] = sv; sm.red[35] = scn; }
-                }
+                // the two order-sensitive sums: terms formed by the whole CTA, folded by thread 0
+                // (Schur complement) and thread 32 (score of the new vertex); meanwhile the other
+                // threads (reverse mapping) form d_j = sum_i inv[i][j] r_i, i in solver order
+                schur_terms_fill(sm, m, LD);
+                __syncthreads();
+                if (tid == 0) sm.red[36] = schur_fold(sm, m, (double)n);
+                if (tid == 32 % T) sm.red[35] = evaluate_serial<KIND>(sm, n);
                 for (int a = T - 1 - tid; a <= m; a += T) {
                     const int jp = (a == 0) ? 0 : sm.perm[a - 1] + 1;
                     double acc = __dmul_rn(sm.inv[jp], sm.r[0]);
