@@ -19,6 +19,7 @@
 // (ballot for Bernoulli, rank-select for the budget, 2-state Viterbi for the sequence).
 // No FMA contraction in the inverse updates: the pivoting sequence is sensitive to last bits.
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -401,10 +402,10 @@ __global__ void sparsemap_fwd_kernel(const float* __restrict__ x, const float* _
                     for (int i = tid; i < hw; i += T)
                         sm.d[i] = (i == rem) ? 0.0 : __dmul_rn(-sval, sm.inv[rem * LD + i]);
                     __syncthreads();
-                    for (int e = tid; e < hw * hw; e += T) {
-                        const int i = e / hw, j = e - i * hw;
-                        const double upd = __dmul_rn(__dmul_rn(invs, sm.d[i]), sm.d[j]);
-                        sm.inv[i * LD + j] = __dsub_rn(sm.inv[i * LD + j], upd);
+                    for (int i = tid >> 5; i < hw; i += T >> 5) {
+                        const double di = __dmul_rn(invs, sm.d[i]);
+                        for (int j = tid & 31; j < hw; j += 32)
+                            sm.inv[i * LD + j] = __dsub_rn(sm.inv[i * LD + j], __dmul_rn(di, sm.d[j]));
                     }
                     __syncthreads();
                     // clear the freed row/column, drop it from the order, recycle the slot
@@ -451,8 +452,8 @@ __global__ void sparsemap_fwd_kernel(const float* __restrict__ x, const float* _
                     for (int q = 0; q < W; ++q) eq = eq && (ya[q] == sm.ynew[q]);
                     same |= eq ? 1 : 0;
                 }
-                same = block_sum_int(same, sm.red);
-                if (same > 0) {
+                same = __syncthreads_or(same);
+                if (same) {
                     st = SMLVM_SOLVE_REPEATED_CONFIG;
                     ++it;
                     break;
@@ -502,11 +503,12 @@ __global__ void sparsemap_fwd_kernel(const float* __restrict__ x, const float* _
                 if (tid == 0) sm.r[0] = 1.0;
                 for (int a = tid; a < m; a += T) sm.r[sm.perm[a] + 1] = 1.0;
                 __syncthreads();
-                for (int e = tid; e < hw * hw; e += T) {
-                    const int i = e / hw, j = e - i * hw;
-                    if (sm.r[i] != 0.0 && sm.r[j] != 0.0) {
-                        const double upd = __dmul_rn(__dmul_rn(invs, sm.d[i]), sm.d[j]);
-                        sm.inv[i * LD + j] = __dadd_rn(sm.inv[i * LD + j], upd);
+                for (int i = tid >> 5; i < hw; i += T >> 5) {
+                    if (sm.r[i] == 0.0) continue;
+                    const double di = __dmul_rn(invs, sm.d[i]);
+                    for (int j = tid & 31; j < hw; j += 32) {
+                        if (sm.r[j] != 0.0)
+                            sm.inv[i * LD + j] = __dadd_rn(sm.inv[i * LD + j], __dmul_rn(di, sm.d[j]));
                     }
                 }
                 __syncthreads();
@@ -670,7 +672,15 @@ extern "C" int smlvm_sparsemap_fwd(const float* x, const float* t, const double*
     if (x == nullptr || p_pad == nullptr || aset_bits == nullptr || counts == nullptr)
         return SMLVM_ERR_ARG;
     const size_t smem = solver_smem_bytes(n);
-    const int threads = n <= 32 ? 64 : (n <= 64 ? 128 : 256);
+    int threads = n <= 32 ? 64 : (n <= 64 ? 128 : 256);
+    {
+        static int ovr = -1;
+        if (ovr < 0) {
+            const char* e = getenv("SMLVM_SMAP_THREADS");
+            ovr = e ? atoi(e) : 0;
+        }
+        if (ovr >= 32 && ovr <= 1024 && ovr % 32 == 0) threads = ovr;
+    }
     int64_t cap_grid = (int64_t)device_sm_count() * 64;
     const int grid = (int)(rows < cap_grid ? rows : cap_grid);
     cudaStream_t st = as_stream(stream);
