@@ -21,8 +21,11 @@ from ._native import lib, check, ptr
 class SparsemaxMargStep:
     KERNELS = ("sparsemax_fwd", "scan_counts", "compact_fill", "wloss_dense_fwd", "sparsemax_bwd")
 
-    def __init__(self, rows, cols, device, capacity, entropy_coeff=0.0):
+    def __init__(self, rows, cols, device, capacity, entropy_coeff=0.0, global_rows=None):
+        """``global_rows``: batch size B of the 1/B in the loss and entropy terms when this step
+        owns only a shard / micro-batch of the batch (default: ``rows``)."""
         self.rows, self.cols, self.device = rows, cols, device
+        self.global_rows = int(global_rows) if global_rows is not None else rows
         self.capacity = int(capacity)
         self.entropy_coeff = float(entropy_coeff)
         f32, i32, i64 = torch.float32, torch.int32, torch.int64
@@ -34,7 +37,7 @@ class SparsemaxMargStep:
         self.vals, self.ri, self.ci = e(self.capacity), e(self.capacity, dtype=i32), e(self.capacity, dtype=i32)
         self.row_loss, self.total = e(rows), e(())
         self.dx, self.dloss = e(rows, cols), e(rows, cols)
-        self.dent = torch.full((rows,), -self.entropy_coeff / rows, dtype=f32, device=device) \
+        self.dent = torch.full((rows,), -self.entropy_coeff / self.global_rows, dtype=f32, device=device) \
             if self.entropy_coeff != 0.0 else None
         self.scan_ws = torch.zeros(max(lib.smlvm_scan_workspace_bytes(rows), 64), dtype=torch.uint8, device=device)
         self.red_ws = torch.zeros(lib.smlvm_reduce_workspace_bytes(), dtype=torch.uint8, device=device)
@@ -63,10 +66,10 @@ class SparsemaxMargStep:
                                      ptr(self.ci), rows, K, st), "smlvm_compact_fill")
         mark("wloss_dense_fwd")
         check(lib.smlvm_wloss_dense_fwd(ptr(self.p), ptr(losses), ptr(self.row_loss), ptr(self.total),
-                                        1.0 / rows, rows, K, ptr(self.red_ws), self.red_ws.numel(), st),
+                                        1.0 / self.global_rows, rows, K, ptr(self.red_ws), self.red_ws.numel(), st),
               "smlvm_wloss_dense_fwd")
         mark("sparsemax_bwd")
-        check(lib.smlvm_sparsemax_bwd(ptr(self.p), ptr(self.supp), None, ptr(losses), None, 1.0 / rows,
+        check(lib.smlvm_sparsemax_bwd(ptr(self.p), ptr(self.supp), None, ptr(losses), None, 1.0 / self.global_rows,
                                       ptr(self.dent), ptr(self.dx), ptr(self.dloss), rows, K, st),
               "smlvm_sparsemax_bwd")
         mark(None)
@@ -82,3 +85,69 @@ class SparsemaxMargStep:
             "wloss_dense_fwd": r * (8 * K + 4),                 # P, L in, row loss out
             "sparsemax_bwd": r * (8 * K + 4 + 8 * K) + (4 * r if self.dent is not None else 0),
         }
+
+
+class HostPipelinedMargStep:
+    """The same step for batches that live in (pinned) HOST memory: scores and losses come over
+    PCIe, the gradient and the loss go back.  The batch is cut into ``chunks`` micro-batches
+    (each a shard with loss scale 1/B_global, exactly like the multi-GPU sharding) that flow
+    through three streams -- H2D copy, the five kernels, D2H copy -- over ``nbuf`` rotating
+    device buffer sets, so that the uploads (2 x rows x K x 4 B), the kernels and the downloads
+    (rows x K x 4 B) overlap; PCIe is full duplex, the step time tends to the upload time alone.
+
+    ``run(x_host, l_host, dx_host)`` returns the loss as a 0-d pinned host tensor valid after
+    the CURRENT stream has been synchronised (the call itself does not block).
+    """
+
+    def __init__(self, rows, cols, device, capacity_per_row, entropy_coeff=0.0, chunks=8, nbuf=3):
+        assert rows % chunks == 0, "rows must divide into equal micro-batches"
+        self.rows, self.cols, self.device = rows, cols, device
+        self.chunks, self.nbuf = chunks, min(nbuf, chunks)
+        self.crow = rows // chunks
+        cap = int(capacity_per_row * self.crow) + 1024
+        self.steps = [SparsemaxMargStep(self.crow, cols, device, cap, entropy_coeff, global_rows=rows)
+                      for _ in range(self.nbuf)]
+        self.xd = [torch.empty(self.crow, cols, device=device) for _ in range(self.nbuf)]
+        self.ld = [torch.empty(self.crow, cols, device=device) for _ in range(self.nbuf)]
+        self.s_h2d, self.s_cmp, self.s_d2h = (torch.cuda.Stream(device) for _ in range(3))
+        self.tot_host = torch.zeros(chunks).pin_memory()
+        self.loss_host = torch.zeros(()).pin_memory()
+        self.ev_free = [None] * self.nbuf   # D2H of the chunk that last used buffer b
+        self.h2d_bytes = 2 * rows * cols * 4
+        self.d2h_bytes = rows * cols * 4 + 4 * chunks
+
+    def run(self, x_host, l_host, dx_host):
+        cur = torch.cuda.current_stream(self.device)
+        start = torch.cuda.Event()
+        start.record(cur)
+        for s in (self.s_h2d, self.s_cmp, self.s_d2h):
+            s.wait_event(start)
+        last = None
+        for c in range(self.chunks):
+            b = c % self.nbuf
+            lo, hi = c * self.crow, (c + 1) * self.crow
+            with torch.cuda.stream(self.s_h2d):
+                if self.ev_free[b] is not None:
+                    self.s_h2d.wait_event(self.ev_free[b])
+                self.xd[b].copy_(x_host[lo:hi], non_blocking=True)
+                self.ld[b].copy_(l_host[lo:hi], non_blocking=True)
+                up = torch.cuda.Event()
+                up.record(self.s_h2d)
+            with torch.cuda.stream(self.s_cmp):
+                self.s_cmp.wait_event(up)
+                self.steps[b].run(self.xd[b], self.ld[b])
+                done = torch.cuda.Event()
+                done.record(self.s_cmp)
+            with torch.cuda.stream(self.s_d2h):
+                self.s_d2h.wait_event(done)
+                dx_host[lo:hi].copy_(self.steps[b].dx, non_blocking=True)
+                self.tot_host[c:c + 1].copy_(self.steps[b].total.reshape(1), non_blocking=True)
+                last = torch.cuda.Event()
+                last.record(self.s_d2h)
+                self.ev_free[b] = last
+        cur.wait_event(last)
+        return self.tot_host
+
+    def loss(self):
+        """Sum of the per-micro-batch partial losses (host side; call after synchronising)."""
+        return float(self.tot_host.sum())

@@ -1,0 +1,56 @@
+"""GPU: the pre-allocated pipelines of lvmhelpers.hotpath (what bench.py times) against the
+oracle and against each other (resident step vs host-pipelined micro-batches)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(rows, K, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(rows, K, generator=g), torch.rand(rows, K, generator=g) * 3
+
+
+@pytest.mark.parametrize("rows,K", [(64, 10), (4096, 128), (8192, 256)])
+def test_resident_step_matches_oracle(oracle, rows, K):
+    from lvmhelpers.hotpath import SparsemaxMargStep
+    x, L = _inputs(rows, K, 5)
+    xd, Ld = x.cuda(), L.cuda()
+    nnz = SparsemaxMargStep.size_capacity(xd)
+    step = SparsemaxMargStep(rows, K, xd.device, nnz + 16, entropy_coeff=0.5)
+    total = step.run(xd, Ld)
+    torch.cuda.synchronize()
+    xr = x.clone().requires_grad_(True)
+    Lr = L.clone().requires_grad_(True)
+    P = oracle.sparsemax(xr)
+    obj = (P * Lr).sum(-1).mean() - 0.5 * oracle.entropy(P).mean()
+    obj.backward()
+    assert torch.equal(step.p.cpu(), P.detach())
+    assert abs(total.item() - (P * L).sum(-1).mean().item()) <= 1e-5
+    nz = torch.nonzero(P.detach() > 0)
+    n = nz.shape[0]
+    assert int(step.offsets[-1]) == n
+    assert torch.equal(step.ri[:n].cpu().long(), nz[:, 0]) and torch.equal(step.ci[:n].cpu().long(), nz[:, 1])
+    assert (step.dx.cpu() - xr.grad).abs().max().item() <= 1e-6 * max(1.0, xr.grad.abs().max().item()) * 4
+    assert (step.dloss.cpu() - Lr.grad).abs().max().item() <= 1e-7
+
+
+@pytest.mark.parametrize("chunks", [1, 4, 8])
+def test_host_pipelined_step_equals_resident(chunks):
+    from lvmhelpers.hotpath import SparsemaxMargStep, HostPipelinedMargStep
+    rows, K = 8192 * 4, 128
+    x, L = _inputs(rows, K, 9)
+    xp, Lp = x.pin_memory(), L.pin_memory()
+    dev = torch.device("cuda", 0)
+    xd, Ld = xp.to(dev), Lp.to(dev)
+    nnz = SparsemaxMargStep.size_capacity(xd)
+    step = SparsemaxMargStep(rows, K, dev, nnz + 16, entropy_coeff=1.0)
+    total = step.run(xd, Ld)
+    pipe = HostPipelinedMargStep(rows, K, dev, capacity_per_row=nnz / rows * 1.2 + 1, entropy_coeff=1.0,
+                                 chunks=chunks)
+    dx_host = torch.empty(rows, K).pin_memory()
+    for _ in range(3):   # buffer rotation across calls
+        pipe.run(xp, Lp, dx_host)
+    torch.cuda.synchronize()
+    assert torch.equal(dx_host, step.dx.cpu())
+    assert abs(pipe.loss() - total.item()) <= 1e-5
