@@ -1,0 +1,199 @@
+// k-best bit-vectors, thread-per-row kernel for sm_100a (k <= 16, n <= 128).
+//
+// Same results as topk_bits_kernel in topk_bits.cu (bit-exact with
+// lvmhelpers/binary_topk.h:57-129: list seeded by x0 >= 0 (:110), fp32 scores accumulated in
+// bit order (:27-29), "bit on" taken only if STRICTLY greater (:72), truncation to k after
+// every bit) but organised for instruction count: the group-per-row kernel spends ~3200 warp
+// instructions per row on merge-path binary searches and configuration shuffles and reaches 8 %
+// of the HBM roofline.  Here a THREAD owns a row and runs the reference's own two-pointer list
+// merge; the control flow (list length, loop bounds) is data-independent, so the 32 rows of a
+// warp run in lockstep without divergence, and the lists live in shared memory as
+// [slot][lane] so that every access is conflict-free whatever slot a lane points at.
+//
+//   shared memory per warp: 32 bits x 32 rows of scores transposed as xs[32][33] (coalesced
+//   global reads, conflict-free column reads; restaged every 32 bits), two score lists
+//   S[2][k][32] and two configuration lists C[2][k][32] of W-word vectors (ping-pong; one
+//   64/128-bit access moves a configuration, the new bit is OR-ed in with one LOP3 per word).
+//   The fp32 {0,1} output (4*k*n B/row, the API's format) and the packed bits are written by the
+//   whole warp, one row at a time, fully coalesced.
+#include "common.cuh"
+
+namespace smlvm {
+
+// a configuration = W 32-bit words moved as ONE shared-memory access ([slot][lane] of Cfg<W>)
+template <int W> struct Cfg;
+template <> struct Cfg<1> { uint32_t w[1]; };
+template <> struct __align__(8) Cfg<2> { uint32_t w[2]; };
+template <> struct __align__(16) Cfg<4> { uint32_t w[4]; };
+
+template <int W>
+__global__ void __launch_bounds__(512)
+topk_tile_kernel(const float* __restrict__ x, float* __restrict__ configs, uint32_t* __restrict__ bits,
+                 float* __restrict__ dp_scores, int64_t rows, int n, int k)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int words_n = (n + 31) >> 5;
+    const size_t per_warp = ((size_t)2 * k * W * 32 + 32 * 33 + 2 * k * 32) * 4;
+    Cfg<W>* C = reinterpret_cast<Cfg<W>*>(smem_raw + warp * per_warp);        // [2][k][32]
+    float* xs = reinterpret_cast<float*>(C + 2 * k * 32);                     // [32][33]: 32 bits x 32 rows
+    float* S = xs + 32 * 33;                                                  // [2][k][32]
+
+    const int64_t ntiles = (rows + 31) / 32;
+    for (int64_t t = (int64_t)blockIdx.x * nwarps + warp; t < ntiles; t += (int64_t)gridDim.x * nwarps) {
+        const int64_t row0 = t * 32;
+        const int trows = (int)min((int64_t)32, rows - row0);
+        int cur = 0, len = 2;
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            // ---- stage bits i0..i0+31 of the 32 score rows, transposed (coalesced reads, 8 rows of
+            //      loads in flight per lane before the first dependent store) ---------------------
+            __syncwarp();
+            {
+                const int c = i0 + lane;
+                for (int r0 = 0; r0 < 32; r0 += 8) {
+                    float tmp[8];
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) {
+                        const int r = r0 + rr;
+                        tmp[rr] = (r < trows && c < n) ? __ldcs(x + (row0 + r) * n + c) : 0.f;
+                    }
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) xs[lane * 33 + r0 + rr] = tmp[rr];
+                }
+            }
+            __syncwarp();
+            int ib = 0;
+            if (i0 == 0) {
+                // list = [(x0,{0}), (0,{})] ordered by x0 >= 0        (binary_topk.h:104-116)
+                const float x0 = xs[lane];
+                const bool on_first = x0 >= 0.f;
+                S[0 * 32 + lane] = on_first ? x0 : 0.f;
+                S[1 * 32 + lane] = on_first ? 0.f : x0;
+                Cfg<W> c0, c1;
+#pragma unroll
+                for (int q = 0; q < W; ++q) { c0.w[q] = 0u; c1.w[q] = 0u; }
+                c0.w[0] = on_first ? 1u : 0u;
+                c1.w[0] = on_first ? 0u : 1u;
+                C[0 * 32 + lane] = c0;
+                C[1 * 32 + lane] = c1;
+                ib = 1;
+            }
+            const int iend = min(32, n - i0);
+            for (; ib < iend; ++ib) {
+                const int i = i0 + ib;
+                const float v = xs[ib * 33 + lane];
+                const int outlen = min(k, 2 * len);
+                Cfg<W> bitv;  // the bit of this step as a configuration
+#pragma unroll
+                for (int q = 0; q < W; ++q) bitv.w[q] = (q == (i >> 5)) ? (1u << (i & 31)) : 0u;
+                const float* Sc = S + (cur * k) * 32 + lane;
+                float* Sn = S + ((cur ^ 1) * k) * 32 + lane;
+                const Cfg<W>* Cc = C + (cur * k) * 32 + lane;
+                Cfg<W>* Cn = C + ((cur ^ 1) * k) * 32 + lane;
+                // two-pointer merge of A (bit off) and A + v (bit on): merge_branch, binary_topk.h:57-98
+                int a = 0, b = 0;
+                float sa = Sc[0], sb = __fadd_rn(Sc[0], v);
+                for (int r = 0; r < outlen; ++r) {
+                    const bool takeB = (b < len) && (a >= len || sb > sa);
+                    const int src = takeB ? b : a;
+                    const uint32_t mB = takeB ? 0xffffffffu : 0u;
+                    Sn[r * 32] = takeB ? sb : sa;
+                    Cfg<W> cw = Cc[src * 32];
+#pragma unroll
+                    for (int q = 0; q < W; ++q) cw.w[q] |= bitv.w[q] & mB;
+                    Cn[r * 32] = cw;
+                    // advance the list that was consumed and fetch its next head
+                    const int nxt = src + 1;
+                    const float head = Sc[min(nxt, len - 1) * 32];
+                    if (takeB) { b = nxt; sb = __fadd_rn(head, v); } else { a = nxt; sa = head; }
+                }
+                cur ^= 1;
+                len = outlen;
+            }
+        }
+        __syncwarp();
+
+        // ---- outputs, one row at a time by the whole warp (coalesced) ------------------------
+        const float* Sf = S + (cur * k) * 32;
+        const uint32_t* Cf = reinterpret_cast<const uint32_t*>(C + (cur * k) * 32);  // word q of slot j, row r: [(j*32 + r)*W + q]
+        if (dp_scores != nullptr) {
+            for (int idx = lane; idx < trows * k; idx += 32) {
+                const int r = idx / k, j = idx - r * k;
+                dp_scores[row0 * k + idx] = Sf[j * 32 + r];
+            }
+        }
+        if (bits != nullptr) {
+            const int per_row = k * words_n;
+            for (int idx = lane; idx < trows * per_row; idx += 32) {
+                const int r = idx / per_row, rem = idx - r * per_row;
+                const int j = rem / words_n, q = rem - j * words_n;
+                bits[row0 * per_row + idx] = Cf[(j * 32 + r) * W + q];
+            }
+        }
+        if (configs != nullptr) {
+            const int per_row = k * n;
+            if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(configs) & 15u) == 0) {
+                for (int r = 0; r < trows; ++r) {
+                    float* out = configs + (row0 + r) * per_row;
+                    // flat float4 index over [k][n] with (j, c) carried incrementally: all 32
+                    // lanes store whatever n is
+                    int j = 0, c = lane * 4;
+                    while (c >= n) { c -= n; ++j; }
+                    for (int e = lane * 4; e < per_row; e += 128) {
+                        const uint32_t nib = Cf[(j * 32 + r) * W + (c >> 5)] >> (c & 31);
+                        stg_stream4(out + e, make_float4((float)(nib & 1u), (float)((nib >> 1) & 1u),
+                                                         (float)((nib >> 2) & 1u), (float)((nib >> 3) & 1u)));
+                        c += 128;
+                        while (c >= n) { c -= n; ++j; }
+                    }
+                }
+            } else {
+                for (int r = 0; r < trows; ++r) {
+                    float* out = configs + (row0 + r) * per_row;
+                    for (int j = 0; j < k; ++j)
+                        for (int c = lane; c < n; c += 32)
+                            stg_stream(out + j * n + c, (float)((Cf[(j * 32 + r) * W + (c >> 5)] >> (c & 31)) & 1u));
+                }
+            }
+        }
+    }
+}
+
+bool topk_tile_supported(int n, int k) { return k <= 16 && n <= 128; }
+
+int topk_tile_launch(const float* x, float* configs, uint32_t* bits, float* dp_scores, int64_t rows, int n,
+                     int k, cudaStream_t st)
+{
+    const int words_n = (n + 31) >> 5;
+    const int W = words_n <= 1 ? 1 : (words_n <= 2 ? 2 : 4);
+    const size_t per_warp = ((size_t)2 * k * W * 32 + 32 * 33 + 2 * k * 32) * 4;
+    int warps = (int)((200 * 1024) / per_warp);
+    warps = warps > 16 ? 16 : (warps < 1 ? 1 : warps);
+    const int64_t ntiles = (rows + 31) / 32;
+    if (ntiles < (int64_t)warps * device_sm_count()) {  // small batches: spread the tiles over the SMs
+        const int w2 = (int)((ntiles + device_sm_count() - 1) / device_sm_count());
+        warps = w2 < 1 ? 1 : (w2 < warps ? w2 : warps);
+    }
+    const size_t smem = per_warp * warps;
+    const int64_t need = (ntiles + warps - 1) / warps;
+    const int64_t cap = (int64_t)device_sm_count();
+    const int grid = (int)(need < cap ? need : cap);
+#define SMLVM_TOPK_TILE_CASE(WW)                                                                          \
+    case WW: {                                                                                            \
+        cudaError_t e = cudaFuncSetAttribute(topk_tile_kernel<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             200 * 1024);                                                 \
+        if (e != cudaSuccess) return (int)e;                                                              \
+        topk_tile_kernel<WW><<<grid, warps * 32, smem, st>>>(x, configs, bits, dp_scores, rows, n, k);    \
+        break;                                                                                            \
+    }
+    switch (W) {
+        SMLVM_TOPK_TILE_CASE(1)
+        SMLVM_TOPK_TILE_CASE(2)
+        SMLVM_TOPK_TILE_CASE(4)
+    }
+#undef SMLVM_TOPK_TILE_CASE
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SMLVM_OK : (int)e;
+}
+
+}  // namespace smlvm

@@ -26,6 +26,28 @@ def test_topk_matches_oracle(oracle, rows, n, k):
         assert np.array_equal(cfg.cpu().numpy(), oracle.topk(s, k, which="ref_topk"))
 
 
+@pytest.mark.parametrize("rows,n,k", [(16384 + 5, 128, 10), (20000, 32, 10), (16400, 100, 16), (16390, 7, 5),
+                                      (16384, 1, 2), (16384, 64, 2), (16384, 33, 16)])
+def test_topk_tile_kernel(oracle, rows, n, k):
+    """rows >= 16384, k <= 16, n <= 128: the thread-per-row kernel (topk_tile.cu), with ties
+    (quantised rows), a partial last tile and all three word widths."""
+    from lvmhelpers import ops
+    rng = np.random.default_rng(n * 31 + k)
+    s = rng.standard_normal((rows, n)).astype(np.float32)
+    s[::7] = np.round(s[::7] * 2) / 2
+    s[5] = 0.0
+    ref, ref_sc = oracle.topk(s, k, return_scores=True)
+    cfg, bits, sc = ops.topk_bits(torch.from_numpy(s).cuda(), k, want_scores=True)
+    assert np.array_equal(cfg.cpu().numpy(), ref)
+    assert np.array_equal(sc.cpu().numpy(), ref_sc)
+    b = bits.cpu().numpy().astype(np.uint32)
+    idx = np.arange(n)
+    assert np.array_equal(((b[:, :, idx // 32] >> (idx % 32)) & 1).astype(np.float32), ref)
+    # bits-only / configs-only calls give the same answers
+    _, bits2, _ = ops.topk_bits(torch.from_numpy(s).cuda(), k, want_configs=False)
+    assert torch.equal(bits2, bits)
+
+
 def test_topk_ties_and_zeros(oracle):
     """Quantised scores: many exact ties and exact zeros exercise the strict-> rule."""
     from lvmhelpers import ops

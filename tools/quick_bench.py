@@ -33,7 +33,7 @@ def timeit(fn, warm=3, reps=10):
 def main():
     res = {}
     dev = "cuda"
-    which = sys.argv[1:] or ["sparsemax", "compact", "wloss", "topk", "smap"]
+    which = sys.argv[1:] or ["sparsemax", "compact", "wloss", "topk", "smap", "ragged"]
     if "sparsemax" in which:
         for rows, K, scale in [(1 << 20, 128, 1.0), (1 << 20, 128, 0.3), (1 << 19, 256, 0.1), (1 << 22, 10, 1.0),
                                (1 << 16, 1024, 1.0), (1 << 21, 64, 1.0), (1 << 22, 32, 1.0), (1 << 20, 128, 3.0), (1 << 20, 128, 0.1)]:
@@ -90,6 +90,49 @@ def main():
                 mean_iters=float(st["iters"].float().mean()), max_iters=int(st["iters"].max()),
                 status_hist=torch.bincount(st["status"], minlength=4).tolist())
             print(list(res.items())[-1], flush=True)
+    if "ragged" in which:
+        # ragged weighted loss / entropy, bits re-scoring, solver expansion + backward
+        N = 1 << 24
+        pr = torch.rand(N, device=dev) + 1e-3
+        lo = torch.rand(N, device=dev)
+        g1 = torch.ones((), device=dev)
+        ms = timeit(lambda: ops.wloss_ragged_fwd(pr, lo, scale=1.0, want_total=True, want_entropy=True))
+        res["wloss_ragged_fwd_%d" % N] = dict(ms=ms, gbs=N * 8 / ms / 1e6, frac=N * 8 / ms / 1e6 / PEAK)
+        print(list(res.items())[-1], flush=True)
+        dp, dl = torch.empty_like(pr), torch.empty_like(lo)
+        from lvmhelpers._native import lib, ptr, stream
+        ms = timeit(lambda: lib.smlvm_wloss_ragged_bwd(ptr(pr), ptr(lo), ptr(g1), ptr(g1), 1.0, ptr(dp), ptr(dl), N,
+                                                       stream()))
+        res["wloss_ragged_bwd_%d" % N] = dict(ms=ms, gbs=N * 16 / ms / 1e6, frac=N * 16 / ms / 1e6 / PEAK)
+        print(list(res.items())[-1], flush=True)
+        rows, n, k = 1 << 20, 128, 10
+        x = torch.randn(rows, n, device=dev)
+        _, bits, _ = ops.topk_bits(x, k, want_configs=False)
+        ms = timeit(lambda: ops.bits_score(x, bits))
+        byt = rows * (4 * n + k * 4 * (n // 32) + 4 * k)
+        res["bits_score_fwd_%dx%d_k%d" % (rows, n, k)] = dict(ms=ms, gbs=byt / ms / 1e6, frac=byt / ms / 1e6 / PEAK)
+        print(list(res.items())[-1], flush=True)
+        ds = torch.randn(rows, k, device=dev)
+        dxo = torch.empty(rows, n, device=dev)
+        ms = timeit(lambda: lib.smlvm_bits_score_bwd(ptr(bits), ptr(ds), ptr(dxo), rows, n, k, stream()))
+        res["bits_score_bwd_%dx%d_k%d" % (rows, n, k)] = dict(ms=ms, gbs=byt / ms / 1e6, frac=byt / ms / 1e6 / PEAK)
+        print(list(res.items())[-1], flush=True)
+        rows, n = 1 << 14, 128
+        xs = torch.randn(rows, n, device=dev)
+        st = ops.sparsemap_solve(xs, 0, max_iter=300)
+        off = ops.scan_counts(st["kept"])
+        tot = int(off[-1])
+        ms = timeit(lambda: ops.sparsemap_expand(st, True, off, tot))
+        byt = tot * (4 * n + 8) + rows * (n + 1) * (4 + 4 * (n // 32))
+        res["smap_expand_%dx%d" % (rows, n)] = dict(ms=ms, items=tot, gbs=byt / ms / 1e6, frac=byt / ms / 1e6 / PEAK)
+        print(list(res.items())[-1], flush=True)
+        dpp = torch.randn(tot, device=dev)
+        ms = timeit(lambda: ops.sparsemap_bwd(st, dpp, off, True))
+        mA = st["counts"].double()
+        byt = float((mA * mA * 8).sum()) + tot * 4 + rows * n * 4
+        res["smap_bwd_%dx%d" % (rows, n)] = dict(ms=ms, gbs=byt / ms / 1e6, frac=byt / ms / 1e6 / PEAK,
+                                                 note="bytes = S (fp64 |A|^2) + dp + dx")
+        print(list(res.items())[-1], flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", "quick_bench.json"), "w"), indent=1)
 
