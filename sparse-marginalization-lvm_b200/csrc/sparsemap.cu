@@ -46,10 +46,12 @@ struct SolverSmem {
     int* misc;      // [8]
 };
 
-__host__ __device__ inline size_t solver_smem_bytes(int n)
+// `cap` = largest active set this launch can hold (a capacity tier, <= n + 1)
+__host__ __device__ inline size_t solver_smem_bytes(int n, int cap)
 {
-    const int cap = n + 1, LD = (n + 2) | 1, W = (n + 31) / 32;
-    size_t dbl = (size_t)LD * LD + 3 * cap + 2 * LD + 4 * n + 40 + (size_t)(cap + 1) * (cap + 2) / 2;
+    const int LD = (cap + 1) | 1, W = (n + 31) / 32;
+    const int LV = LD > n ? LD : n;  // d doubles as the budget oracle's gain vector [n]
+    size_t dbl = (size_t)LD * LD + 3 * cap + 2 * LV + 4 * n + 40 + (size_t)(cap + 1) * (cap + 2) / 2;
     size_t b = dbl * sizeof(double);
     b += (size_t)(2 * cap + 8) * sizeof(int);
     b += (size_t)(cap * W + W) * sizeof(uint32_t);
@@ -57,17 +59,18 @@ __host__ __device__ inline size_t solver_smem_bytes(int n)
     return (b + 15) & ~(size_t)15;
 }
 
-__device__ inline SolverSmem carve(unsigned char* raw, int n)
+__device__ inline SolverSmem carve(unsigned char* raw, int n, int cap)
 {
-    const int cap = n + 1, LD = (n + 2) | 1, W = (n + 31) / 32;
+    const int LD = (cap + 1) | 1, W = (n + 31) / 32;
     SolverSmem s;
     double* d = reinterpret_cast<double*>(raw);
     s.inv = d; d += (size_t)LD * LD;
     s.score = d; d += cap;
     s.p = d; d += cap;
     s.z = d; d += cap;
-    s.d = d; d += LD;
-    s.r = d; d += LD;
+    const int LV = LD > n ? LD : n;
+    s.d = d; d += LV;
+    s.r = d; d += LV;
     s.eta = d; d += n;
     s.t = d; d += n;
     s.son = d; d += n;
@@ -268,18 +271,22 @@ __device__ __forceinline__ int common_values(const uint32_t* a, const uint32_t* 
 template <int KIND>
 __global__ void sparsemap_fwd_kernel(const float* __restrict__ x, const float* __restrict__ t,
                                      const double* __restrict__ init_scores, int budget,
-                                     int max_iter, int64_t rows, int n, float* __restrict__ p_pad,
+                                     int max_iter, int64_t rows, int n, int cap, int first_tier,
+                                     int last_tier, float* __restrict__ p_pad,
                                      uint32_t* __restrict__ aset_bits, int32_t* __restrict__ counts,
                                      int32_t* __restrict__ kept, int32_t* __restrict__ iters,
                                      int32_t* __restrict__ status, double* __restrict__ S_pad)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int cap = n + 1, LD = (n + 2) | 1, W = (n + 31) / 32;  // odd LD: row-wise reads spread over banks
-    const SolverSmem sm = carve(smem_raw, n);
+    const int cap_out = n + 1;                    // layout of the padded outputs (ABI)
+    const int LD = (cap + 1) | 1, W = (n + 31) / 32;  // odd LD: row-wise reads spread over banks
+    const SolverSmem sm = carve(smem_raw, n, cap);
     const int tid = threadIdx.x, T = blockDim.x;
 
     for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
         __syncthreads();
+        // later capacity tiers only re-solve the samples an earlier tier could not hold
+        if (!first_tier && counts[row] != -1) continue;
         // ---- load the sample -----------------------------------------------------------
         for (int i = tid; i < n; i += T) {
             sm.eta[i] = (double)x[row * n + i];
@@ -491,6 +498,11 @@ __global__ void sparsemap_fwd_kernel(const float* __restrict__ x, const float* _
                     ++it;
                     break;
                 }
+                if (m == cap) {  // the active set outgrows this tier
+                    st = last_tier ? SMLVM_SOLVE_SINGULAR : -1;
+                    ++it;
+                    break;
+                }
                 const double invs = __ddiv_rn(1.0, sval);
                 const int snew = sm.freestk[nfree - 1];
                 const int pn = snew + 1;
@@ -539,21 +551,25 @@ __global__ void sparsemap_fwd_kernel(const float* __restrict__ x, const float* _
 
         // ---- outputs (solver order) -----------------------------------------------------
         __syncthreads();
+        if (st == -1) {  // hand the sample to the next capacity tier
+            if (tid == 0) counts[row] = -1;
+            continue;
+        }
         int kp = 0;
-        for (int a = tid; a < cap; a += T) {
+        for (int a = tid; a < cap_out; a += T) {
             float pf = 0.f;
             if (a < m) {
                 pf = (float)sm.p[sm.perm[a]];
                 kp += pf > 0.f ? 1 : 0;
             }
-            p_pad[row * cap + a] = pf;
+            p_pad[row * cap_out + a] = pf;
         }
-        for (int e = tid; e < cap * W; e += T) {
+        for (int e = tid; e < cap_out * W; e += T) {
             const int a = e / W, q = e - a * W;
-            aset_bits[(row * cap + a) * W + q] = (a < m) ? sm.bits[sm.perm[a] * W + q] : 0u;
+            aset_bits[(row * cap_out + a) * W + q] = (a < m) ? sm.bits[sm.perm[a] * W + q] : 0u;
         }
         if (S_pad != nullptr) {
-            double* S = S_pad + row * (int64_t)cap * cap;
+            double* S = S_pad + row * (int64_t)cap_out * cap_out;
             for (int e = tid; e < m * m; e += T) {
                 const int a = e / m, c = e - a * m;
                 S[e] = sm.inv[(sm.perm[a] + 1) * LD + sm.perm[c] + 1];
@@ -671,7 +687,6 @@ extern "C" int smlvm_sparsemap_fwd(const float* x, const float* t, const double*
     if (rows == 0) return SMLVM_OK;
     if (x == nullptr || p_pad == nullptr || aset_bits == nullptr || counts == nullptr)
         return SMLVM_ERR_ARG;
-    const size_t smem = solver_smem_bytes(n);
     int threads = n <= 32 ? 64 : (n <= 64 ? 128 : 256);
     {
         static int ovr = -1;
@@ -681,18 +696,47 @@ extern "C" int smlvm_sparsemap_fwd(const float* x, const float* t, const double*
         }
         if (ovr >= 32 && ovr <= 1024 && ovr % 32 == 0) threads = ovr;
     }
-    int64_t cap_grid = (int64_t)device_sm_count() * 64;
+    // Capacity tiers.  The (|A|+1)^2 fp64 inverse dominates shared memory: sized for the worst case
+    // |A| = n + 1 it allows ONE sample per SM at n = 128, although typical active sets hold 40-60
+    // vertices.  Samples are first solved with a small capacity (4 then 2 CTAs per SM); a sample
+    // whose active set outgrows its tier is flagged (counts = -1) and re-solved from scratch by the
+    // next tier.  Same stream, no host synchronisation; an empty tier costs one trivial launch.
+    int tiers[3];
+    int ntier = 0;
+    {
+        static int single = -1;
+        if (single < 0) {
+            const char* e = getenv("SMLVM_SMAP_SINGLE_TIER");
+            single = (e && atoi(e)) ? 1 : 0;
+        }
+        if (!single && n + 1 > 64) tiers[ntier++] = 64;
+        if (!single && n + 1 > 88) tiers[ntier++] = 88;
+        tiers[ntier++] = n + 1;
+    }
+    // one CTA per sample: the hardware scheduler evens out the data-dependent solve lengths
+    // (measured best against persistent grids of 16/64/256 CTAs per SM at n = 32 and n = 128)
+    int64_t cap_grid = 0x7fffffff;
+    {
+        static int gf = -1;
+        if (gf < 0) {
+            const char* e = getenv("SMLVM_SMAP_GRID_FACTOR");
+            gf = e ? atoi(e) : 0;
+        }
+        if (gf > 0) cap_grid = (int64_t)device_sm_count() * gf;
+    }
     const int grid = (int)(rows < cap_grid ? rows : cap_grid);
     cudaStream_t st = as_stream(stream);
 #define SMLVM_SMAP_LAUNCH(K)                                                                       \
     do {                                                                                           \
         cudaError_t e =                                                                            \
             cudaFuncSetAttribute(sparsemap_fwd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                 (int)smem);                                                       \
+                                 (int)solver_smem_bytes(n, n + 1));                                \
         if (e != cudaSuccess) return (int)e;                                                       \
-        sparsemap_fwd_kernel<K><<<grid, threads, smem, st>>>(x, t, init_scores, budget, max_iter,  \
-                                                             rows, n, p_pad, aset_bits, counts,    \
-                                                             kept, iters, status, S_pad);          \
+        for (int ti = 0; ti < ntier; ++ti) {                                                       \
+            sparsemap_fwd_kernel<K><<<grid, threads, solver_smem_bytes(n, tiers[ti]), st>>>(       \
+                x, t, init_scores, budget, max_iter, rows, n, tiers[ti], ti == 0, ti == ntier - 1, \
+                p_pad, aset_bits, counts, kept, iters, status, S_pad);                             \
+        }                                                                                          \
     } while (0)
     if (kind == SMLVM_FACTOR_BERNOULLI) SMLVM_SMAP_LAUNCH(SMLVM_FACTOR_BERNOULLI);
     else if (kind == SMLVM_FACTOR_BUDGET) SMLVM_SMAP_LAUNCH(SMLVM_FACTOR_BUDGET);
