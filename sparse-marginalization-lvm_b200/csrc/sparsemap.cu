@@ -37,7 +37,7 @@ struct SolverSmem {
     double* son;    // [n]      oracle input, "on" half
     double* soff;   // [n]      oracle input, "off" half
     double* red;    // [40]     reduction scratch
-    double* terms;  // [(cap+1)(cap+2)/2] Schur-complement terms in libad3's summation order
+    double* terms;  // [terms_chunk(cap)] Schur-complement terms in libad3's summation order
     int* perm;      // [cap]    solver order -> slot
     int* freestk;   // [cap]    free slots (stack)
     uint32_t* bits; // [cap*W]  by slot
@@ -46,12 +46,21 @@ struct SolverSmem {
     int* misc;      // [8]
 };
 
+// The Schur terms of one insertion ((|A|+1)(|A|+2)/2 of them) are produced and folded in rounds
+// of whole matrix rows through a buffer of this many doubles (one round up to |A| = 46).
+constexpr int kTermsChunk = 1152;
+__host__ __device__ inline int terms_chunk(int cap)
+{
+    const int full = (cap + 1) * (cap + 2) / 2;
+    return full < kTermsChunk ? full : kTermsChunk;
+}
+
 // `cap` = largest active set this launch can hold (a capacity tier, <= n + 1)
 __host__ __device__ inline size_t solver_smem_bytes(int n, int cap)
 {
     const int LD = (cap + 1) | 1, W = (n + 31) / 32;
     const int LV = LD > n ? LD : n;  // d doubles as the budget oracle's gain vector [n]
-    size_t dbl = (size_t)LD * LD + 3 * cap + 2 * LV + 4 * n + 40 + (size_t)(cap + 1) * (cap + 2) / 2;
+    size_t dbl = (size_t)LD * LD + 3 * cap + 2 * LV + 4 * n + 40 + (size_t)terms_chunk(cap);
     size_t b = dbl * sizeof(double);
     b += (size_t)(2 * cap + 8) * sizeof(int);
     b += (size_t)(cap * W + W) * sizeof(uint32_t);
@@ -76,7 +85,7 @@ __device__ inline SolverSmem carve(unsigned char* raw, int n, int cap)
     s.son = d; d += n;
     s.soff = d; d += n;
     s.red = d; d += 40;
-    s.terms = d; d += (size_t)(cap + 1) * (cap + 2) / 2;
+    s.terms = d; d += terms_chunk(cap);
     int* ip = reinterpret_cast<int*>(d);
     s.perm = ip; ip += cap;
     s.freestk = ip; ip += cap;
@@ -230,13 +239,16 @@ __device__ double evaluate_serial(const SolverSmem& sm, int n)
 // ONE thread folds them in sequence -- the fold is a pure DSUB dependency chain fed by
 // independent 64-bit shared loads (ncu r01: the shuffle-fed version cost ~45 cycles per term and
 // kept the other 7 warps at the barrier 60 % of the time).
-__device__ __forceinline__ void schur_terms_fill(const SolverSmem& sm, int m, int LD)
+// rows [a0, a1) of the upper triangle -> sm.terms (row-major, packed)
+__device__ __forceinline__ void schur_terms_fill(const SolverSmem& sm, int m, int LD, int a0, int a1)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int a = warp; a <= m; a += nw) {
+    for (int a = a0 + warp; a < a1; a += nw) {
         const int ip = (a == 0) ? 0 : sm.perm[a - 1] + 1;
         const double ri = sm.r[ip];
-        double* out = sm.terms + (a * (m + 1) - (a * (a - 1)) / 2) - a;  // + b
+        // rows a0..a-1 hold (m+1-a0) + ... + (m+2-a) terms
+        const int off = (a - a0) * (m + 1) - ((a - a0) * (a0 + a - 1)) / 2;
+        double* out = sm.terms + off - a;  // + b
         for (int b = a + lane; b <= m; b += 32) {
             const int jp = (b == 0) ? 0 : sm.perm[b - 1] + 1;
             const double v = sm.inv[ip * LD + jp];
@@ -245,10 +257,8 @@ __device__ __forceinline__ void schur_terms_fill(const SolverSmem& sm, int m, in
         }
     }
 }
-__device__ __forceinline__ double schur_fold(const SolverSmem& sm, int m, double r0)
+__device__ __forceinline__ double schur_fold(const SolverSmem& sm, int total, double s)
 {
-    const int total = ((m + 1) * (m + 2)) / 2;
-    double s = r0;
     int e = 0;
     for (; e + 8 <= total; e += 8) {
         double t[8];
@@ -259,6 +269,17 @@ __device__ __forceinline__ double schur_fold(const SolverSmem& sm, int m, double
     }
     for (; e < total; ++e) s = __dsub_rn(s, sm.terms[e]);
     return s;
+}
+// rows [a0, a1) that fit one round of the terms buffer (at least one row: a row has <= cap+1 terms)
+__device__ __forceinline__ int schur_round_end(int m, int a0, int chunk, int& count)
+{
+    int a1 = a0, c = 0;
+    while (a1 <= m && c + (m + 1 - a1) <= chunk) {
+        c += m + 1 - a1;
+        ++a1;
+    }
+    count = c;
+    return a1;
 }
 
 __device__ __forceinline__ int common_values(const uint32_t* a, const uint32_t* b, int W, int n)
@@ -477,9 +498,13 @@ __global__ void sparsemap_fwd_kernel(const float* __restrict__ x, const float* _
                 // the two order-sensitive sums: terms formed by the whole CTA, folded by thread 0
                 // (Schur complement) and thread 32 (score of the new vertex); meanwhile the other
                 // threads (reverse mapping) form d_j = sum_i inv[i][j] r_i, i in solver order
-                schur_terms_fill(sm, m, LD);
+                const int chunk = terms_chunk(cap);
+                int cnt0 = 0;
+                int a_next = schur_round_end(m, 0, chunk, cnt0);
+                schur_terms_fill(sm, m, LD, 0, a_next);
                 __syncthreads();
-                if (tid == 0) sm.red[36] = schur_fold(sm, m, (double)n);
+                double sfold = (double)n;
+                if (tid == 0) sfold = schur_fold(sm, cnt0, sfold);
                 if (tid == 32 % T) sm.red[35] = evaluate_serial<KIND>(sm, n);
                 for (int a = T - 1 - tid; a <= m; a += T) {
                     const int jp = (a == 0) ? 0 : sm.perm[a - 1] + 1;
@@ -491,6 +516,16 @@ __global__ void sparsemap_fwd_kernel(const float* __restrict__ x, const float* _
                     }
                     sm.d[jp] = acc;
                 }
+                while (a_next <= m) {  // further rounds (|A| > 46): refill, fold on
+                    __syncthreads();
+                    int cnt = 0;
+                    const int a_beg = a_next;
+                    a_next = schur_round_end(m, a_beg, chunk, cnt);
+                    schur_terms_fill(sm, m, LD, a_beg, a_next);
+                    __syncthreads();
+                    if (tid == 0) sfold = schur_fold(sm, cnt, sfold);
+                }
+                if (tid == 0) sm.red[36] = sfold;
                 __syncthreads();
                 const double sval = sm.red[36];
                 if (sval > -1e-9 && sval < 1e-9) {
@@ -698,7 +733,8 @@ extern "C" int smlvm_sparsemap_fwd(const float* x, const float* t, const double*
     }
     // Capacity tiers.  The (|A|+1)^2 fp64 inverse dominates shared memory: sized for the worst case
     // |A| = n + 1 it allows ONE sample per SM at n = 128, although typical active sets hold 40-60
-    // vertices.  Samples are first solved with a small capacity (4 then 2 CTAs per SM); a sample
+    // vertices.  Samples are first solved with the capacities that let 4, then 2, CTAs share an SM
+    // (70 and 97 vertices at n = 128); a sample
     // whose active set outgrows its tier is flagged (counts = -1) and re-solved from scratch by the
     // next tier.  Same stream, no host synchronisation; an empty tier costs one trivial launch.
     int tiers[3];
@@ -709,8 +745,18 @@ extern "C" int smlvm_sparsemap_fwd(const float* x, const float* t, const double*
             const char* e = getenv("SMLVM_SMAP_SINGLE_TIER");
             single = (e && atoi(e)) ? 1 : 0;
         }
-        if (!single && n + 1 > 64) tiers[ntier++] = 64;
-        if (!single && n + 1 > 88) tiers[ntier++] = 88;
+        // largest capacity that still lets `ctas` CTAs share the 227 KB (+1 KB reserved each) of an SM
+        auto cap_for = [&](int ctas) {
+            const size_t budget_b = (size_t)(227 * 1024) / ctas - 1024;
+            int c = n + 1;
+            while (c > 8 && solver_smem_bytes(n, c) > budget_b) --c;
+            return c;
+        };
+        if (!single) {
+            const int c4 = cap_for(4), c2 = cap_for(2);
+            if (c4 < n + 1 && 5 * c4 >= 2 * n) tiers[ntier++] = c4;          // useful only if >= 0.4 n
+            if (c2 < n + 1 && (ntier == 0 || c2 > tiers[ntier - 1])) tiers[ntier++] = c2;
+        }
         tiers[ntier++] = n + 1;
     }
     // one CTA per sample: the hardware scheduler evens out the data-dependent solve lengths
