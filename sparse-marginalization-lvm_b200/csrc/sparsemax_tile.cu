@@ -235,29 +235,32 @@ sparsemax_fwd_tile(const float* __restrict__ x, float* __restrict__ p, int32_t* 
         const uint32_t lsw = (uint32_t)lane & (uint32_t)((NC - 1) & 31);
         const uint32_t swz = rowa ^ (lsw << 4);
 
-        // ---- pass A: 8 class maxima -> row max and a first lower bound on tau ----------------
-        // For ANY subset T of the row, tau >= (sum_T X' - 1) / |T|  (Michelot).  The maxima of 8
-        // disjoint classes (float4 component x chunk parity) are 8 distinct entries; the best
-        // prefix of their sorted order gives the starting bound (>= -1, the bound of {max}).
-        float cm[8];
+        // ---- pass A: class maxima -> row max and a first lower bound on tau -------------------
+        // For ANY subset T of the row, tau >= (sum_T X' - 1) / |T|  (Michelot).  The maxima of
+        // NCLS disjoint classes (float4 component x chunk index mod NCLS/4) are NCLS distinct
+        // entries; the best prefix of their sorted order gives the starting bound (>= -1, the
+        // bound of {max}).  16 classes keep rows with supports of 20-30 entries (K = 256 at the
+        // signal-game score scale) under the 32-candidate list without a tightening pass.
+        constexpr int NCLS = (NC >= 16) ? 16 : 8;
+        float cm[NCLS];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) cm[j] = -CUDART_INF_F;
+        for (int j = 0; j < NCLS; ++j) cm[j] = -CUDART_INF_F;
 #pragma unroll
         for (int i = 0; i < NC; ++i) {
             const float4 q = lds128(swz ^ (i << 4));
-            const int o = (i & 1) * 4;
+            const int o = (i & (NCLS / 4 - 1)) * 4;
             cm[o + 0] = fmaxf(cm[o + 0], q.x);
             cm[o + 1] = fmaxf(cm[o + 1], q.y);
             cm[o + 2] = fmaxf(cm[o + 2], q.z);
             cm[o + 3] = fmaxf(cm[o + 3], q.w);
         }
-        sort_desc_regs<8>(cm);
+        sort_desc_regs<NCLS>(cm);
         const float m = cm[0];
         float thr = -1.0f;
         {
             float run = 0.f;
 #pragma unroll
-            for (int j = 2; j <= 8; ++j) {
+            for (int j = 2; j <= NCLS; ++j) {
                 run += __fsub_rn(cm[j - 1], m);
                 thr = fmaxf(thr, (run - 1.f) * (1.f / (float)j));
             }

@@ -104,17 +104,51 @@ class Marginalizer(torch.nn.Module):
     """
 
     def __init__(self, encoder, decoder, loss_fun,
-                 encoder_entropy_coeff=0.0, decoder_entropy_coeff=0.0):
+                 encoder_entropy_coeff=0.0, decoder_entropy_coeff=0.0, compact_support=False):
+        """``compact_support`` (extension, default off = the reference's loop): run the decoder
+        ONCE on the compacted (sample, latent) pairs of the support instead of once per active
+        latent value on the full batch.  Same loss and gradients for a
+        decoder that treats rows independently; a decoder that draws random numbers consumes them
+        in a different order (experiments/semi_supervised-vae/archs.py:185-187)."""
         super().__init__()
         self.encoder = encoder
         self.decoder = decoder
         self.loss = loss_fun
         self.encoder_entropy_coeff = encoder_entropy_coeff
         self.decoder_entropy_coeff = decoder_entropy_coeff
+        self.compact_support = compact_support
+
+    def _forward_compact(self, encoder_input, decoder_input, labels, discrete_latent_z, encoder_probs,
+                         encoder_entropy, side):
+        """decoder calls proportional to the support: one ragged batch of N = sum_b |supp(b)| rows."""
+        batch_size = encoder_probs.shape[0]
+        comp = ops.compact(encoder_probs.detach(), side["nnz"])
+        rows, cols = comp["rows"].long(), comp["cols"].long()
+        take = lambda t: t.index_select(0, rows) if torch.is_tensor(t) else t
+        decoder_output = self.decoder(cols, take(decoder_input))
+        loss_components, logs = self.loss(take(encoder_input), take(discrete_latent_z), take(decoder_input),
+                                          decoder_output, take(labels))
+        # differentiable values of the support entries: gather from P (autograd scatters back)
+        p_vals = encoder_probs.reshape(-1).index_select(0, rows * encoder_probs.shape[-1] + cols)
+        loss_mean = ops.ragged_loss(p_vals, loss_components, 1.0 / batch_size)
+        for k, v in logs.items():
+            if hasattr(v, 'mean'):
+                # sum_z mean_b p[b,z] v[b,z]  ==  (p_vals . v) / B
+                logs[k] = (p_vals.detach() * v.detach().reshape(-1).to(p_vals.dtype)).sum() / batch_size
+        full_loss = loss_mean - encoder_entropy.mean() * self.encoder_entropy_coeff
+        logs['loss'] = loss_mean
+        logs['encoder_entropy'] = encoder_entropy.mean()
+        logs['support'] = (encoder_probs != 0).sum(-1).to(torch.float).mean()
+        logs['distr'] = encoder_probs
+        logs['decoder_rows'] = comp["total"]
+        return {'loss': full_loss, 'log': logs}
 
     def forward(self, encoder_input, decoder_input, labels):
         discrete_latent_z, encoder_probs, encoder_entropy = self.encoder(encoder_input)
         batch_size, latent_size = encoder_probs.shape
+        if self.compact_support and getattr(encoder_probs, "_smlvm", None) is not None:
+            return self._forward_compact(encoder_input, decoder_input, labels, discrete_latent_z,
+                                         encoder_probs, encoder_entropy, encoder_probs._smlvm)
 
         # marg.py:87 -- columns whose total mass is exactly zero are skipped
         active = (encoder_probs.detach().sum(0) != 0).tolist()

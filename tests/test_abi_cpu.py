@@ -124,7 +124,10 @@ def test_wrapper_api_surface_matches_reference():
     assert list(inspect.signature(marg.ExplicitWrapper.__init__).parameters) == ["self", "agent", "normalizer"]
     sig = ["self", "encoder", "decoder", "loss_fun", "encoder_entropy_coeff", "decoder_entropy_coeff"]
     for cls in (marg.Marginalizer, structmarg.TopKSparsemaxMarg, structmarg.SparseMAPMarg):
-        assert list(inspect.signature(cls.__init__).parameters) == sig
+        assert list(inspect.signature(cls.__init__).parameters)[:6] == sig
+    # the only extension: an opt-in keyword, default = the reference's behaviour
+    extra = inspect.signature(marg.Marginalizer.__init__).parameters
+    assert list(extra)[6:] == ["compact_support"] and extra["compact_support"].default is False
     p = inspect.signature(structmarg.TopKSparsemaxWrapper.__init__).parameters
     assert list(p) == ["self", "agent", "k"] and p["k"].default == 10
     p = inspect.signature(structmarg.SparseMAPWrapper.__init__).parameters

@@ -181,3 +181,19 @@ def test_sparsemap_marg_vs_reference_wrapper(wrap, name, budget, init):
     lo = res["log"]["loss_output"].cpu().numpy()
     assert np.allclose(lo, wrap[f"{name}_log_loss_output"], rtol=1e-5, atol=1e-5)  # same vertices, same order
     _check(wrap, name, res, {"enc_w": enc.weight, "enc_b": enc.bias, "dec": dec.weight}, rtol=5e-5)
+
+
+def test_marginalizer_compact_support_equals_reference_loop(wrap):
+    """decoder on the compacted (sample, latent) pairs only.  Same loss,
+    logs and gradients as the reference's per-column loop (deterministic decoder), with
+    decoder rows = total support instead of K_active * B."""
+    from lvmhelpers.marg import ExplicitWrapper, Marginalizer
+    from lvmhelpers.utils import DeterministicWrapper
+    x, labels, enc, dec = _cuda_case(1, 10, True)
+    m = Marginalizer(ExplicitWrapper(enc, normalizer="sparsemax"), DeterministicWrapper(CatDecoder(dec)),
+                     loss_fun, encoder_entropy_coeff=0.1, compact_support=True)
+    res = m(x, x, labels)
+    res["loss"].backward()
+    _check(wrap, "marg", res, {"enc_w": enc.weight, "enc_b": enc.bias, "dec": dec.weight})
+    n_support = int((wrap["marg_log_distr"] > 0).sum())
+    assert res["log"]["decoder_rows"] == n_support < 64 * 10
