@@ -1,4 +1,4 @@
-// Batched sparsemax forward, TMA-staged tile kernel for sm_100a (K in {32,64,128,256}).
+// Batched sparsemax forward, TMA-staged tile kernel for sm_100a (K in {32,64,128}).
 //
 // Same semantics as sparsemax.cu (entmax.sparsemax evaluated with torch CPU ops,
 // lvmhelpers/marg.py:51, lvmhelpers/structmarg.py:48) but organised around the observation
@@ -25,7 +25,10 @@
 //     whole warp, which evaluates them with the bitonic-sort path of sparsemax_exact.cuh.
 //
 // Work per row drops from ~430 to ~50 warp instructions; HBM traffic stays at the algorithmic
-// 8K bytes per row.
+// 8K bytes per row.  Measured against the register kernel on 2^27 elements (tools/fwd_sweep.py,
+// scores N(0, s^2)): 2.4x faster at K = 128, s = 1 (support 3.5), 2.1x at s = 0.3 (8.5), 1.4x at
+// s = 0.1 (20), 0.9x at s = 0.03 (49 of 128 in the support).  K = 256 is left to the register
+// kernel: with 32 KB tiles only 3 warp pipelines fit an SM and flat rows run 1.5-2.4x slower.
 #include <math_constants.h>
 #include <stdlib.h>
 
@@ -36,7 +39,7 @@
 namespace smlvm {
 
 constexpr int kCap = 32;        // candidate-list entries per row
-constexpr int kMaxPasses = 24;  // Michelot tightening passes before a row is declared slow
+constexpr int kMaxPasses = 3;   // bound-tightening passes before a row is treated as wide
 
 // Descending bitonic network over a register array (compile-time indices, no divergence).
 template <int N>
@@ -384,8 +387,110 @@ sparsemax_fwd_tile(const float* __restrict__ x, float* __restrict__ p, int32_t* 
             }
         }
 
-        // ---- wide-support rows: the whole warp, one row at a time ---------------------------
-        unsigned sm = __ballot_sync(kFull, slow && live);
+        // ---- wide-support rows (more than kCap entries at the bound), still one thread per row ----
+        // Michelot's iteration to a fixed point over the whole row (no list), the reference's tau
+        // from an fp64 sum over the support, then a check WITH ROUNDING MARGINS that the reference's
+        // sort-based support test yields exactly this support (same margins as the register kernel,
+        // sparsemax.cu): inside needs x' - tau > 1e-6, outside (tau - x') k > 2^-24 (3.06 K + 1).
+        // A row that fails the check (an entry within ~1e-6 of the threshold) goes to the whole-warp
+        // sort below.  ~45 instructions per element instead of a 430-instruction cooperative sort.
+        bool coop = false;
+        if (__any_sync(kFull, slow)) {
+            if (slow) {
+                // whole-row passes: 8 chunks unrolled per step (rolled outer loop keeps the code and
+                // register footprint of this rarely-taken path small), four independent accumulator
+                // chains per pass (one per float4 component) for instruction-level parallelism
+                float tq = thr;
+                int c = 0, c_prev = -1;
+                bool converged = false;
+                for (int iter = 0; iter < 64; ++iter) {
+                    float s4[4] = {0.f, 0.f, 0.f, 0.f};
+                    int c4[4] = {0, 0, 0, 0};
+#pragma unroll 1
+                    for (int i0 = 0; i0 < NC; i0 += 8) {
+#pragma unroll
+                        for (int ii = 0; ii < 8; ++ii) {
+                            const float4 q = lds128(swz ^ ((i0 + ii) << 4));
+                            const float xv[4] = {__fsub_rn(q.x, m), __fsub_rn(q.y, m), __fsub_rn(q.z, m),
+                                                 __fsub_rn(q.w, m)};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (xv[e] > tq) { s4[e] += xv[e]; ++c4[e]; }
+                        }
+                    }
+                    c = (c4[0] + c4[1]) + (c4[2] + c4[3]);
+                    if (c == c_prev) { converged = true; break; }
+                    c_prev = c;
+                    tq = fmaxf(tq, __fdividef((s4[0] + s4[1]) + (s4[2] + s4[3]) - 1.f, (float)max(c, 1)));
+                }
+                const int kk = max(c, 1);
+                double d4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
+                for (int i0 = 0; i0 < NC; i0 += 8) {
+#pragma unroll
+                    for (int ii = 0; ii < 8; ++ii) {
+                        const float4 q = lds128(swz ^ ((i0 + ii) << 4));
+                        const float xv[4] = {__fsub_rn(q.x, m), __fsub_rn(q.y, m), __fsub_rn(q.z, m),
+                                             __fsub_rn(q.w, m)};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (xv[e] > tq) d4[e] += (double)xv[e];
+                    }
+                }
+                const double sd = (d4[0] + d4[1]) + (d4[2] + d4[3]);
+                const float kf = (float)kk;
+                tau = __fdiv_rn(__fsub_rn((float)sd, 1.0f), kf);
+                const float thr_in = tau + 1e-6f;
+                const float thr_out = tau - __fdividef((3.06f * (float)K + 1.f) * 1.2e-7f, kf) - 3e-7f;
+                bool b4[4] = {!converged, false, false, false};
+#pragma unroll 1
+                for (int i0 = 0; i0 < NC; i0 += 8) {
+#pragma unroll
+                    for (int ii = 0; ii < 8; ++ii) {
+                        const float4 q = lds128(swz ^ ((i0 + ii) << 4));
+                        const float xv[4] = {__fsub_rn(q.x, m), __fsub_rn(q.y, m), __fsub_rn(q.z, m),
+                                             __fsub_rn(q.w, m)};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            b4[e] |= (xv[e] > tq) ? !(xv[e] > thr_in) : !(xv[e] < thr_out);
+                    }
+                }
+                if (b4[0] | b4[1] | b4[2] | b4[3]) {
+                    coop = true;
+                } else if (live) {
+                    const float eps = 1.1920928955078125e-07f;
+                    k = kk;
+                    float h4[4] = {0.f, 0.f, 0.f, 0.f};
+                    int n4[4] = {0, 0, 0, 0};
+#pragma unroll 1
+                    for (int i0 = 0; i0 < NC; i0 += 8) {
+#pragma unroll
+                        for (int ii = 0; ii < 8; ++ii) {
+                            const int i = i0 + ii;
+                            const float4 q = lds128(swz ^ (i << 4));
+                            float pe[4] = {__fsub_rn(q.x, m), __fsub_rn(q.y, m), __fsub_rn(q.z, m),
+                                           __fsub_rn(q.w, m)};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                if (pe[e] == 0.f) first = min(first, (int)((uint32_t)(4 * i + e) ^ (lsw << 2)));
+                                pe[e] = fmaxf(__fsub_rn(pe[e], tau), 0.f);
+                                if (pe[e] > 0.f) {
+                                    ++n4[e];
+                                    const float ps = fminf(fmaxf(pe[e], eps), 1.f - eps);
+                                    h4[e] = fmaf(ps, __logf(ps), h4[e]);
+                                }
+                            }
+                            sts128(swz ^ (i << 4), make_float4(pe[0], pe[1], pe[2], pe[3]));
+                        }
+                    }
+                    nz = (n4[0] + n4[1]) + (n4[2] + n4[3]);
+                    h = (h4[0] + h4[1]) + (h4[2] + h4[3]);
+                }
+            }
+        }
+
+        // ---- rows with an entry at the threshold: the whole warp, one row at a time (exact sort) ----
+        unsigned sm = __ballot_sync(kFull, coop && live);
         while (sm) {
             const int r = __ffs(sm) - 1;
             sm &= sm - 1;
@@ -448,7 +553,7 @@ static int launch_tile(const float* x, float* p, int32_t* supp, int32_t* nnz, fl
     return e == cudaSuccess ? SMLVM_OK : (int)e;
 }
 
-bool sparsemax_tile_supported(int cols) { return cols == 32 || cols == 64 || cols == 128 || cols == 256; }
+bool sparsemax_tile_supported(int cols) { return cols == 32 || cols == 64 || cols == 128; }
 
 int sparsemax_fwd_tile_launch(const float* x, float* p, int32_t* supp, int32_t* nnz, float* ent, int64_t* amax,
                               int64_t rows, int cols, cudaStream_t st)
@@ -467,9 +572,6 @@ int sparsemax_fwd_tile_launch(const float* x, float* p, int32_t* supp, int32_t* 
         case 128:
             if (variant == 1) return launch_tile<128, 2, 6>(x, p, supp, nnz, ent, amax, rows, st);
             return launch_tile<128, 1, 10>(x, p, supp, nnz, ent, amax, rows, st);
-        case 256:
-            if (variant == 1) return launch_tile<256, 1, 6>(x, p, supp, nnz, ent, amax, rows, st);
-            return launch_tile<256, 2, 3>(x, p, supp, nnz, ent, amax, rows, st);
         default: return SMLVM_ERR_UNSUPPORTED;
     }
 }
