@@ -75,25 +75,36 @@ scan_counts_kernel(const int32_t* __restrict__ counts, int64_t* __restrict__ off
     }
     long long excl = warp_off + incl - local;
 
-    // publish aggregate, look back for the exclusive prefix of this tile
-    if (tid == 0) {
+    // publish aggregate, look back for the exclusive prefix of this tile: warp 0 inspects 32
+    // predecessor descriptors per step (a single thread walking them one by one made this kernel
+    // a 29 us latency chain at 512 tiles)
+    if (w == 0) {
         long long prefix = 0;
         if (tile == 0) {
-            atomicExch(&desc[0], kFlagInc | (unsigned long long)tile_total);
+            if (lane == 0) atomicExch(&desc[0], kFlagInc | (unsigned long long)tile_total);
         } else {
-            atomicExch(&desc[tile], kFlagAgg | (unsigned long long)tile_total);
-            long long j = (long long)tile - 1;
+            if (lane == 0) atomicExch(&desc[tile], kFlagAgg | (unsigned long long)tile_total);
+            long long top = (long long)tile - 1;
             while (true) {
-                unsigned long long d = atomicAdd(&desc[j], 0ull);
-                unsigned long long f = d & ~kValMask;
-                if (f == 0ull) { __nanosleep(20); continue; }
-                prefix += (long long)(d & kValMask);
-                if (f == kFlagInc) break;
-                --j;
+                const long long idx = top - lane;
+                // before tile 0 there is a virtual inclusive prefix of 0
+                const unsigned long long d = (idx >= 0) ? atomicAdd(&desc[idx], 0ull) : kFlagInc;
+                const unsigned long long fl = d & ~kValMask;
+                const unsigned inc = __ballot_sync(kFull, fl == kFlagInc);
+                const unsigned empty = __ballot_sync(kFull, fl == 0ull);
+                const int first_inc = inc ? (__ffs(inc) - 1) : 32;
+                const unsigned needed = (first_inc >= 31) ? kFull : ((2u << first_inc) - 1u);
+                if (empty & needed) { __nanosleep(20); continue; }  // a needed predecessor is not published yet
+                long long val = (lane <= first_inc) ? (long long)(d & kValMask) : 0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(kFull, val, o);
+                prefix += val;
+                if (first_inc < 32) break;
+                top -= 32;
             }
-            atomicExch(&desc[tile], kFlagInc | (unsigned long long)(prefix + tile_total));
+            if (lane == 0) atomicExch(&desc[tile], kFlagInc | (unsigned long long)(prefix + tile_total));
         }
-        s_prefix = prefix;
+        if (lane == 0) s_prefix = prefix;
     }
     __syncthreads();
     long long run = s_prefix + excl;
