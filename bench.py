@@ -208,12 +208,41 @@ def timed(fn, steps, warmup, world, device):
     return dist_max(e0.elapsed_time(e1), world, device), t_host0, t_host1
 
 
+def small_config_latency(device):
+    """The launch-bound experiment shapes (BASELINE configs 1-2, B = 64): microseconds per step of
+    the categorical pipeline, eager launches vs one CUDA-graph replay."""
+    from lvmhelpers.hotpath import SparsemaxMargStep
+    out = {}
+    for name, K, scale in (("C1_ssvae_64x10", 10, 3.0), ("C2_signal_game_64x256", 256, 0.1)):
+        g = torch.Generator().manual_seed(42)
+        x = (torch.randn(64, K, generator=g) * scale).to(device)
+        L = (torch.rand(64, K, generator=g) * 3).to(device)
+        step = SparsemaxMargStep(64, K, device, 64 * K + 16, entropy_coeff=1.0)
+        graph = step.capture(x, L)
+        res = {}
+        for label, fn in (("eager_us", lambda: step.run(x, L)), ("graph_us", graph.replay)):
+            for _ in range(20):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(200):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            res[label] = e0.elapsed_time(e1) / 200 * 1e3
+        out[name] = res
+    return out
+
+
 def extra_paths(args, world, device, rank):
     """The other named shapes of configs[4]: top-k sparsemax and SparseMAP at width 128 (public
     wrapper API, forward + backward, CUDA events, max over ranks)."""
     from lvmhelpers import ops
     from lvmhelpers.structmarg import TopKSparsemaxWrapper
     out = {}
+    if rank == 0:
+        out["small_configs"] = small_config_latency(device)
     g = torch.Generator().manual_seed(1000 + rank)
 
     rows = args.path_rows_topk

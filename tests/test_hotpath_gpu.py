@@ -54,3 +54,28 @@ def test_host_pipelined_step_equals_resident(chunks):
     torch.cuda.synchronize()
     assert torch.equal(dx_host, step.dx.cpu())
     assert abs(pipe.loss() - total.item()) <= 1e-5
+
+
+@pytest.mark.parametrize("rows,K", [(64, 10), (64, 256), (8192, 128)])
+def test_cuda_graph_replay_equals_eager(rows, K):
+    from lvmhelpers.hotpath import SparsemaxMargStep
+    x, L = _inputs(rows, K, 11)
+    xd, Ld = x.cuda(), L.cuda()
+    nnz = SparsemaxMargStep.size_capacity(xd)
+    step = SparsemaxMargStep(rows, K, xd.device, nnz + 4096, entropy_coeff=1.0)
+    step.run(xd, Ld)
+    torch.cuda.synchronize()
+    ref = (step.dx.clone(), step.dloss.clone(), step.total.clone(), step.ri[:nnz].clone())
+    g = step.capture(xd, Ld)
+    # new data in the SAME buffers, then replay: the graph must recompute from the buffers
+    x2, L2 = _inputs(rows, K, 12)
+    xd.copy_(x2.cuda()); Ld.copy_(L2.cuda())
+    g.replay()
+    torch.cuda.synchronize()
+    assert not torch.equal(step.dx, ref[0])
+    xd.copy_(x.cuda()); Ld.copy_(L.cuda())
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(step.dx, ref[0]) and torch.equal(step.dloss, ref[1])
+    assert torch.equal(step.total, ref[2]) and torch.equal(step.ri[:nnz], ref[3])
