@@ -211,6 +211,15 @@ int smlvm_wloss_ragged_fwd(const float* p, const float* loss, const int64_t* off
 int smlvm_wloss_ragged_bwd(const float* p, const float* loss, const float* g, const float* gent,
                            float scale, float* dp, float* dloss, int64_t n_items, void* stream);
 
+/* Segmented log-sum-exp over a ragged batch: out[r] = log sum_{j in [offsets[r], offsets[r+1])}
+ * exp(sign * v[j] + shift); -inf for an empty segment.
+ * replaces: the per-sample loop `torch.logsumexp(logp_x_given_z[torch.tensor(idxs) == k] + logp_z)`
+ *           of compute_importance_sampling, experiments/bit_vector-vae/train.py:320-330 (an
+ *           O(B * N) host loop), and the masked_scatter + dense logsumexp of :331-345, with
+ *           v = loss_output, sign = -1, shift = logp_z.                                         */
+int smlvm_segment_logsumexp(const float* v, const int64_t* offsets, float sign, float shift,
+                            float* out, int64_t rows, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,6 +8,8 @@
 // Totals are accumulated in fp64 and finished by the last CTA in a fixed order, so the
 // scalar is run-to-run deterministic.  Streaming kernels: 8 B per (p, loss) pair forward,
 // 8 B read + 8 B written backward.
+#include <math_constants.h>
+
 #include "common.cuh"
 
 namespace smlvm {
@@ -164,9 +166,50 @@ static int grid_1d(int64_t work_items, int per_cta)
     return (int)(need < cap ? (need > 0 ? need : 1) : cap);
 }
 
+// out[r] = log sum_{j in segment r} exp(sign * v_j + shift); one 8-lane group per segment
+// (supports are short), max-shifted, -inf for an empty segment.
+__global__ void __launch_bounds__(kThreads)
+segment_logsumexp_kernel(const float* __restrict__ v, const int64_t* __restrict__ offsets, float sign,
+                         float shift, float* __restrict__ out, int64_t rows)
+{
+    constexpr int G = 8;
+    constexpr int RPW = kWarp / G;
+    const int64_t tid = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * kThreads;
+    const int l = threadIdx.x % G;
+    const int g = (threadIdx.x & 31) / G;
+    for (int64_t r0 = (tid / kWarp) * RPW; r0 < rows; r0 += (nthreads / kWarp) * RPW) {
+        const int64_t r = r0 + g;
+        const bool live = r < rows;
+        const int64_t b = live ? __ldg(offsets + r) : 0, e = live ? __ldg(offsets + r + 1) : 0;
+        float mx = -CUDART_INF_F;
+        for (int64_t i = b + l; i < e; i += G) mx = fmaxf(mx, fmaf(sign, __ldg(v + i), shift));
+        mx = group_max<G>(mx);
+        float acc = 0.f;
+        if (mx > -CUDART_INF_F)
+            for (int64_t i = b + l; i < e; i += G) acc += expf(fmaf(sign, __ldg(v + i), shift) - mx);
+        acc = group_sum<G>(acc);
+        if (live && l == 0) out[r] = (mx > -CUDART_INF_F) ? mx + logf(acc) : -CUDART_INF_F;
+    }
+}
+
 }  // namespace smlvm
 
 using namespace smlvm;
+
+extern "C" int smlvm_segment_logsumexp(const float* v, const int64_t* offsets, float sign, float shift,
+                                       float* out, int64_t rows, void* stream)
+{
+    if (rows < 0) return SMLVM_ERR_ARG;
+    if (rows == 0) return SMLVM_OK;
+    if (v == nullptr || offsets == nullptr || out == nullptr) return SMLVM_ERR_ARG;
+    int64_t need = (rows + 31) / 32;
+    int64_t cap = (int64_t)device_sm_count() * 16;
+    segment_logsumexp_kernel<<<(int)(need < cap ? need : cap), kThreads, 0, as_stream(stream)>>>(
+        v, offsets, sign, shift, out, rows);
+    SMLVM_LAUNCH_CHECK();
+    return SMLVM_OK;
+}
 
 extern "C" size_t smlvm_reduce_workspace_bytes(void) { return 64 + 3 * sizeof(double) * kMaxCtas; }
 

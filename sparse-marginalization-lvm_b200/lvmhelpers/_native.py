@@ -47,6 +47,7 @@ _PROTOTYPES = {
     "smlvm_wloss_dense_fwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _f32, _i64, _i32, _vp, _sz, _vp]),
     "smlvm_wloss_ragged_fwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _i64, _vp, _sz, _vp]),
     "smlvm_wloss_ragged_bwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _f32, _vp, _vp, _i64, _vp]),
+    "smlvm_segment_logsumexp": (ctypes.c_int, [_vp, _vp, _f32, _f32, _vp, _i64, _vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)

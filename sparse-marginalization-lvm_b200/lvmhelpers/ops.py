@@ -271,6 +271,19 @@ def ragged_entropy(p, scale):
     return _RaggedEntropy.apply(_f32c(p, "p"), float(scale))
 
 
+def segment_logsumexp(values, offsets, sign=1.0, shift=0.0):
+    """out[r] = logsumexp(sign * values[offsets[r]:offsets[r+1]] + shift)  ([rows] fp32, -inf for an
+    empty segment).  The ragged counterpart of the per-sample loop of ``compute_importance_sampling``
+    (experiments/bit_vector-vae/train.py:320-345): ``segment_logsumexp(loss_output, offsets, -1,
+    logp_z)`` is its ``logp_x_deterministic_term``.  No gradient (evaluation metric)."""
+    values = _f32c(values.detach(), "values")
+    rows = offsets.numel() - 1
+    out = torch.empty(rows, dtype=torch.float32, device=values.device)
+    check(lib.smlvm_segment_logsumexp(ptr(values), ptr(offsets), float(sign), float(shift), ptr(out),
+                                      rows, stream()), "smlvm_segment_logsumexp")
+    return out
+
+
 # --------------------------------------------------------------------------------------
 # (3a) top-k bit-vectors
 # --------------------------------------------------------------------------------------

@@ -104,3 +104,23 @@ def test_ragged_loss_and_entropy_autograd():
     pl = (p * l).double()
     ref_rows = torch.stack([pl[0:10].sum(), pl[10:10].sum(), pl[10:500].sum(), pl[500:].sum()])
     assert torch.allclose(rows.cpu().double(), ref_rows, rtol=1e-5)
+
+
+def test_segment_logsumexp_matches_reference_loop():
+    """compute_importance_sampling's per-sample loop (experiments/bit_vector-vae/train.py:320-330)
+    restated with torch ops vs the segmented kernel; empty segments give -inf."""
+    import math
+    from lvmhelpers import ops
+    g = torch.Generator().manual_seed(3)
+    sizes = torch.randint(0, 40, (500,), generator=g)
+    sizes[7] = 0
+    idxs = torch.repeat_interleave(torch.arange(500), sizes)
+    loss_output = torch.rand(int(sizes.sum()), generator=g) * 500 + 1500
+    logp_z = 32 * math.log(0.5)
+    ref = torch.stack([torch.logsumexp(-loss_output[idxs == k] + logp_z, dim=0) for k in range(500)])
+    offsets = torch.cat([torch.zeros(1, dtype=torch.int64), sizes.cumsum(0)]).cuda()
+    out = ops.segment_logsumexp(loss_output.cuda(), offsets, sign=-1.0, shift=logp_z).cpu()
+    assert torch.isinf(out[7]) and out[7] < 0
+    fin = torch.isfinite(ref)
+    assert torch.equal(fin, torch.isfinite(out))
+    assert (out[fin] - ref[fin]).abs().max().item() <= 1e-3 * 1e-2 + 2e-4 * 1  # |v| ~ 2000: fp32 ulp 1.2e-4
