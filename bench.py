@@ -284,6 +284,11 @@ def extra_paths(args, world, device, rank):
                      "unit": UNIT, "mean_support": n_items / rows,
                      "mean_iterations": float(st["iters"].float().mean()),
                      "status_hist": torch.bincount(st["status"], minlength=4).tolist(),
+                     "max_iterations": int(st["iters"].max()),
+                     "capacity_tiers": [{"capacity": c, "smem_bytes_per_cta": b, "ctas_per_sm": o,
+                                         "samples_final_size_in_tier": int(((st["counts"] <= c) & (st["counts"] > lo)).sum())}
+                                        for (c, b, o), lo in zip(ops.sparsemap_plan(128),
+                                                                 [0] + [t[0] for t in ops.sparsemap_plan(128)][:-1])],
                      "hbm_frac_of_algorithmic_bytes": (fwd_bytes + bwd_bytes) / (ms / 3 * 1e-3) / 1e9
                      / measured_hbm_peak()[0]}
     return out

@@ -19,6 +19,7 @@
 // (ballot for Bernoulli, rank-select for the budget, 2-state Viterbi for the sequence).
 // No FMA contraction in the inverse updates: the pivoting sequence is sensitive to last bits.
 #include <math_constants.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -704,11 +705,58 @@ sparsemap_bwd_kernel(const float* __restrict__ dp, const int64_t* __restrict__ o
     }
 }
 
+// Capacity tiers of the forward solver for n bits (ascending, last = n + 1); returns their number.
+static int plan_tiers(int n, int (&tiers)[3])
+{
+    static int single = -1;
+    static int forced[3] = {0, 0, 0};
+    if (single < 0) {
+        const char* e = getenv("SMLVM_SMAP_SINGLE_TIER");
+        single = (e && atoi(e)) ? 1 : 0;
+        const char* t = getenv("SMLVM_SMAP_TIERS");  // experiments: "56,106"
+        if (t) sscanf(t, "%d,%d", &forced[0], &forced[1]);
+    }
+    // largest capacity that still lets `ctas` CTAs share the 227 KB (+1 KB reserved each) of an SM
+    auto cap_for = [&](int ctas) {
+        const size_t budget_b = (size_t)(227 * 1024) / ctas - 1024;
+        int c = n + 1;
+        while (c > 8 && solver_smem_bytes(n, c) > budget_b) --c;
+        return c;
+    };
+    int ntier = 0;
+    if (!single) {
+        int c4 = cap_for(4), c2 = cap_for(2);
+        if (forced[0] > 0) c4 = forced[0];
+        if (forced[1] > 0) c2 = forced[1];
+        if (c4 < n + 1 && 5 * c4 >= 2 * n) tiers[ntier++] = c4;          // useful only if >= 0.4 n
+        if (c2 < n + 1 && (ntier == 0 || c2 > tiers[ntier - 1])) tiers[ntier++] = c2;
+    }
+    tiers[ntier++] = n + 1;
+    return ntier;
+}
+
 }  // namespace smlvm
 
 using namespace smlvm;
 
 extern "C" int32_t smlvm_sparsemap_capacity(int32_t n) { return n + 1; }
+
+extern "C" int32_t smlvm_sparsemap_plan(int32_t n, int32_t* caps, int32_t* smem_bytes, int32_t* ctas_per_sm)
+{
+    if (n < 1 || n > SMLVM_SPARSEMAP_MAX_BITS) return 0;
+    int tiers[3];
+    const int nt = plan_tiers(n, tiers);
+    for (int i = 0; i < nt; ++i) {
+        const size_t b = solver_smem_bytes(n, tiers[i]);
+        if (caps) caps[i] = tiers[i];
+        if (smem_bytes) smem_bytes[i] = (int32_t)b;
+        if (ctas_per_sm) {
+            int c = (int)((size_t)(227 * 1024) / (b + 1024));
+            ctas_per_sm[i] = c < 1 ? 1 : (c > 32 ? 32 : c);
+        }
+    }
+    return nt;
+}
 
 extern "C" int smlvm_sparsemap_fwd(const float* x, const float* t, const double* init_scores,
                                    int32_t kind, int32_t budget, int32_t max_iter, int64_t rows,
@@ -738,27 +786,7 @@ extern "C" int smlvm_sparsemap_fwd(const float* x, const float* t, const double*
     // whose active set outgrows its tier is flagged (counts = -1) and re-solved from scratch by the
     // next tier.  Same stream, no host synchronisation; an empty tier costs one trivial launch.
     int tiers[3];
-    int ntier = 0;
-    {
-        static int single = -1;
-        if (single < 0) {
-            const char* e = getenv("SMLVM_SMAP_SINGLE_TIER");
-            single = (e && atoi(e)) ? 1 : 0;
-        }
-        // largest capacity that still lets `ctas` CTAs share the 227 KB (+1 KB reserved each) of an SM
-        auto cap_for = [&](int ctas) {
-            const size_t budget_b = (size_t)(227 * 1024) / ctas - 1024;
-            int c = n + 1;
-            while (c > 8 && solver_smem_bytes(n, c) > budget_b) --c;
-            return c;
-        };
-        if (!single) {
-            const int c4 = cap_for(4), c2 = cap_for(2);
-            if (c4 < n + 1 && 5 * c4 >= 2 * n) tiers[ntier++] = c4;          // useful only if >= 0.4 n
-            if (c2 < n + 1 && (ntier == 0 || c2 > tiers[ntier - 1])) tiers[ntier++] = c2;
-        }
-        tiers[ntier++] = n + 1;
-    }
+    const int ntier = plan_tiers(n, tiers);
     // one CTA per sample: the hardware scheduler evens out the data-dependent solve lengths
     // (measured best against persistent grids of 16/64/256 CTAs per SM at n = 32 and n = 128)
     int64_t cap_grid = 0x7fffffff;

@@ -334,6 +334,14 @@ def bits_score(x, bits):
 # --------------------------------------------------------------------------------------
 # (3b) SparseMAP
 # --------------------------------------------------------------------------------------
+def sparsemap_plan(n):
+    """[(capacity, shared-memory bytes per CTA, CTAs per SM)] for each capacity tier of the solver."""
+    import ctypes
+    caps, smem, ctas = ((ctypes.c_int32 * 3)() for _ in range(3))
+    nt = lib.smlvm_sparsemap_plan(int(n), caps, smem, ctas)
+    return [(caps[i], smem[i], ctas[i]) for i in range(nt)]
+
+
 def sparsemap_solve(x, kind, budget=0, t=None, init_scores=None, max_iter=100, keep_S=True):
     """Batched active-set solve.  x [rows, n] -> padded solver state (dict), no host sync."""
     x = _f32c(x, "scores")
