@@ -291,6 +291,28 @@ def extra_paths(args, world, device, rank):
                                                                  [0] + [t[0] for t in ops.sparsemap_plan(128)][:-1])],
                      "hbm_frac_of_algorithmic_bytes": (fwd_bytes + bwd_bytes) / (ms / 3 * 1e-3) / 1e9
                      / measured_hbm_peak()[0]}
+    if rank == 0 and world == 1 and not args.no_cpu:
+        # the reference's CPU implementations of the same branches on the box's host cores, bounded
+        # samples, single-threaded as in the reference (pbinary_topk.pyx:31-34 and the per-sample
+        # solver loop structmarg.py:181-196 are serial): oracle/_ref where the reference compiled,
+        # else the oracle port
+        import numpy as np
+        import oracle
+        rng = np.random.default_rng(7)
+        xs = rng.standard_normal((20000, 128)).astype(np.float32)
+        which = "ref_topk" if oracle.have_ref("ref_topk") else "oracle"
+        t0 = time.perf_counter()
+        oracle.topk(xs, 10, which=which)
+        out["topk_sparsemax_n128_k10"]["cpu_topk_only"] = {
+            "value": 20000 / (time.perf_counter() - t0), "unit": "rows/s", "cores": 1,
+            "kind": "reference" if which == "ref_topk" else "port", "sample": "20000 rows, top-k search alone"}
+        for name, kind, budget in (("sparsemap_bernoulli_n128", 0, 0), ("sparsemap_budget64_n128", 1, 64)):
+            xs = rng.standard_normal((384, 128)).astype(np.float32)
+            t0 = time.perf_counter()
+            oracle.sparsemap_batch_counts(xs, kind, budget, 300)
+            out[name]["cpu_solver_only"] = {
+                "value": 384 / (time.perf_counter() - t0), "unit": UNIT, "cores": 1, "kind": "port",
+                "sample": "384 samples, forward solve alone, tight C++ loop (no Python per-sample overhead)"}
     return out
 
 

@@ -221,15 +221,22 @@ __device__ __forceinline__ double factor_map(const SolverSmem& sm, int n, int bu
 template <int KIND>
 __device__ double evaluate_serial(const SolverSmem& sm, int n)
 {
+    // only the set bits contribute: a clear bit adds an exact 0.0 in libad3's loop
     double acc = 0.0;
-    uint32_t prev = 0u;
-    for (int i = 0; i < n; ++i) {
-        const uint32_t bit = (sm.ynew[i >> 5] >> (i & 31)) & 1u;
-        acc = __dadd_rn(acc, bit ? sm.eta[i] : 0.0);
-        if (KIND == SMLVM_FACTOR_SEQUENCE_BINARY) {
-            acc = __dadd_rn(acc, (bit & prev) ? sm.t[i - 1] : 0.0);
-            prev = bit;
+    const int W = (n + 31) >> 5;
+    uint32_t carry = 0u;  // bit 31 of the previous word (the left neighbour of bit 0)
+    for (int q = 0; q < W; ++q) {
+        const uint32_t word = sm.ynew[q];
+        uint32_t rem = word;
+        const uint32_t pairs = word & ((word << 1) | carry);  // bit i set with bit i-1 set
+        while (rem) {
+            const int b = __ffs(rem) - 1;
+            rem &= rem - 1;
+            const int i = q * 32 + b;
+            acc = __dadd_rn(acc, sm.eta[i]);
+            if (KIND == SMLVM_FACTOR_SEQUENCE_BINARY && ((pairs >> b) & 1u)) acc = __dadd_rn(acc, sm.t[i - 1]);
         }
+        carry = word >> 31;
     }
     return acc;
 }
@@ -274,6 +281,12 @@ __device__ __forceinline__ double schur_fold(const SolverSmem& sm, int total, do
 // rows [a0, a1) that fit one round of the terms buffer (at least one row: a row has <= cap+1 terms)
 __device__ __forceinline__ int schur_round_end(int m, int a0, int chunk, int& count)
 {
+    // common case (|A| <= 46): everything that is left fits one round
+    const int rest = ((m + 1 - a0) * (m + 2 - a0)) / 2;
+    if (rest <= chunk) {
+        count = rest;
+        return m + 1;
+    }
     int a1 = a0, c = 0;
     while (a1 <= m && c + (m + 1 - a1) <= chunk) {
         c += m + 1 - a1;
