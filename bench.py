@@ -245,6 +245,37 @@ def extra_paths(args, world, device, rank):
         out["small_configs"] = small_config_latency(device)
     g = torch.Generator().manual_seed(1000 + rank)
 
+    # the categorical step with the decoder on the SUPPORT only (ragged losses): same rows, same scores
+    from lvmhelpers.hotpath import SparsemaxMargStep, SparsemaxMargCompactStep
+    crow = args.rows
+    xc = torch.randn(crow, args.cols, generator=g).to(device)
+    n_items = SparsemaxMargStep.size_capacity(xc)
+    lr = (torch.rand(n_items, generator=g) * 3).to(device)
+    cstep = SparsemaxMargCompactStep(crow, args.cols, device, n_items + 1024, entropy_coeff=1.0)
+    marks = []
+
+    def rec(name):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        marks.append((name, ev))
+
+    ms, _, _ = timed(lambda: cstep.run(xc, lr, n_items, rec), 20, 5, world, device)
+    per_step = len(SparsemaxMargCompactStep.KERNELS) + 1
+    marks = marks[5 * per_step:]
+    dur = {k: 0.0 for k in SparsemaxMargCompactStep.KERNELS}
+    for i in range(len(marks) - 1):
+        if marks[i][0] is not None:
+            dur[marks[i][0]] += marks[i][1].elapsed_time(marks[i + 1][1]) / 20
+    ab = cstep.algorithmic_bytes(n_items)
+    peak = measured_hbm_peak()[0]
+    out["sparsemax_marg_compact_support"] = {
+        "rows_per_gpu": crow, "cols": args.cols, "support_items": n_items, "ms_per_step": ms / 20,
+        "value": crow * world / (ms / 20 * 1e-3), "unit": UNIT,
+        "note": "decoder on the support only: ragged losses [N], ragged weighted loss, backward over the support",
+        "kernels": {k: {"ms": dur[k], "algorithmic_bytes": ab[k], "frac": ab[k] / (dur[k] * 1e-3) / 1e9 / peak}
+                    for k in dur}}
+    del cstep, xc, lr
+
     rows = args.path_rows_topk
     x = torch.randn(rows, 128, generator=g).to(device).requires_grad_(True)
     wrap = TopKSparsemaxWrapper(torch.nn.Identity(), k=10)

@@ -91,6 +91,18 @@ int smlvm_sparsemax_bwd(const float* p, const int32_t* supp_size, const float* d
                         const float* dent, float* dx, float* dloss, int64_t rows, int32_t cols,
                         void* stream);
 
+/* The same Jacobian-vector product when the upstream gradient lives on the SUPPORT only (the
+ * decoder ran on the compacted (row, col) pairs): offsets[rows+1], col_idx[N], vals[N] are the
+ * compaction of p (smlvm_compact_fill); dp[N], loss[N] ragged (either may be NULL), dent[rows]
+ * optional.  dx[rows,cols] is written in full (zero outside the support); dloss[N] (NULL to skip)
+ * = loss_scale * vals.  Reads O(N) instead of O(rows*cols).
+ * replaces: SparsemaxFunction.backward composed with the boolean-mask indexing backward of
+ *           lvmhelpers/structmarg.py:116-126,140 (`p_flat[mask] @ loss`).                          */
+int smlvm_sparsemax_bwd_ragged(const int64_t* offsets, const int32_t* col_idx, const float* vals,
+                               const int32_t* supp_size, const float* dp, const float* loss,
+                               const float* loss_scale_dev, float loss_scale_host, const float* dent,
+                               float* dx, float* dloss, int64_t rows, int32_t cols, void* stream);
+
 /* ------------------------------------------------------------------------- *
  * (2) support compaction
  * replaces: `mask = p.view(-1) > 0; t[mask]` lvmhelpers/structmarg.py:116-126 and the

@@ -210,14 +210,6 @@ sparsemax_fwd_reg(const float* __restrict__ x, float* __restrict__ p, int32_t* _
     }
 }
 
-// d entropy / d p for entropy() of marg.py:6-28: -(log p~ + 1) where the clamp
-// passes gradient (eps <= p <= 1-eps) and p > 0; 0 elsewhere.
-__device__ __forceinline__ float dent_dp(float p)
-{
-    const float eps = 1.1920928955078125e-07f;
-    return (p >= eps && p <= 1.f - eps) ? -(__logf(p) + 1.f) : 0.f;  // MUFU.LG2: |err| < 2e-6
-}
-
 // U rows per group and iteration: every load of the U rows is issued before the first
 // dependent instruction, so a warp keeps 2*U..3*U 128-bit requests per lane in flight
 // (ncu r01: the one-row version stalled 19 cycles per issue on the long scoreboard, 71 % of
@@ -475,6 +467,44 @@ sparsemax_bwd_wide(const float* __restrict__ p, const int32_t* __restrict__ supp
     }
 }
 
+// ---- backward over the support only (ragged upstream gradient) ---------------------------------
+// dx is zero outside the support: the dense matrix is cleared by a memset node and one thread per
+// row scatters g_j - mean(g) at its (few) support columns.  Reads 12-20 B per support entry instead
+// of 8K-12K B per row.
+__global__ void __launch_bounds__(256)
+sparsemax_bwd_ragged_kernel(const int64_t* __restrict__ offsets, const int32_t* __restrict__ cols,
+                            const float* __restrict__ vals, const int32_t* __restrict__ supp,
+                            const float* __restrict__ dp, const float* __restrict__ loss,
+                            const float* __restrict__ loss_scale_dev, float loss_scale_host,
+                            const float* __restrict__ dent, float* __restrict__ dx, float* __restrict__ dloss,
+                            int64_t rows, int K)
+{
+    float ls = loss_scale_host;
+    if (loss_scale_dev != nullptr) ls *= __ldg(loss_scale_dev);
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = __ldg(offsets + r), e = __ldg(offsets + r + 1);
+        const float de = dent != nullptr ? __ldg(dent + r) : 0.f;
+        float sum = 0.f;
+        for (int64_t j = b; j < e; ++j) {
+            const float pj = __ldg(vals + j);
+            float g = dp != nullptr ? __ldg(dp + j) : 0.f;
+            if (loss != nullptr) g = fmaf(ls, __ldg(loss + j), g);
+            if (dent != nullptr) g = fmaf(de, dent_dp(pj), g);
+            sum += g;
+            if (dloss != nullptr) dloss[j] = ls * pj;
+        }
+        const float vhat = __fdiv_rn(sum, (float)__ldg(supp + r));
+        float* out = dx + r * (int64_t)K;
+        for (int64_t j = b; j < e; ++j) {
+            const float pj = __ldg(vals + j);
+            float g = dp != nullptr ? __ldg(dp + j) : 0.f;
+            if (loss != nullptr) g = fmaf(ls, __ldg(loss + j), g);
+            if (dent != nullptr) g = fmaf(de, dent_dp(pj), g);
+            out[__ldg(cols + j)] = __fsub_rn(g, vhat);
+        }
+    }
+}
+
 // ---- host dispatch ----------------------------------------------------------------
 
 struct RegShape {
@@ -541,6 +571,12 @@ static void launch_bwd(bool vec, int grid, cudaStream_t st, const float* p, cons
     }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// sparsemax_bwd_tile.cu
+bool bwd_ragged_tile_supported(int cols);
+int bwd_ragged_tile_launch(const int64_t* offsets, const int32_t* cols_idx, const float* vals, const int32_t* supp,
+                           const float* dp, const float* loss, const float* lsd, float lsh, const float* dent,
+                           float* dx, float* dloss, int64_t rows, int K, cudaStream_t st);
 
 // sparsemax_tile.cu
 bool sparsemax_tile_supported(int cols);
@@ -626,6 +662,29 @@ extern "C" int smlvm_sparsemax_bwd(const float* p, const int32_t* supp_size, con
         sparsemax_bwd_wide<<<grid, kWideThreads, 0, st>>>(p, supp_size, dp, loss, loss_scale_dev,
                                                           loss_scale_host, dent, dx, dloss, rows, cols);
     }
+    SMLVM_LAUNCH_CHECK();
+    return SMLVM_OK;
+}
+
+extern "C" int smlvm_sparsemax_bwd_ragged(const int64_t* offsets, const int32_t* col_idx, const float* vals,
+                                          const int32_t* supp_size, const float* dp, const float* loss,
+                                          const float* loss_scale_dev, float loss_scale_host, const float* dent,
+                                          float* dx, float* dloss, int64_t rows, int32_t cols, void* stream)
+{
+    if (rows < 0 || cols < 1) return SMLVM_ERR_ARG;
+    if (rows == 0) return SMLVM_OK;
+    if (offsets == nullptr || col_idx == nullptr || vals == nullptr || supp_size == nullptr || dx == nullptr)
+        return SMLVM_ERR_ARG;
+    cudaStream_t st = as_stream(stream);
+    if (bwd_ragged_tile_supported(cols) && aligned16(dx))
+        return bwd_ragged_tile_launch(offsets, col_idx, vals, supp_size, dp, loss, loss_scale_dev, loss_scale_host,
+                                      dent, dx, dloss, rows, cols, st);
+    cudaError_t e = cudaMemsetAsync(dx, 0, (size_t)rows * cols * sizeof(float), st);
+    if (e != cudaSuccess) return (int)e;
+    int64_t need = (rows + 255) / 256;
+    int64_t cap = (int64_t)device_sm_count() * 16;
+    sparsemax_bwd_ragged_kernel<<<(int)(need < cap ? need : cap), 256, 0, st>>>(
+        offsets, col_idx, vals, supp_size, dp, loss, loss_scale_dev, loss_scale_host, dent, dx, dloss, rows, cols);
     SMLVM_LAUNCH_CHECK();
     return SMLVM_OK;
 }

@@ -137,4 +137,13 @@ __device__ __forceinline__ void exact_threshold_sorted(const float (&v)[E], int 
     tau_out = __fdiv_rn(ck, (float)ks);
 }
 
+// d entropy / d p for entropy() of marg.py:6-28: -(log p~ + 1) where the clamp
+// passes gradient (eps <= p <= 1-eps) and p > 0; 0 elsewhere.
+__device__ __forceinline__ float dent_dp(float p)
+{
+    const float eps = 1.1920928955078125e-07f;
+    return (p >= eps && p <= 1.f - eps) ? -(__logf(p) + 1.f) : 0.f;  // MUFU.LG2: |err| < 2e-6
+}
+
+
 }  // namespace smlvm

@@ -99,6 +99,55 @@ class SparsemaxMargStep:
         }
 
 
+class SparsemaxMargCompactStep:
+    """The categorical step when the decoder runs on the SUPPORT only (the paper's point; the
+    reference's structured marginalizers work this way, structmarg.py:116-140): losses arrive as a
+    ragged vector over the compacted (row, col) pairs.
+
+        scores [B,K] --sparsemax fwd--> P, supp, nnz, entropy        scan --> offsets
+        P, offsets   --compact fill--> (value, row, col)              [decoder: ragged losses]
+        vals, losses --ragged weighted loss--> mean loss
+        support lists --ragged bwd--> dscores [B,K] (zero off the support), dlosses [N]
+    """
+    KERNELS = ("sparsemax_fwd", "scan_counts", "compact_fill", "wloss_ragged_fwd", "sparsemax_bwd_ragged")
+
+    def __init__(self, rows, cols, device, capacity, entropy_coeff=0.0, global_rows=None):
+        self.base = SparsemaxMargStep(rows, cols, device, capacity, entropy_coeff, global_rows)
+        self.dloss_ragged = torch.empty(self.base.capacity, dtype=torch.float32, device=device)
+
+    def run(self, x, losses_ragged, n_items, rec=None):
+        b = self.base
+        st = torch.cuda.current_stream().cuda_stream
+        rows, K = b.rows, b.cols
+        mark = rec if rec is not None else (lambda name: None)
+        mark("sparsemax_fwd")
+        check(lib.smlvm_sparsemax_fwd(ptr(x), ptr(b.p), ptr(b.supp), ptr(b.nnz), ptr(b.ent), ptr(b.amax), rows, K, st),
+              "smlvm_sparsemax_fwd")
+        mark("scan_counts")
+        check(lib.smlvm_scan_counts(ptr(b.nnz), ptr(b.offsets), rows, ptr(b.scan_ws), b.scan_ws.numel(), st),
+              "smlvm_scan_counts")
+        mark("compact_fill")
+        check(lib.smlvm_compact_fill(ptr(b.p), ptr(b.offsets), ptr(b.vals), ptr(b.ri), ptr(b.ci), rows, K, st),
+              "smlvm_compact_fill")
+        mark("wloss_ragged_fwd")
+        check(lib.smlvm_wloss_ragged_fwd(ptr(b.vals), ptr(losses_ragged), None, None, ptr(b.total), None,
+                                         1.0 / b.global_rows, 0, n_items, ptr(b.red_ws), b.red_ws.numel(), st),
+              "smlvm_wloss_ragged_fwd")
+        mark("sparsemax_bwd_ragged")
+        check(lib.smlvm_sparsemax_bwd_ragged(ptr(b.offsets), ptr(b.ci), ptr(b.vals), ptr(b.supp), None,
+                                             ptr(losses_ragged), None, 1.0 / b.global_rows, ptr(b.dent), ptr(b.dx),
+                                             ptr(self.dloss_ragged), rows, K, st), "smlvm_sparsemax_bwd_ragged")
+        mark(None)
+        return b.total
+
+    def algorithmic_bytes(self, total_nnz):
+        r, K, N_ = self.base.rows, self.base.cols, total_nnz
+        d = self.base.algorithmic_bytes(total_nnz)
+        return {"sparsemax_fwd": d["sparsemax_fwd"], "scan_counts": d["scan_counts"], "compact_fill": d["compact_fill"],
+                "wloss_ragged_fwd": 8 * N_ + 4,
+                "sparsemax_bwd_ragged": 4 * r * K + r * (8 + 4 + 4) + N_ * (4 + 4 + 4 + 4)}
+
+
 class HostPipelinedMargStep:
     """The same step for batches that live in (pinned) HOST memory: scores and losses come over
     PCIe, the gradient and the loss go back.  The batch is cut into ``chunks`` micro-batches

@@ -99,6 +99,33 @@ class _FusedMarginalObjective(torch.autograd.Function):
         return dscores, dlosses, None, None, None, None
 
 
+class _CompactMarginalObjective(torch.autograd.Function):
+    """The same objective when the losses exist on the support only (decoder run on the compacted
+    (sample, latent) pairs): (p_vals . loss) / B - coeff * mean_b H.  Backward: one launch over the
+    support (``smlvm_sparsemax_bwd_ragged``): O(N) reads, dP never materialised, dense dscores."""
+
+    @staticmethod
+    def forward(ctx, scores, loss_ragged, comp_offsets, comp_cols, comp_vals, supp, ent_rows, coeff):
+        rows, K = scores.shape
+        _, total, _ = ops.wloss_ragged_fwd(comp_vals, loss_ragged, scale=1.0 / rows, want_total=True)
+        ctx.save_for_backward(loss_ragged, comp_offsets, comp_cols, comp_vals, supp)
+        ctx.coeff, ctx.shape = float(coeff), (rows, K)
+        return total - ctx.coeff * ent_rows.mean(), total.clone()
+
+    @staticmethod
+    def backward(ctx, g_full, g_total):
+        loss_ragged, offsets, cols, vals, supp = ctx.saved_tensors
+        rows, K = ctx.shape
+        g = (g_full + g_total).contiguous().float()
+        dent = None
+        if ctx.coeff != 0.0:
+            dent = (g_full.float() * (-ctx.coeff / rows)).expand(rows).contiguous()
+        comp = dict(offsets=offsets, cols=cols, vals=vals)
+        dscores, dloss = ops.sparsemax_bwd_ragged(comp, supp, (rows, K), loss=loss_ragged, loss_scale=g,
+                                                  loss_scale_host=1.0 / rows, dent=dent, want_dloss=True)
+        return dscores, dloss, None, None, None, None, None, None
+
+
 class ExplicitWrapper(nn.Module):
     """scores -> (sample, distribution, entropy) (reference marg.py:31-54).
 
@@ -167,14 +194,14 @@ class Marginalizer(torch.nn.Module):
         decoder_output = self.decoder(cols, take(decoder_input))
         loss_components, logs = self.loss(take(encoder_input), take(discrete_latent_z), take(decoder_input),
                                           decoder_output, take(labels))
-        # differentiable values of the support entries: gather from P (autograd scatters back)
-        p_vals = encoder_probs.reshape(-1).index_select(0, rows * encoder_probs.shape[-1] + cols)
-        loss_mean = ops.ragged_loss(p_vals, loss_components, 1.0 / batch_size)
+        p_vals = comp["vals"]
+        full_loss, loss_mean = _CompactMarginalObjective.apply(
+            side["scores"], loss_components, comp["offsets"], comp["cols"], comp["vals"], side["supp"],
+            side["entropy"].detach(), float(self.encoder_entropy_coeff))
         for k, v in logs.items():
             if hasattr(v, 'mean'):
                 # sum_z mean_b p[b,z] v[b,z]  ==  (p_vals . v) / B
-                logs[k] = (p_vals.detach() * v.detach().reshape(-1).to(p_vals.dtype)).sum() / batch_size
-        full_loss = loss_mean - encoder_entropy.mean() * self.encoder_entropy_coeff
+                logs[k] = (p_vals * v.detach().reshape(-1).to(p_vals.dtype)).sum() / batch_size
         logs['loss'] = loss_mean
         logs['encoder_entropy'] = encoder_entropy.mean()
         logs['support'] = (encoder_probs != 0).sum(-1).to(torch.float).mean()

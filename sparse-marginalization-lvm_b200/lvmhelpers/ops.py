@@ -59,6 +59,24 @@ def sparsemax_bwd(p, supp, dp=None, loss=None, loss_scale=None, loss_scale_host=
     return (dx, dloss) if want_dloss else dx
 
 
+def sparsemax_bwd_ragged(comp, supp, shape, dp=None, loss=None, loss_scale=None, loss_scale_host=1.0,
+                         dent=None, want_dloss=False, out=None):
+    """The Jacobian-vector product from gradients that live on the support only (``comp`` = the
+    compaction of P: offsets / cols / vals); see smlvm_sparsemax_bwd_ragged in include/smlvm.h.
+    Returns dx [rows, K] (and dloss [N] = loss_scale * vals with ``want_dloss``)."""
+    rows, K = shape
+    dev = comp["vals"].device
+    dx = torch.empty((rows, K), dtype=torch.float32, device=dev) if out is None else out
+    dloss = torch.empty_like(comp["vals"]) if want_dloss else None
+    dp = None if dp is None else _f32c(dp, "dp")
+    loss = None if loss is None else _f32c(loss, "loss")
+    dent = None if dent is None else _f32c(dent, "dent")
+    check(lib.smlvm_sparsemax_bwd_ragged(ptr(comp["offsets"]), ptr(comp["cols"]), ptr(comp["vals"]), ptr(supp),
+                                         ptr(dp), ptr(loss), ptr(loss_scale), float(loss_scale_host), ptr(dent),
+                                         ptr(dx), ptr(dloss), rows, K, stream()), "smlvm_sparsemax_bwd_ragged")
+    return (dx, dloss) if want_dloss else dx
+
+
 class _Sparsemax(torch.autograd.Function):
     """P = sparsemax(X) with entmax's saved state (supp_size, P)."""
 

@@ -79,3 +79,26 @@ def test_cuda_graph_replay_equals_eager(rows, K):
     torch.cuda.synchronize()
     assert torch.equal(step.dx, ref[0]) and torch.equal(step.dloss, ref[1])
     assert torch.equal(step.total, ref[2]) and torch.equal(step.ri[:nnz], ref[3])
+
+
+@pytest.mark.parametrize("rows,K", [(64, 10), (4096, 128), (5000, 33)])
+def test_compact_step_matches_oracle(oracle, rows, K):
+    """Losses on the support only: same loss and dscores as the dense objective whose loss matrix
+    carries the ragged values at the support positions (entries off the support never matter)."""
+    from lvmhelpers.hotpath import SparsemaxMargStep, SparsemaxMargCompactStep
+    x, L = _inputs(rows, K, 21)
+    xd = x.cuda()
+    nnz = SparsemaxMargStep.size_capacity(xd)
+    step = SparsemaxMargCompactStep(rows, K, xd.device, nnz + 16, entropy_coeff=0.3)
+    xr = x.clone().requires_grad_(True)
+    P = oracle.sparsemax(xr)
+    mask = P.detach() > 0
+    Lr = L[mask].clone().requires_grad_(True)           # ragged losses, row-major support order
+    total = step.run(xd, Lr.detach().cuda(), int(mask.sum()))
+    torch.cuda.synchronize()
+    obj = (P[mask] * Lr).sum() / rows - 0.3 * oracle.entropy(P).mean()
+    obj.backward()
+    assert abs(total.item() - (P[mask] * Lr).sum().item() / rows) <= 1e-5
+    assert (step.base.dx.cpu() - xr.grad).abs().max().item() <= 4e-6 * max(1.0, xr.grad.abs().max().item())
+    assert (step.dloss_ragged[:int(mask.sum())].cpu() - Lr.grad).abs().max().item() <= 1e-7
+    assert (step.base.dx.cpu()[~mask] == 0).all()
