@@ -10,6 +10,7 @@
 
 #include "common.cuh"
 #include "sparsemax_exact.cuh"
+#include "tile_ptx.cuh"
 
 namespace smlvm {
 
@@ -99,6 +100,113 @@ bwd_ragged_tile_kernel(const int64_t* __restrict__ offsets, const int32_t* __res
     }
 }
 
+// Variant that builds each 32-row tile of dx in shared memory (zero fill, scatter) and writes it with
+// one bulk (TMA) store: DRAM sees dx written once, in full lines, and no scattered 4-byte stores.
+__global__ void __launch_bounds__(512, 1)
+bwd_ragged_tma_kernel(const int64_t* __restrict__ offsets, const int32_t* __restrict__ cols,
+                      const float* __restrict__ vals, const int32_t* __restrict__ supp,
+                      const float* __restrict__ dp, const float* __restrict__ loss,
+                      const float* __restrict__ loss_scale_dev, float loss_scale_host,
+                      const float* __restrict__ dent, float* __restrict__ dx, float* __restrict__ dloss,
+                      int64_t rows, int K)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int tile_f = kTileRows * K;
+    float* tile = reinterpret_cast<float*>(smem_raw) + (size_t)warp * (tile_f + 4 * kStage);
+    float* s_val = tile + tile_f;
+    float* s_g = s_val + kStage;
+    float* s_loss = s_g + kStage;
+    int* s_col = reinterpret_cast<int*>(s_loss + kStage);
+    const uint32_t ta = smem_u32(tile);
+    float ls = loss_scale_host;
+    if (loss_scale_dev != nullptr) ls *= __ldg(loss_scale_dev);
+
+    const int64_t ntiles = (rows + kTileRows - 1) / kTileRows;
+    for (int64_t t = (int64_t)warp * gridDim.x + blockIdx.x; t < ntiles; t += (int64_t)gridDim.x * nwarps) {
+        const int64_t row0 = t * kTileRows;
+        const int trows = (int)min((int64_t)kTileRows, rows - row0);
+        const bool live = lane < trows;
+        const int64_t row = row0 + lane;
+        const int64_t b = live ? __ldg(offsets + row) : 0, e = live ? __ldg(offsets + row + 1) : 0;
+        const float kf = live ? (float)__ldg(supp + row) : 1.f;
+        const float de = (dent != nullptr && live) ? __ldg(dent + row) : 0.f;
+        const int64_t tb = __shfl_sync(kFull, b, 0);
+        const int64_t te = __shfl_sync(kFull, e, trows - 1);
+        const int tcnt = (int)(te - tb);
+        const bool staged = tcnt <= kStage;
+        // issue the staged loads before waiting on the previous store: their latency overlaps it
+        float r_val[kStage / 32], r_g[kStage / 32], r_loss[kStage / 32];
+        int r_col[kStage / 32];
+        if (staged) {
+#pragma unroll
+            for (int u = 0; u < kStage / 32; ++u) {
+                const int i = lane + 32 * u;
+                const bool in = i < tcnt;
+                r_val[u] = in ? __ldg(vals + tb + i) : 0.f;
+                r_col[u] = in ? __ldg(cols + tb + i) : 0;
+                r_g[u] = (in && dp != nullptr) ? __ldg(dp + tb + i) : 0.f;
+                r_loss[u] = (in && loss != nullptr) ? __ldg(loss + tb + i) : 0.f;
+            }
+        }
+        // the previous store of this warp must have finished READING the tile
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+        for (int i = lane; i < tile_f / 4; i += 32) sts128(ta + (i << 4), make_float4(0.f, 0.f, 0.f, 0.f));
+        if (staged) {
+#pragma unroll
+            for (int u = 0; u < kStage / 32; ++u) {
+                const int i = lane + 32 * u;
+                if (i < tcnt) {
+                    s_val[i] = r_val[u];
+                    s_col[i] = r_col[u];
+                    s_g[i] = r_g[u];
+                    s_loss[i] = r_loss[u];
+                    if (dloss != nullptr) dloss[tb + i] = ls * r_val[u];
+                }
+            }
+        }
+        __syncwarp();
+        if (staged) {
+            const int jb = (int)(b - tb), je = (int)(e - tb);
+            float sum = 0.f;
+            for (int j = jb; j < je; ++j) {
+                float g = fmaf(ls, s_loss[j], s_g[j]);
+                if (dent != nullptr) g = fmaf(de, dent_dp(s_val[j]), g);
+                s_g[j] = g;
+                sum += g;
+            }
+            const float vhat = __fdiv_rn(sum, kf);
+            for (int j = jb; j < je; ++j) tile[lane * K + s_col[j]] = __fsub_rn(s_g[j], vhat);
+        } else {
+            float sum = 0.f;
+            for (int64_t j = b; j < e; ++j) {
+                const float pj = __ldg(vals + j);
+                float g = dp != nullptr ? __ldg(dp + j) : 0.f;
+                if (loss != nullptr) g = fmaf(ls, __ldg(loss + j), g);
+                if (dent != nullptr) g = fmaf(de, dent_dp(pj), g);
+                sum += g;
+                if (dloss != nullptr) dloss[j] = ls * pj;
+            }
+            const float vhat = __fdiv_rn(sum, kf);
+            for (int64_t j = b; j < e; ++j) {
+                const float pj = __ldg(vals + j);
+                float g = dp != nullptr ? __ldg(dp + j) : 0.f;
+                if (loss != nullptr) g = fmaf(ls, __ldg(loss + j), g);
+                if (dent != nullptr) g = fmaf(de, dent_dp(pj), g);
+                tile[lane * K + __ldg(cols + j)] = __fsub_rn(g, vhat);
+            }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            bulk_store(dx + row0 * K, ta, (uint32_t)trows * K * 4u);
+            bulk_commit();
+        }
+    }
+    if (lane == 0) bulk_wait_read0();
+}
+
 bool bwd_ragged_tile_supported(int cols) { return cols % 4 == 0 && cols >= 4; }
 
 int bwd_ragged_tile_launch(const int64_t* offsets, const int32_t* cols_idx, const float* vals, const int32_t* supp,
@@ -109,6 +217,33 @@ int bwd_ragged_tile_launch(const int64_t* offsets, const int32_t* cols_idx, cons
     const int64_t need = (ngroups + kBwdWarps - 1) / kBwdWarps;
     const int64_t cap = (int64_t)device_sm_count() * 6;
     const int grid = (int)(need < cap ? need : cap);
+    static int tma = -1;
+    if (tma < 0) {
+        const char* ev = getenv("SMLVM_BWD_RAGGED_TMA");
+        tma = (ev && atoi(ev) == 0) ? 0 : 1;
+    }
+    if (tma && K <= 512 && rows >= 4096) {
+        const size_t per_warp = ((size_t)kTileRows * K + 4 * kStage) * 4;
+        int warps = (int)((200 * 1024) / per_warp);
+        warps = warps > 16 ? 16 : (warps < 1 ? 1 : warps);
+        const size_t smem = per_warp * warps;
+        static bool configured_dev[64] = {false};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!configured_dev[dev & 63]) {
+            cudaError_t ea = cudaFuncSetAttribute(bwd_ragged_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  200 * 1024);
+            if (ea != cudaSuccess) return (int)ea;
+            configured_dev[dev & 63] = true;
+        }
+        const int64_t nt = (rows + kTileRows - 1) / kTileRows;
+        const int64_t nd = (nt + warps - 1) / warps;
+        const int64_t cp = (int64_t)device_sm_count();
+        bwd_ragged_tma_kernel<<<(int)(nd < cp ? nd : cp), warps * 32, smem, st>>>(offsets, cols_idx, vals, supp, dp, loss,
+                                                                                   lsd, lsh, dent, dx, dloss, rows, K);
+        cudaError_t e2 = cudaGetLastError();
+        return e2 == cudaSuccess ? SMLVM_OK : (int)e2;
+    }
     // clear dx with a memset node (7.2 TB/s), then scatter: fusing the clear into the kernel measured
     // no better (0.21 ms vs 0.20), the scattered stores queue behind the streaming clears in the LSU
     static int fused = -1;
