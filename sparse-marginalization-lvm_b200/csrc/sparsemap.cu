@@ -373,6 +373,7 @@ __global__ void sparsemap_fwd_kernel(const float* __restrict__ x, const float* _
                 for (int a = tid; a <= m; a += T) {
                     const int rp = (a == 0) ? 0 : sm.perm[a - 1] + 1;
                     double acc = sm.inv[rp * LD];  // column 0 times b_0 = 1
+#pragma unroll 4
                     for (int j = 1; j <= m; ++j) {
                         const int sj = sm.perm[j - 1];
                         acc = __dadd_rn(acc, __dmul_rn(sm.inv[rp * LD + sj + 1], sm.score[sj]));
@@ -469,6 +470,7 @@ __global__ void sparsemap_fwd_kernel(const float* __restrict__ x, const float* _
                 // ---- u = M z (solver order), oracle scores eta - u ---------------------------
                 for (int i = tid; i < n; i += T) {
                     double uon = 0.0, uoff = 0.0;
+#pragma unroll 4
                     for (int a = 0; a < m; ++a) {
                         const int s = sm.perm[a];
                         const double zz = sm.z[s];
@@ -523,6 +525,7 @@ __global__ void sparsemap_fwd_kernel(const float* __restrict__ x, const float* _
                 for (int a = T - 1 - tid; a <= m; a += T) {
                     const int jp = (a == 0) ? 0 : sm.perm[a - 1] + 1;
                     double acc = __dmul_rn(sm.inv[jp], sm.r[0]);
+#pragma unroll 4
                     for (int b = 1; b <= m; ++b) {
                         const int ip = sm.perm[b - 1] + 1;
                         const double ri = sm.r[ip];
