@@ -96,11 +96,12 @@ topk_tile_kernel(const float* __restrict__ x, float* __restrict__ configs, uint3
                 for (int r = 0; r < outlen; ++r) {
                     const bool takeB = (b < len) && (a >= len || sb > sa);
                     const int src = takeB ? b : a;
-                    const uint32_t mB = takeB ? 0xffffffffu : 0u;
                     Sn[r * 32] = takeB ? sb : sa;
                     Cfg<W> cw = Cc[src * 32];
+                    if (takeB) {  // predicated ORs (one per word)
 #pragma unroll
-                    for (int q = 0; q < W; ++q) cw.w[q] |= bitv.w[q] & mB;
+                        for (int q = 0; q < W; ++q) cw.w[q] |= bitv.w[q];
+                    }
                     Cn[r * 32] = cw;
                     // advance the list that was consumed and fetch its next head
                     const int nxt = src + 1;
