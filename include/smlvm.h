@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SMLVM_ABI_VERSION 1
+#define SMLVM_ABI_VERSION 2
 
 #define SMLVM_OK 0
 #define SMLVM_ERR_ARG (-1)         /* null pointer, negative size, bad enum        */
@@ -41,6 +41,7 @@ extern "C" {
 #define SMLVM_SPARSEMAX_MAX_COLS 8192 /* register path <=1024, shared-memory path beyond */
 #define SMLVM_TOPK_MAX_BITS 512       /* = CODE_MAX_SIZE, lvmhelpers/binary_topk.h:13    */
 #define SMLVM_TOPK_MAX_K 32
+#define SMLVM_SUPPORT_SLOTS 8          /* (value, column) pairs per row the forward hands to the compaction */
 #define SMLVM_SPARSEMAP_MAX_BITS 128  /* (n+1)^2 fp64 inverse must fit 227 KB smem       */
 
 /* factor kinds of the SparseMAP solver */
@@ -70,10 +71,14 @@ const char* smlvm_error_string(int code);
  *   supp_size[rows]  int32  entmax's support size k (count of rho*S_rho > cumsum_rho - 1)
  *   nnz[rows]        int32  number of p > 0 (what the compaction will emit)
  *   entropy[rows]    fp32   -sum_{p>0} clamp(p,eps,1-eps) log clamp(p,eps,1-eps)
- *   argmax[rows]     int64  first index of the row maximum of x                          */
+ *   argmax[rows]     int64  first index of the row maximum of x
+ *   support_slots[rows, SMLVM_SUPPORT_SLOTS, 2] fp32  up to 8 (value, column-as-int-bits) pairs of
+ *                    the row's support in any order (column -1 = empty; column -2 in slot 0 = the
+ *                    row does not fit); hand it to smlvm_compact_fill so that the compaction does
+ *                    not re-read p                                                            */
 int smlvm_sparsemax_fwd(const float* x, float* p, int32_t* supp_size, int32_t* nnz,
-                        float* entropy, int64_t* argmax, int64_t rows, int32_t cols,
-                        void* stream);
+                        float* entropy, int64_t* argmax, float* support_slots, int64_t rows,
+                        int32_t cols, void* stream);
 
 /* Jacobian-vector product over the support, fused with the gradient sources the
  * callers feed it.  Effective upstream gradient per element
@@ -121,9 +126,12 @@ int smlvm_scan_counts(const int32_t* counts, int64_t* offsets, int64_t rows, voi
 int smlvm_compact_count(const float* p, int32_t* counts, int64_t rows, int32_t cols, void* stream);
 
 /* Emits, for every p[r,c] > 0 in row-major order at position offsets[r] + rank:
- *   vals (fp32), row_idx (int32), col_idx (int32); each output may be NULL.               */
-int smlvm_compact_fill(const float* p, const int64_t* offsets, float* vals, int32_t* row_idx,
-                       int32_t* col_idx, int64_t rows, int32_t cols, void* stream);
+ *   vals (fp32), row_idx (int32), col_idx (int32); each output may be NULL.
+ * support_slots (NULL = scan p): the pairs written by smlvm_sparsemax_fwd; with them the kernel
+ * streams 64 B per row instead of the whole row of p (rows that did not fit are scanned).       */
+int smlvm_compact_fill(const float* p, const int64_t* offsets, const float* support_slots,
+                       float* vals, int32_t* row_idx, int32_t* col_idx, int64_t rows, int32_t cols,
+                       void* stream);
 
 /* ------------------------------------------------------------------------- *
  * (3a) k-best bit-vectors

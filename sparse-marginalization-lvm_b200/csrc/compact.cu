@@ -256,6 +256,8 @@ static int launch_compact(const float* p, const int64_t* offsets, int32_t* count
 }
 
 // compact_tile.cu
+int compact_fill_slots_launch(const float* p, const float* slots, const int64_t* offsets, float* vals,
+                              int32_t* row_idx, int32_t* col_idx, int64_t rows, int cols, cudaStream_t st);
 bool compact_tile_supported(int cols);
 int compact_fill_tile_launch(const float* p, const int64_t* offsets, float* vals, int32_t* row_idx,
                              int32_t* col_idx, int64_t rows, int cols, cudaStream_t st);
@@ -317,13 +319,16 @@ extern "C" int smlvm_compact_count(const float* p, int32_t* counts, int64_t rows
                                  as_stream(stream));
 }
 
-extern "C" int smlvm_compact_fill(const float* p, const int64_t* offsets, float* vals,
-                                  int32_t* row_idx, int32_t* col_idx, int64_t rows, int32_t cols,
-                                  void* stream)
+extern "C" int smlvm_compact_fill(const float* p, const int64_t* offsets, const float* support_slots,
+                                  float* vals, int32_t* row_idx, int32_t* col_idx, int64_t rows,
+                                  int32_t cols, void* stream)
 {
     if (rows < 0 || cols < 1) return SMLVM_ERR_ARG;
     if (rows == 0) return SMLVM_OK;
     if (p == nullptr || offsets == nullptr) return SMLVM_ERR_ARG;
+    if (support_slots != nullptr)
+        return compact_fill_slots_launch(p, support_slots, offsets, vals, row_idx, col_idx, rows, cols,
+                                         as_stream(stream));
     const int ovr = compact_path_override();
     if (compact_tile_supported(cols) && (reinterpret_cast<uintptr_t>(p) & 15u) == 0 && ovr != 1 &&
         (rows >= kCompactTileMinRows || ovr == 2))

@@ -17,44 +17,6 @@
 
 namespace smlvm {
 
-// bit (4*i + e) of the swizzled mask belongs to column (4*i + e) ^ (lsw << 2): permute the
-// nibbles of the K-bit mask by XOR-ing their index with lsw (one butterfly level per bit).
-template <int MW>
-__device__ __forceinline__ void unswizzle_mask(uint32_t (&m)[MW], uint32_t lsw)
-{
-#pragma unroll
-    for (int w = 0; w < MW; ++w) {
-        uint32_t v = m[w];
-        uint32_t t = ((v & 0xF0F0F0F0u) >> 4) | ((v & 0x0F0F0F0Fu) << 4);
-        v = (lsw & 1u) ? t : v;
-        t = __byte_perm(v, 0, 0x2301);
-        v = (lsw & 2u) ? t : v;
-        t = __byte_perm(v, 0, 0x1032);
-        v = (lsw & 4u) ? t : v;
-        m[w] = v;
-    }
-    if (MW >= 2) {
-#pragma unroll
-        for (int w = 0; w < MW; w += 2) {
-            const uint32_t a = m[w], b = m[w + 1 < MW ? w + 1 : w];
-            const bool sw = (lsw & 8u) != 0;
-            m[w] = sw ? b : a;
-            if (w + 1 < MW) m[w + 1] = sw ? a : b;
-        }
-    }
-    if (MW >= 4) {
-#pragma unroll
-        for (int w = 0; w < MW; ++w) {
-            if ((w & 2) == 0 && w + 2 < MW) {
-                const uint32_t a = m[w], b = m[w + 2];
-                const bool sw = (lsw & 16u) != 0;
-                m[w] = sw ? b : a;
-                m[w + 2] = sw ? a : b;
-            }
-        }
-    }
-}
-
 template <int K, int W>
 __global__ void __launch_bounds__(W * 32, 1)
 compact_fill_tile(const float* __restrict__ p, const int64_t* __restrict__ offsets, float* __restrict__ vals,
@@ -167,6 +129,133 @@ static int launch_compact_tile(const float* p, const int64_t* offsets, float* va
     const int64_t cap = (int64_t)device_sm_count() * ctas_per_sm;
     const int grid = (int)(need < cap ? need : cap);
     kern<<<grid, W * 32, smem, st>>>(p, offsets, vals, row_idx, col_idx, rows);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SMLVM_OK : (int)e;
+}
+
+// Fill from the per-row support slots the forward kernel can emit (slots[rows][8] of (value, column),
+// 64 B per row, unordered; column -1 = empty, slot 0 column -2 = "this row does not fit: scan P").
+// A thread owns a row: it sorts its <= 8 pairs by column (register network) and writes them at
+// offsets[row]; rows that do not fit are compacted by the whole warp from P.  Streams 64 + 8 B per
+// row instead of the 4K-byte row.
+__global__ void __launch_bounds__(256)
+compact_fill_slots_kernel(const float* __restrict__ p, const float* __restrict__ slots,
+                          const int64_t* __restrict__ offsets, float* __restrict__ vals,
+                          int32_t* __restrict__ row_idx, int32_t* __restrict__ col_idx, int64_t rows, int K)
+{
+    constexpr int NS = SMLVM_SUPPORT_SLOTS;
+    const int lane = threadIdx.x & 31;
+    const int64_t ngroups = (rows + 31) / 32;
+    const int64_t stride = (int64_t)gridDim.x * 8;
+    for (int64_t t = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); t < ngroups; t += stride) {
+        const int64_t r = t * 32 + lane;
+        const bool live = r < rows;
+        const int64_t b = live ? __ldg(offsets + r) : 0;
+        const int cnt = live ? (int)(__ldg(offsets + r + 1) - b) : 0;
+        float v[NS];
+        int c[NS];
+        const float4* src = reinterpret_cast<const float4*>(slots + (live ? r : 0) * (2 * NS));
+#pragma unroll
+        for (int j = 0; j < NS; j += 2) {
+            const float4 q = __ldg(src + j / 2);
+            v[j] = q.x; c[j] = __float_as_int(q.y); v[j + 1] = q.z; c[j + 1] = __float_as_int(q.w);
+        }
+        const bool scan = live && (cnt > NS || c[0] == -2);
+        if (live && !scan) {
+            // sort by column ascending, empty slots (-1) last: odd-even transposition network
+#pragma unroll
+            for (int j = 0; j < NS; ++j) c[j] = (c[j] < 0) ? 0x7fffffff : c[j];
+#pragma unroll
+            for (int pass = 0; pass < NS; ++pass) {
+#pragma unroll
+                for (int j = pass & 1; j + 1 < NS; j += 2) {
+                    const bool sw = c[j] > c[j + 1];
+                    const int ca = sw ? c[j + 1] : c[j], cb = sw ? c[j] : c[j + 1];
+                    const float va = sw ? v[j + 1] : v[j], vb = sw ? v[j] : v[j + 1];
+                    c[j] = ca; c[j + 1] = cb; v[j] = va; v[j + 1] = vb;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < NS; ++j) {
+                if (j < cnt) {
+                    if (vals != nullptr) vals[b + j] = v[j];
+                    if (row_idx != nullptr) row_idx[b + j] = (int32_t)r;
+                    if (col_idx != nullptr) col_idx[b + j] = c[j];
+                }
+            }
+        }
+        // rows that did not fit the slots: the warp scans P, 32 columns at a time
+        unsigned todo = __ballot_sync(kFull, scan);
+        while (todo) {
+            const int src_lane = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int64_t rr = t * 32 + src_lane;
+            int64_t out = __shfl_sync(kFull, b, src_lane);
+            const float* pr = p + rr * K;
+            for (int c0 = 0; c0 < K; c0 += 32) {
+                const int col = c0 + lane;
+                const float pv = col < K ? __ldg(pr + col) : 0.f;
+                const unsigned bal = __ballot_sync(kFull, pv > 0.f);
+                if (pv > 0.f) {
+                    const int64_t o = out + __popc(bal & ((1u << lane) - 1u));
+                    if (vals != nullptr) vals[o] = pv;
+                    if (row_idx != nullptr) row_idx[o] = (int32_t)rr;
+                    if (col_idx != nullptr) col_idx[o] = col;
+                }
+                out += __popc(bal);
+            }
+        }
+    }
+}
+
+int compact_fill_slots_launch(const float* p, const float* slots, const int64_t* offsets, float* vals,
+                              int32_t* row_idx, int32_t* col_idx, int64_t rows, int cols, cudaStream_t st)
+{
+    int64_t need = (rows + 255) / 256;
+    int64_t cap = (int64_t)device_sm_count() * 16;
+    compact_fill_slots_kernel<<<(int)(need < cap ? need : cap), 256, 0, st>>>(p, slots, offsets, vals, row_idx,
+                                                                            col_idx, rows, cols);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SMLVM_OK : (int)e;
+}
+
+// slots from P for callers whose forward path did not emit them (small batches, other widths): a
+// warp per row gathers the first 8 non-zeros; rows with more are marked "scan P".
+__global__ void __launch_bounds__(256)
+support_slots_kernel(const float* __restrict__ p, float* __restrict__ slots, int64_t rows, int K)
+{
+    constexpr int NS = SMLVM_SUPPORT_SLOTS;
+    const int lane = threadIdx.x & 31;
+    const int64_t warps_total = (int64_t)gridDim.x * 8;
+    for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += warps_total) {
+        float* dst = slots + r * (2 * NS);
+        if (lane < NS) {
+            dst[2 * lane] = 0.f;
+            dst[2 * lane + 1] = __int_as_float(-1);
+        }
+        __syncwarp();
+        int out = 0;
+        for (int c0 = 0; c0 < K; c0 += 32) {
+            const int col = c0 + lane;
+            const float pv = col < K ? __ldg(p + r * K + col) : 0.f;
+            const unsigned bal = __ballot_sync(kFull, pv > 0.f);
+            const int o = out + __popc(bal & ((1u << lane) - 1u));
+            if (pv > 0.f && o < NS) {
+                dst[2 * o] = pv;
+                dst[2 * o + 1] = __int_as_float(col);
+            }
+            out += __popc(bal);
+        }
+        __syncwarp();
+        if (out > NS && lane == 0) dst[1] = __int_as_float(-2);
+    }
+}
+
+int support_slots_launch(const float* p, float* slots, int64_t rows, int cols, cudaStream_t st)
+{
+    int64_t need = (rows + 7) / 8;
+    int64_t cap = (int64_t)device_sm_count() * 16;
+    support_slots_kernel<<<(int)(need < cap ? need : cap), 256, 0, st>>>(p, slots, rows, cols);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? SMLVM_OK : (int)e;
 }

@@ -581,7 +581,9 @@ int bwd_ragged_tile_launch(const int64_t* offsets, const int32_t* cols_idx, cons
 // sparsemax_tile.cu
 bool sparsemax_tile_supported(int cols);
 int sparsemax_fwd_tile_launch(const float* x, float* p, int32_t* supp, int32_t* nnz, float* ent, int64_t* amax,
-                              int64_t rows, int cols, cudaStream_t st);
+                              float* support_slots, int64_t rows, int cols, cudaStream_t st);
+// compact_tile.cu
+int support_slots_launch(const float* p, float* slots, int64_t rows, int cols, cudaStream_t st);
 
 // Forward path selection.  The TMA-staged tile kernel wins once there are enough 32-row tiles to
 // occupy the SMs; tiny batches (the B = 64 experiment shapes) are launch-bound and stay on the
@@ -602,8 +604,8 @@ constexpr int64_t kTileMinRows = 4096;
 using namespace smlvm;
 
 extern "C" int smlvm_sparsemax_fwd(const float* x, float* p, int32_t* supp_size, int32_t* nnz,
-                                   float* entropy, int64_t* argmax, int64_t rows, int32_t cols,
-                                   void* stream)
+                                   float* entropy, int64_t* argmax, float* support_slots, int64_t rows,
+                                   int32_t cols, void* stream)
 {
     if (rows < 0 || cols < 1) return SMLVM_ERR_ARG;
     if (rows == 0) return SMLVM_OK;
@@ -613,7 +615,7 @@ extern "C" int smlvm_sparsemax_fwd(const float* x, float* p, int32_t* supp_size,
     const int ovr = fwd_path_override();
     if (sparsemax_tile_supported(cols) && aligned16(x) && aligned16(p) && ovr != 1 &&
         (rows >= kTileMinRows || ovr == 2))
-        return sparsemax_fwd_tile_launch(x, p, supp_size, nnz, entropy, argmax, rows, cols, st);
+        return sparsemax_fwd_tile_launch(x, p, supp_size, nnz, entropy, argmax, support_slots, rows, cols, st);
     if (cols <= 1024) {
         RegShape sh = pick_shape(cols);
         const bool vec = (cols % 4 == 0) && aligned16(x) && aligned16(p);
@@ -635,6 +637,7 @@ extern "C" int smlvm_sparsemax_fwd(const float* x, float* p, int32_t* supp_size,
                                                              rows, cols, N);
     }
     SMLVM_LAUNCH_CHECK();
+    if (support_slots != nullptr) return support_slots_launch(p, support_slots, rows, cols, st);
     return SMLVM_OK;
 }
 

@@ -39,6 +39,7 @@
 namespace smlvm {
 
 constexpr int kCap = 32;        // candidate-list entries per row
+constexpr int kSupportSlots = SMLVM_SUPPORT_SLOTS;
 constexpr int kMaxPasses = 3;   // bound-tightening passes before a row is treated as wide
 
 // Descending bitonic network over a register array (compile-time indices, no divergence).
@@ -177,7 +178,7 @@ template <int K, int S, int W>
 __global__ void __launch_bounds__(W * 32, 1)
 sparsemax_fwd_tile(const float* __restrict__ x, float* __restrict__ p, int32_t* __restrict__ supp,
                    int32_t* __restrict__ nnz, float* __restrict__ ent, int64_t* __restrict__ amax,
-                   int64_t rows)
+                   float* __restrict__ slots, int64_t rows)
 {
     static_assert(S == 1 || S == 2, "1- or 2-stage ring");
     constexpr int NC = K / 4;   // 128-bit chunks per row
@@ -376,8 +377,11 @@ sparsemax_fwd_tile(const float* __restrict__ x, float* __restrict__ p, int32_t* 
                     const float sv = lval[j * 32];
                     const float pe = fmaxf(__fsub_rn(sv, tau), 0.f);
                     if (pe > 0.f) {
-                        const uint32_t col = (uint32_t)lrho[j * 32] ^ (lsw << 2);
+                        const uint8_t rho = lrho[j * 32];
+                        const uint32_t col = (uint32_t)rho ^ (lsw << 2);
                         if (live) sts32(rowa + (col << 2), pe);
+                        lval[nz * 32] = pe;   // compact the support to the front of the list (nz <= j):
+                        lrho[nz * 32] = rho;  // read back by the slot emission below
                         ++nz;
                         const float ps = fminf(fmaxf(pe, eps), 1.f - eps);
                         h = fmaf(ps, __logf(ps), h);
@@ -500,6 +504,26 @@ sparsemax_fwd_tile(const float* __restrict__ x, float* __restrict__ p, int32_t* 
             if (lane == r) { k = k2; nz = nz2; h = h2; first = f2; }
         }
 
+        // ---- per-row support slots for the compaction (saves it the re-read of P) ----------------
+        // up to 8 (value, column) pairs per row, 64 B; a row that does not fit (or did not come
+        // through the candidate list) is marked "scan P" and the fill falls back for that row
+        if (slots != nullptr && live) {
+            float sv[kSupportSlots];
+            int sc[kSupportSlots];
+            const bool fits = !slow && nz <= kSupportSlots;
+#pragma unroll
+            for (int j = 0; j < kSupportSlots; ++j) {
+                const bool on = fits && j < nz;
+                sv[j] = on ? lval[j * 32] : 0.f;     // the list holds P on its first nz entries (sorted by value)
+                sc[j] = on ? (int)((uint32_t)lrho[j * 32] ^ (lsw << 2)) : -1;
+            }
+            if (!fits) sc[0] = -2;
+            float4* dst = reinterpret_cast<float4*>(slots + (row0 + lane) * (2 * kSupportSlots));
+#pragma unroll
+            for (int j = 0; j < kSupportSlots; j += 2)
+                dst[j / 2] = make_float4(sv[j], __int_as_float(sc[j]), sv[j + 1], __int_as_float(sc[j + 1]));
+        }
+
         if (live) {
             const int64_t row = row0 + lane;
             if (supp != nullptr) supp[row] = k;
@@ -527,7 +551,7 @@ sparsemax_fwd_tile(const float* __restrict__ x, float* __restrict__ p, int32_t* 
 
 template <int K, int S, int W>
 static int launch_tile(const float* x, float* p, int32_t* supp, int32_t* nnz, float* ent, int64_t* amax,
-                       int64_t rows, cudaStream_t st)
+                       float* slots, int64_t rows, cudaStream_t st)
 {
     auto kern = sparsemax_fwd_tile<K, S, W>;
     const size_t smem = TileSmem<K, S>::total(W);
@@ -548,7 +572,7 @@ static int launch_tile(const float* x, float* p, int32_t* supp, int32_t* nnz, fl
     const int64_t need = (ntiles + W - 1) / W;
     const int64_t cap = (int64_t)device_sm_count() * ctas_per_sm;
     const int grid = (int)(need < cap ? need : cap);
-    kern<<<grid, W * 32, smem, st>>>(x, p, supp, nnz, ent, amax, rows);
+    kern<<<grid, W * 32, smem, st>>>(x, p, supp, nnz, ent, amax, slots, rows);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? SMLVM_OK : (int)e;
 }
@@ -556,7 +580,7 @@ static int launch_tile(const float* x, float* p, int32_t* supp, int32_t* nnz, fl
 bool sparsemax_tile_supported(int cols) { return cols == 32 || cols == 64 || cols == 128; }
 
 int sparsemax_fwd_tile_launch(const float* x, float* p, int32_t* supp, int32_t* nnz, float* ent, int64_t* amax,
-                              int64_t rows, int cols, cudaStream_t st)
+                              float* slots, int64_t rows, int cols, cudaStream_t st)
 {
     // (stages, warps) per K: as many independent warp pipelines as 227 KB of shared memory hold
     static int variant = -1;
@@ -565,13 +589,13 @@ int sparsemax_fwd_tile_launch(const float* x, float* p, int32_t* supp, int32_t* 
         variant = e ? atoi(e) : 0;
     }
     switch (cols) {
-        case 32: return launch_tile<32, 2, 8>(x, p, supp, nnz, ent, amax, rows, st);
+        case 32: return launch_tile<32, 2, 8>(x, p, supp, nnz, ent, amax, slots, rows, st);
         case 64:
-            if (variant == 1) return launch_tile<64, 1, 12>(x, p, supp, nnz, ent, amax, rows, st);
-            return launch_tile<64, 2, 8>(x, p, supp, nnz, ent, amax, rows, st);
+            if (variant == 1) return launch_tile<64, 1, 12>(x, p, supp, nnz, ent, amax, slots, rows, st);
+            return launch_tile<64, 2, 8>(x, p, supp, nnz, ent, amax, slots, rows, st);
         case 128:
-            if (variant == 1) return launch_tile<128, 2, 6>(x, p, supp, nnz, ent, amax, rows, st);
-            return launch_tile<128, 1, 10>(x, p, supp, nnz, ent, amax, rows, st);
+            if (variant == 1) return launch_tile<128, 2, 6>(x, p, supp, nnz, ent, amax, slots, rows, st);
+            return launch_tile<128, 1, 10>(x, p, supp, nnz, ent, amax, slots, rows, st);
         default: return SMLVM_ERR_UNSUPPORTED;
     }
 }

@@ -74,4 +74,43 @@ __device__ __forceinline__ void sts32(uint32_t a, float v)
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
 }
 
+// bit (4*i + e) of the swizzled mask belongs to column (4*i + e) ^ (lsw << 2): permute the
+// nibbles of the K-bit mask by XOR-ing their index with lsw (one butterfly level per bit).
+template <int MW>
+__device__ __forceinline__ void unswizzle_mask(uint32_t (&m)[MW], uint32_t lsw)
+{
+#pragma unroll
+    for (int w = 0; w < MW; ++w) {
+        uint32_t v = m[w];
+        uint32_t t = ((v & 0xF0F0F0F0u) >> 4) | ((v & 0x0F0F0F0Fu) << 4);
+        v = (lsw & 1u) ? t : v;
+        t = __byte_perm(v, 0, 0x2301);
+        v = (lsw & 2u) ? t : v;
+        t = __byte_perm(v, 0, 0x1032);
+        v = (lsw & 4u) ? t : v;
+        m[w] = v;
+    }
+    if (MW >= 2) {
+#pragma unroll
+        for (int w = 0; w < MW; w += 2) {
+            const uint32_t a = m[w], b = m[w + 1 < MW ? w + 1 : w];
+            const bool sw = (lsw & 8u) != 0;
+            m[w] = sw ? b : a;
+            if (w + 1 < MW) m[w + 1] = sw ? a : b;
+        }
+    }
+    if (MW >= 4) {
+#pragma unroll
+        for (int w = 0; w < MW; ++w) {
+            if ((w & 2) == 0 && w + 2 < MW) {
+                const uint32_t a = m[w], b = m[w + 2];
+                const bool sw = (lsw & 16u) != 0;
+                m[w] = sw ? b : a;
+                m[w + 2] = sw ? a : b;
+            }
+        }
+    }
+}
+
+
 }  // namespace smlvm

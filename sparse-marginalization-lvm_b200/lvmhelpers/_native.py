@@ -12,7 +12,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsmlvm.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 FACTOR_BERNOULLI, FACTOR_BUDGET, FACTOR_SEQUENCE_BINARY = 0, 1, 2
 SOLVE_STATUS = {0: "converged", 1: "max_iter", 2: "repeated_config", 3: "singular"}
@@ -21,6 +21,7 @@ SPARSEMAX_MAX_COLS = 8192
 TOPK_MAX_BITS = 512
 TOPK_MAX_K = 32
 SPARSEMAP_MAX_BITS = 128
+SUPPORT_SLOTS = 8
 
 _vp = ctypes.c_void_p
 _i32, _i64, _f32, _sz = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t
@@ -29,13 +30,13 @@ _i32, _i64, _f32, _sz = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c
 _PROTOTYPES = {
     "smlvm_version": (ctypes.c_int, []),
     "smlvm_error_string": (ctypes.c_char_p, [ctypes.c_int]),
-    "smlvm_sparsemax_fwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "smlvm_sparsemax_fwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "smlvm_sparsemax_bwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _i64, _i32, _vp]),
     "smlvm_sparsemax_bwd_ragged": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _i64, _i32, _vp]),
     "smlvm_scan_workspace_bytes": (_sz, [_i64]),
     "smlvm_scan_counts": (ctypes.c_int, [_vp, _vp, _i64, _vp, _sz, _vp]),
     "smlvm_compact_count": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp]),
-    "smlvm_compact_fill": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "smlvm_compact_fill": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "smlvm_topk_bits": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     "smlvm_bits_score_fwd": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     "smlvm_bits_score_bwd": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp]),

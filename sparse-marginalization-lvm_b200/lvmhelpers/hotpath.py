@@ -33,6 +33,7 @@ class SparsemaxMargStep:
         self.p = e(rows, cols)
         self.supp, self.nnz = e(rows, dtype=i32), e(rows, dtype=i32)
         self.ent, self.amax = e(rows), e(rows, dtype=i64)
+        self.slots = e(rows, N.SUPPORT_SLOTS, 2)   # support (value, column) pairs: fwd -> compaction
         self.offsets = e(rows + 1, dtype=i64)
         self.vals, self.ri, self.ci = e(self.capacity), e(self.capacity, dtype=i32), e(self.capacity, dtype=i32)
         self.row_loss, self.total = e(rows), e(())
@@ -57,12 +58,12 @@ class SparsemaxMargStep:
         mark = rec if rec is not None else (lambda name: None)
         mark("sparsemax_fwd")
         check(lib.smlvm_sparsemax_fwd(ptr(x), ptr(self.p), ptr(self.supp), ptr(self.nnz), ptr(self.ent),
-                                      ptr(self.amax), rows, K, st), "smlvm_sparsemax_fwd")
+                                      ptr(self.amax), ptr(self.slots), rows, K, st), "smlvm_sparsemax_fwd")
         mark("scan_counts")
         check(lib.smlvm_scan_counts(ptr(self.nnz), ptr(self.offsets), rows, ptr(self.scan_ws),
                                     self.scan_ws.numel(), st), "smlvm_scan_counts")
         mark("compact_fill")
-        check(lib.smlvm_compact_fill(ptr(self.p), ptr(self.offsets), ptr(self.vals), ptr(self.ri),
+        check(lib.smlvm_compact_fill(ptr(self.p), ptr(self.offsets), ptr(self.slots), ptr(self.vals), ptr(self.ri),
                                      ptr(self.ci), rows, K, st), "smlvm_compact_fill")
         mark("wloss_dense_fwd")
         check(lib.smlvm_wloss_dense_fwd(ptr(self.p), ptr(losses), ptr(self.row_loss), ptr(self.total),
@@ -91,9 +92,11 @@ class SparsemaxMargStep:
         """Bytes each kernel must move per launch (fp32 = 4 B)."""
         r, K, N_ = self.rows, self.cols, total_nnz
         return {
-            "sparsemax_fwd": r * (8 * K + 4 + 4 + 4 + 8),       # X in, P out, supp/nnz/entropy/argmax
+            "sparsemax_fwd": r * (8 * K + 4 + 4 + 4 + 8 + 64),  # X in, P out, supp/nnz/entropy/argmax/support slots
             "scan_counts": r * (4 + 8),                         # counts in, offsets out
-            "compact_fill": r * (4 * K + 8) + 12 * N_,          # P + offsets in, (val,row,col) out
+            # support slots (64 B) + two offsets in, (val,row,col) out; the survey's figure for a fill
+            # that scans P is r * (4 * K + 8) + 12 * N_ -- the slots written by the forward replace that read
+            "compact_fill": r * (64 + 16) + 12 * N_,
             "wloss_dense_fwd": r * (8 * K + 4),                 # P, L in, row loss out
             "sparsemax_bwd": r * (8 * K + 4 + 8 * K) + (4 * r if self.dent is not None else 0),
         }
@@ -121,14 +124,14 @@ class SparsemaxMargCompactStep:
         rows, K = b.rows, b.cols
         mark = rec if rec is not None else (lambda name: None)
         mark("sparsemax_fwd")
-        check(lib.smlvm_sparsemax_fwd(ptr(x), ptr(b.p), ptr(b.supp), ptr(b.nnz), ptr(b.ent), ptr(b.amax), rows, K, st),
-              "smlvm_sparsemax_fwd")
+        check(lib.smlvm_sparsemax_fwd(ptr(x), ptr(b.p), ptr(b.supp), ptr(b.nnz), ptr(b.ent), ptr(b.amax), ptr(b.slots),
+                                      rows, K, st), "smlvm_sparsemax_fwd")
         mark("scan_counts")
         check(lib.smlvm_scan_counts(ptr(b.nnz), ptr(b.offsets), rows, ptr(b.scan_ws), b.scan_ws.numel(), st),
               "smlvm_scan_counts")
         mark("compact_fill")
-        check(lib.smlvm_compact_fill(ptr(b.p), ptr(b.offsets), ptr(b.vals), ptr(b.ri), ptr(b.ci), rows, K, st),
-              "smlvm_compact_fill")
+        check(lib.smlvm_compact_fill(ptr(b.p), ptr(b.offsets), ptr(b.slots), ptr(b.vals), ptr(b.ri), ptr(b.ci), rows, K,
+                                     st), "smlvm_compact_fill")
         mark("wloss_ragged_fwd")
         check(lib.smlvm_wloss_ragged_fwd(ptr(b.vals), ptr(losses_ragged), None, None, ptr(b.total), None,
                                          1.0 / b.global_rows, 0, n_items, ptr(b.red_ws), b.red_ws.numel(), st),

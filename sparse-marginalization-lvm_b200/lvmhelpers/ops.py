@@ -23,8 +23,9 @@ def _f32c(t, name):
 # --------------------------------------------------------------------------------------
 # (1) sparsemax
 # --------------------------------------------------------------------------------------
-def sparsemax_fwd(x, want_entropy=False, want_argmax=False, want_nnz=True):
-    """x [rows, K] -> dict(p, supp [int32], nnz [int32]|None, entropy|None, argmax [int64]|None).
+def sparsemax_fwd(x, want_entropy=False, want_argmax=False, want_nnz=True, want_slots=False):
+    """x [rows, K] -> dict(p, supp [int32], nnz [int32]|None, entropy|None, argmax [int64]|None,
+    slots [rows, 8, 2] fp32 | None  (support (value, column) pairs for ``compact``)).
 
     entmax.sparsemax forward (lvmhelpers/marg.py:51) fused with entropy() (marg.py:6-28)
     and scores.argmax(-1) (marg.py:53).
@@ -36,9 +37,10 @@ def sparsemax_fwd(x, want_entropy=False, want_argmax=False, want_nnz=True):
     nnz = torch.empty(rows, dtype=torch.int32, device=x.device) if want_nnz else None
     ent = torch.empty(rows, dtype=torch.float32, device=x.device) if want_entropy else None
     amax = torch.empty(rows, dtype=torch.int64, device=x.device) if want_argmax else None
-    check(lib.smlvm_sparsemax_fwd(ptr(x), ptr(p), ptr(supp), ptr(nnz), ptr(ent), ptr(amax),
+    slots = torch.empty((rows, N.SUPPORT_SLOTS, 2), dtype=torch.float32, device=x.device) if want_slots else None
+    check(lib.smlvm_sparsemax_fwd(ptr(x), ptr(p), ptr(supp), ptr(nnz), ptr(ent), ptr(amax), ptr(slots),
                                   rows, K, stream()), "smlvm_sparsemax_fwd")
-    return dict(p=p, supp=supp, nnz=nnz, entropy=ent, argmax=amax)
+    return dict(p=p, supp=supp, nnz=nnz, entropy=ent, argmax=amax, slots=slots)
 
 
 def sparsemax_bwd(p, supp, dp=None, loss=None, loss_scale=None, loss_scale_host=1.0, dent=None,
@@ -148,20 +150,21 @@ def compact_count(p):
     return counts
 
 
-def compact_fill(p, offsets, total, want_vals=True, want_rows=True, want_cols=True):
+def compact_fill(p, offsets, total, want_vals=True, want_rows=True, want_cols=True, slots=None):
     p = _f32c(p, "p")
     rows, K = p.shape
     dev = p.device
     vals = torch.empty(total, dtype=torch.float32, device=dev) if want_vals else None
     ri = torch.empty(total, dtype=torch.int32, device=dev) if want_rows else None
     ci = torch.empty(total, dtype=torch.int32, device=dev) if want_cols else None
-    check(lib.smlvm_compact_fill(ptr(p), ptr(offsets), ptr(vals), ptr(ri), ptr(ci), rows, K,
+    check(lib.smlvm_compact_fill(ptr(p), ptr(offsets), ptr(slots), ptr(vals), ptr(ri), ptr(ci), rows, K,
                                  stream()), "smlvm_compact_fill")
     return vals, ri, ci
 
 
-def compact(p, nnz=None):
-    """Row-major compaction of p > 0 (== torch.nonzero(p > 0) order).
+def compact(p, nnz=None, slots=None):
+    """Row-major compaction of p > 0 (== torch.nonzero(p > 0) order).  ``slots``: the support
+    pairs of ``sparsemax_fwd(want_slots=True)`` (the fill then does not re-read p).
 
     Returns dict(offsets [rows+1] int64, total int, vals, rows, cols).  One D2H read (total).
     """
@@ -169,7 +172,7 @@ def compact(p, nnz=None):
         nnz = compact_count(p)
     offsets = scan_counts(nnz)
     total = int(offsets[-1].item())
-    vals, ri, ci = compact_fill(p, offsets, total)
+    vals, ri, ci = compact_fill(p, offsets, total, slots=slots)
     return dict(offsets=offsets, total=total, vals=vals, rows=ri, cols=ci)
 
 

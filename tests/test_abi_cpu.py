@@ -53,7 +53,7 @@ def test_library_is_sm100a_only():
 def test_version_and_error_strings():
     from lvmhelpers import _native
     lib = _native.lib
-    assert lib.smlvm_version() == _native.ABI_VERSION == 1
+    assert lib.smlvm_version() == _native.ABI_VERSION == 2
     assert b"argument" in lib.smlvm_error_string(-1).lower()
     for code in (0, -1, -2, -3, 1, 700, 12345):
         assert lib.smlvm_error_string(code) is not None
@@ -63,11 +63,11 @@ def test_argument_validation_needs_no_device():
     """Argument errors are reported before any CUDA call (negative sizes, NULL pointers,
     shapes outside the documented limits)."""
     from lvmhelpers._native import lib
-    assert lib.smlvm_sparsemax_fwd(None, None, None, None, None, None, -1, 4, None) == -1
-    assert lib.smlvm_sparsemax_fwd(None, None, None, None, None, None, 4, 0, None) == -1
-    assert lib.smlvm_sparsemax_fwd(None, None, None, None, None, None, 0, 4, None) == 0   # empty batch
-    assert lib.smlvm_sparsemax_fwd(None, None, None, None, None, None, 4, 4, None) == -1  # NULL x
-    assert lib.smlvm_sparsemax_fwd(1 << 20, 1 << 21, None, None, None, None, 4, 10000, None) == -2
+    assert lib.smlvm_sparsemax_fwd(None, None, None, None, None, None, None, -1, 4, None) == -1
+    assert lib.smlvm_sparsemax_fwd(None, None, None, None, None, None, None, 4, 0, None) == -1
+    assert lib.smlvm_sparsemax_fwd(None, None, None, None, None, None, None, 0, 4, None) == 0   # empty batch
+    assert lib.smlvm_sparsemax_fwd(None, None, None, None, None, None, None, 4, 4, None) == -1  # NULL x
+    assert lib.smlvm_sparsemax_fwd(1 << 20, 1 << 21, None, None, None, None, None, 4, 10000, None) == -2
     assert lib.smlvm_sparsemax_bwd(None, None, None, None, None, 1.0, None, None, None, 0, 4, None) == 0
     assert lib.smlvm_topk_bits(1 << 20, 1 << 21, None, None, 4, 3, 9, None) == -1   # k > 2^n
     assert lib.smlvm_topk_bits(1 << 20, 1 << 21, None, None, 4, 8, 1, None) == -1   # k < 2 (binary_topk.h:102)

@@ -48,6 +48,23 @@ def test_compaction_tile_kernel(rows, K, density):
     assert torch.equal(comp["vals"], P[P > 0])
 
 
+@pytest.mark.parametrize("rows,K", [(64, 10), (100, 33), (4096 + 5, 128), (5000, 64), (4097, 256), (3, 1000)])
+@pytest.mark.parametrize("scale", [0.03, 0.3, 1.0])
+def test_compaction_from_forward_slots(rows, K, scale):
+    """The forward kernel's support slots (tile path, and register path + slot kernel) feed the
+    fill: same (value, row, col) triples as the scan of P, bit-exact -- including rows with more
+    than 8 non-zeros (small score scales), which the fill scans from P."""
+    from lvmhelpers import ops
+    x = torch.randn(rows, K, generator=torch.Generator().manual_seed(K + rows)) * scale
+    out = ops.sparsemax_fwd(x.cuda(), want_slots=True)
+    P = out["p"]
+    ref = torch.nonzero(P > 0)
+    comp = ops.compact(P, out["nnz"], slots=out["slots"])
+    assert comp["total"] == ref.shape[0]
+    assert torch.equal(comp["rows"].long(), ref[:, 0]) and torch.equal(comp["cols"].long(), ref[:, 1])
+    assert torch.equal(comp["vals"], P[P > 0])
+
+
 def test_compaction_edge_cases():
     from lvmhelpers import ops
     # empty rows, full rows, negative and zero entries
