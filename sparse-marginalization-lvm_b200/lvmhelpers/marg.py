@@ -146,11 +146,11 @@ class ExplicitWrapper(nn.Module):
         if self.normalizer_name == 'sparsemax':
             shp = scores.shape
             flat = scores.reshape(-1, shp[-1])
-            distr, entropy_distr, sample, nnz, supp = ops.sparsemax_stats(flat)
+            distr, entropy_distr, sample, nnz, supp, slots = ops.sparsemax_stats(flat)
             distr = distr.reshape(shp)
             # side channel for Marginalizer: lets it fuse loss + entropy gradients into
             # one backward launch (dP never materialised)
-            distr._smlvm = dict(scores=flat, nnz=nnz, entropy=entropy_distr, supp=supp)
+            distr._smlvm = dict(scores=flat, nnz=nnz, entropy=entropy_distr, supp=supp, slots=slots)
             return sample.reshape(shp[:-1]), distr, entropy_distr.reshape(shp[:-1])
         if self.normalizer_name == 'softmax':
             distr = torch.softmax(scores, dim=-1)
@@ -188,7 +188,7 @@ class Marginalizer(torch.nn.Module):
                          encoder_entropy, side):
         """decoder calls proportional to the support: one ragged batch of N = sum_b |supp(b)| rows."""
         batch_size = encoder_probs.shape[0]
-        comp = ops.compact(encoder_probs.detach(), side["nnz"])
+        comp = ops.compact(encoder_probs.detach(), side["nnz"], slots=side["slots"])
         rows, cols = comp["rows"].long(), comp["cols"].long()
         take = lambda t: t.index_select(0, rows) if torch.is_tensor(t) else t
         decoder_output = self.decoder(cols, take(decoder_input))

@@ -99,14 +99,14 @@ class _SparsemaxStats(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x):
-        out = sparsemax_fwd(x, want_entropy=True, want_argmax=True, want_nnz=True)
+        out = sparsemax_fwd(x, want_entropy=True, want_argmax=True, want_nnz=True, want_slots=True)
         ctx.save_for_backward(out["supp"], out["p"])
-        ctx.mark_non_differentiable(out["argmax"], out["nnz"], out["supp"])
+        ctx.mark_non_differentiable(out["argmax"], out["nnz"], out["supp"], out["slots"])
         ctx.set_materialize_grads(False)
-        return out["p"], out["entropy"], out["argmax"], out["nnz"], out["supp"]
+        return out["p"], out["entropy"], out["argmax"], out["nnz"], out["supp"], out["slots"]
 
     @staticmethod
-    def backward(ctx, dp, dent, _damax, _dnnz, _dsupp):
+    def backward(ctx, dp, dent, _damax, _dnnz, _dsupp, _dslots):
         supp, p = ctx.saved_tensors
         if dp is None and dent is None:
             return torch.zeros_like(p)
@@ -123,7 +123,8 @@ def sparsemax(X, dim=-1):
 
 
 def sparsemax_stats(X):
-    """X [rows, K] -> (P, entropy [rows], argmax [rows] int64, nnz [rows] int32, supp [rows] int32)."""
+    """X [rows, K] -> (P, entropy [rows], argmax [rows] int64, nnz [rows] int32, supp [rows] int32,
+    support slots [rows, 8, 2] for ``compact``)."""
     return _SparsemaxStats.apply(X)
 
 

@@ -46,8 +46,8 @@ class _CompactValues(torch.autograd.Function):
         return d, None
 
 
-def _compact_with_flat(p, nnz):
-    comp = ops.compact(p.detach(), nnz)
+def _compact_with_flat(p, nnz, slots=None):
+    comp = ops.compact(p.detach(), nnz, slots=slots)
     comp["flat_idx"] = comp["rows"].to(torch.int64) * p.shape[-1] + comp["cols"].to(torch.int64)
     return comp
 
@@ -74,9 +74,9 @@ class TopKSparsemaxWrapper(nn.Module):
         bit_vector_z, bits, _ = ops.topk_bits(scores.detach(), self.k)
         # rank them: scores_k = einsum("bkj,bj->bk"), differentiable w.r.t. scores (:47)
         scores_k = ops.bits_score(scores, bits)
-        distr, _, _, nnz, _ = ops.sparsemax_stats(scores_k)
+        distr, _, _, nnz, _, slots = ops.sparsemax_stats(scores_k)
         # entropy over the support (:51-58)
-        comp = _compact_with_flat(distr, nnz)
+        comp = _compact_with_flat(distr, nnz, slots)
         vals = _CompactValues.apply(distr, comp)
         entropy_distr = ops.ragged_entropy(vals, 1.0 / batch_size)
         distr._smlvm_compact = comp
