@@ -91,10 +91,13 @@ int smlvm_sparsemax_fwd(const float* x, float* p, int32_t* supp_size, int32_t* n
  * replaces: SparsemaxFunction.backward (entmax) + the autograd of
  *           `encoder_probs.unsqueeze(1).bmm(losses.unsqueeze(-1))` marg.py:125 and of
  *           entropy() marg.py:6-28 w.r.t. p.                                              */
+/* support_slots (NULL = read the dense rows): the pairs written by smlvm_sparsemax_fwd for THIS p;
+ * with them the kernel reads 64 B per row plus one sector of loss / dp per non-zero and never reads
+ * p, loss or dp in full (rows marked "does not fit" are processed densely).                       */
 int smlvm_sparsemax_bwd(const float* p, const int32_t* supp_size, const float* dp,
                         const float* loss, const float* loss_scale_dev, float loss_scale_host,
-                        const float* dent, float* dx, float* dloss, int64_t rows, int32_t cols,
-                        void* stream);
+                        const float* dent, const float* support_slots, float* dx, float* dloss,
+                        int64_t rows, int32_t cols, void* stream);
 
 /* The same Jacobian-vector product when the upstream gradient lives on the SUPPORT only (the
  * decoder ran on the compacted (row, col) pairs): offsets[rows+1], col_idx[N], vals[N] are the
@@ -217,11 +220,12 @@ int smlvm_sparsemap_bwd(const float* dp, const int64_t* offsets, int32_t only_po
 
 /* Dense: row_loss[r] = sum_c p[r,c]*loss[r,c] (NULL to skip); total[0] (fp32 device scalar,
  * NULL to skip) = scale * sum_r row_loss[r], accumulated in fp64 in a fixed order.
- * workspace: smlvm_reduce_workspace_bytes() bytes.                                          */
+ * workspace: smlvm_reduce_workspace_bytes() bytes.  support_slots (NULL = read p and loss in
+ * full): the forward's (value, column) pairs; only loss entries on the support are then read.      */
 size_t smlvm_reduce_workspace_bytes(void);
-int smlvm_wloss_dense_fwd(const float* p, const float* loss, float* row_loss, float* total,
-                          float scale, int64_t rows, int32_t cols, void* workspace,
-                          size_t workspace_bytes, void* stream);
+int smlvm_wloss_dense_fwd(const float* p, const float* loss, const float* support_slots,
+                          float* row_loss, float* total, float scale, int64_t rows, int32_t cols,
+                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* Ragged: offsets[rows+1] segments over p[N], loss[N].
  *   row_loss[r] = sum_{j in seg r} p_j*loss_j      (NULL to skip; offsets may then be NULL)

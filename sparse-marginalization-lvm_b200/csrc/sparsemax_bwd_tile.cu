@@ -207,6 +207,144 @@ bwd_ragged_tma_kernel(const int64_t* __restrict__ offsets, const int32_t* __rest
     if (lane == 0) bulk_wait_read0();
 }
 
+// Dense backward driven by the forward's support slots (the gradient sources dp / loss are DENSE
+// matrices, as in marg.py:125, but only their entries on the support matter): per 32-row tile the warp
+// builds dX and dL = ls * P in two shared-memory tiles (zero fill, scatter of <= 8 values per row) and
+// writes each with one bulk (TMA) store.  Reads 64 B of slots + one sector of loss (and dp) per
+// non-zero instead of the 8K..12K bytes of the rows of P, loss, dp; rows marked "scan" are processed
+// densely by the whole warp straight into the tiles.
+__global__ void __launch_bounds__(512, 1)
+bwd_slots_tma_kernel(const float* __restrict__ p, const int32_t* __restrict__ supp, const float* __restrict__ dp,
+                     const float* __restrict__ loss, const float* __restrict__ loss_scale_dev,
+                     float loss_scale_host, const float* __restrict__ dent, const float* __restrict__ slots,
+                     float* __restrict__ dx, float* __restrict__ dloss, int64_t rows, int K)
+{
+    constexpr int NS = SMLVM_SUPPORT_SLOTS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int tile_f = kTileRows * K;
+    const int ntile_bufs = dloss != nullptr ? 2 : 1;
+    float* tx = reinterpret_cast<float*>(smem_raw) + (size_t)warp * ntile_bufs * tile_f;
+    float* tl = tx + tile_f;
+    const uint32_t txa = smem_u32(tx), tla = smem_u32(tl);
+    float ls = loss_scale_host;
+    if (loss_scale_dev != nullptr) ls *= __ldg(loss_scale_dev);
+
+    const int64_t ntiles = (rows + kTileRows - 1) / kTileRows;
+    for (int64_t t = (int64_t)warp * gridDim.x + blockIdx.x; t < ntiles; t += (int64_t)gridDim.x * nwarps) {
+        const int64_t row0 = t * kTileRows;
+        const int trows = (int)min((int64_t)kTileRows, rows - row0);
+        const bool live = lane < trows;
+        const int64_t row = row0 + lane;
+        // ---- all loads first: slots, per-row scalars, then the gathers ---------------------------
+        float v[NS], lv[NS], gv[NS];
+        int c[NS];
+        const float4* src = reinterpret_cast<const float4*>(slots + (live ? row : 0) * (2 * NS));
+#pragma unroll
+        for (int j = 0; j < NS; j += 2) {
+            const float4 q = __ldg(src + j / 2);
+            v[j] = q.x; c[j] = __float_as_int(q.y); v[j + 1] = q.z; c[j + 1] = __float_as_int(q.w);
+        }
+        const float kf = live ? (float)__ldg(supp + row) : 1.f;
+        const float de = (dent != nullptr && live) ? __ldg(dent + row) : 0.f;
+        const bool scan = live && c[0] == -2;
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+            const bool on = live && !scan && c[j] >= 0;
+            lv[j] = (on && loss != nullptr) ? __ldg(loss + row * K + c[j]) : 0.f;
+            gv[j] = (on && dp != nullptr) ? __ldg(dp + row * K + c[j]) : 0.f;
+        }
+        // the previous stores of this warp must have finished READING the tiles
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+        for (int i = lane; i < tile_f / 4; i += 32) {
+            sts128(txa + (i << 4), make_float4(0.f, 0.f, 0.f, 0.f));
+            if (dloss != nullptr) sts128(tla + (i << 4), make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+        __syncwarp();
+        if (live && !scan) {
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < NS; ++j) {
+                float g = fmaf(ls, lv[j], gv[j]);
+                if (dent != nullptr) g = fmaf(de, dent_dp(v[j]), g);
+                g = (c[j] >= 0) ? g : 0.f;
+                gv[j] = g;
+                sum += g;
+            }
+            const float vhat = __fdiv_rn(sum, kf);
+#pragma unroll
+            for (int j = 0; j < NS; ++j) {
+                if (c[j] >= 0) {
+                    tx[lane * K + c[j]] = __fsub_rn(gv[j], vhat);
+                    if (dloss != nullptr) tl[lane * K + c[j]] = ls * v[j];
+                }
+            }
+        }
+        // ---- rows whose support does not fit the slots: dense, by the whole warp -------------------
+        unsigned todo = __ballot_sync(kFull, scan);
+        while (todo) {
+            const int rl = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int64_t rr = row0 + rl;
+            const float de_r = __shfl_sync(kFull, de, rl), kf_r = __shfl_sync(kFull, kf, rl);
+            float sum = 0.f;
+            for (int col = lane; col < K; col += 32) {
+                const float pv = __ldg(p + rr * K + col);
+                float g = dp != nullptr ? __ldg(dp + rr * K + col) : 0.f;
+                if (loss != nullptr) g = fmaf(ls, __ldg(loss + rr * K + col), g);
+                if (dent != nullptr) g = fmaf(de_r, dent_dp(pv), g);
+                g = (pv != 0.f) ? g : 0.f;
+                tx[rl * K + col] = g;                      // parked; centred below
+                if (dloss != nullptr) tl[rl * K + col] = ls * pv;
+                sum += g;
+            }
+            sum = group_sum<32>(sum);
+            const float vhat = __fdiv_rn(sum, kf_r);
+            for (int col = lane; col < K; col += 32) {
+                const float pv = __ldg(p + rr * K + col);
+                tx[rl * K + col] = (pv != 0.f) ? __fsub_rn(tx[rl * K + col], vhat) : 0.f;
+            }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            bulk_store(dx + row0 * K, txa, (uint32_t)trows * K * 4u);
+            if (dloss != nullptr) bulk_store(dloss + row0 * K, tla, (uint32_t)trows * K * 4u);
+            bulk_commit();
+        }
+    }
+    if (lane == 0) bulk_wait_read0();
+}
+
+bool bwd_slots_supported(int cols) { return cols % 4 == 0 && cols >= 4 && cols <= 256; }
+
+int bwd_slots_launch(const float* p, const int32_t* supp, const float* dp, const float* loss, const float* lsd,
+                     float lsh, const float* dent, const float* slots, float* dx, float* dloss, int64_t rows, int K,
+                     cudaStream_t st)
+{
+    const size_t per_warp = (size_t)(dloss != nullptr ? 2 : 1) * kTileRows * K * 4;
+    int warps = (int)((200 * 1024) / per_warp);
+    warps = warps > 16 ? 16 : (warps < 1 ? 1 : warps);
+    const size_t smem = per_warp * warps;
+    static bool configured_dev[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured_dev[dev & 63]) {
+        cudaError_t ea = cudaFuncSetAttribute(bwd_slots_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              200 * 1024);
+        if (ea != cudaSuccess) return (int)ea;
+        configured_dev[dev & 63] = true;
+    }
+    const int64_t nt = (rows + kTileRows - 1) / kTileRows;
+    const int64_t nd = (nt + warps - 1) / warps;
+    const int64_t cp = (int64_t)device_sm_count();
+    bwd_slots_tma_kernel<<<(int)(nd < cp ? nd : cp), warps * 32, smem, st>>>(p, supp, dp, loss, lsd, lsh, dent, slots, dx,
+                                                                              dloss, rows, K);
+    cudaError_t e2 = cudaGetLastError();
+    return e2 == cudaSuccess ? SMLVM_OK : (int)e2;
+}
+
 bool bwd_ragged_tile_supported(int cols) { return cols % 4 == 0 && cols >= 4; }
 
 int bwd_ragged_tile_launch(const int64_t* offsets, const int32_t* cols_idx, const float* vals, const int32_t* supp,

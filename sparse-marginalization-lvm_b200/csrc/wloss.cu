@@ -166,6 +166,57 @@ static int grid_1d(int64_t work_items, int per_cta)
     return (int)(need < cap ? (need > 0 ? need : 1) : cap);
 }
 
+// Dense weighted loss driven by the forward's support slots: row_loss[r] = sum_j val_j * L[r, col_j]
+// -- 64 B of slots + one sector of L per non-zero instead of the 8K-byte rows of P and L.  A thread
+// owns a row; rows marked "scan" (support does not fit the slots) are dotted densely by the warp.
+__global__ void __launch_bounds__(kThreads)
+wloss_slots_kernel(const float* __restrict__ p, const float* __restrict__ loss, const float* __restrict__ slots,
+                   float* __restrict__ row_loss, float* __restrict__ total, float scale, int64_t rows, int K,
+                   ReduceWs ws)
+{
+    constexpr int NS = SMLVM_SUPPORT_SLOTS;
+    __shared__ double smem[kThreads / 32 + 1];
+    const int lane = threadIdx.x & 31;
+    const int64_t ngroups = (rows + 31) / 32;
+    const int64_t stride = (int64_t)gridDim.x * (kThreads / kWarp);
+    double acc_total = 0.0;
+    for (int64_t t = (int64_t)blockIdx.x * (kThreads / kWarp) + (threadIdx.x >> 5); t < ngroups; t += stride) {
+        const int64_t r = t * 32 + lane;
+        const bool live = r < rows;
+        float v[NS];
+        int c[NS];
+        const float4* src = reinterpret_cast<const float4*>(slots + (live ? r : 0) * (2 * NS));
+#pragma unroll
+        for (int j = 0; j < NS; j += 2) {
+            const float4 q = __ldg(src + j / 2);
+            v[j] = q.x; c[j] = __float_as_int(q.y); v[j + 1] = q.z; c[j + 1] = __float_as_int(q.w);
+        }
+        const bool scan = live && c[0] == -2;
+        float lv[NS];
+#pragma unroll
+        for (int j = 0; j < NS; ++j) lv[j] = (live && !scan && c[j] >= 0) ? __ldg(loss + r * K + c[j]) : 0.f;
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < NS; ++j) s = fmaf(v[j], lv[j], s);  // empty slots carry v = 0
+        if (scan) s = 0.f;
+        unsigned todo = __ballot_sync(kFull, scan);
+        while (todo) {
+            const int src_lane = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int64_t rr = t * 32 + src_lane;
+            float part = 0.f;
+            for (int col = lane; col < K; col += 32) part = fmaf(__ldg(p + rr * K + col), __ldg(loss + rr * K + col), part);
+            part = group_sum<32>(part);
+            if (lane == src_lane) s = part;
+        }
+        if (live) {
+            if (row_loss != nullptr) row_loss[r] = s;
+            acc_total += (double)s;
+        }
+    }
+    if (total != nullptr) finish_totals(ws, acc_total, 0.0, scale, total, nullptr, smem);
+}
+
 // out[r] = log sum_{j in segment r} exp(sign * v_j + shift); one 8-lane group per segment
 // (supports are short), max-shifted, -inf for an empty segment.
 __global__ void __launch_bounds__(kThreads)
@@ -213,15 +264,22 @@ extern "C" int smlvm_segment_logsumexp(const float* v, const int64_t* offsets, f
 
 extern "C" size_t smlvm_reduce_workspace_bytes(void) { return 64 + 3 * sizeof(double) * kMaxCtas; }
 
-extern "C" int smlvm_wloss_dense_fwd(const float* p, const float* loss, float* row_loss,
-                                     float* total, float scale, int64_t rows, int32_t cols,
-                                     void* workspace, size_t workspace_bytes, void* stream)
+extern "C" int smlvm_wloss_dense_fwd(const float* p, const float* loss, const float* support_slots,
+                                     float* row_loss, float* total, float scale, int64_t rows,
+                                     int32_t cols, void* workspace, size_t workspace_bytes, void* stream)
 {
     if (rows < 0 || cols < 1) return SMLVM_ERR_ARG;
     if (p == nullptr || loss == nullptr) return SMLVM_ERR_ARG;
     if (total != nullptr && (workspace == nullptr || workspace_bytes < smlvm_reduce_workspace_bytes()))
         return SMLVM_ERR_WORKSPACE;
     cudaStream_t st = as_stream(stream);
+    if (support_slots != nullptr && rows > 0) {
+        const int grid = grid_1d(rows, kThreads);
+        wloss_slots_kernel<<<grid, kThreads, 0, st>>>(p, loss, support_slots, row_loss, total, scale, rows, cols,
+                                                      ws_view(workspace));
+        SMLVM_LAUNCH_CHECK();
+        return SMLVM_OK;
+    }
     int G = 1;
     while (G < 32 && G * 4 < cols) G <<= 1;
     const bool vec = (cols % 4 == 0) && ((reinterpret_cast<uintptr_t>(p) & 15u) == 0) &&

@@ -21,9 +21,17 @@ from ._native import lib, check, ptr
 class SparsemaxMargStep:
     KERNELS = ("sparsemax_fwd", "scan_counts", "compact_fill", "wloss_dense_fwd", "sparsemax_bwd")
 
-    def __init__(self, rows, cols, device, capacity, entropy_coeff=0.0, global_rows=None):
+    def __init__(self, rows, cols, device, capacity, entropy_coeff=0.0, global_rows=None, use_slots=None):
         """``global_rows``: batch size B of the 1/B in the loss and entropy terms when this step
-        owns only a shard / micro-batch of the batch (default: ``rows``)."""
+        owns only a shard / micro-batch of the batch (default: ``rows``).
+        ``use_slots``: let the weighted loss and the backward read the losses only at the support
+        entries the forward handed over (64 B of slots + one sector per non-zero instead of the rows
+        of P and L).  Default: on when the expected support (``capacity / rows``) is at most 6 entries
+        per row -- rows that do not fit the 8 slots fall back to dense processing one by one, which
+        only pays when they are rare."""
+        if use_slots is None:
+            use_slots = capacity <= 6 * rows
+        self.use_slots = bool(use_slots)
         self.rows, self.cols, self.device = rows, cols, device
         self.global_rows = int(global_rows) if global_rows is not None else rows
         self.capacity = int(capacity)
@@ -66,12 +74,13 @@ class SparsemaxMargStep:
         check(lib.smlvm_compact_fill(ptr(self.p), ptr(self.offsets), ptr(self.slots), ptr(self.vals), ptr(self.ri),
                                      ptr(self.ci), rows, K, st), "smlvm_compact_fill")
         mark("wloss_dense_fwd")
-        check(lib.smlvm_wloss_dense_fwd(ptr(self.p), ptr(losses), ptr(self.row_loss), ptr(self.total),
+        slots = ptr(self.slots) if self.use_slots else None
+        check(lib.smlvm_wloss_dense_fwd(ptr(self.p), ptr(losses), slots, ptr(self.row_loss), ptr(self.total),
                                         1.0 / self.global_rows, rows, K, ptr(self.red_ws), self.red_ws.numel(), st),
               "smlvm_wloss_dense_fwd")
         mark("sparsemax_bwd")
         check(lib.smlvm_sparsemax_bwd(ptr(self.p), ptr(self.supp), None, ptr(losses), None, 1.0 / self.global_rows,
-                                      ptr(self.dent), ptr(self.dx), ptr(self.dloss), rows, K, st),
+                                      ptr(self.dent), slots, ptr(self.dx), ptr(self.dloss), rows, K, st),
               "smlvm_sparsemax_bwd")
         mark(None)
         return self.total
@@ -97,8 +106,11 @@ class SparsemaxMargStep:
             # support slots (64 B) + two offsets in, (val,row,col) out; the survey's figure for a fill
             # that scans P is r * (4 * K + 8) + 12 * N_ -- the slots written by the forward replace that read
             "compact_fill": r * (64 + 16) + 12 * N_,
-            "wloss_dense_fwd": r * (8 * K + 4),                 # P, L in, row loss out
-            "sparsemax_bwd": r * (8 * K + 4 + 8 * K) + (4 * r if self.dent is not None else 0),
+            # P, L in, row loss out  /  P, L, supp (+dent) in, dX, dL out.  With support slots the reads
+            # shrink to the slots + one 32-byte sector of L per non-zero
+            "wloss_dense_fwd": (r * (64 + 4) + 32 * N_) if self.use_slots else r * (8 * K + 4),
+            "sparsemax_bwd": ((r * (64 + 4 + 8 * K) + 32 * N_) if self.use_slots else r * (8 * K + 4 + 8 * K))
+                             + (4 * r if self.dent is not None else 0),
         }
 
 

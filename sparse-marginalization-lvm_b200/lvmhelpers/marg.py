@@ -75,10 +75,11 @@ class _FusedMarginalObjective(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, scores, losses, p, supp, ent_rows, coeff):
+    def forward(ctx, scores, losses, p, supp, ent_rows, coeff, slots=None):
         rows = p.shape[0]
-        row_loss, total = ops.wloss_dense_fwd(p, losses, scale=1.0 / rows)
+        row_loss, total = ops.wloss_dense_fwd(p, losses, scale=1.0 / rows, slots=slots)
         ctx.save_for_backward(p, supp, losses)
+        ctx.slots = slots
         ctx.coeff = float(coeff)
         ctx.mark_non_differentiable(row_loss)
         full = total - ctx.coeff * ent_rows.mean()
@@ -95,8 +96,8 @@ class _FusedMarginalObjective(torch.autograd.Function):
         # one launch: dscores (sparsemax Jacobian of g*L/B + entropy term) and dlosses = g*P/B
         dscores, dlosses = ops.sparsemax_bwd(p, supp, loss=losses, loss_scale=g,
                                              loss_scale_host=1.0 / rows, dent=dent,
-                                             want_dloss=True)
-        return dscores, dlosses, None, None, None, None
+                                             want_dloss=True, slots=ctx.slots)
+        return dscores, dlosses, None, None, None, None, None
 
 
 class _CompactMarginalObjective(torch.autograd.Function):
@@ -244,7 +245,7 @@ class Marginalizer(torch.nn.Module):
         if side is not None and encoder_probs.is_cuda:
             full_loss, loss_mean, _ = _FusedMarginalObjective.apply(
                 side["scores"], losses, encoder_probs.detach(), side["supp"],
-                side["entropy"].detach(), float(self.encoder_entropy_coeff))
+                side["entropy"].detach(), float(self.encoder_entropy_coeff), side.get("slots"))
         else:
             entropy_loss = -(encoder_entropy.mean() * self.encoder_entropy_coeff)
             loss = (encoder_probs * losses).sum(-1)

@@ -44,9 +44,11 @@ def sparsemax_fwd(x, want_entropy=False, want_argmax=False, want_nnz=True, want_
 
 
 def sparsemax_bwd(p, supp, dp=None, loss=None, loss_scale=None, loss_scale_host=1.0, dent=None,
-                  want_dloss=False, out=None, out_dloss=None):
+                  want_dloss=False, out=None, out_dloss=None, slots=None):
     """Fused Jacobian-vector product; see smlvm_sparsemax_bwd in include/smlvm.h.
-    With want_dloss also returns dloss = loss_scale * p (decoder side of the weighted loss)."""
+    With want_dloss also returns dloss = loss_scale * p (decoder side of the weighted loss).
+    ``slots``: the forward's support pairs for this ``p`` (only the support entries of dp / loss are
+    then read)."""
     rows, K = p.shape
     dx = torch.empty_like(p) if out is None else out
     dloss = None
@@ -56,7 +58,7 @@ def sparsemax_bwd(p, supp, dp=None, loss=None, loss_scale=None, loss_scale_host=
     loss = None if loss is None else _f32c(loss, "loss")
     dent = None if dent is None else _f32c(dent, "dent")
     check(lib.smlvm_sparsemax_bwd(ptr(p), ptr(supp), ptr(dp), ptr(loss), ptr(loss_scale),
-                                  float(loss_scale_host), ptr(dent), ptr(dx), ptr(dloss), rows, K,
+                                  float(loss_scale_host), ptr(dent), ptr(slots), ptr(dx), ptr(dloss), rows, K,
                                   stream()), "smlvm_sparsemax_bwd")
     return (dx, dloss) if want_dloss else dx
 
@@ -180,7 +182,7 @@ def compact(p, nnz=None, slots=None):
 # --------------------------------------------------------------------------------------
 # (4) weighted loss
 # --------------------------------------------------------------------------------------
-def wloss_dense_fwd(p, loss, scale=1.0, want_rows=True, want_total=True):
+def wloss_dense_fwd(p, loss, scale=1.0, want_rows=True, want_total=True, slots=None):
     p = _f32c(p, "p")
     loss = _f32c(loss, "loss")
     rows, K = p.shape
@@ -188,7 +190,7 @@ def wloss_dense_fwd(p, loss, scale=1.0, want_rows=True, want_total=True):
     row_loss = torch.empty(rows, dtype=torch.float32, device=dev) if want_rows else None
     total = torch.empty((), dtype=torch.float32, device=dev) if want_total else None
     ws = N.reduce_workspace(dev)
-    check(lib.smlvm_wloss_dense_fwd(ptr(p), ptr(loss), ptr(row_loss), ptr(total), float(scale),
+    check(lib.smlvm_wloss_dense_fwd(ptr(p), ptr(loss), ptr(slots), ptr(row_loss), ptr(total), float(scale),
                                     rows, K, ptr(ws), ws.numel(), stream()),
           "smlvm_wloss_dense_fwd")
     return row_loss, total

@@ -202,3 +202,31 @@ def test_ragged_backward_equals_dense_backward(rows, K):
     assert torch.equal(got != 0, ref != 0)
     assert (got - ref).abs().max().item() <= 2e-6 * max(1.0, ref.abs().max().item())
     assert torch.equal(dl, 0.5 * comp["vals"])
+
+
+@pytest.mark.parametrize("rows,K", [(4096, 128), (5001, 64), (4100, 36), (4096, 256), (8192, 32)])
+@pytest.mark.parametrize("scale", [0.05, 0.5, 2.0])
+def test_slot_driven_dense_kernels_equal_dense_reads(rows, K, scale):
+    """smlvm_wloss_dense_fwd / smlvm_sparsemax_bwd with the forward's support slots (reading L and dP
+    only on the support; rows with more than 8 non-zeros fall back to dense processing inside the
+    kernel) == the same calls without slots."""
+    from lvmhelpers import ops
+    g = torch.Generator().manual_seed(rows + K)
+    x = (torch.randn(rows, K, generator=g) * scale).cuda()
+    L = (torch.rand(rows, K, generator=g) * 3).cuda()
+    dP = torch.randn(rows, K, generator=g).cuda()
+    dent = torch.randn(rows, generator=g).cuda()
+    out = ops.sparsemax_fwd(x, want_slots=True)
+    P, supp, slots = out["p"], out["supp"], out["slots"]
+    r0, t0 = ops.wloss_dense_fwd(P, L, scale=1.0 / rows)
+    r1, t1 = ops.wloss_dense_fwd(P, L, scale=1.0 / rows, slots=slots)
+    assert (r0 - r1).abs().max().item() <= 2e-6 * max(1.0, r0.abs().max().item())
+    assert abs(t0.item() - t1.item()) <= 1e-5 * max(1.0, abs(t0.item()))
+    for kw in (dict(dp=dP), dict(loss=L, loss_scale_host=0.25, dent=dent), dict(dp=dP, loss=L, dent=dent)):
+        a, al = ops.sparsemax_bwd(P, supp, want_dloss=True, **kw)
+        b, bl = ops.sparsemax_bwd(P, supp, want_dloss=True, slots=slots, **kw)
+        assert torch.equal(a != 0, b != 0)
+        assert (a - b).abs().max().item() <= 4e-6 * max(1.0, a.abs().max().item())
+        assert torch.equal(al, bl)
+    c = ops.sparsemax_bwd(P, supp, dp=dP, slots=slots)          # without dloss: single tile per warp
+    assert (c - ops.sparsemax_bwd(P, supp, dp=dP)).abs().max().item() <= 4e-6 * max(1.0, dP.abs().max().item())
