@@ -209,10 +209,12 @@ bwd_ragged_tma_kernel(const int64_t* __restrict__ offsets, const int32_t* __rest
 
 // Dense backward driven by the forward's support slots (the gradient sources dp / loss are DENSE
 // matrices, as in marg.py:125, but only their entries on the support matter): per 32-row tile the warp
-// builds dX and dL = ls * P in two shared-memory tiles (zero fill, scatter of <= 8 values per row) and
-// writes each with one bulk (TMA) store.  Reads 64 B of slots + one sector of loss (and dp) per
+// builds dX, then dL = ls * P, in ONE shared-memory tile (zero fill, scatter of <= 8 values per row)
+// and writes each with one bulk (TMA) store.  Reads 64 B of slots + one sector of loss (and dp) per
 // non-zero instead of the 8K..12K bytes of the rows of P, loss, dp; rows marked "scan" are processed
-// densely by the whole warp straight into the tiles.
+// densely by the whole warp straight into the tile.  One 16 KB tile per warp keeps 12 warps per SM
+// (two tiles per warp: 6 warps, 0.28 ms -- the kernel is bound by the latency of the two dependent
+// load rounds, slots then gathers, which more warps hide).
 __global__ void __launch_bounds__(512, 1)
 bwd_slots_tma_kernel(const float* __restrict__ p, const int32_t* __restrict__ supp, const float* __restrict__ dp,
                      const float* __restrict__ loss, const float* __restrict__ loss_scale_dev,
@@ -223,10 +225,8 @@ bwd_slots_tma_kernel(const float* __restrict__ p, const int32_t* __restrict__ su
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int tile_f = kTileRows * K;
-    const int ntile_bufs = dloss != nullptr ? 2 : 1;
-    float* tx = reinterpret_cast<float*>(smem_raw) + (size_t)warp * ntile_bufs * tile_f;
-    float* tl = tx + tile_f;
-    const uint32_t txa = smem_u32(tx), tla = smem_u32(tl);
+    float* tile = reinterpret_cast<float*>(smem_raw) + (size_t)warp * tile_f;
+    const uint32_t ta = smem_u32(tile);
     float ls = loss_scale_host;
     if (loss_scale_dev != nullptr) ls *= __ldg(loss_scale_dev);
 
@@ -254,14 +254,7 @@ bwd_slots_tma_kernel(const float* __restrict__ p, const int32_t* __restrict__ su
             lv[j] = (on && loss != nullptr) ? __ldg(loss + row * K + c[j]) : 0.f;
             gv[j] = (on && dp != nullptr) ? __ldg(dp + row * K + c[j]) : 0.f;
         }
-        // the previous stores of this warp must have finished READING the tiles
-        if (lane == 0) bulk_wait_read0();
-        __syncwarp();
-        for (int i = lane; i < tile_f / 4; i += 32) {
-            sts128(txa + (i << 4), make_float4(0.f, 0.f, 0.f, 0.f));
-            if (dloss != nullptr) sts128(tla + (i << 4), make_float4(0.f, 0.f, 0.f, 0.f));
-        }
-        __syncwarp();
+        float vhat = 0.f;
         if (live && !scan) {
             float sum = 0.f;
 #pragma unroll
@@ -272,58 +265,67 @@ bwd_slots_tma_kernel(const float* __restrict__ p, const int32_t* __restrict__ su
                 gv[j] = g;
                 sum += g;
             }
-            const float vhat = __fdiv_rn(sum, kf);
+            vhat = __fdiv_rn(sum, kf);
+        }
+        const unsigned scan_rows = __ballot_sync(kFull, scan);
+
+        for (int phase = 0; phase < (dloss != nullptr ? 2 : 1); ++phase) {
+            // the previous store of this warp must have finished READING the tile
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+            for (int i = lane; i < tile_f / 4; i += 32) sts128(ta + (i << 4), make_float4(0.f, 0.f, 0.f, 0.f));
+            __syncwarp();
+            if (live && !scan) {
 #pragma unroll
-            for (int j = 0; j < NS; ++j) {
-                if (c[j] >= 0) {
-                    tx[lane * K + c[j]] = __fsub_rn(gv[j], vhat);
-                    if (dloss != nullptr) tl[lane * K + c[j]] = ls * v[j];
+                for (int j = 0; j < NS; ++j)
+                    if (c[j] >= 0) tile[lane * K + c[j]] = (phase == 0) ? __fsub_rn(gv[j], vhat) : ls * v[j];
+            }
+            // rows whose support does not fit the slots: dense, by the whole warp
+            unsigned todo = scan_rows;
+            while (todo) {
+                const int rl = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int64_t rr = row0 + rl;
+                if (phase == 1) {
+                    for (int col = lane; col < K; col += 32) tile[rl * K + col] = ls * __ldg(p + rr * K + col);
+                    continue;
+                }
+                const float de_r = __shfl_sync(kFull, de, rl), kf_r = __shfl_sync(kFull, kf, rl);
+                float sum = 0.f;
+                for (int col = lane; col < K; col += 32) {
+                    const float pv = __ldg(p + rr * K + col);
+                    float g = dp != nullptr ? __ldg(dp + rr * K + col) : 0.f;
+                    if (loss != nullptr) g = fmaf(ls, __ldg(loss + rr * K + col), g);
+                    if (dent != nullptr) g = fmaf(de_r, dent_dp(pv), g);
+                    g = (pv != 0.f) ? g : 0.f;
+                    tile[rl * K + col] = g;  // parked; centred below
+                    sum += g;
+                }
+                sum = group_sum<32>(sum);
+                const float vh = __fdiv_rn(sum, kf_r);
+                for (int col = lane; col < K; col += 32) {
+                    const float pv = __ldg(p + rr * K + col);
+                    tile[rl * K + col] = (pv != 0.f) ? __fsub_rn(tile[rl * K + col], vh) : 0.f;
                 }
             }
-        }
-        // ---- rows whose support does not fit the slots: dense, by the whole warp -------------------
-        unsigned todo = __ballot_sync(kFull, scan);
-        while (todo) {
-            const int rl = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int64_t rr = row0 + rl;
-            const float de_r = __shfl_sync(kFull, de, rl), kf_r = __shfl_sync(kFull, kf, rl);
-            float sum = 0.f;
-            for (int col = lane; col < K; col += 32) {
-                const float pv = __ldg(p + rr * K + col);
-                float g = dp != nullptr ? __ldg(dp + rr * K + col) : 0.f;
-                if (loss != nullptr) g = fmaf(ls, __ldg(loss + rr * K + col), g);
-                if (dent != nullptr) g = fmaf(de_r, dent_dp(pv), g);
-                g = (pv != 0.f) ? g : 0.f;
-                tx[rl * K + col] = g;                      // parked; centred below
-                if (dloss != nullptr) tl[rl * K + col] = ls * pv;
-                sum += g;
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                bulk_store((phase == 0 ? dx : dloss) + row0 * K, ta, (uint32_t)trows * K * 4u);
+                bulk_commit();
             }
-            sum = group_sum<32>(sum);
-            const float vhat = __fdiv_rn(sum, kf_r);
-            for (int col = lane; col < K; col += 32) {
-                const float pv = __ldg(p + rr * K + col);
-                tx[rl * K + col] = (pv != 0.f) ? __fsub_rn(tx[rl * K + col], vhat) : 0.f;
-            }
-        }
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-            bulk_store(dx + row0 * K, txa, (uint32_t)trows * K * 4u);
-            if (dloss != nullptr) bulk_store(dloss + row0 * K, tla, (uint32_t)trows * K * 4u);
-            bulk_commit();
         }
     }
     if (lane == 0) bulk_wait_read0();
 }
 
-bool bwd_slots_supported(int cols) { return cols % 4 == 0 && cols >= 4 && cols <= 256; }
+bool bwd_slots_supported(int cols) { return cols % 4 == 0 && cols >= 4 && cols <= 512; }
 
 int bwd_slots_launch(const float* p, const int32_t* supp, const float* dp, const float* loss, const float* lsd,
                      float lsh, const float* dent, const float* slots, float* dx, float* dloss, int64_t rows, int K,
                      cudaStream_t st)
 {
-    const size_t per_warp = (size_t)(dloss != nullptr ? 2 : 1) * kTileRows * K * 4;
+    const size_t per_warp = (size_t)kTileRows * K * 4;
     int warps = (int)((200 * 1024) / per_warp);
     warps = warps > 16 ? 16 : (warps < 1 ? 1 : warps);
     const size_t smem = per_warp * warps;
