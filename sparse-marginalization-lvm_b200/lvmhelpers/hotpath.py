@@ -26,11 +26,12 @@ class SparsemaxMargStep:
         owns only a shard / micro-batch of the batch (default: ``rows``).
         ``use_slots``: let the weighted loss and the backward read the losses only at the support
         entries the forward handed over (64 B of slots + one sector per non-zero instead of the rows
-        of P and L).  Default: on when the expected support (``capacity / rows``) is at most 6 entries
-        per row -- rows that do not fit the 8 slots fall back to dense processing one by one, which
-        only pays when they are rare."""
+        of P and L), and the compaction read the slots instead of P.  Default: on for large batches
+        (>= 4096 rows) whose expected support (``capacity / rows``) is at most 6 entries per row -- rows
+        that do not fit the 8 slots fall back to dense processing one by one inside a warp, which only
+        pays when they are rare and there are many warps."""
         if use_slots is None:
-            use_slots = capacity <= 6 * rows
+            use_slots = capacity <= 6 * rows and rows >= 4096
         self.use_slots = bool(use_slots)
         self.rows, self.cols, self.device = rows, cols, device
         self.global_rows = int(global_rows) if global_rows is not None else rows
@@ -65,16 +66,16 @@ class SparsemaxMargStep:
         rows, K = self.rows, self.cols
         mark = rec if rec is not None else (lambda name: None)
         mark("sparsemax_fwd")
+        slots = ptr(self.slots) if self.use_slots else None
         check(lib.smlvm_sparsemax_fwd(ptr(x), ptr(self.p), ptr(self.supp), ptr(self.nnz), ptr(self.ent),
-                                      ptr(self.amax), ptr(self.slots), rows, K, st), "smlvm_sparsemax_fwd")
+                                      ptr(self.amax), slots, rows, K, st), "smlvm_sparsemax_fwd")
         mark("scan_counts")
         check(lib.smlvm_scan_counts(ptr(self.nnz), ptr(self.offsets), rows, ptr(self.scan_ws),
                                     self.scan_ws.numel(), st), "smlvm_scan_counts")
         mark("compact_fill")
-        check(lib.smlvm_compact_fill(ptr(self.p), ptr(self.offsets), ptr(self.slots), ptr(self.vals), ptr(self.ri),
+        check(lib.smlvm_compact_fill(ptr(self.p), ptr(self.offsets), slots, ptr(self.vals), ptr(self.ri),
                                      ptr(self.ci), rows, K, st), "smlvm_compact_fill")
         mark("wloss_dense_fwd")
-        slots = ptr(self.slots) if self.use_slots else None
         check(lib.smlvm_wloss_dense_fwd(ptr(self.p), ptr(losses), slots, ptr(self.row_loss), ptr(self.total),
                                         1.0 / self.global_rows, rows, K, ptr(self.red_ws), self.red_ws.numel(), st),
               "smlvm_wloss_dense_fwd")
@@ -101,11 +102,12 @@ class SparsemaxMargStep:
         """Bytes each kernel must move per launch (fp32 = 4 B)."""
         r, K, N_ = self.rows, self.cols, total_nnz
         return {
-            "sparsemax_fwd": r * (8 * K + 4 + 4 + 4 + 8 + 64),  # X in, P out, supp/nnz/entropy/argmax/support slots
+            # X in, P out, supp/nnz/entropy/argmax (+ 64 B of support slots)
+            "sparsemax_fwd": r * (8 * K + 4 + 4 + 4 + 8 + (64 if self.use_slots else 0)),
             "scan_counts": r * (4 + 8),                         # counts in, offsets out
             # support slots (64 B) + two offsets in, (val,row,col) out; the survey's figure for a fill
             # that scans P is r * (4 * K + 8) + 12 * N_ -- the slots written by the forward replace that read
-            "compact_fill": r * (64 + 16) + 12 * N_,
+            "compact_fill": (r * (64 + 16) if self.use_slots else r * (4 * K + 8)) + 12 * N_,
             # P, L in, row loss out  /  P, L, supp (+dent) in, dX, dL out.  With support slots the reads
             # shrink to the slots + one 32-byte sector of L per non-zero
             "wloss_dense_fwd": (r * (64 + 4) + 32 * N_) if self.use_slots else r * (8 * K + 4),
@@ -136,13 +138,14 @@ class SparsemaxMargCompactStep:
         rows, K = b.rows, b.cols
         mark = rec if rec is not None else (lambda name: None)
         mark("sparsemax_fwd")
-        check(lib.smlvm_sparsemax_fwd(ptr(x), ptr(b.p), ptr(b.supp), ptr(b.nnz), ptr(b.ent), ptr(b.amax), ptr(b.slots),
+        slots = ptr(b.slots) if b.use_slots else None
+        check(lib.smlvm_sparsemax_fwd(ptr(x), ptr(b.p), ptr(b.supp), ptr(b.nnz), ptr(b.ent), ptr(b.amax), slots,
                                       rows, K, st), "smlvm_sparsemax_fwd")
         mark("scan_counts")
         check(lib.smlvm_scan_counts(ptr(b.nnz), ptr(b.offsets), rows, ptr(b.scan_ws), b.scan_ws.numel(), st),
               "smlvm_scan_counts")
         mark("compact_fill")
-        check(lib.smlvm_compact_fill(ptr(b.p), ptr(b.offsets), ptr(b.slots), ptr(b.vals), ptr(b.ri), ptr(b.ci), rows, K,
+        check(lib.smlvm_compact_fill(ptr(b.p), ptr(b.offsets), slots, ptr(b.vals), ptr(b.ri), ptr(b.ci), rows, K,
                                      st), "smlvm_compact_fill")
         mark("wloss_ragged_fwd")
         check(lib.smlvm_wloss_ragged_fwd(ptr(b.vals), ptr(losses_ragged), None, None, ptr(b.total), None,

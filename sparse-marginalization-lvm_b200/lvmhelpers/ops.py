@@ -13,6 +13,13 @@ from . import _native as N
 from ._native import lib, check, ptr, stream
 
 
+SLOTS_MIN_ROWS = 4096
+
+
+def _slots_or_none(slots):
+    return slots if (slots is not None and slots.numel() > 0) else None
+
+
 def _f32c(t, name):
     N.require_cuda(t, name)
     if t.dtype != torch.float32:
@@ -58,7 +65,7 @@ def sparsemax_bwd(p, supp, dp=None, loss=None, loss_scale=None, loss_scale_host=
     loss = None if loss is None else _f32c(loss, "loss")
     dent = None if dent is None else _f32c(dent, "dent")
     check(lib.smlvm_sparsemax_bwd(ptr(p), ptr(supp), ptr(dp), ptr(loss), ptr(loss_scale),
-                                  float(loss_scale_host), ptr(dent), ptr(slots), ptr(dx), ptr(dloss), rows, K,
+                                  float(loss_scale_host), ptr(dent), ptr(_slots_or_none(slots)), ptr(dx), ptr(dloss), rows, K,
                                   stream()), "smlvm_sparsemax_bwd")
     return (dx, dloss) if want_dloss else dx
 
@@ -101,11 +108,15 @@ class _SparsemaxStats(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x):
-        out = sparsemax_fwd(x, want_entropy=True, want_argmax=True, want_nnz=True, want_slots=True)
+        # support slots only pay on large batches (rows that do not fit them are processed one by one
+        # inside a warp); small batches are launch-bound and keep the plain kernels
+        big = x.shape[0] >= SLOTS_MIN_ROWS
+        out = sparsemax_fwd(x, want_entropy=True, want_argmax=True, want_nnz=True, want_slots=big)
         ctx.save_for_backward(out["supp"], out["p"])
-        ctx.mark_non_differentiable(out["argmax"], out["nnz"], out["supp"], out["slots"])
+        slots = out["slots"] if big else torch.empty(0, device=x.device)
+        ctx.mark_non_differentiable(out["argmax"], out["nnz"], out["supp"], slots)
         ctx.set_materialize_grads(False)
-        return out["p"], out["entropy"], out["argmax"], out["nnz"], out["supp"], out["slots"]
+        return out["p"], out["entropy"], out["argmax"], out["nnz"], out["supp"], slots
 
     @staticmethod
     def backward(ctx, dp, dent, _damax, _dnnz, _dsupp, _dslots):
@@ -175,7 +186,7 @@ def compact(p, nnz=None, slots=None):
         nnz = compact_count(p)
     offsets = scan_counts(nnz)
     total = int(offsets[-1].item())
-    vals, ri, ci = compact_fill(p, offsets, total, slots=slots)
+    vals, ri, ci = compact_fill(p, offsets, total, slots=_slots_or_none(slots))
     return dict(offsets=offsets, total=total, vals=vals, rows=ri, cols=ci)
 
 
@@ -190,7 +201,7 @@ def wloss_dense_fwd(p, loss, scale=1.0, want_rows=True, want_total=True, slots=N
     row_loss = torch.empty(rows, dtype=torch.float32, device=dev) if want_rows else None
     total = torch.empty((), dtype=torch.float32, device=dev) if want_total else None
     ws = N.reduce_workspace(dev)
-    check(lib.smlvm_wloss_dense_fwd(ptr(p), ptr(loss), ptr(slots), ptr(row_loss), ptr(total), float(scale),
+    check(lib.smlvm_wloss_dense_fwd(ptr(p), ptr(loss), ptr(_slots_or_none(slots)), ptr(row_loss), ptr(total), float(scale),
                                     rows, K, ptr(ws), ws.numel(), stream()),
           "smlvm_wloss_dense_fwd")
     return row_loss, total
