@@ -93,11 +93,13 @@ int smlvm_sparsemax_fwd(const float* x, float* p, int32_t* supp_size, int32_t* n
  *           entropy() marg.py:6-28 w.r.t. p.                                              */
 /* support_slots (NULL = read the dense rows): the pairs written by smlvm_sparsemax_fwd for THIS p;
  * with them the kernel reads 64 B per row plus one sector of loss / dp per non-zero and never reads
- * p, loss or dp in full (rows marked "does not fit" are processed densely).                       */
+ * p, loss or dp in full (rows marked "does not fit" are processed densely).  loss_slots (optional,
+ * with support_slots): loss already gathered on the support by smlvm_wloss_dense_fwd
+ * ([rows, SMLVM_SUPPORT_SLOTS] fp32, same slot order) -- streamed instead of gathered again.        */
 int smlvm_sparsemax_bwd(const float* p, const int32_t* supp_size, const float* dp,
                         const float* loss, const float* loss_scale_dev, float loss_scale_host,
-                        const float* dent, const float* support_slots, float* dx, float* dloss,
-                        int64_t rows, int32_t cols, void* stream);
+                        const float* dent, const float* support_slots, const float* loss_slots,
+                        float* dx, float* dloss, int64_t rows, int32_t cols, void* stream);
 
 /* The same Jacobian-vector product when the upstream gradient lives on the SUPPORT only (the
  * decoder ran on the compacted (row, col) pairs): offsets[rows+1], col_idx[N], vals[N] are the
@@ -221,11 +223,12 @@ int smlvm_sparsemap_bwd(const float* dp, const int64_t* offsets, int32_t only_po
 /* Dense: row_loss[r] = sum_c p[r,c]*loss[r,c] (NULL to skip); total[0] (fp32 device scalar,
  * NULL to skip) = scale * sum_r row_loss[r], accumulated in fp64 in a fixed order.
  * workspace: smlvm_reduce_workspace_bytes() bytes.  support_slots (NULL = read p and loss in
- * full): the forward's (value, column) pairs; only loss entries on the support are then read.      */
+ * full): the forward's (value, column) pairs; only loss entries on the support are then read, and
+ * written to loss_slots[rows, SMLVM_SUPPORT_SLOTS] (NULL to skip) for smlvm_sparsemax_bwd.          */
 size_t smlvm_reduce_workspace_bytes(void);
 int smlvm_wloss_dense_fwd(const float* p, const float* loss, const float* support_slots,
-                          float* row_loss, float* total, float scale, int64_t rows, int32_t cols,
-                          void* workspace, size_t workspace_bytes, void* stream);
+                          float* loss_slots, float* row_loss, float* total, float scale, int64_t rows,
+                          int32_t cols, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Ragged: offsets[rows+1] segments over p[N], loss[N].
  *   row_loss[r] = sum_{j in seg r} p_j*loss_j      (NULL to skip; offsets may then be NULL)

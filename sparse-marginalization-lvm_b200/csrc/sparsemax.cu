@@ -575,8 +575,8 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // sparsemax_bwd_tile.cu
 bool bwd_slots_supported(int cols);
 int bwd_slots_launch(const float* p, const int32_t* supp, const float* dp, const float* loss, const float* lsd,
-                     float lsh, const float* dent, const float* slots, float* dx, float* dloss, int64_t rows, int K,
-                     cudaStream_t st);
+                     float lsh, const float* dent, const float* slots, const float* loss_slots, float* dx,
+                     float* dloss, int64_t rows, int K, cudaStream_t st);
 bool bwd_ragged_tile_supported(int cols);
 int bwd_ragged_tile_launch(const int64_t* offsets, const int32_t* cols_idx, const float* vals, const int32_t* supp,
                            const float* dp, const float* loss, const float* lsd, float lsh, const float* dent,
@@ -648,7 +648,8 @@ extern "C" int smlvm_sparsemax_fwd(const float* x, float* p, int32_t* supp_size,
 extern "C" int smlvm_sparsemax_bwd(const float* p, const int32_t* supp_size, const float* dp,
                                    const float* loss, const float* loss_scale_dev,
                                    float loss_scale_host, const float* dent, const float* support_slots,
-                                   float* dx, float* dloss, int64_t rows, int32_t cols, void* stream)
+                                   const float* loss_slots, float* dx, float* dloss, int64_t rows,
+                                   int32_t cols, void* stream)
 {
     if (rows < 0 || cols < 1) return SMLVM_ERR_ARG;
     if (rows == 0) return SMLVM_OK;
@@ -657,8 +658,8 @@ extern "C" int smlvm_sparsemax_bwd(const float* p, const int32_t* supp_size, con
     cudaStream_t st = as_stream(stream);
     if (support_slots != nullptr && bwd_slots_supported(cols) && rows >= kTileMinRows && aligned16(dx) &&
         (dloss == nullptr || aligned16(dloss)))
-        return bwd_slots_launch(p, supp_size, dp, loss, loss_scale_dev, loss_scale_host, dent, support_slots, dx,
-                                dloss, rows, cols, st);
+        return bwd_slots_launch(p, supp_size, dp, loss, loss_scale_dev, loss_scale_host, dent, support_slots,
+                                loss_slots, dx, dloss, rows, cols, st);
     if (cols <= 1024) {
         RegShape sh = pick_shape(cols);
         const bool vec = (cols % 4 == 0) && aligned16(p) && aligned16(dx) &&

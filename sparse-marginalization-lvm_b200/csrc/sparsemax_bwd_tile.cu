@@ -219,7 +219,8 @@ __global__ void __launch_bounds__(512, 1)
 bwd_slots_tma_kernel(const float* __restrict__ p, const int32_t* __restrict__ supp, const float* __restrict__ dp,
                      const float* __restrict__ loss, const float* __restrict__ loss_scale_dev,
                      float loss_scale_host, const float* __restrict__ dent, const float* __restrict__ slots,
-                     float* __restrict__ dx, float* __restrict__ dloss, int64_t rows, int K)
+                     const float* __restrict__ loss_slots, float* __restrict__ dx, float* __restrict__ dloss,
+                     int64_t rows, int K)
 {
     constexpr int NS = SMLVM_SUPPORT_SLOTS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -248,10 +249,18 @@ bwd_slots_tma_kernel(const float* __restrict__ p, const int32_t* __restrict__ su
         const float kf = live ? (float)__ldg(supp + row) : 1.f;
         const float de = (dent != nullptr && live) ? __ldg(dent + row) : 0.f;
         const bool scan = live && c[0] == -2;
+        if (loss_slots != nullptr && loss != nullptr) {
+            // the weighted-loss forward already gathered L on the support: stream it
+            const float4* ls4 = reinterpret_cast<const float4*>(loss_slots + (live ? row : 0) * NS);
+            const float4 a4 = __ldg(ls4), b4 = __ldg(ls4 + 1);
+            lv[0] = a4.x; lv[1] = a4.y; lv[2] = a4.z; lv[3] = a4.w;
+            lv[4] = b4.x; lv[5] = b4.y; lv[6] = b4.z; lv[7] = b4.w;
+        }
 #pragma unroll
         for (int j = 0; j < NS; ++j) {
             const bool on = live && !scan && c[j] >= 0;
-            lv[j] = (on && loss != nullptr) ? __ldg(loss + row * K + c[j]) : 0.f;
+            if (loss_slots == nullptr || loss == nullptr)
+                lv[j] = (on && loss != nullptr) ? __ldg(loss + row * K + c[j]) : 0.f;
             gv[j] = (on && dp != nullptr) ? __ldg(dp + row * K + c[j]) : 0.f;
         }
         float vhat = 0.f;
@@ -322,8 +331,8 @@ bwd_slots_tma_kernel(const float* __restrict__ p, const int32_t* __restrict__ su
 bool bwd_slots_supported(int cols) { return cols % 4 == 0 && cols >= 4 && cols <= 512; }
 
 int bwd_slots_launch(const float* p, const int32_t* supp, const float* dp, const float* loss, const float* lsd,
-                     float lsh, const float* dent, const float* slots, float* dx, float* dloss, int64_t rows, int K,
-                     cudaStream_t st)
+                     float lsh, const float* dent, const float* slots, const float* loss_slots, float* dx,
+                     float* dloss, int64_t rows, int K, cudaStream_t st)
 {
     const size_t per_warp = (size_t)kTileRows * K * 4;
     int warps = (int)((200 * 1024) / per_warp);
@@ -341,8 +350,8 @@ int bwd_slots_launch(const float* p, const int32_t* supp, const float* dp, const
     const int64_t nt = (rows + kTileRows - 1) / kTileRows;
     const int64_t nd = (nt + warps - 1) / warps;
     const int64_t cp = (int64_t)device_sm_count();
-    bwd_slots_tma_kernel<<<(int)(nd < cp ? nd : cp), warps * 32, smem, st>>>(p, supp, dp, loss, lsd, lsh, dent, slots, dx,
-                                                                              dloss, rows, K);
+    bwd_slots_tma_kernel<<<(int)(nd < cp ? nd : cp), warps * 32, smem, st>>>(p, supp, dp, loss, lsd, lsh, dent, slots,
+                                                                              loss_slots, dx, dloss, rows, K);
     cudaError_t e2 = cudaGetLastError();
     return e2 == cudaSuccess ? SMLVM_OK : (int)e2;
 }

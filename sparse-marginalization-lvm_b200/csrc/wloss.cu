@@ -171,8 +171,8 @@ static int grid_1d(int64_t work_items, int per_cta)
 // owns a row; rows marked "scan" (support does not fit the slots) are dotted densely by the warp.
 __global__ void __launch_bounds__(kThreads)
 wloss_slots_kernel(const float* __restrict__ p, const float* __restrict__ loss, const float* __restrict__ slots,
-                   float* __restrict__ row_loss, float* __restrict__ total, float scale, int64_t rows, int K,
-                   ReduceWs ws)
+                   float* __restrict__ loss_slots, float* __restrict__ row_loss, float* __restrict__ total,
+                   float scale, int64_t rows, int K, ReduceWs ws)
 {
     constexpr int NS = SMLVM_SUPPORT_SLOTS;
     __shared__ double smem[kThreads / 32 + 1];
@@ -199,6 +199,11 @@ wloss_slots_kernel(const float* __restrict__ p, const float* __restrict__ loss, 
 #pragma unroll
         for (int j = 0; j < NS; ++j) s = fmaf(v[j], lv[j], s);  // empty slots carry v = 0
         if (scan) s = 0.f;
+        if (loss_slots != nullptr && live) {  // the gathered losses, for the backward to stream
+            float4* dst = reinterpret_cast<float4*>(loss_slots + r * NS);
+            dst[0] = make_float4(lv[0], lv[1], lv[2], lv[3]);
+            dst[1] = make_float4(lv[4], lv[5], lv[6], lv[7]);
+        }
         unsigned todo = __ballot_sync(kFull, scan);
         while (todo) {
             const int src_lane = __ffs(todo) - 1;
@@ -265,8 +270,9 @@ extern "C" int smlvm_segment_logsumexp(const float* v, const int64_t* offsets, f
 extern "C" size_t smlvm_reduce_workspace_bytes(void) { return 64 + 3 * sizeof(double) * kMaxCtas; }
 
 extern "C" int smlvm_wloss_dense_fwd(const float* p, const float* loss, const float* support_slots,
-                                     float* row_loss, float* total, float scale, int64_t rows,
-                                     int32_t cols, void* workspace, size_t workspace_bytes, void* stream)
+                                     float* loss_slots, float* row_loss, float* total, float scale,
+                                     int64_t rows, int32_t cols, void* workspace, size_t workspace_bytes,
+                                     void* stream)
 {
     if (rows < 0 || cols < 1) return SMLVM_ERR_ARG;
     if (p == nullptr || loss == nullptr) return SMLVM_ERR_ARG;
@@ -275,8 +281,8 @@ extern "C" int smlvm_wloss_dense_fwd(const float* p, const float* loss, const fl
     cudaStream_t st = as_stream(stream);
     if (support_slots != nullptr && rows > 0) {
         const int grid = grid_1d(rows, kThreads);
-        wloss_slots_kernel<<<grid, kThreads, 0, st>>>(p, loss, support_slots, row_loss, total, scale, rows, cols,
-                                                      ws_view(workspace));
+        wloss_slots_kernel<<<grid, kThreads, 0, st>>>(p, loss, support_slots, loss_slots, row_loss, total, scale,
+                                                      rows, cols, ws_view(workspace));
         SMLVM_LAUNCH_CHECK();
         return SMLVM_OK;
     }

@@ -31,7 +31,7 @@ _PROTOTYPES = {
     "smlvm_version": (ctypes.c_int, []),
     "smlvm_error_string": (ctypes.c_char_p, [ctypes.c_int]),
     "smlvm_sparsemax_fwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
-    "smlvm_sparsemax_bwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "smlvm_sparsemax_bwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "smlvm_sparsemax_bwd_ragged": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _i64, _i32, _vp]),
     "smlvm_scan_workspace_bytes": (_sz, [_i64]),
     "smlvm_scan_counts": (ctypes.c_int, [_vp, _vp, _i64, _vp, _sz, _vp]),
@@ -47,7 +47,7 @@ _PROTOTYPES = {
     "smlvm_sparsemap_expand": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _i32, _vp]),
     "smlvm_sparsemap_bwd": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "smlvm_reduce_workspace_bytes": (_sz, []),
-    "smlvm_wloss_dense_fwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _f32, _i64, _i32, _vp, _sz, _vp]),
+    "smlvm_wloss_dense_fwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _i32, _vp, _sz, _vp]),
     "smlvm_wloss_ragged_fwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _i64, _vp, _sz, _vp]),
     "smlvm_wloss_ragged_bwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _f32, _vp, _vp, _i64, _vp]),
     "smlvm_segment_logsumexp": (ctypes.c_int, [_vp, _vp, _f32, _f32, _vp, _i64, _vp]),

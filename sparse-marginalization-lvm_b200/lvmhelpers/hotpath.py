@@ -42,7 +42,8 @@ class SparsemaxMargStep:
         self.p = e(rows, cols)
         self.supp, self.nnz = e(rows, dtype=i32), e(rows, dtype=i32)
         self.ent, self.amax = e(rows), e(rows, dtype=i64)
-        self.slots = e(rows, N.SUPPORT_SLOTS, 2)   # support (value, column) pairs: fwd -> compaction
+        self.slots = e(rows, N.SUPPORT_SLOTS, 2)   # support (value, column) pairs: fwd -> compaction, loss, bwd
+        self.loss_slots = e(rows, N.SUPPORT_SLOTS)  # losses gathered on the support: weighted loss -> bwd
         self.offsets = e(rows + 1, dtype=i64)
         self.vals, self.ri, self.ci = e(self.capacity), e(self.capacity, dtype=i32), e(self.capacity, dtype=i32)
         self.row_loss, self.total = e(rows), e(())
@@ -76,12 +77,13 @@ class SparsemaxMargStep:
         check(lib.smlvm_compact_fill(ptr(self.p), ptr(self.offsets), slots, ptr(self.vals), ptr(self.ri),
                                      ptr(self.ci), rows, K, st), "smlvm_compact_fill")
         mark("wloss_dense_fwd")
-        check(lib.smlvm_wloss_dense_fwd(ptr(self.p), ptr(losses), slots, ptr(self.row_loss), ptr(self.total),
+        lslots = ptr(self.loss_slots) if self.use_slots else None
+        check(lib.smlvm_wloss_dense_fwd(ptr(self.p), ptr(losses), slots, lslots, ptr(self.row_loss), ptr(self.total),
                                         1.0 / self.global_rows, rows, K, ptr(self.red_ws), self.red_ws.numel(), st),
               "smlvm_wloss_dense_fwd")
         mark("sparsemax_bwd")
         check(lib.smlvm_sparsemax_bwd(ptr(self.p), ptr(self.supp), None, ptr(losses), None, 1.0 / self.global_rows,
-                                      ptr(self.dent), slots, ptr(self.dx), ptr(self.dloss), rows, K, st),
+                                      ptr(self.dent), slots, lslots, ptr(self.dx), ptr(self.dloss), rows, K, st),
               "smlvm_sparsemax_bwd")
         mark(None)
         return self.total
@@ -110,8 +112,8 @@ class SparsemaxMargStep:
             "compact_fill": (r * (64 + 16) if self.use_slots else r * (4 * K + 8)) + 12 * N_,
             # P, L in, row loss out  /  P, L, supp (+dent) in, dX, dL out.  With support slots the reads
             # shrink to the slots + one 32-byte sector of L per non-zero
-            "wloss_dense_fwd": (r * (64 + 4) + 32 * N_) if self.use_slots else r * (8 * K + 4),
-            "sparsemax_bwd": ((r * (64 + 4 + 8 * K) + 32 * N_) if self.use_slots else r * (8 * K + 4 + 8 * K))
+            "wloss_dense_fwd": (r * (64 + 32 + 4) + 32 * N_) if self.use_slots else r * (8 * K + 4),
+            "sparsemax_bwd": (r * (64 + 32 + 4 + 8 * K) if self.use_slots else r * (8 * K + 4 + 8 * K))
                              + (4 * r if self.dent is not None else 0),
         }
 

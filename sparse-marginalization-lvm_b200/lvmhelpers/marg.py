@@ -77,9 +77,9 @@ class _FusedMarginalObjective(torch.autograd.Function):
     @staticmethod
     def forward(ctx, scores, losses, p, supp, ent_rows, coeff, slots=None):
         rows = p.shape[0]
-        row_loss, total = ops.wloss_dense_fwd(p, losses, scale=1.0 / rows, slots=slots)
+        row_loss, total, lslots = ops.wloss_dense_fwd(p, losses, scale=1.0 / rows, slots=slots, want_loss_slots=True)
         ctx.save_for_backward(p, supp, losses)
-        ctx.slots = slots
+        ctx.slots, ctx.loss_slots = slots, lslots
         ctx.coeff = float(coeff)
         ctx.mark_non_differentiable(row_loss)
         full = total - ctx.coeff * ent_rows.mean()
@@ -96,7 +96,7 @@ class _FusedMarginalObjective(torch.autograd.Function):
         # one launch: dscores (sparsemax Jacobian of g*L/B + entropy term) and dlosses = g*P/B
         dscores, dlosses = ops.sparsemax_bwd(p, supp, loss=losses, loss_scale=g,
                                              loss_scale_host=1.0 / rows, dent=dent,
-                                             want_dloss=True, slots=ctx.slots)
+                                             want_dloss=True, slots=ctx.slots, loss_slots=ctx.loss_slots)
         return dscores, dlosses, None, None, None, None, None
 
 

@@ -51,7 +51,7 @@ def sparsemax_fwd(x, want_entropy=False, want_argmax=False, want_nnz=True, want_
 
 
 def sparsemax_bwd(p, supp, dp=None, loss=None, loss_scale=None, loss_scale_host=1.0, dent=None,
-                  want_dloss=False, out=None, out_dloss=None, slots=None):
+                  want_dloss=False, out=None, out_dloss=None, slots=None, loss_slots=None):
     """Fused Jacobian-vector product; see smlvm_sparsemax_bwd in include/smlvm.h.
     With want_dloss also returns dloss = loss_scale * p (decoder side of the weighted loss).
     ``slots``: the forward's support pairs for this ``p`` (only the support entries of dp / loss are
@@ -65,7 +65,8 @@ def sparsemax_bwd(p, supp, dp=None, loss=None, loss_scale=None, loss_scale_host=
     loss = None if loss is None else _f32c(loss, "loss")
     dent = None if dent is None else _f32c(dent, "dent")
     check(lib.smlvm_sparsemax_bwd(ptr(p), ptr(supp), ptr(dp), ptr(loss), ptr(loss_scale),
-                                  float(loss_scale_host), ptr(dent), ptr(_slots_or_none(slots)), ptr(dx), ptr(dloss), rows, K,
+                                  float(loss_scale_host), ptr(dent), ptr(_slots_or_none(slots)), ptr(_slots_or_none(loss_slots)),
+                                  ptr(dx), ptr(dloss), rows, K,
                                   stream()), "smlvm_sparsemax_bwd")
     return (dx, dloss) if want_dloss else dx
 
@@ -193,7 +194,9 @@ def compact(p, nnz=None, slots=None):
 # --------------------------------------------------------------------------------------
 # (4) weighted loss
 # --------------------------------------------------------------------------------------
-def wloss_dense_fwd(p, loss, scale=1.0, want_rows=True, want_total=True, slots=None):
+def wloss_dense_fwd(p, loss, scale=1.0, want_rows=True, want_total=True, slots=None, want_loss_slots=False):
+    """... With ``slots`` and ``want_loss_slots`` also returns the losses gathered on the support
+    ([rows, 8]) as a third value, for ``sparsemax_bwd(loss_slots=...)``."""
     p = _f32c(p, "p")
     loss = _f32c(loss, "loss")
     rows, K = p.shape
@@ -201,9 +204,14 @@ def wloss_dense_fwd(p, loss, scale=1.0, want_rows=True, want_total=True, slots=N
     row_loss = torch.empty(rows, dtype=torch.float32, device=dev) if want_rows else None
     total = torch.empty((), dtype=torch.float32, device=dev) if want_total else None
     ws = N.reduce_workspace(dev)
-    check(lib.smlvm_wloss_dense_fwd(ptr(p), ptr(loss), ptr(_slots_or_none(slots)), ptr(row_loss), ptr(total), float(scale),
+    slots = _slots_or_none(slots)
+    lslots = torch.empty((rows, N.SUPPORT_SLOTS), dtype=torch.float32, device=dev) \
+        if (want_loss_slots and slots is not None) else None
+    check(lib.smlvm_wloss_dense_fwd(ptr(p), ptr(loss), ptr(slots), ptr(lslots), ptr(row_loss), ptr(total), float(scale),
                                     rows, K, ptr(ws), ws.numel(), stream()),
           "smlvm_wloss_dense_fwd")
+    if want_loss_slots:
+        return row_loss, total, lslots
     return row_loss, total
 
 

@@ -68,7 +68,7 @@ def test_argument_validation_needs_no_device():
     assert lib.smlvm_sparsemax_fwd(None, None, None, None, None, None, None, 0, 4, None) == 0   # empty batch
     assert lib.smlvm_sparsemax_fwd(None, None, None, None, None, None, None, 4, 4, None) == -1  # NULL x
     assert lib.smlvm_sparsemax_fwd(1 << 20, 1 << 21, None, None, None, None, None, 4, 10000, None) == -2
-    assert lib.smlvm_sparsemax_bwd(None, None, None, None, None, 1.0, None, None, None, None, 0, 4, None) == 0
+    assert lib.smlvm_sparsemax_bwd(None, None, None, None, None, 1.0, None, None, None, None, None, 0, 4, None) == 0
     assert lib.smlvm_topk_bits(1 << 20, 1 << 21, None, None, 4, 3, 9, None) == -1   # k > 2^n
     assert lib.smlvm_topk_bits(1 << 20, 1 << 21, None, None, 4, 8, 1, None) == -1   # k < 2 (binary_topk.h:102)
     assert lib.smlvm_topk_bits(1 << 20, 1 << 21, None, None, 4, 600, 4, None) == -2  # n > CODE_MAX_SIZE

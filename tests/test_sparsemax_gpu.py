@@ -228,5 +228,10 @@ def test_slot_driven_dense_kernels_equal_dense_reads(rows, K, scale):
         assert torch.equal(a != 0, b != 0)
         assert (a - b).abs().max().item() <= 4e-6 * max(1.0, a.abs().max().item())
         assert torch.equal(al, bl)
-    c = ops.sparsemax_bwd(P, supp, dp=dP, slots=slots)          # without dloss: single tile per warp
+    # losses gathered once by the weighted-loss forward, streamed by the backward
+    _, _, lsl = ops.wloss_dense_fwd(P, L, scale=1.0 / rows, slots=slots, want_loss_slots=True)
+    d0 = ops.sparsemax_bwd(P, supp, loss=L, loss_scale_host=0.25, dent=dent)
+    d1 = ops.sparsemax_bwd(P, supp, loss=L, loss_scale_host=0.25, dent=dent, slots=slots, loss_slots=lsl)
+    assert (d0 - d1).abs().max().item() <= 4e-6 * max(1.0, d0.abs().max().item())
+    c = ops.sparsemax_bwd(P, supp, dp=dP, slots=slots)          # without dloss
     assert (c - ops.sparsemax_bwd(P, supp, dp=dP)).abs().max().item() <= 4e-6 * max(1.0, dP.abs().max().item())
