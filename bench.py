@@ -417,7 +417,11 @@ def run_native(args, rank, local_rank, world):
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(top)
+        tj = json.load(open(tpath))
+        suffix = "" if step.use_slots else "_without_slots"
+        traffic = tj.get(top + suffix, tj.get(top))
+        for k in kernels:   # measured DRAM bytes per launch (ncu), next to the algorithmic figure
+            kernels[k]["traffic"] = tj.get(k + suffix, tj.get(k))
     step_bytes = sum(abytes.values())
     ms_per_step = ms / args.steps
     value = rows * world / (ms_per_step * 1e-3)

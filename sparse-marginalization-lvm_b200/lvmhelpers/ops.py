@@ -195,8 +195,10 @@ def compact(p, nnz=None, slots=None):
 # (4) weighted loss
 # --------------------------------------------------------------------------------------
 def wloss_dense_fwd(p, loss, scale=1.0, want_rows=True, want_total=True, slots=None, want_loss_slots=False):
-    """... With ``slots`` and ``want_loss_slots`` also returns the losses gathered on the support
-    ([rows, 8]) as a third value, for ``sparsemax_bwd(loss_slots=...)``."""
+    """Row losses sum_c p[r,c] * loss[r,c] and scale * their sum (marg.py:125-126) -> (row_loss, total).
+    ``slots``: the forward's support pairs -- only the loss entries on the support are then read;
+    with ``want_loss_slots`` the gathered losses ([rows, 8]) are returned as a third value for
+    ``sparsemax_bwd(loss_slots=...)``."""
     p = _f32c(p, "p")
     loss = _f32c(loss, "loss")
     rows, K = p.shape
