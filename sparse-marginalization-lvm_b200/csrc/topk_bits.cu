@@ -146,24 +146,43 @@ __global__ void __launch_bounds__(kThreads)
 bits_score_bwd_kernel(const uint32_t* __restrict__ bits, const float* __restrict__ ds,
                       float* __restrict__ dx, int64_t rows, int n, int k)
 {
-    extern __shared__ float stage_all[];
+    extern __shared__ __align__(16) float stage_all[];
     const int words_n = (n + 31) >> 5;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int per_warp = k + k * words_n;
+    const int kpad = (k + 3) & ~3;                      // keeps the word array 16-byte aligned
+    const int per_warp = kpad + ((k * words_n + 3) & ~3);
     float* dss = stage_all + warp * per_warp;
-    uint32_t* ws = reinterpret_cast<uint32_t*>(dss + k);
+    uint32_t* ws = reinterpret_cast<uint32_t*>(dss + kpad);
     const int64_t warps_total = (int64_t)gridDim.x * (kThreads / kWarp);
     for (int64_t r = (int64_t)blockIdx.x * (kThreads / kWarp) + warp; r < rows; r += warps_total) {
         __syncwarp();
         for (int j = lane; j < k; j += 32) dss[j] = __ldg(ds + r * k + j);
         for (int e = lane; e < k * words_n; e += 32) ws[e] = __ldg(bits + r * k * words_n + e);
         __syncwarp();
-        for (int q = 0; q < words_n; ++q) {
-            float acc = 0.f;
-            for (int j = 0; j < k; ++j)
-                acc += ((ws[j * words_n + q] >> lane) & 1u) ? dss[j] : 0.f;
-            const int i = q * 32 + lane;
-            if (i < n) stg_stream(dx + r * n + i, acc);
+        if (words_n == 4) {
+            // n in (96, 128]: the four words of a configuration in one 128-bit shared load
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            for (int j = 0; j < k; ++j) {
+                const uint4 w4 = *reinterpret_cast<const uint4*>(ws + 4 * j);
+                const float dj = dss[j];
+                a0 += ((w4.x >> lane) & 1u) ? dj : 0.f;
+                a1 += ((w4.y >> lane) & 1u) ? dj : 0.f;
+                a2 += ((w4.z >> lane) & 1u) ? dj : 0.f;
+                a3 += ((w4.w >> lane) & 1u) ? dj : 0.f;
+            }
+            float* out = dx + r * n;
+            stg_stream(out + lane, a0);
+            stg_stream(out + 32 + lane, a1);
+            stg_stream(out + 64 + lane, a2);
+            if (96 + lane < n) stg_stream(out + 96 + lane, a3);
+        } else {
+            for (int q = 0; q < words_n; ++q) {
+                float acc = 0.f;
+                for (int j = 0; j < k; ++j)
+                    acc += ((ws[j * words_n + q] >> lane) & 1u) ? dss[j] : 0.f;
+                const int i = q * 32 + lane;
+                if (i < n) stg_stream(dx + r * n + i, acc);
+            }
         }
     }
 }
@@ -265,7 +284,7 @@ extern "C" int smlvm_bits_score_bwd(const uint32_t* bits, const float* dscores_k
     if (bits == nullptr || dscores_k == nullptr || dx == nullptr) return SMLVM_ERR_ARG;
     int64_t need = (rows + 7) / 8;
     int64_t cap = (int64_t)device_sm_count() * 8;
-    const size_t smem = (size_t)(kThreads / kWarp) * (k + k * ((n + 31) / 32)) * sizeof(float);
+    const size_t smem = (size_t)(kThreads / kWarp) * (((k + 3) & ~3) + ((k * ((n + 31) / 32) + 3) & ~3)) * sizeof(float);
     bits_score_bwd_kernel<<<(int)(need < cap ? need : cap), kThreads, smem, as_stream(stream)>>>(
         bits, dscores_k, dx, rows, n, k);
     SMLVM_LAUNCH_CHECK();
