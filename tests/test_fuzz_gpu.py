@@ -1,0 +1,25 @@
+"""Randomised parity sweep of the categorical pipeline (forward, slots, compaction, slot-driven loss and
+backward) against the CPU oracle: random shapes and scales plus adversarial rows (exact ties, constant rows,
+gaps of exactly 1, -inf masks, huge magnitudes, one-hot rows).  tools/fuzz_sparsemax.py is the long form."""
+import importlib.util
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _fuzz():
+    spec = importlib.util.spec_from_file_location("fuzz_sparsemax", os.path.join(ROOT, "tools", "fuzz_sparsemax.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("seed", [3, 11])
+def test_fuzz_categorical_pipeline(seed):
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    assert _fuzz().run(seed=seed, n_cases=12, verbose=False) == 0
