@@ -11,8 +11,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _fuzz():
-    spec = importlib.util.spec_from_file_location("fuzz_sparsemax", os.path.join(ROOT, "tools", "fuzz_sparsemax.py"))
+def _fuzz(name="fuzz_sparsemax"):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "tools", name + ".py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
@@ -23,3 +23,17 @@ def test_fuzz_categorical_pipeline(seed):
     if not torch.cuda.is_available():
         pytest.skip("needs a GPU")
     assert _fuzz().run(seed=seed, n_cases=12, verbose=False) == 0
+
+
+def test_fuzz_topk_bits():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    assert _fuzz("fuzz_solver").run_topk(seed=5, n_cases=15, verbose=False) == 0
+
+
+def test_fuzz_sparsemap_solver():
+    """Every sample's active-set size and iteration count against the oracle's batch loop (capacity tiers
+    included: n = 128 rows that outgrow a tier are re-solved), full solutions on a sample of rows."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    assert _fuzz("fuzz_solver").run_solver(seed=5, n_cases=8, rows=256, verbose=False) == 0
