@@ -61,7 +61,8 @@ __host__ __device__ inline size_t solver_smem_bytes(int n, int cap)
 {
     const int LD = (cap + 1) | 1, W = (n + 31) / 32;
     const int LV = LD > n ? LD : n;  // d doubles as the budget oracle's gain vector [n]
-    size_t dbl = (size_t)LD * LD + 3 * cap + 2 * LV + 4 * n + 40 + (size_t)terms_chunk(cap);
+    const int ne = (n + 1) & ~1, ce = (terms_chunk(cap) + 1) & ~1;
+    size_t dbl = (size_t)LD * LD + 3 * cap + 2 * LV + 2 * n + 2 * ne + 40 + (size_t)ce;
     size_t b = dbl * sizeof(double);
     b += (size_t)(2 * cap + 8) * sizeof(int);
     b += (size_t)(cap * W + W) * sizeof(uint32_t);
@@ -72,8 +73,13 @@ __host__ __device__ inline size_t solver_smem_bytes(int n, int cap)
 __device__ inline SolverSmem carve(unsigned char* raw, int n, int cap)
 {
     const int LD = (cap + 1) | 1, W = (n + 31) / 32;
+    const int ne = (n + 1) & ~1, ce = (terms_chunk(cap) + 1) & ~1;
     SolverSmem s;
     double* d = reinterpret_cast<double*>(raw);
+    // the three arrays that are folded in sequence come first: 16-byte aligned, son/soff contiguous
+    s.terms = d; d += ce;
+    s.son = d; d += ne;
+    s.soff = d; d += ne;
     s.inv = d; d += (size_t)LD * LD;
     s.score = d; d += cap;
     s.p = d; d += cap;
@@ -83,10 +89,7 @@ __device__ inline SolverSmem carve(unsigned char* raw, int n, int cap)
     s.r = d; d += LV;
     s.eta = d; d += n;
     s.t = d; d += n;
-    s.son = d; d += n;
-    s.soff = d; d += n;
     s.red = d; d += 40;
-    s.terms = d; d += terms_chunk(cap);
     int* ip = reinterpret_cast<int*>(d);
     s.perm = ip; ip += cap;
     s.freestk = ip; ip += cap;
@@ -105,10 +108,10 @@ __device__ __forceinline__ int block_sum_int(int v, double* red)
 
 // ---- factor MAP oracles: read (son, soff[, t]), write the vertex to sm.ynew, return value ----
 
-// lvmhelpers/bernoulli.h:14-35
+// lvmhelpers/bernoulli.h:14-35.  Thread i reads the scores it wrote itself; one barrier.
 __device__ double map_bernoulli(const SolverSmem& sm, int n)
 {
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int n32 = (n + 31) & ~31;
     double part = 0.0;
     for (int i = threadIdx.x; i < n32; i += blockDim.x) {
@@ -119,7 +122,13 @@ __device__ double map_bernoulli(const SolverSmem& sm, int n)
         const unsigned b = __ballot_sync(kFull, y);
         if (lane == 0) sm.ynew[i >> 5] = b;
     }
-    return block_sum(part, sm.red);
+    if (warp * 32 < n32) part = group_sum<32>(part);
+    if (lane == 0) sm.red[warp] = part;
+    __syncthreads();
+    double tot = 0.0;
+    const int wn = min(nw, n32 >> 5);
+    for (int w = 0; w < wn; ++w) tot += sm.red[w];
+    return tot;
 }
 
 // lvmhelpers/budget.h:24-85.  Uses sm.d as the gain vector.
@@ -216,28 +225,65 @@ __device__ __forceinline__ double factor_map(const SolverSmem& sm, int n, int bu
 // sums (z, tau, d, u) are sequential per thread anyway; the two whole-matrix / whole-vector sums
 // below are chains: warp 0 forms 32 terms at a time in parallel and folds them in sequence.
 
-// score of the vertex in sm.ynew under (eta, 0[, t]): bernoulli.h:38-54 / sequence.h:154-179.
-// ONE thread, sequential fp64 adds in bit order (adding 0.0 for a clear bit is exact).
-template <int KIND>
-__device__ double evaluate_serial(const SolverSmem& sm, int n)
+// acc = (((acc -+ t_0) -+ t_1) -+ ...) over `total` doubles of a 16-byte aligned shared array, by ONE
+// thread.  The next eight terms are loaded (128-bit) while the current eight are folded, so the chain
+// advances at DADD latency instead of load + DADD latency.
+template <bool SUB>
+__device__ __forceinline__ double fold_serial(const double* terms, int total, double s)
 {
-    // only the set bits contribute: a clear bit adds an exact 0.0 in libad3's loop
-    double acc = 0.0;
+    const double2* t2 = reinterpret_cast<const double2*>(terms);
+    int e = 0;
+    if (total >= 8) {
+        double2 c0 = t2[0], c1 = t2[1], c2 = t2[2], c3 = t2[3];
+        for (e = 8; e + 8 <= total; e += 8) {
+            const double2 n0 = t2[(e >> 1)], n1 = t2[(e >> 1) + 1], n2 = t2[(e >> 1) + 2], n3 = t2[(e >> 1) + 3];
+#define SMLVM_FOLD(v) s = SUB ? __dsub_rn(s, (v)) : __dadd_rn(s, (v))
+            SMLVM_FOLD(c0.x); SMLVM_FOLD(c0.y); SMLVM_FOLD(c1.x); SMLVM_FOLD(c1.y);
+            SMLVM_FOLD(c2.x); SMLVM_FOLD(c2.y); SMLVM_FOLD(c3.x); SMLVM_FOLD(c3.y);
+            c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        }
+        SMLVM_FOLD(c0.x); SMLVM_FOLD(c0.y); SMLVM_FOLD(c1.x); SMLVM_FOLD(c1.y);
+        SMLVM_FOLD(c2.x); SMLVM_FOLD(c2.y); SMLVM_FOLD(c3.x); SMLVM_FOLD(c3.y);
+    }
+    for (; e < total; ++e) SMLVM_FOLD(terms[e]);
+#undef SMLVM_FOLD
+    return s;
+}
+
+// score of the vertex in sm.ynew under (eta, 0[, t]): bernoulli.h:38-54 / sequence.h:154-179 -- a
+// sequential fp64 sum in bit order (adding 0.0 for a clear bit is exact, so only set bits count).
+// One WARP: the set bits' scores are compacted in bit order into `list` (son/soff, free between two
+// oracle calls; for the sequence every set bit is followed by its transition score or an exact 0.0),
+// then lane 0 folds the dense list.  Result valid in lane 0.
+template <int KIND>
+__device__ double evaluate_warp(const SolverSmem& sm, int n)
+{
+    const int lane = threadIdx.x & 31;
     const int W = (n + 31) >> 5;
+    double* list = sm.son;  // [2 * even(n)] with soff
+    int base = 0;
     uint32_t carry = 0u;  // bit 31 of the previous word (the left neighbour of bit 0)
     for (int q = 0; q < W; ++q) {
         const uint32_t word = sm.ynew[q];
-        uint32_t rem = word;
-        const uint32_t pairs = word & ((word << 1) | carry);  // bit i set with bit i-1 set
-        while (rem) {
-            const int b = __ffs(rem) - 1;
-            rem &= rem - 1;
-            const int i = q * 32 + b;
-            acc = __dadd_rn(acc, sm.eta[i]);
-            if (KIND == SMLVM_FACTOR_SEQUENCE_BINARY && ((pairs >> b) & 1u)) acc = __dadd_rn(acc, sm.t[i - 1]);
+        const int i = q * 32 + lane;
+        const bool on = (word >> lane) & 1u;
+        const int rank = base + __popc(word & ((1u << lane) - 1u));
+        if (KIND == SMLVM_FACTOR_SEQUENCE_BINARY) {
+            const uint32_t pairs = word & ((word << 1) | carry);  // bit i set with bit i-1 set
+            if (on) {
+                list[2 * rank] = sm.eta[i];
+                list[2 * rank + 1] = ((pairs >> lane) & 1u) ? sm.t[i - 1] : 0.0;
+            }
+        } else if (on) {
+            list[rank] = sm.eta[i];
         }
+        base += __popc(word);
         carry = word >> 31;
     }
+    __syncwarp();
+    double acc = 0.0;
+    if (lane == 0)
+        acc = fold_serial<false>(list, KIND == SMLVM_FACTOR_SEQUENCE_BINARY ? 2 * base : base, 0.0);
     return acc;
 }
 
@@ -267,16 +313,7 @@ __device__ __forceinline__ void schur_terms_fill(const SolverSmem& sm, int m, in
 }
 __device__ __forceinline__ double schur_fold(const SolverSmem& sm, int total, double s)
 {
-    int e = 0;
-    for (; e + 8 <= total; e += 8) {
-        double t[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) t[q] = sm.terms[e + q];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) s = __dsub_rn(s, t[q]);
-    }
-    for (; e < total; ++e) s = __dsub_rn(s, sm.terms[e]);
-    return s;
+    return fold_serial<true>(sm.terms, total, s);
 }
 // rows [a0, a1) that fit one round of the terms buffer (at least one row: a row has <= cap+1 terms)
 __device__ __forceinline__ int schur_round_end(int m, int a0, int chunk, int& count)
@@ -304,7 +341,7 @@ __device__ __forceinline__ int common_values(const uint32_t* a, const uint32_t* 
 }
 
 template <int KIND>
-__global__ void sparsemap_fwd_kernel(const float* __restrict__ x, const float* __restrict__ t,
+__global__ void __launch_bounds__(256, 4) sparsemap_fwd_kernel(const float* __restrict__ x, const float* __restrict__ t,
                                      const double* __restrict__ init_scores, int budget,
                                      int max_iter, int64_t rows, int n, int cap, int first_tier,
                                      int last_tier, float* __restrict__ p_pad,
@@ -343,9 +380,8 @@ __global__ void sparsemap_fwd_kernel(const float* __restrict__ x, const float* _
         // (init_active_set_from_scores, sparsemap.py:25-27, or the LP solution under eta)
         factor_map<KIND>(sm, n, budget, init_scores != nullptr ? nullptr : sm.t);
         __syncthreads();
-        {
-            double sc0 = 0.0;
-            if (tid == 0) sc0 = evaluate_serial<KIND>(sm, n);
+        if (tid < 32) {
+            const double sc0 = evaluate_warp<KIND>(sm, n);
             if (tid == 0) {
                 sm.perm[0] = 0;
                 sm.score[0] = sc0;
@@ -356,8 +392,8 @@ __global__ void sparsemap_fwd_kernel(const float* __restrict__ x, const float* _
                 sm.inv[LD] = 1.0;
                 sm.inv[LD + 1] = 0.0;
             }
-            for (int q = tid; q < W; q += T) sm.bits[q] = sm.ynew[q];
         }
+        for (int q = tid; q < W; q += T) sm.bits[q] = sm.ynew[q];
         int m = 1;          // |A|
         int nfree = cap - 1; // free-stack height (slot 0 popped)
         int hw = 2;          // physical indices < hw have been touched
@@ -365,8 +401,11 @@ __global__ void sparsemap_fwd_kernel(const float* __restrict__ x, const float* _
         double tau = 0.0;
         int st = SMLVM_SOLVE_MAX_ITER;
         int it = 0;
+        const int eval_warp = T > 32 ? 1 : 0;  // folds the new vertex's score while thread 0 folds the Schur terms
         __syncthreads();
 
+        // Barrier discipline: every phase below ends with ONE barrier; what a phase reads was written
+        // before the previous barrier, what it writes is not read by anyone inside the same phase.
         for (it = 0; it < max_iter; ++it) {
             if (changed) {
                 // ---- [tau; z] = inv * [1; score], rows in solver order ---------------------
@@ -416,20 +455,23 @@ __global__ void sparsemap_fwd_kernel(const float* __restrict__ x, const float* _
                 __syncthreads();
                 const bool exist_blocking = sm.misc[0] != 0;
                 if (!exist_blocking) {
+                    // p is next read by a later line search (barriers in between): no barrier here
                     for (int a = tid; a < m; a += T) {
                         const int s = sm.perm[a];
                         sm.p[s] = sm.z[s];
                     }
                     changed = false;
-                    __syncthreads();
                 } else {
                     const int blocking = sm.misc[1];
                     double alpha = sm.red[37];
                     if (alpha > 1.0) alpha = 1.0;
                     const int srem = sm.perm[blocking];
                     const int rem = srem + 1;
+                    // the order entries that slide down over the removed one, read before the barrier
+                    int shift_a = -1, shift_s = 0;
                     for (int a = tid; a < m; a += T) {
                         const int s = sm.perm[a];
+                        if (a >= blocking && a + 1 < m) { shift_a = a; shift_s = sm.perm[a + 1]; }
                         if (alpha == 1.0) {
                             sm.p[s] = sm.z[s];
                         } else {
@@ -445,22 +487,22 @@ __global__ void sparsemap_fwd_kernel(const float* __restrict__ x, const float* _
                     for (int i = tid; i < hw; i += T)
                         sm.d[i] = (i == rem) ? 0.0 : __dmul_rn(-sval, sm.inv[rem * LD + i]);
                     __syncthreads();
+                    // (the freed row and column are cleared in the same pass: d[rem] = 0 leaves
+                    //  them untouched by the down-date itself)
                     for (int i = tid >> 5; i < hw; i += T >> 5) {
                         const double di = __dmul_rn(invs, sm.d[i]);
-                        for (int j = tid & 31; j < hw; j += 32)
-                            sm.inv[i * LD + j] = __dsub_rn(sm.inv[i * LD + j], __dmul_rn(di, sm.d[j]));
+                        for (int j = tid & 31; j < hw; j += 32) {
+                            const double v = __dsub_rn(sm.inv[i * LD + j], __dmul_rn(di, sm.d[j]));
+                            sm.inv[i * LD + j] = (i == rem || j == rem) ? 0.0 : v;
+                        }
                     }
-                    __syncthreads();
-                    // clear the freed row/column, drop it from the order, recycle the slot
-                    for (int i = tid; i < hw; i += T) {
-                        sm.inv[rem * LD + i] = 0.0;
-                        sm.inv[i * LD + rem] = 0.0;
-                    }
-                    __syncthreads();
-                    if (tid == 0) {
+                    // drop the vertex from the order (T >= m is not guaranteed: strided), recycle the slot
+                    if (T >= m) {
+                        if (shift_a >= 0) sm.perm[shift_a] = shift_s;
+                    } else if (tid == 0) {
                         for (int a = blocking; a + 1 < m; ++a) sm.perm[a] = sm.perm[a + 1];
-                        sm.freestk[nfree] = srem;
                     }
+                    if (tid == 0) sm.freestk[nfree] = srem;
                     ++nfree;
                     --m;
                     changed = true;
@@ -480,21 +522,23 @@ __global__ void sparsemap_fwd_kernel(const float* __restrict__ x, const float* _
                     sm.son[i] = __dsub_rn(sm.eta[i], uon);
                     sm.soff[i] = __dsub_rn(0.0, uoff);
                 }
-                __syncthreads();
-                const double value = factor_map<KIND>(sm, n, budget, sm.t);
-                __syncthreads();
+                // Bernoulli / budget oracles read, per thread, the scores that thread wrote
+                if (KIND == SMLVM_FACTOR_SEQUENCE_BINARY) __syncthreads();
+                const double value = factor_map<KIND>(sm, n, budget, sm.t);  // ends behind a barrier
                 if (value <= tau + 1e-9) {
                     st = SMLVM_SOLVE_CONVERGED;
                     ++it;
                     break;
                 }
-                // already active?  (libad3 clears its cache here; we keep the solution)
+                // ---- insertion: r = [1, common(y_j, y^)]; y^ already active iff common == n ---
+                // (libad3 clears its cache in that case; we keep the solution)
                 int same = 0;
+                if (tid == 0) sm.r[0] = 1.0;
                 for (int a = tid; a < m; a += T) {
-                    const uint32_t* ya = sm.bits + sm.perm[a] * W;
-                    bool eq = true;
-                    for (int q = 0; q < W; ++q) eq = eq && (ya[q] == sm.ynew[q]);
-                    same |= eq ? 1 : 0;
+                    const int s = sm.perm[a];
+                    const int c = common_values(sm.bits + s * W, sm.ynew, W, n);
+                    sm.r[s + 1] = (double)c;
+                    same |= (c == n) ? 1 : 0;
                 }
                 same = __syncthreads_or(same);
                 if (same) {
@@ -502,18 +546,12 @@ __global__ void sparsemap_fwd_kernel(const float* __restrict__ x, const float* _
                     ++it;
                     break;
                 }
-                // ---- insertion: r = [1, common(y_j, y^)], d = inv r, s = n - r'd -------------
-                for (int i = tid; i < hw; i += T) sm.r[i] = 0.0;
-                __syncthreads();
-                if (tid == 0) sm.r[0] = 1.0;
-                for (int a = tid; a < m; a += T) {
-                    const int s = sm.perm[a];
-                    sm.r[s + 1] = (double)common_values(sm.bits + s * W, sm.ynew, W, n);
-                }
-                __syncthreads();
-                // the two order-sensitive sums: terms formed by the whole CTA, folded by thread 0
-                // (Schur complement) and thread 32 (score of the new vertex); meanwhile the other
-                // threads (reverse mapping) form d_j = sum_i inv[i][j] r_i, i in solver order
+                // ---- d = inv r, s = n - r'd ---------------------------------------------------
+                // the two order-sensitive sums: Schur terms formed by the whole CTA, folded by thread 0;
+                // the score of the new vertex compacted and folded by another warp; meanwhile the
+                // threads at the far end form d_j = sum_i inv[i][j] r_i (i in solver order) for EVERY
+                // touched index j: on a free slot the column of inv is zero, so d_j = 0 and the
+                // rank-one update below leaves free rows and columns at zero without any flags.
                 const int chunk = terms_chunk(cap);
                 int cnt0 = 0;
                 int a_next = schur_round_end(m, 0, chunk, cnt0);
@@ -521,9 +559,11 @@ __global__ void sparsemap_fwd_kernel(const float* __restrict__ x, const float* _
                 __syncthreads();
                 double sfold = (double)n;
                 if (tid == 0) sfold = schur_fold(sm, cnt0, sfold);
-                if (tid == 32 % T) sm.red[35] = evaluate_serial<KIND>(sm, n);
-                for (int a = T - 1 - tid; a <= m; a += T) {
-                    const int jp = (a == 0) ? 0 : sm.perm[a - 1] + 1;
+                if ((tid >> 5) == eval_warp) {
+                    const double scn = evaluate_warp<KIND>(sm, n);
+                    if ((tid & 31) == 0) sm.red[35] = scn;
+                }
+                for (int jp = T - 1 - tid; jp < hw; jp += T) {
                     double acc = __dmul_rn(sm.inv[jp], sm.r[0]);
 #pragma unroll 4
                     for (int b = 1; b <= m; ++b) {
@@ -559,36 +599,28 @@ __global__ void sparsemap_fwd_kernel(const float* __restrict__ x, const float* _
                 const int snew = sm.freestk[nfree - 1];
                 const int pn = snew + 1;
                 const int hw_new = max(hw, pn + 1);
-                // zero d on inactive indices (r is zero there, but d was only written for active)
-                // -> use r as the activity mask: r[0] = 1 and r[slot+1] >= 0 ... common can be 0,
-                //    so mark activity explicitly through a pass over perm.
-                for (int i = tid; i < hw_new; i += T) sm.r[i] = 0.0;  // reuse r as activity flags
-                __syncthreads();
-                if (tid == 0) sm.r[0] = 1.0;
-                for (int a = tid; a < m; a += T) sm.r[sm.perm[a] + 1] = 1.0;
-                __syncthreads();
+                // ---- block update of inv: old part += d d'/s, new row/column = -d/s, corner 1/s.
+                // One phase: the rank-one pass skips row / column pn (a free slot: d = 0 there),
+                // which the row/column pass writes.
                 for (int i = tid >> 5; i < hw; i += T >> 5) {
-                    if (sm.r[i] == 0.0) continue;
+                    if (i == pn) continue;
                     const double di = __dmul_rn(invs, sm.d[i]);
                     for (int j = tid & 31; j < hw; j += 32) {
-                        if (sm.r[j] != 0.0)
+                        if (j != pn)
                             sm.inv[i * LD + j] = __dadd_rn(sm.inv[i * LD + j], __dmul_rn(di, sm.d[j]));
                     }
                 }
-                __syncthreads();
                 for (int i = tid; i < hw_new; i += T) {
                     if (i == pn) continue;
-                    const double v = (sm.r[i] != 0.0) ? __dmul_rn(-invs, sm.d[i]) : 0.0;
+                    const double v = __dmul_rn(-invs, sm.d[i]);
                     sm.inv[i * LD + pn] = v;
                     sm.inv[pn * LD + i] = v;
                 }
-                if (tid == 0) sm.inv[pn * LD + pn] = invs;
                 for (int q = tid; q < W; q += T) sm.bits[snew * W + q] = sm.ynew[q];
-                __syncthreads();
-                const double scn = sm.red[35];
                 if (tid == 0) {
+                    sm.inv[pn * LD + pn] = invs;
                     sm.perm[m] = snew;
-                    sm.score[snew] = scn;
+                    sm.score[snew] = sm.red[35];
                     sm.p[snew] = 0.0;
                     sm.z[snew] = 0.0;
                 }
@@ -821,6 +853,9 @@ extern "C" int smlvm_sparsemap_fwd(const float* x, const float* t, const double*
         cudaError_t e =                                                                            \
             cudaFuncSetAttribute(sparsemap_fwd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                  (int)solver_smem_bytes(n, n + 1));                                \
+        if (e != cudaSuccess) return (int)e;                                                       \
+        e = cudaFuncSetAttribute(sparsemap_fwd_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, \
+                                 (int)cudaSharedmemCarveoutMaxShared);                             \
         if (e != cudaSuccess) return (int)e;                                                       \
         for (int ti = 0; ti < ntier; ++ti) {                                                       \
             sparsemap_fwd_kernel<K><<<grid, threads, solver_smem_bytes(n, tiers[ti]), st>>>(       \
