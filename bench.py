@@ -343,8 +343,8 @@ def extra_paths(args, world, device, rank):
                      "max_iterations": int(st["iters"].max()),
                      "capacity_tiers": [{"capacity": c, "smem_bytes_per_cta": b, "ctas_per_sm": o,
                                          "samples_final_size_in_tier": int(((st["counts"] <= c) & (st["counts"] > lo)).sum())}
-                                        for (c, b, o), lo in zip(ops.sparsemap_plan(128),
-                                                                 [0] + [t[0] for t in ops.sparsemap_plan(128)][:-1])],
+                                        for (c, b, o), lo in zip(ops.sparsemap_plan(128, kind),
+                                                                 [0] + [t[0] for t in ops.sparsemap_plan(128, kind)][:-1])],
                      "hbm_frac_of_algorithmic_bytes": (fwd_bytes + bwd_bytes) / (ms / 3 * 1e-3) / 1e9
                      / measured_hbm_peak()[0]}
     if rank == 0 and world == 1 and not args.no_cpu:

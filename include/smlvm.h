@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SMLVM_ABI_VERSION 2
+#define SMLVM_ABI_VERSION 3
 
 #define SMLVM_OK 0
 #define SMLVM_ERR_ARG (-1)         /* null pointer, negative size, bad enum        */
@@ -174,12 +174,13 @@ int smlvm_bits_score_bwd(const uint32_t* bits, const float* dscores_k, float* dx
 /* Capacity (vertices per sample) the padded outputs must have: n + 1.                     */
 int32_t smlvm_sparsemap_capacity(int32_t n);
 
-/* How smlvm_sparsemap_fwd will run for n bits: the solver keeps a sample's (|A|+1)^2 fp64 inverse in
+/* How smlvm_sparsemap_fwd will run for n bits of factor `kind`: the solver keeps a sample's (|A|+1)^2 fp64 inverse in
  * shared memory and works through up to 3 capacity tiers (largest active set a launch can hold;
  * the last is n + 1); a sample that outgrows a tier is re-solved by the next.  Writes, per tier,
  * the capacity, the dynamic shared memory per CTA and the resident CTAs (= samples in flight) per
  * SM; each output may be NULL, arrays need 3 entries.  Returns the number of tiers.            */
-int32_t smlvm_sparsemap_plan(int32_t n, int32_t* caps, int32_t* smem_bytes, int32_t* ctas_per_sm);
+int32_t smlvm_sparsemap_plan(int32_t n, int32_t kind, int32_t* caps, int32_t* smem_bytes,
+                             int32_t* ctas_per_sm);
 
 /* x[rows,n] on-scores (off-scores are 0, sparsemap.py:22);
  * t[rows,n-1] 1->1 transition scores (sequence-binary only, else NULL);

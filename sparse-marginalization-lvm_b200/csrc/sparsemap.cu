@@ -38,7 +38,7 @@ struct SolverSmem {
     double* son;    // [n]      oracle input, "on" half
     double* soff;   // [n]      oracle input, "off" half
     double* red;    // [40]     reduction scratch
-    double* terms;  // [terms_chunk(cap)] Schur-complement terms in libad3's summation order
+    double* terms;  // [terms_doubles(cap)] Schur-complement terms in libad3's summation order (double buffer)
     int* perm;      // [cap]    solver order -> slot
     int* freestk;   // [cap]    free slots (stack)
     uint32_t* bits; // [cap*W]  by slot
@@ -47,13 +47,15 @@ struct SolverSmem {
     int* misc;      // [8]
 };
 
-// The Schur terms of one insertion ((|A|+1)(|A|+2)/2 of them) are produced and folded in rounds
-// of whole matrix rows through a buffer of this many doubles (one round up to |A| = 46).
-constexpr int kTermsChunk = 1152;
-__host__ __device__ inline int terms_chunk(int cap)
+// The Schur terms of one insertion ((|A|+1)(|A|+2)/2 of them) are produced in rounds of whole matrix rows
+// into one half of a double buffer of kTermsChunk doubles per half while thread 0 folds the other half
+// (a row has at most n + 2 <= kTermsChunk terms).  Up to |A| = 18 a single round, single buffer.
+constexpr int kTermsChunk = 192;
+static_assert(kTermsChunk >= SMLVM_SPARSEMAP_MAX_BITS + 2 && kTermsChunk % 2 == 0, "a matrix row must fit one round");
+__host__ __device__ inline int terms_doubles(int cap)
 {
     const int full = (cap + 1) * (cap + 2) / 2;
-    return full < kTermsChunk ? full : kTermsChunk;
+    return full <= kTermsChunk ? ((full + 1) & ~1) : 2 * kTermsChunk;
 }
 
 // `cap` = largest active set this launch can hold (a capacity tier, <= n + 1)
@@ -61,7 +63,7 @@ __host__ __device__ inline size_t solver_smem_bytes(int n, int cap)
 {
     const int LD = (cap + 1) | 1, W = (n + 31) / 32;
     const int LV = LD > n ? LD : n;  // d doubles as the budget oracle's gain vector [n]
-    const int ne = (n + 1) & ~1, ce = (terms_chunk(cap) + 1) & ~1;
+    const int ne = (n + 1) & ~1, ce = terms_doubles(cap);
     size_t dbl = (size_t)LD * LD + 3 * cap + 2 * LV + 2 * n + 2 * ne + 40 + (size_t)ce;
     size_t b = dbl * sizeof(double);
     b += (size_t)(2 * cap + 8) * sizeof(int);
@@ -73,7 +75,7 @@ __host__ __device__ inline size_t solver_smem_bytes(int n, int cap)
 __device__ inline SolverSmem carve(unsigned char* raw, int n, int cap)
 {
     const int LD = (cap + 1) | 1, W = (n + 31) / 32;
-    const int ne = (n + 1) & ~1, ce = (terms_chunk(cap) + 1) & ~1;
+    const int ne = (n + 1) & ~1, ce = terms_doubles(cap);
     SolverSmem s;
     double* d = reinterpret_cast<double*>(raw);
     // the three arrays that are folded in sequence come first: 16-byte aligned, son/soff contiguous
@@ -293,16 +295,18 @@ __device__ double evaluate_warp(const SolverSmem& sm, int n)
 // ONE thread folds them in sequence -- the fold is a pure DSUB dependency chain fed by
 // independent 64-bit shared loads (ncu r01: the shuffle-fed version cost ~45 cycles per term and
 // kept the other 7 warps at the barrier 60 % of the time).
-// rows [a0, a1) of the upper triangle -> sm.terms (row-major, packed)
-__device__ __forceinline__ void schur_terms_fill(const SolverSmem& sm, int m, int LD, int a0, int a1)
+// rows [a0, a1) of the upper triangle -> out (row-major, packed), by warps w0 .. nw-1 of the CTA
+__device__ __forceinline__ void schur_terms_fill(const SolverSmem& sm, double* dst, int m, int LD, int a0, int a1,
+                                                 int w0)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) - w0, nw = (blockDim.x >> 5) - w0;
+    if (warp < 0) return;
     for (int a = a0 + warp; a < a1; a += nw) {
         const int ip = (a == 0) ? 0 : sm.perm[a - 1] + 1;
         const double ri = sm.r[ip];
         // rows a0..a-1 hold (m+1-a0) + ... + (m+2-a) terms
         const int off = (a - a0) * (m + 1) - ((a - a0) * (a0 + a - 1)) / 2;
-        double* out = sm.terms + off - a;  // + b
+        double* out = dst + off - a;  // + b
         for (int b = a + lane; b <= m; b += 32) {
             const int jp = (b == 0) ? 0 : sm.perm[b - 1] + 1;
             const double v = sm.inv[ip * LD + jp];
@@ -310,10 +314,6 @@ __device__ __forceinline__ void schur_terms_fill(const SolverSmem& sm, int m, in
                               : __dmul_rn(__dmul_rn(__dmul_rn(2.0, ri), sm.r[jp]), v);
         }
     }
-}
-__device__ __forceinline__ double schur_fold(const SolverSmem& sm, int total, double s)
-{
-    return fold_serial<true>(sm.terms, total, s);
 }
 // rows [a0, a1) that fit one round of the terms buffer (at least one row: a row has <= cap+1 terms)
 __device__ __forceinline__ int schur_round_end(int m, int a0, int chunk, int& count)
@@ -552,35 +552,39 @@ __global__ void __launch_bounds__(256, 4) sparsemap_fwd_kernel(const float* __re
                 // threads at the far end form d_j = sum_i inv[i][j] r_i (i in solver order) for EVERY
                 // touched index j: on a free slot the column of inv is zero, so d_j = 0 and the
                 // rank-one update below leaves free rows and columns at zero without any flags.
-                const int chunk = terms_chunk(cap);
-                int cnt0 = 0;
-                int a_next = schur_round_end(m, 0, chunk, cnt0);
-                schur_terms_fill(sm, m, LD, 0, a_next);
+                int cnt_cur = 0;
+                int a_end = schur_round_end(m, 0, kTermsChunk, cnt_cur);
+                schur_terms_fill(sm, sm.terms, m, LD, 0, a_end, 0);
                 __syncthreads();
                 double sfold = (double)n;
-                if (tid == 0) sfold = schur_fold(sm, cnt0, sfold);
-                if ((tid >> 5) == eval_warp) {
-                    const double scn = evaluate_warp<KIND>(sm, n);
-                    if ((tid & 31) == 0) sm.red[35] = scn;
-                }
-                for (int jp = T - 1 - tid; jp < hw; jp += T) {
-                    double acc = __dmul_rn(sm.inv[jp], sm.r[0]);
-#pragma unroll 4
-                    for (int b = 1; b <= m; ++b) {
-                        const int ip = sm.perm[b - 1] + 1;
-                        const double ri = sm.r[ip];
-                        if (ri != 0.0) acc = __dadd_rn(acc, __dmul_rn(sm.inv[ip * LD + jp], ri));
+                const int fill_w0 = T > 32 ? 1 : 0;  // warp 0 folds: the others fill the next round meanwhile
+                for (int half = 0, first = 1;; half ^= 1, first = 0) {
+                    int cnt_nxt = 0, a_nxt = a_end;
+                    if (a_end <= m) {
+                        a_nxt = schur_round_end(m, a_end, kTermsChunk, cnt_nxt);
+                        schur_terms_fill(sm, sm.terms + (half ^ 1) * kTermsChunk, m, LD, a_end, a_nxt, fill_w0);
                     }
-                    sm.d[jp] = acc;
-                }
-                while (a_next <= m) {  // further rounds (|A| > 46): refill, fold on
+                    if (tid == 0) sfold = fold_serial<true>(sm.terms + half * kTermsChunk, cnt_cur, sfold);
+                    if (first) {
+                        if ((tid >> 5) == eval_warp) {
+                            const double scn = evaluate_warp<KIND>(sm, n);
+                            if ((tid & 31) == 0) sm.red[35] = scn;
+                        }
+                        for (int jp = T - 1 - tid; jp < hw; jp += T) {
+                            double acc = __dmul_rn(sm.inv[jp], sm.r[0]);
+#pragma unroll 4
+                            for (int b = 1; b <= m; ++b) {
+                                const int ip = sm.perm[b - 1] + 1;
+                                const double ri = sm.r[ip];
+                                if (ri != 0.0) acc = __dadd_rn(acc, __dmul_rn(sm.inv[ip * LD + jp], ri));
+                            }
+                            sm.d[jp] = acc;
+                        }
+                    }
+                    if (a_end > m) break;  // that was the last round
                     __syncthreads();
-                    int cnt = 0;
-                    const int a_beg = a_next;
-                    a_next = schur_round_end(m, a_beg, chunk, cnt);
-                    schur_terms_fill(sm, m, LD, a_beg, a_next);
-                    __syncthreads();
-                    if (tid == 0) sfold = schur_fold(sm, cnt, sfold);
+                    a_end = a_nxt;
+                    cnt_cur = cnt_nxt;
                 }
                 if (tid == 0) sm.red[36] = sfold;
                 __syncthreads();
@@ -753,8 +757,25 @@ sparsemap_bwd_kernel(const float* __restrict__ dp, const int64_t* __restrict__ o
     }
 }
 
+// Threads per CTA (= per sample).  Serial phases dominate, so small CTAs: more samples per SM.
+static int solver_threads(int n, int kind)
+{
+    static int ovr = -1;
+    if (ovr < 0) {
+        const char* e = getenv("SMLVM_SMAP_THREADS");
+        ovr = e ? atoi(e) : 0;
+    }
+    if (ovr >= 32 && ovr <= 256 && ovr % 32 == 0) return ovr;
+    if (n <= 32) return 64;
+    if (n <= 64) return 128;
+    return kind == SMLVM_FACTOR_BUDGET ? 256 : 128;
+}
+
 // Capacity tiers of the forward solver for n bits (ascending, last = n + 1); returns their number.
-static int plan_tiers(int n, int (&tiers)[3])
+// First tier: the capacity that lets 5 samples share an SM (4 for the budget factor, whose active
+// sets run larger: measured at n = 128, bernoulli q99 = 57 vertices, budget-64 q99 = 83), second
+// tier 2 per SM, last tier n + 1.
+static int plan_tiers(int n, int kind, int (&tiers)[3])
 {
     static int single = -1;
     static int forced[3] = {0, 0, 0};
@@ -773,10 +794,10 @@ static int plan_tiers(int n, int (&tiers)[3])
     };
     int ntier = 0;
     if (!single) {
-        int c4 = cap_for(4), c2 = cap_for(2);
-        if (forced[0] > 0) c4 = forced[0];
+        int c1 = cap_for(kind == SMLVM_FACTOR_BUDGET ? 4 : 5), c2 = cap_for(2);
+        if (forced[0] > 0) c1 = forced[0];
         if (forced[1] > 0) c2 = forced[1];
-        if (c4 < n + 1 && 5 * c4 >= 2 * n) tiers[ntier++] = c4;          // useful only if >= 0.4 n
+        if (c1 < n + 1 && 5 * c1 >= 2 * n) tiers[ntier++] = c1;          // useful only if >= 0.4 n
         if (c2 < n + 1 && (ntier == 0 || c2 > tiers[ntier - 1])) tiers[ntier++] = c2;
     }
     tiers[ntier++] = n + 1;
@@ -789,17 +810,21 @@ using namespace smlvm;
 
 extern "C" int32_t smlvm_sparsemap_capacity(int32_t n) { return n + 1; }
 
-extern "C" int32_t smlvm_sparsemap_plan(int32_t n, int32_t* caps, int32_t* smem_bytes, int32_t* ctas_per_sm)
+extern "C" int32_t smlvm_sparsemap_plan(int32_t n, int32_t kind, int32_t* caps, int32_t* smem_bytes,
+                                        int32_t* ctas_per_sm)
 {
     if (n < 1 || n > SMLVM_SPARSEMAP_MAX_BITS) return 0;
+    if (kind < SMLVM_FACTOR_BERNOULLI || kind > SMLVM_FACTOR_SEQUENCE_BINARY) return 0;
     int tiers[3];
-    const int nt = plan_tiers(n, tiers);
+    const int nt = plan_tiers(n, kind, tiers);
+    const int by_regs = 65536 / (64 * solver_threads(n, kind));  // __launch_bounds__(256, 4): <= 64 registers
     for (int i = 0; i < nt; ++i) {
         const size_t b = solver_smem_bytes(n, tiers[i]);
         if (caps) caps[i] = tiers[i];
         if (smem_bytes) smem_bytes[i] = (int32_t)b;
         if (ctas_per_sm) {
             int c = (int)((size_t)(227 * 1024) / (b + 1024));
+            c = c < by_regs ? c : by_regs;
             ctas_per_sm[i] = c < 1 ? 1 : (c > 32 ? 32 : c);
         }
     }
@@ -818,23 +843,15 @@ extern "C" int smlvm_sparsemap_fwd(const float* x, const float* t, const double*
     if (rows == 0) return SMLVM_OK;
     if (x == nullptr || p_pad == nullptr || aset_bits == nullptr || counts == nullptr)
         return SMLVM_ERR_ARG;
-    int threads = n <= 32 ? 64 : (n <= 64 ? 128 : 256);
-    {
-        static int ovr = -1;
-        if (ovr < 0) {
-            const char* e = getenv("SMLVM_SMAP_THREADS");
-            ovr = e ? atoi(e) : 0;
-        }
-        if (ovr >= 32 && ovr <= 1024 && ovr % 32 == 0) threads = ovr;
-    }
+    const int threads = solver_threads(n, kind);
     // Capacity tiers.  The (|A|+1)^2 fp64 inverse dominates shared memory: sized for the worst case
     // |A| = n + 1 it allows ONE sample per SM at n = 128, although typical active sets hold 40-60
-    // vertices.  Samples are first solved with the capacities that let 4, then 2, CTAs share an SM
-    // (70 and 97 vertices at n = 128); a sample
+    // vertices.  Samples are first solved with the capacities that let 5 (budget: 4), then 2, CTAs
+    // share an SM (62 / 72 and 110 vertices at n = 128); a sample
     // whose active set outgrows its tier is flagged (counts = -1) and re-solved from scratch by the
     // next tier.  Same stream, no host synchronisation; an empty tier costs one trivial launch.
     int tiers[3];
-    const int ntier = plan_tiers(n, tiers);
+    const int ntier = plan_tiers(n, kind, tiers);
     // one CTA per sample: the hardware scheduler evens out the data-dependent solve lengths
     // (measured best against persistent grids of 16/64/256 CTAs per SM at n = 32 and n = 128)
     int64_t cap_grid = 0x7fffffff;

@@ -12,7 +12,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsmlvm.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 FACTOR_BERNOULLI, FACTOR_BUDGET, FACTOR_SEQUENCE_BINARY = 0, 1, 2
 SOLVE_STATUS = {0: "converged", 1: "max_iter", 2: "repeated_config", 3: "singular"}
@@ -41,7 +41,7 @@ _PROTOTYPES = {
     "smlvm_bits_score_fwd": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     "smlvm_bits_score_bwd": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     "smlvm_sparsemap_capacity": (_i32, [_i32]),
-    "smlvm_sparsemap_plan": (_i32, [_i32, _vp, _vp, _vp]),
+    "smlvm_sparsemap_plan": (_i32, [_i32, _i32, _vp, _vp, _vp]),
     "smlvm_sparsemap_fwd": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i64, _i32,
                                            _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "smlvm_sparsemap_expand": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _i32, _vp]),

@@ -379,11 +379,11 @@ def bits_score(x, bits):
 # --------------------------------------------------------------------------------------
 # (3b) SparseMAP
 # --------------------------------------------------------------------------------------
-def sparsemap_plan(n):
+def sparsemap_plan(n, kind=0):
     """[(capacity, shared-memory bytes per CTA, CTAs per SM)] for each capacity tier of the solver."""
     import ctypes
     caps, smem, ctas = ((ctypes.c_int32 * 3)() for _ in range(3))
-    nt = lib.smlvm_sparsemap_plan(int(n), caps, smem, ctas)
+    nt = lib.smlvm_sparsemap_plan(int(n), int(kind), caps, smem, ctas)
     return [(caps[i], smem[i], ctas[i]) for i in range(nt)]
 
 

@@ -18,13 +18,16 @@ torch.manual_seed(0)
 x = torch.randn(rows, n, device="cuda")
 st = ops.sparsemap_solve(x, kind, budget=budget, max_iter=300)
 torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
+times = []
 for _ in range(reps):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     st = ops.sparsemap_solve(x, kind, budget=budget, max_iter=300)
-e1.record()
-torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / reps
-print("rows %d n %d kind %d budget %d: %.3f ms, %.0f samples/s, mean iters %.1f, mean |A| %.1f, status %s" % (
-    rows, n, kind, budget, ms, rows / ms * 1e3, st["iters"].float().mean().item(),
+    e1.record()
+    torch.cuda.synchronize()
+    times.append(e0.elapsed_time(e1))
+times.sort()
+ms = times[0]
+print("rows %d n %d kind %d budget %d: min %.3f ms (median %.3f, max %.3f of %d), %.0f samples/s, mean iters %.1f, mean |A| %.1f, status %s" % (
+    rows, n, kind, budget, ms, times[len(times) // 2], times[-1], reps, rows / ms * 1e3, st["iters"].float().mean().item(),
     st["counts"].float().mean().item(), torch.bincount(st["status"], minlength=4).tolist()))
