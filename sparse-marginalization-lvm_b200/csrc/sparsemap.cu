@@ -13,9 +13,10 @@
 //          blocking constraint leaves A (block down-date of inv);
 //          else: u = M z, y^ = MAP(eta - u); stop if value <= tau + 1e-9; else y^ joins A
 //          (block update of inv, Schur complement s = <y^,y^> - r' inv r).
-// Everything lives in shared memory in fp64: inv as a dense (n+2)^2 matrix addressed through a
-// slot indirection (perm: solver order -> slot) so that removals do not move data, vertices as
-// bitmasks (Gram entries are n - popc(a ^ b)), MAP oracles as block-wide primitives
+// Everything lives in shared memory in fp64, in SOLVER ORDER (index a + 1 of inv = a-th vertex of the
+// active set, as in libad3): every sum walks memory directly, an insertion appends a row and a
+// column, a removal (rare: ~1 per sample for Bernoulli, ~10 for the budget) closes the gap while it
+// down-dates.  Nothing is ever zero-filled: loops are bounded by |A|.  Vertices are bitmasks (Gram entries are n - popc(a ^ b)), MAP oracles as block-wide primitives
 // (ballot for Bernoulli, rank-select for the budget, 2-state Viterbi for the sequence).
 // No FMA contraction in the inverse updates: the pivoting sequence is sensitive to last bits.
 #include <math_constants.h>
@@ -27,11 +28,11 @@
 namespace smlvm {
 
 struct SolverSmem {
-    double* inv;    // [LD*LD]  physical index 0 = constraint row, slot s -> s + 1
-    double* score;  // [cap]    by slot: score(y_slot) under eta
-    double* p;      // [cap]    by slot
-    double* z;      // [cap]    by slot
-    double* d;      // [LD]     by physical index
+    double* inv;    // [LD*LD]  index 0 = constraint row, vertex a -> a + 1
+    double* score;  // [cap]    score(y_a) under eta
+    double* p;      // [cap]
+    double* z;      // [cap]
+    double* d;      // [LD]
     double* r;      // [LD]
     double* eta;    // [n]      on-scores (off-scores are 0)
     double* t;      // [n]      transition scores (n-1 used)
@@ -39,9 +40,7 @@ struct SolverSmem {
     double* soff;   // [n]      oracle input, "off" half
     double* red;    // [40]     reduction scratch
     double* terms;  // [terms_doubles(cap)] Schur-complement terms in libad3's summation order (double buffer)
-    int* perm;      // [cap]    solver order -> slot
-    int* freestk;   // [cap]    free slots (stack)
-    uint32_t* bits; // [cap*W]  by slot
+    uint32_t* bits; // [cap*W]
     uint32_t* ynew; // [W]
     unsigned char* bp;  // [2*n] Viterbi back-pointers
     int* misc;      // [8]
@@ -66,7 +65,7 @@ __host__ __device__ inline size_t solver_smem_bytes(int n, int cap)
     const int ne = (n + 1) & ~1, ce = terms_doubles(cap);
     size_t dbl = (size_t)LD * LD + 3 * cap + 2 * LV + 2 * n + 2 * ne + 40 + (size_t)ce;
     size_t b = dbl * sizeof(double);
-    b += (size_t)(2 * cap + 8) * sizeof(int);
+    b += (size_t)8 * sizeof(int);
     b += (size_t)(cap * W + W) * sizeof(uint32_t);
     b += (size_t)2 * n + 16;
     return (b + 15) & ~(size_t)15;
@@ -93,8 +92,6 @@ __device__ inline SolverSmem carve(unsigned char* raw, int n, int cap)
     s.t = d; d += n;
     s.red = d; d += 40;
     int* ip = reinterpret_cast<int*>(d);
-    s.perm = ip; ip += cap;
-    s.freestk = ip; ip += cap;
     s.misc = ip; ip += 8;
     uint32_t* up = reinterpret_cast<uint32_t*>(ip);
     s.bits = up; up += cap * W;
@@ -302,16 +299,14 @@ __device__ __forceinline__ void schur_terms_fill(const SolverSmem& sm, double* d
     const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) - w0, nw = (blockDim.x >> 5) - w0;
     if (warp < 0) return;
     for (int a = a0 + warp; a < a1; a += nw) {
-        const int ip = (a == 0) ? 0 : sm.perm[a - 1] + 1;
-        const double ri = sm.r[ip];
+        const double ri = sm.r[a];
         // rows a0..a-1 hold (m+1-a0) + ... + (m+2-a) terms
         const int off = (a - a0) * (m + 1) - ((a - a0) * (a0 + a - 1)) / 2;
         double* out = dst + off - a;  // + b
         for (int b = a + lane; b <= m; b += 32) {
-            const int jp = (b == 0) ? 0 : sm.perm[b - 1] + 1;
-            const double v = sm.inv[ip * LD + jp];
+            const double v = sm.inv[a * LD + b];
             out[b] = (b == a) ? __dmul_rn(__dmul_rn(ri, ri), v)
-                              : __dmul_rn(__dmul_rn(__dmul_rn(2.0, ri), sm.r[jp]), v);
+                              : __dmul_rn(__dmul_rn(__dmul_rn(2.0, ri), sm.r[b]), v);
         }
     }
 }
@@ -372,8 +367,6 @@ __global__ void __launch_bounds__(256, 4) sparsemap_fwd_kernel(const float* __re
                 sm.soff[i] = 0.0;
             }
         }
-        for (int i = tid; i < LD * LD; i += T) sm.inv[i] = 0.0;
-        for (int i = tid; i < cap; i += T) sm.freestk[i] = cap - 1 - i;  // pop order 0,1,2,...
         __syncthreads();
 
         // ---- seed: single MAP vertex, weight 1, inv = [[-n, 1], [1, 0]] ---------------------
@@ -383,7 +376,6 @@ __global__ void __launch_bounds__(256, 4) sparsemap_fwd_kernel(const float* __re
         if (tid < 32) {
             const double sc0 = evaluate_warp<KIND>(sm, n);
             if (tid == 0) {
-                sm.perm[0] = 0;
                 sm.score[0] = sc0;
                 sm.p[0] = 1.0;
                 sm.z[0] = 1.0;
@@ -395,8 +387,6 @@ __global__ void __launch_bounds__(256, 4) sparsemap_fwd_kernel(const float* __re
         }
         for (int q = tid; q < W; q += T) sm.bits[q] = sm.ynew[q];
         int m = 1;          // |A|
-        int nfree = cap - 1; // free-stack height (slot 0 popped)
-        int hw = 2;          // physical indices < hw have been touched
         bool changed = true;
         double tau = 0.0;
         int st = SMLVM_SOLVE_MAX_ITER;
@@ -408,16 +398,13 @@ __global__ void __launch_bounds__(256, 4) sparsemap_fwd_kernel(const float* __re
         // before the previous barrier, what it writes is not read by anyone inside the same phase.
         for (it = 0; it < max_iter; ++it) {
             if (changed) {
-                // ---- [tau; z] = inv * [1; score], rows in solver order ---------------------
+                // ---- [tau; z] = inv * [1; score] -----------------------------------------------
                 for (int a = tid; a <= m; a += T) {
-                    const int rp = (a == 0) ? 0 : sm.perm[a - 1] + 1;
-                    double acc = sm.inv[rp * LD];  // column 0 times b_0 = 1
-#pragma unroll 4
-                    for (int j = 1; j <= m; ++j) {
-                        const int sj = sm.perm[j - 1];
-                        acc = __dadd_rn(acc, __dmul_rn(sm.inv[rp * LD + sj + 1], sm.score[sj]));
-                    }
-                    if (a == 0) sm.red[38] = acc; else sm.z[sm.perm[a - 1]] = acc;
+                    const double* row = sm.inv + a * LD;
+                    double acc = row[0];  // column 0 times b_0 = 1
+#pragma unroll 8
+                    for (int j = 1; j <= m; ++j) acc = __dadd_rn(acc, __dmul_rn(row[j], sm.score[j - 1]));
+                    if (a == 0) sm.red[38] = acc; else sm.z[a - 1] = acc;
                 }
                 __syncthreads();
                 tau = sm.red[38];
@@ -428,8 +415,7 @@ __global__ void __launch_bounds__(256, 4) sparsemap_fwd_kernel(const float* __re
                     int besti = 0x7fffffff;
                     int anyneg = 0;
                     for (int a = tid; a < m; a += 32) {
-                        const int s = sm.perm[a];
-                        const double zz = sm.z[s], pp = sm.p[s];
+                        const double zz = sm.z[a], pp = sm.p[a];
                         if (zz >= pp) continue;
                         if (zz < 0.0) anyneg = 1;
                         const double ratio = __ddiv_rn(pp, __dsub_rn(pp, zz));
@@ -456,67 +442,74 @@ __global__ void __launch_bounds__(256, 4) sparsemap_fwd_kernel(const float* __re
                 const bool exist_blocking = sm.misc[0] != 0;
                 if (!exist_blocking) {
                     // p is next read by a later line search (barriers in between): no barrier here
-                    for (int a = tid; a < m; a += T) {
-                        const int s = sm.perm[a];
-                        sm.p[s] = sm.z[s];
-                    }
+                    for (int a = tid; a < m; a += T) sm.p[a] = sm.z[a];
                     changed = false;
                 } else {
                     const int blocking = sm.misc[1];
                     double alpha = sm.red[37];
                     if (alpha > 1.0) alpha = 1.0;
-                    const int srem = sm.perm[blocking];
-                    const int rem = srem + 1;
-                    // the order entries that slide down over the removed one, read before the barrier
-                    int shift_a = -1, shift_s = 0;
+                    const int rem = blocking + 1;
                     for (int a = tid; a < m; a += T) {
-                        const int s = sm.perm[a];
-                        if (a >= blocking && a + 1 < m) { shift_a = a; shift_s = sm.perm[a + 1]; }
                         if (alpha == 1.0) {
-                            sm.p[s] = sm.z[s];
+                            sm.p[a] = sm.z[a];
                         } else {
-                            const double v = __dadd_rn(__dmul_rn(__dsub_rn(1.0, alpha), sm.p[s]),
-                                                       __dmul_rn(alpha, sm.z[s]));
-                            sm.z[s] = v;
-                            sm.p[s] = v;
+                            const double v = __dadd_rn(__dmul_rn(__dsub_rn(1.0, alpha), sm.p[a]),
+                                                       __dmul_rn(alpha, sm.z[a]));
+                            sm.z[a] = v;
+                            sm.p[a] = v;
                         }
                     }
-                    // ---- down-date inv: d = -(1/inv_rr) inv[r,:],  inv -= inv_rr d d' ---------
+                    // ---- down-date inv: d = -(1/inv_rr) inv[r,:],  inv -= inv_rr d d', then drop
+                    //      row and column r (the rest slides up / left: solver order is memory order)
                     const double invs = sm.inv[rem * LD + rem];
                     const double sval = __ddiv_rn(1.0, invs);
-                    for (int i = tid; i < hw; i += T)
+                    for (int i = tid; i <= m; i += T)
                         sm.d[i] = (i == rem) ? 0.0 : __dmul_rn(-sval, sm.inv[rem * LD + i]);
                     __syncthreads();
-                    // (the freed row and column are cleared in the same pass: d[rem] = 0 leaves
-                    //  them untouched by the down-date itself)
-                    for (int i = tid >> 5; i < hw; i += T >> 5) {
+                    // pass 1, a warp per row: down-date and close the column gap inside the row
+                    // (32 columns at a time: read, then write one place to the left beyond r)
+                    for (int i = tid >> 5; i <= m; i += T >> 5) {
+                        if (i == rem) continue;
                         const double di = __dmul_rn(invs, sm.d[i]);
-                        for (int j = tid & 31; j < hw; j += 32) {
-                            const double v = __dsub_rn(sm.inv[i * LD + j], __dmul_rn(di, sm.d[j]));
-                            sm.inv[i * LD + j] = (i == rem || j == rem) ? 0.0 : v;
+                        double* row = sm.inv + i * LD;
+                        for (int j0 = 0; j0 <= m; j0 += 32) {
+                            const int j = j0 + (tid & 31);
+                            double v = 0.0;
+                            if (j <= m) v = __dsub_rn(row[j], __dmul_rn(di, sm.d[j]));
+                            __syncwarp();
+                            if (j <= m && j != rem) row[j - (j > rem ? 1 : 0)] = v;
+                            __syncwarp();
                         }
                     }
-                    // drop the vertex from the order (T >= m is not guaranteed: strided), recycle the slot
-                    if (T >= m) {
-                        if (shift_a >= 0) sm.perm[shift_a] = shift_s;
-                    } else if (tid == 0) {
-                        for (int a = blocking; a + 1 < m; ++a) sm.perm[a] = sm.perm[a + 1];
+                    __syncthreads();
+                    // pass 2, a thread per column: rows beyond r move up; the last threads slide the
+                    // per-vertex vectors and bitmasks down over the removed vertex
+                    for (int j = tid; j < m; j += T)
+                        for (int i = rem; i < m; ++i) sm.inv[i * LD + j] = sm.inv[(i + 1) * LD + j];
+                    {
+                        const int v = T - 1 - tid;  // 0: score, 1: p, 2: z, 3..: one bitmask word each
+                        if (v < 3) {
+                            double* vec = v == 0 ? sm.score : (v == 1 ? sm.p : sm.z);
+                            for (int a = blocking; a + 1 < m; ++a) vec[a] = vec[a + 1];
+                        } else if (v < 3 + W) {
+                            uint32_t* col = sm.bits + (v - 3);
+                            for (int a = blocking; a + 1 < m; ++a) col[a * W] = col[(a + 1) * W];
+                        }
                     }
-                    if (tid == 0) sm.freestk[nfree] = srem;
-                    ++nfree;
                     --m;
                     changed = true;
                     __syncthreads();
                 }
             } else {
-                // ---- u = M z (solver order), oracle scores eta - u ---------------------------
+                // ---- u = M z, oracle scores eta - u ----------------------------------------------
                 for (int i = tid; i < n; i += T) {
                     double uon = 0.0, uoff = 0.0;
-#pragma unroll 4
+                    const uint32_t* bw = sm.bits + (i >> 5);
+                    const int sh = i & 31;
+#pragma unroll 8
                     for (int a = 0; a < m; ++a) {
-                        const int s = sm.perm[a];
-                        const double zz = sm.z[s];
-                        if ((sm.bits[s * W + (i >> 5)] >> (i & 31)) & 1u) uon = __dadd_rn(uon, zz);
+                        const double zz = sm.z[a];
+                        if ((bw[a * W] >> sh) & 1u) uon = __dadd_rn(uon, zz);
                         else uoff = __dadd_rn(uoff, zz);
                     }
                     sm.son[i] = __dsub_rn(sm.eta[i], uon);
@@ -535,9 +528,8 @@ __global__ void __launch_bounds__(256, 4) sparsemap_fwd_kernel(const float* __re
                 int same = 0;
                 if (tid == 0) sm.r[0] = 1.0;
                 for (int a = tid; a < m; a += T) {
-                    const int s = sm.perm[a];
-                    const int c = common_values(sm.bits + s * W, sm.ynew, W, n);
-                    sm.r[s + 1] = (double)c;
+                    const int c = common_values(sm.bits + a * W, sm.ynew, W, n);
+                    sm.r[a + 1] = (double)c;
                     same |= (c == n) ? 1 : 0;
                 }
                 same = __syncthreads_or(same);
@@ -549,9 +541,7 @@ __global__ void __launch_bounds__(256, 4) sparsemap_fwd_kernel(const float* __re
                 // ---- d = inv r, s = n - r'd ---------------------------------------------------
                 // the two order-sensitive sums: Schur terms formed by the whole CTA, folded by thread 0;
                 // the score of the new vertex compacted and folded by another warp; meanwhile the
-                // threads at the far end form d_j = sum_i inv[i][j] r_i (i in solver order) for EVERY
-                // touched index j: on a free slot the column of inv is zero, so d_j = 0 and the
-                // rank-one update below leaves free rows and columns at zero without any flags.
+                // threads at the far end form d_j = sum_i inv[i][j] r_i.
                 int cnt_cur = 0;
                 int a_end = schur_round_end(m, 0, kTermsChunk, cnt_cur);
                 schur_terms_fill(sm, sm.terms, m, LD, 0, a_end, 0);
@@ -570,15 +560,14 @@ __global__ void __launch_bounds__(256, 4) sparsemap_fwd_kernel(const float* __re
                             const double scn = evaluate_warp<KIND>(sm, n);
                             if ((tid & 31) == 0) sm.red[35] = scn;
                         }
-                        for (int jp = T - 1 - tid; jp < hw; jp += T) {
-                            double acc = __dmul_rn(sm.inv[jp], sm.r[0]);
-#pragma unroll 4
+                        for (int j = T - 1 - tid; j <= m; j += T) {
+                            double acc = __dmul_rn(sm.inv[j], sm.r[0]);
+#pragma unroll 8
                             for (int b = 1; b <= m; ++b) {
-                                const int ip = sm.perm[b - 1] + 1;
-                                const double ri = sm.r[ip];
-                                if (ri != 0.0) acc = __dadd_rn(acc, __dmul_rn(sm.inv[ip * LD + jp], ri));
+                                const double ri = sm.r[b];
+                                if (ri != 0.0) acc = __dadd_rn(acc, __dmul_rn(sm.inv[b * LD + j], ri));
                             }
-                            sm.d[jp] = acc;
+                            sm.d[j] = acc;
                         }
                     }
                     if (a_end > m) break;  // that was the last round
@@ -600,37 +589,26 @@ __global__ void __launch_bounds__(256, 4) sparsemap_fwd_kernel(const float* __re
                     break;
                 }
                 const double invs = __ddiv_rn(1.0, sval);
-                const int snew = sm.freestk[nfree - 1];
-                const int pn = snew + 1;
-                const int hw_new = max(hw, pn + 1);
-                // ---- block update of inv: old part += d d'/s, new row/column = -d/s, corner 1/s.
-                // One phase: the rank-one pass skips row / column pn (a free slot: d = 0 there),
-                // which the row/column pass writes.
-                for (int i = tid >> 5; i < hw; i += T >> 5) {
-                    if (i == pn) continue;
+                const int pn = m + 1;
+                // ---- block update of inv: old part += d d'/s, new row/column = -d/s, corner 1/s ----
+                for (int i = tid >> 5; i <= m; i += T >> 5) {
                     const double di = __dmul_rn(invs, sm.d[i]);
-                    for (int j = tid & 31; j < hw; j += 32) {
-                        if (j != pn)
-                            sm.inv[i * LD + j] = __dadd_rn(sm.inv[i * LD + j], __dmul_rn(di, sm.d[j]));
-                    }
+                    double* row = sm.inv + i * LD;
+                    for (int j = tid & 31; j <= m; j += 32) row[j] = __dadd_rn(row[j], __dmul_rn(di, sm.d[j]));
                 }
-                for (int i = tid; i < hw_new; i += T) {
-                    if (i == pn) continue;
+                for (int i = tid; i <= m; i += T) {
                     const double v = __dmul_rn(-invs, sm.d[i]);
                     sm.inv[i * LD + pn] = v;
                     sm.inv[pn * LD + i] = v;
                 }
-                for (int q = tid; q < W; q += T) sm.bits[snew * W + q] = sm.ynew[q];
+                for (int q = tid; q < W; q += T) sm.bits[m * W + q] = sm.ynew[q];
                 if (tid == 0) {
                     sm.inv[pn * LD + pn] = invs;
-                    sm.perm[m] = snew;
-                    sm.score[snew] = sm.red[35];
-                    sm.p[snew] = 0.0;
-                    sm.z[snew] = 0.0;
+                    sm.score[m] = sm.red[35];
+                    sm.p[m] = 0.0;
+                    sm.z[m] = 0.0;
                 }
-                --nfree;
                 ++m;
-                hw = hw_new;
                 changed = true;
                 __syncthreads();
             }
@@ -647,20 +625,20 @@ __global__ void __launch_bounds__(256, 4) sparsemap_fwd_kernel(const float* __re
         for (int a = tid; a < cap_out; a += T) {
             float pf = 0.f;
             if (a < m) {
-                pf = (float)sm.p[sm.perm[a]];
+                pf = (float)sm.p[a];
                 kp += pf > 0.f ? 1 : 0;
             }
             p_pad[row * cap_out + a] = pf;
         }
         for (int e = tid; e < cap_out * W; e += T) {
             const int a = e / W, q = e - a * W;
-            aset_bits[(row * cap_out + a) * W + q] = (a < m) ? sm.bits[sm.perm[a] * W + q] : 0u;
+            aset_bits[(row * cap_out + a) * W + q] = (a < m) ? sm.bits[a * W + q] : 0u;
         }
         if (S_pad != nullptr) {
             double* S = S_pad + row * (int64_t)cap_out * cap_out;
             for (int e = tid; e < m * m; e += T) {
                 const int a = e / m, c = e - a * m;
-                S[e] = sm.inv[(sm.perm[a] + 1) * LD + sm.perm[c] + 1];
+                S[e] = sm.inv[(a + 1) * LD + c + 1];
             }
         }
         if (kept != nullptr) {
