@@ -301,6 +301,38 @@ def extra_paths(args, world, device, rank):
                     for k in dur}}
     del cstep, xc, lr
 
+    # (e) the one collective the path has in training: the sum-all-reduce of the wrapped encoder's parameter
+    # gradients (lvmhelpers/dist.py::GradAllReducer over NCCL), launched asynchronously behind the sharded step.
+    # A dummy Linear(cols, cols) encoder feeds the categorical step; rows sharded, losses scaled by 1 / B_global.
+    from lvmhelpers.dist import GradAllReducer
+    erow = min(args.rows, 262144)
+    enc = torch.nn.Linear(args.cols, args.cols).to(device)
+    with torch.no_grad():
+        for prm in enc.parameters():     # same weights on every rank
+            prm.copy_(torch.randn(prm.shape, generator=torch.Generator().manual_seed(5)) * 0.1)
+    einp = torch.randn(erow, args.cols, generator=g).to(device)
+    eloss = (torch.rand(erow, args.cols, generator=g) * 3).to(device)
+    estep = SparsemaxMargStep(erow, args.cols, device, 6 * erow, entropy_coeff=1.0, global_rows=erow * world)
+    reducer = GradAllReducer(enc.parameters())
+
+    def enc_step(reduce):
+        enc.zero_grad(set_to_none=True)
+        scores = enc(einp)
+        estep.run(scores.detach(), eloss)
+        scores.backward(estep.dx)
+        if reduce:
+            reducer.start()
+            reducer.finish()
+
+    ms_local, _, _ = timed(lambda: enc_step(False), 10, 3, world, device)
+    ms_red, _, _ = timed(lambda: enc_step(True), 10, 3, world, device)
+    out["sharded_step_with_encoder_allreduce"] = {
+        "rows_per_gpu": erow, "encoder": "Linear(%d, %d), fp32" % (args.cols, args.cols),
+        "allreduce_bytes": sum(prm.numel() * 4 for prm in enc.parameters()), "backend": "nccl" if world > 1 else "none",
+        "ms_per_step_without_allreduce": ms_local / 10, "ms_per_step": ms_red / 10,
+        "value": erow * world / (ms_red / 10 * 1e-3), "unit": UNIT}
+    del estep, einp, eloss
+
     rows = args.path_rows_topk
     x = torch.randn(rows, 128, generator=g).to(device).requires_grad_(True)
     wrap = TopKSparsemaxWrapper(torch.nn.Identity(), k=10)
