@@ -26,6 +26,57 @@ template <> struct Cfg<1> { uint32_t w[1]; };
 template <> struct __align__(8) Cfg<2> { uint32_t w[2]; };
 template <> struct __align__(16) Cfg<4> { uint32_t w[4]; };
 
+// Bits ib0 .. iend-1 of one 32-bit block (word WQ of the configurations) for the row of this lane.
+// While the list is still growing (len < k) the merge checks both list ends (merge_branch,
+// binary_topk.h:57-98); once it is full, a + b = r < k = len for every output, so neither list can
+// run out: the loop is compare / select / move, with the new bit OR-ed into word WQ only.
+template <int W, int WQ>
+__device__ __forceinline__ void topk_merge_block(Cfg<W>* C, float* S, const float* xs, int lane, int k, int ib0,
+                                                 int iend, int& cur, int& len)
+{
+    for (int ib = ib0; ib < iend; ++ib) {
+        const float v = xs[ib * 33 + lane];
+        const uint32_t bit = 1u << ib;
+        const char* ScB = reinterpret_cast<const char*>(S + (cur * k) * 32 + lane);
+        float* Sn = S + ((cur ^ 1) * k) * 32 + lane;
+        const char* CcB = reinterpret_cast<const char*>(C + (cur * k) * 32 + lane);
+        Cfg<W>* Cn = C + ((cur ^ 1) * k) * 32 + lane;
+        const float s0 = *reinterpret_cast<const float*>(ScB);
+        if (len == k) {
+            int b = 0;
+            float sa = s0, sb = __fadd_rn(s0, v);
+            for (int r = 0; r < k; ++r) {
+                const bool takeB = sb > sa;                    // strictly greater (binary_topk.h:72)
+                const int src = takeB ? b : r - b;             // a = r - b
+                Sn[r * 32] = takeB ? sb : sa;
+                Cfg<W> cw = *reinterpret_cast<const Cfg<W>*>(CcB + src * (32 * (int)sizeof(Cfg<W>)));
+                if (takeB) cw.w[WQ] |= bit;
+                Cn[r * 32] = cw;
+                const float head = *reinterpret_cast<const float*>(ScB + (src + 1) * 128);
+                if (takeB) { ++b; sb = __fadd_rn(head, v); } else { sa = head; }
+            }
+        } else {
+            const int outlen = min(k, 2 * len);
+            int a = 0, b = 0;
+            float sa = s0, sb = __fadd_rn(s0, v);
+            for (int r = 0; r < outlen; ++r) {
+                const bool takeB = (b < len) && (a >= len || sb > sa);
+                const int src = takeB ? b : a;
+                Sn[r * 32] = takeB ? sb : sa;
+                Cfg<W> cw = *reinterpret_cast<const Cfg<W>*>(CcB + src * (32 * (int)sizeof(Cfg<W>)));
+                if (takeB) cw.w[WQ] |= bit;
+                Cn[r * 32] = cw;
+                // advance the list that was consumed and fetch its next head
+                const int nxt = src + 1;
+                const float head = *reinterpret_cast<const float*>(ScB + min(nxt, len - 1) * 128);
+                if (takeB) { b = nxt; sb = __fadd_rn(head, v); } else { a = nxt; sa = head; }
+            }
+            len = outlen;
+        }
+        cur ^= 1;
+    }
+}
+
 template <int W>
 __global__ void __launch_bounds__(512)
 topk_tile_kernel(const float* __restrict__ x, float* __restrict__ configs, uint32_t* __restrict__ bits,
@@ -34,10 +85,10 @@ topk_tile_kernel(const float* __restrict__ x, float* __restrict__ configs, uint3
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int words_n = (n + 31) >> 5;
-    const size_t per_warp = ((size_t)2 * k * W * 32 + 32 * 33 + 2 * k * 32) * 4;
+    const size_t per_warp = ((size_t)2 * k * W * 32 + 32 * 33 + (2 * k + 1) * 32) * 4;
     Cfg<W>* C = reinterpret_cast<Cfg<W>*>(smem_raw + warp * per_warp);        // [2][k][32]
     float* xs = reinterpret_cast<float*>(C + 2 * k * 32);                     // [32][33]: 32 bits x 32 rows
-    float* S = xs + 32 * 33;                                                  // [2][k][32]
+    float* S = xs + 32 * 33;                                                  // [2][k][32] (+ one slot of slack)
 
     const int64_t ntiles = (rows + 31) / 32;
     for (int64_t t = (int64_t)blockIdx.x * nwarps + warp; t < ntiles; t += (int64_t)gridDim.x * nwarps) {
@@ -79,37 +130,18 @@ topk_tile_kernel(const float* __restrict__ x, float* __restrict__ configs, uint3
                 ib = 1;
             }
             const int iend = min(32, n - i0);
-            for (; ib < iend; ++ib) {
-                const int i = i0 + ib;
-                const float v = xs[ib * 33 + lane];
-                const int outlen = min(k, 2 * len);
-                Cfg<W> bitv;  // the bit of this step as a configuration
-#pragma unroll
-                for (int q = 0; q < W; ++q) bitv.w[q] = (q == (i >> 5)) ? (1u << (i & 31)) : 0u;
-                const float* Sc = S + (cur * k) * 32 + lane;
-                float* Sn = S + ((cur ^ 1) * k) * 32 + lane;
-                const Cfg<W>* Cc = C + (cur * k) * 32 + lane;
-                Cfg<W>* Cn = C + ((cur ^ 1) * k) * 32 + lane;
-                // two-pointer merge of A (bit off) and A + v (bit on): merge_branch, binary_topk.h:57-98
-                int a = 0, b = 0;
-                float sa = Sc[0], sb = __fadd_rn(Sc[0], v);
-                for (int r = 0; r < outlen; ++r) {
-                    const bool takeB = (b < len) && (a >= len || sb > sa);
-                    const int src = takeB ? b : a;
-                    Sn[r * 32] = takeB ? sb : sa;
-                    Cfg<W> cw = Cc[src * 32];
-                    if (takeB) {  // predicated ORs (one per word)
-#pragma unroll
-                        for (int q = 0; q < W; ++q) cw.w[q] |= bitv.w[q];
-                    }
-                    Cn[r * 32] = cw;
-                    // advance the list that was consumed and fetch its next head
-                    const int nxt = src + 1;
-                    const float head = Sc[min(nxt, len - 1) * 32];
-                    if (takeB) { b = nxt; sb = __fadd_rn(head, v); } else { a = nxt; sa = head; }
+            if (W == 1) {
+                topk_merge_block<W, 0>(C, S, xs, lane, k, ib, iend, cur, len);
+            } else if (W == 2) {
+                if (i0 == 0) topk_merge_block<W, 0>(C, S, xs, lane, k, ib, iend, cur, len);
+                else topk_merge_block<W, (W > 1 ? 1 : 0)>(C, S, xs, lane, k, ib, iend, cur, len);
+            } else {
+                switch (i0 >> 5) {
+                    case 0: topk_merge_block<W, 0>(C, S, xs, lane, k, ib, iend, cur, len); break;
+                    case 1: topk_merge_block<W, (W > 1 ? 1 : 0)>(C, S, xs, lane, k, ib, iend, cur, len); break;
+                    case 2: topk_merge_block<W, (W > 2 ? 2 : 0)>(C, S, xs, lane, k, ib, iend, cur, len); break;
+                    default: topk_merge_block<W, (W > 3 ? 3 : 0)>(C, S, xs, lane, k, ib, iend, cur, len); break;
                 }
-                cur ^= 1;
-                len = outlen;
             }
         }
         __syncwarp();
@@ -167,7 +199,7 @@ int topk_tile_launch(const float* x, float* configs, uint32_t* bits, float* dp_s
 {
     const int words_n = (n + 31) >> 5;
     const int W = words_n <= 1 ? 1 : (words_n <= 2 ? 2 : 4);
-    const size_t per_warp = ((size_t)2 * k * W * 32 + 32 * 33 + 2 * k * 32) * 4;
+    const size_t per_warp = ((size_t)2 * k * W * 32 + 32 * 33 + (2 * k + 1) * 32) * 4;
     int warps = (int)((200 * 1024) / per_warp);
     warps = warps > 16 ? 16 : (warps < 1 ? 1 : warps);
     const int64_t ntiles = (rows + 31) / 32;
