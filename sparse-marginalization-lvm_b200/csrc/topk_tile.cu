@@ -26,6 +26,26 @@ template <> struct Cfg<1> { uint32_t w[1]; };
 template <> struct __align__(8) Cfg<2> { uint32_t w[2]; };
 template <> struct __align__(16) Cfg<4> { uint32_t w[4]; };
 
+// Moves words 0 .. WQ of a configuration (the higher words are still zero in every slot while the
+// bits of block WQ are being merged), OR-ing `bit` into word WQ when `on`.
+template <int W, int WQ>
+__device__ __forceinline__ void move_cfg(const char* src, Cfg<W>* dst, bool on, uint32_t bit)
+{
+    if (WQ == 0) {
+        uint32_t w = *reinterpret_cast<const uint32_t*>(src);
+        if (on) w |= bit;
+        dst->w[0] = w;
+    } else if (WQ == 1) {
+        uint2 w = *reinterpret_cast<const uint2*>(src);
+        if (on) w.y |= bit;
+        *reinterpret_cast<uint2*>(dst) = w;
+    } else {
+        Cfg<W> cw = *reinterpret_cast<const Cfg<W>*>(src);
+        if (on) cw.w[WQ] |= bit;
+        *dst = cw;
+    }
+}
+
 // Bits ib0 .. iend-1 of one 32-bit block (word WQ of the configurations) for the row of this lane.
 // While the list is still growing (len < k) the merge checks both list ends (merge_branch,
 // binary_topk.h:57-98); once it is full, a + b = r < k = len for every output, so neither list can
@@ -49,9 +69,7 @@ __device__ __forceinline__ void topk_merge_block(Cfg<W>* C, float* S, const floa
                 const bool takeB = sb > sa;                    // strictly greater (binary_topk.h:72)
                 const int src = takeB ? b : r - b;             // a = r - b
                 Sn[r * 32] = takeB ? sb : sa;
-                Cfg<W> cw = *reinterpret_cast<const Cfg<W>*>(CcB + src * (32 * (int)sizeof(Cfg<W>)));
-                if (takeB) cw.w[WQ] |= bit;
-                Cn[r * 32] = cw;
+                move_cfg<W, WQ>(CcB + src * (32 * (int)sizeof(Cfg<W>)), Cn + r * 32, takeB, bit);
                 const float head = *reinterpret_cast<const float*>(ScB + (src + 1) * 128);
                 if (takeB) { ++b; sb = __fadd_rn(head, v); } else { sa = head; }
             }
@@ -63,9 +81,7 @@ __device__ __forceinline__ void topk_merge_block(Cfg<W>* C, float* S, const floa
                 const bool takeB = (b < len) && (a >= len || sb > sa);
                 const int src = takeB ? b : a;
                 Sn[r * 32] = takeB ? sb : sa;
-                Cfg<W> cw = *reinterpret_cast<const Cfg<W>*>(CcB + src * (32 * (int)sizeof(Cfg<W>)));
-                if (takeB) cw.w[WQ] |= bit;
-                Cn[r * 32] = cw;
+                move_cfg<W, WQ>(CcB + src * (32 * (int)sizeof(Cfg<W>)), Cn + r * 32, takeB, bit);
                 // advance the list that was consumed and fetch its next head
                 const int nxt = src + 1;
                 const float head = *reinterpret_cast<const float*>(ScB + min(nxt, len - 1) * 128);
@@ -123,6 +139,8 @@ topk_tile_kernel(const float* __restrict__ x, float* __restrict__ configs, uint3
                 Cfg<W> c0, c1;
 #pragma unroll
                 for (int q = 0; q < W; ++q) { c0.w[q] = 0u; c1.w[q] = 0u; }
+                // every slot of both sides starts from zero: a block only moves words 0 .. its own
+                for (int slot = 2; slot < 2 * k; ++slot) C[slot * 32 + lane] = c0;
                 c0.w[0] = on_first ? 1u : 0u;
                 c1.w[0] = on_first ? 0u : 1u;
                 C[0 * 32 + lane] = c0;
