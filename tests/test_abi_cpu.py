@@ -141,3 +141,22 @@ def test_wrapper_api_surface_matches_reference():
     assert callable(marg.entropy) and callable(structmarg.entropy)
     assert callable(pbinary_topk.batched_topk) and callable(pbinary_topk.binary_topk)
     assert hasattr(utils, "DeterministicWrapper")
+
+
+def test_sparsemap_plan_needs_no_device():
+    """Capacity tiers of the solver: ascending, last = n + 1, within the 227 KB of an SM; the budget
+    factor starts with a larger first tier than Bernoulli (its active sets run larger)."""
+    from lvmhelpers import ops
+    from lvmhelpers._native import lib
+    for kind in (0, 1, 2):
+        for n in (1, 5, 32, 64, 100, 128):
+            tiers = ops.sparsemap_plan(n, kind)
+            assert 1 <= len(tiers) <= 3
+            caps = [c for c, _, _ in tiers]
+            assert caps == sorted(set(caps)) and caps[-1] == n + 1 == lib.smlvm_sparsemap_capacity(n)
+            for cap, smem, ctas in tiers:
+                assert 0 < smem <= 227 * 1024 and 1 <= ctas <= 32
+                assert ctas * (smem + 1024) <= 228 * 1024
+    assert ops.sparsemap_plan(128, 1)[0][0] > ops.sparsemap_plan(128, 0)[0][0]
+    assert ops.sparsemap_plan(128, 0)[0][2] == 5 and ops.sparsemap_plan(128, 1)[0][2] == 4
+    assert ops.sparsemap_plan(129, 0) == [] and ops.sparsemap_plan(8, 7) == []
