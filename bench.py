@@ -349,6 +349,40 @@ def extra_paths(args, world, device, rank):
     out["topk_sparsemax_n128_k10"] = {"rows_per_gpu": rows, "ms_per_step": ms / 5,
                                      "value": rows * world / (ms / 5 * 1e-3), "unit": UNIT}
 
+    # the same branch through its consumer, TopKSparsemaxMarg (structmarg.py:82-153): candidates handed over
+    # packed, only the support expanded to fp32 for the (dummy) decoder -- against the dense [B,k,n] hand-over
+    from lvmhelpers.structmarg import TopKSparsemaxMarg
+
+    class _Opaque(torch.nn.Module):     # hides the wrapper's type: the Marg then takes the dense tensor
+        def __init__(self, w):
+            super().__init__()
+            self.w = w
+
+        def forward(self, *a):
+            return self.w(*a)
+
+    def _dec(z, dec_in):
+        return z
+
+    def _loss(enc_in, z, dec_in, dec_out, lab):
+        return dec_out.sum(-1) * 3.0 + lab, {}
+
+    dec_in = torch.zeros(rows, 1, device=device)
+    lab = torch.rand(rows, generator=g).to(device)
+    res_marg = {}
+    for label, enc_mod in (("ms_per_step", wrap), ("ms_per_step_dense_candidates", _Opaque(wrap))):
+        marg = TopKSparsemaxMarg(enc_mod, _dec, _loss, encoder_entropy_coeff=1.0)
+
+        def marg_step():
+            x.grad = None
+            marg(x, dec_in, lab)["loss"].backward()
+
+        ms, _, _ = timed(marg_step, 5, 2, world, device)
+        res_marg[label] = ms / 5
+    out["topk_sparsemax_marg_n128_k10"] = dict(res_marg, rows_per_gpu=rows, unit=UNIT,
+                                               value=rows * world / (res_marg["ms_per_step"] * 1e-3))
+    del dec_in, lab
+
     for name, kind, budget in (("sparsemap_bernoulli_n128", 0, 0), ("sparsemap_budget64_n128", 1, 64)):
         rows = args.path_rows_smap
         xs = torch.randn(rows, 128, generator=g).to(device).requires_grad_(True)

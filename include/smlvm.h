@@ -160,6 +160,11 @@ int smlvm_bits_score_fwd(const uint32_t* bits, const float* x, float* scores_k, 
 /* dx[rows,n] = sum_k dscores_k[r,k] * bits[r,k,j]  (autograd of the einsum w.r.t. scores)   */
 int smlvm_bits_score_bwd(const uint32_t* bits, const float* dscores_k, float* dx, int64_t rows,
                          int32_t n, int32_t k, void* stream);
+/* out[n_out,n] fp32 {0,1} = the n bits of packed row index[e] of bits[*,W] (index NULL: row e).
+ * replaces: `bit_vector_z.view(-1, n)[mask]` lvmhelpers/structmarg.py:116-126 (with index = the
+ * compacted candidate ids of smlvm_compact_fill) without materialising the dense [B,k,n] tensor. */
+int smlvm_bits_expand(const uint32_t* bits, const int64_t* index, float* out, int64_t n_out,
+                      int32_t n, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * (3b) SparseMAP active-set solver, one CTA per sample

@@ -227,6 +227,31 @@ static int topk_path_override()
 }
 constexpr int64_t kTopkTileMinRows = 16384;
 
+// out[e, :] = the n bits of packed row index[e] (index == NULL: row e) as fp32 {0,1}: the
+// boolean-mask indexing `bit_vector_z.view(-1, n)[mask]` of structmarg.py:116-126 from packed bits,
+// so that the dense [B,k,n] fp32 tensor is never materialised.  One warp per output row.
+__global__ void __launch_bounds__(256)
+bits_expand_kernel(const uint32_t* __restrict__ bits, const int64_t* __restrict__ index, float* __restrict__ out,
+                   int64_t n_out, int n)
+{
+    const int W = (n + 31) >> 5, lane = threadIdx.x & 31;
+    const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n_out; e += warps_total) {
+        const int64_t src = index != nullptr ? __ldg(index + e) : e;
+        const uint32_t* bw = bits + src * W;
+        float* o = out + e * n;
+        if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
+            for (int c = lane * 4; c < n; c += 128) {
+                const uint32_t nib = __ldg(bw + (c >> 5)) >> (c & 31);
+                stg_stream4(o + c, make_float4((float)(nib & 1u), (float)((nib >> 1) & 1u), (float)((nib >> 2) & 1u),
+                                               (float)((nib >> 3) & 1u)));
+            }
+        } else {
+            for (int c = lane; c < n; c += 32) stg_stream(o + c, (float)((__ldg(bw + (c >> 5)) >> (c & 31)) & 1u));
+        }
+    }
+}
+
 }  // namespace smlvm
 
 using namespace smlvm;
@@ -287,6 +312,19 @@ extern "C" int smlvm_bits_score_bwd(const uint32_t* bits, const float* dscores_k
     const size_t smem = (size_t)(kThreads / kWarp) * (((k + 3) & ~3) + ((k * ((n + 31) / 32) + 3) & ~3)) * sizeof(float);
     bits_score_bwd_kernel<<<(int)(need < cap ? need : cap), kThreads, smem, as_stream(stream)>>>(
         bits, dscores_k, dx, rows, n, k);
+    SMLVM_LAUNCH_CHECK();
+    return SMLVM_OK;
+}
+
+extern "C" int smlvm_bits_expand(const uint32_t* bits, const int64_t* index, float* out, int64_t n_out,
+                                 int32_t n, void* stream)
+{
+    if (n_out < 0 || n < 1) return SMLVM_ERR_ARG;
+    if (n_out == 0) return SMLVM_OK;
+    if (bits == nullptr || out == nullptr) return SMLVM_ERR_ARG;
+    int64_t need = (n_out + 7) / 8;
+    int64_t cap = (int64_t)device_sm_count() * 16;
+    bits_expand_kernel<<<(int)(need < cap ? need : cap), 256, 0, as_stream(stream)>>>(bits, index, out, n_out, n);
     SMLVM_LAUNCH_CHECK();
     return SMLVM_OK;
 }

@@ -376,6 +376,21 @@ def bits_score(x, bits):
     return _BitsScore.apply(_f32c(x, "scores"), bits)
 
 
+def bits_expand(bits, index, n):
+    """packed bits [..., W] int32 + candidate ids [N] int64 (None: every row) -> fp32 {0,1} [N, n]:
+    ``bit_vector_z.view(-1, n)[mask]`` (structmarg.py:116-126) without the dense [B,k,n] tensor."""
+    W = (n + 31) // 32
+    if not bits.is_cuda:
+        raise RuntimeError("lvmhelpers (B200): packed bits must be a CUDA tensor; there is no CPU fallback")
+    flat = bits.contiguous().view(-1, W)
+    if index is not None:
+        index = index.to(device=bits.device, dtype=torch.int64).contiguous()
+    n_out = flat.shape[0] if index is None else index.numel()
+    out = torch.empty((n_out, n), dtype=torch.float32, device=bits.device)
+    check(lib.smlvm_bits_expand(ptr(flat), ptr(index), ptr(out), n_out, n, stream()), "smlvm_bits_expand")
+    return out
+
+
 # --------------------------------------------------------------------------------------
 # (3b) SparseMAP
 # --------------------------------------------------------------------------------------

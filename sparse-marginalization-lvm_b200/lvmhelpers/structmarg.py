@@ -7,7 +7,11 @@ and ``log`` keys.  What changed underneath:
   D2H/H2D round trip, structmarg.py:43-44), the re-scoring einsum, the sparsemax over k,
   the support compaction (boolean-mask indexing, :116-126) and the weighted loss (:140)
   are kernels of ``libsmlvm.so``; inputs are gathered by compacted row index instead of
-  being repeated k times and masked (:95-126).
+  being repeated k times and masked (:95-126).  When the wrapper is the encoder of a
+  ``TopKSparsemaxMarg`` (the only way the experiments use it) the k candidates stay PACKED
+  (``PackedBitVectors``: 4 B per 32 bits) and only the candidates on the support are expanded
+  to fp32 for the decoder -- the dense [B,k,n] fp32 tensor is never written.  Called on its
+  own the wrapper returns the reference's dense tensor.
 * SparseMAP: the per-sample Python loop over factor graphs (:181-196) is one batched
   solver launch (one CTA per sample) + one ragged expansion; ``idxs`` / ``support`` are
   still Python lists (one D2H of the per-sample sizes).
@@ -58,6 +62,23 @@ class _IdxList(list):
     tensor = None
 
 
+class PackedBitVectors:
+    """The wrapper's first output when its consumer is ``TopKSparsemaxMarg``: the [B,k,n] {0,1}
+    candidates as packed words [B,k,W].  ``dense()`` gives the reference's fp32 tensor,
+    ``rows(index)`` the fp32 rows of the flattened [B*k, n] view at ``index``."""
+
+    def __init__(self, bits, n):
+        self.bits, self.n = bits, n
+        self.shape = torch.Size((bits.shape[0], bits.shape[1], n))
+        self.device, self.dtype = bits.device, torch.float32
+
+    def dense(self):
+        return ops.bits_expand(self.bits, None, self.n).view(self.shape)
+
+    def rows(self, index):
+        return ops.bits_expand(self.bits, index, self.n)
+
+
 class TopKSparsemaxWrapper(nn.Module):
     """scores -> (k best bit-vectors [B,k,n], sparsemax over their scores [B,k],
     entropy / B)  (reference structmarg.py:23-58)."""
@@ -66,12 +87,15 @@ class TopKSparsemaxWrapper(nn.Module):
         super().__init__()
         self.agent = agent
         self.k = k
+        self.packed_output = False  # TopKSparsemaxMarg turns it on around its own encoder call
 
     def forward(self, *args, **kwargs):
         scores = self.agent(*args, **kwargs)
         batch_size, latent_size = scores.shape
         # the top-k bit-vectors (detached, as the numpy round trip of structmarg.py:43)
-        bit_vector_z, bits, _ = ops.topk_bits(scores.detach(), self.k)
+        bit_vector_z, bits, _ = ops.topk_bits(scores.detach(), self.k, want_configs=not self.packed_output)
+        if self.packed_output:
+            bit_vector_z = PackedBitVectors(bits, latent_size)
         # rank them: scores_k = einsum("bkj,bj->bk"), differentiable w.r.t. scores (:47)
         scores_k = ops.bits_score(scores, bits)
         distr, _, _, nnz, _, slots = ops.sparsemax_stats(scores_k)
@@ -96,8 +120,20 @@ class TopKSparsemaxMarg(torch.nn.Module):
         self.encoder_entropy_coeff = encoder_entropy_coeff
         self.decoder_entropy_coeff = decoder_entropy_coeff
 
+    def _encode(self, encoder_input):
+        """The encoder call of structmarg.py:83; a TopKSparsemaxWrapper hands its candidates over packed
+        for the duration of THIS call only (called on its own it returns the reference's dense tensor)."""
+        enc = self.encoder
+        if not isinstance(enc, TopKSparsemaxWrapper):
+            return enc(encoder_input)
+        prev, enc.packed_output = enc.packed_output, True
+        try:
+            return enc(encoder_input)
+        finally:
+            enc.packed_output = prev
+
     def forward(self, encoder_input, decoder_input, labels):
-        bit_vector_z, encoder_probs, encoder_entropy = self.encoder(encoder_input)
+        bit_vector_z, encoder_probs, encoder_entropy = self._encode(encoder_input)
         batch_size = bit_vector_z.shape[0]
         latent_size = bit_vector_z.shape[-1]
 
@@ -115,7 +151,10 @@ class TopKSparsemaxMarg(torch.nn.Module):
         encoder_input_rep_flat = encoder_input.index_select(0, rows)
         decoder_input_rep_flat = decoder_input.index_select(0, rows)
         labels_rep_flat = labels.index_select(0, rows)
-        bit_vector_z_flat = bit_vector_z.view(-1, latent_size).index_select(0, comp["flat_idx"])
+        if isinstance(bit_vector_z, PackedBitVectors):
+            bit_vector_z_flat = bit_vector_z.rows(comp["flat_idx"])
+        else:
+            bit_vector_z_flat = bit_vector_z.view(-1, latent_size).index_select(0, comp["flat_idx"])
 
         decoder_output = self.decoder(bit_vector_z_flat, decoder_input)
 

@@ -103,3 +103,76 @@ def test_bits_score_fwd_bwd():
     # kernel accumulates in fp64 and rounds once; einsum in fp32 would differ by ~1e-6*|score|
     assert (sk.double() - ref).abs().max().item() <= 1e-6 * ref.abs().max().item()
     assert (x.grad.double() - xr.grad.double()).abs().max().item() <= 1e-5
+
+
+@pytest.mark.parametrize("rows,n,k", [(300, 128, 10), (64, 32, 10), (50, 33, 4), (20, 7, 5), (10, 200, 3)])
+def test_bits_expand_matches_dense_configs(rows, n, k):
+    """smlvm_bits_expand: packed candidates -> fp32 rows, all of them and an arbitrary selection
+    (`bit_vector_z.view(-1, n)[mask]`, structmarg.py:116-126)."""
+    from lvmhelpers import ops
+    g = torch.Generator().manual_seed(n + k)
+    x = torch.randn(rows, n, generator=g).cuda()
+    cfg, bits, _ = ops.topk_bits(x, k)
+    assert torch.equal(ops.bits_expand(bits, None, n).view(rows, k, n), cfg)
+    sel = torch.randperm(rows * k, generator=g)[: rows * k // 3].cuda()
+    assert torch.equal(ops.bits_expand(bits, sel, n), cfg.view(-1, n).index_select(0, sel))
+    assert ops.bits_expand(bits, sel[:0], n).shape == (0, n)
+
+
+def test_topk_marg_packed_candidates_equal_dense_path():
+    """TopKSparsemaxMarg hands the k candidates over packed and expands only the support; the result
+    (loss, logs, gradients) is the one of the dense [B,k,n] path; called on its own the wrapper still
+    returns the reference's dense tensor."""
+    from lvmhelpers.structmarg import TopKSparsemaxWrapper, TopKSparsemaxMarg, PackedBitVectors
+
+    class Dec(torch.nn.Module):
+        def __init__(self, n):
+            super().__init__()
+            self.lin = torch.nn.Linear(n, 16)
+            self.seen = None
+
+        def forward(self, z, decoder_input):
+            self.seen = z
+            return self.lin(z)
+
+    def loss_fun(enc_in, z, dec_in, dec_out, labels):
+        return ((dec_out - labels) ** 2).sum(-1), {"acc": dec_out.mean(-1)}
+
+    torch.manual_seed(3)
+    n, B = 40, 96
+    enc = torch.nn.Linear(24, n).cuda()
+    dec = Dec(n).cuda()
+    x = torch.randn(B, 24).cuda()
+    labels = torch.randn(B, 16).cuda()
+    wrapper = TopKSparsemaxWrapper(enc, k=7)
+    marg = TopKSparsemaxMarg(wrapper, dec, loss_fun, encoder_entropy_coeff=0.5)
+    res = marg(x, x, labels)
+    res["loss"].backward()
+    g_packed = [p.grad.clone() for p in list(enc.parameters()) + list(dec.parameters())]
+    z_packed = dec.seen.clone()
+
+    # the wrapper on its own: dense tensor, as in the reference
+    z_dense, distr, _ = wrapper(x)
+    assert isinstance(z_dense, torch.Tensor) and z_dense.shape == (B, 7, n) and not wrapper.packed_output
+    mask = distr.reshape(-1) > 0
+    assert torch.equal(z_packed, z_dense.view(-1, n)[mask])
+
+    # dense path through the same Marg: a wrapper subclass the Marg does not recognise
+    class Opaque(torch.nn.Module):
+        def __init__(self, w):
+            super().__init__()
+            self.w = w
+
+        def forward(self, *a):
+            return self.w(*a)
+
+    for p in list(enc.parameters()) + list(dec.parameters()):
+        p.grad = None
+    marg2 = TopKSparsemaxMarg(Opaque(wrapper), dec, loss_fun, encoder_entropy_coeff=0.5)
+    res2 = marg2(x, x, labels)
+    res2["loss"].backward()
+    assert not isinstance(dec.seen, PackedBitVectors) and torch.equal(dec.seen, z_packed)
+    assert torch.equal(res["loss"], res2["loss"])
+    for a, b in zip(g_packed, [p.grad for p in list(enc.parameters()) + list(dec.parameters())]):
+        assert torch.equal(a, b)
+    assert torch.equal(res["log"]["loss_output"], res2["log"]["loss_output"])
