@@ -367,15 +367,25 @@ def extra_paths(args, world, device, rank):
     def _loss(enc_in, z, dec_in, dec_out, lab):
         return dec_out.sum(-1) * 3.0 + lab, {}
 
+    class _AddBias(torch.nn.Module):    # a parameterised encoder, so that the input itself is data (no gradient)
+        def __init__(self):
+            super().__init__()
+            self.bias = torch.nn.Parameter(torch.zeros(128, device=device))
+
+        def forward(self, inp):
+            return inp + self.bias
+
     dec_in = torch.zeros(rows, 1, device=device)
     lab = torch.rand(rows, generator=g).to(device)
+    xin = x.detach()
+    wrap_b = TopKSparsemaxWrapper(_AddBias(), k=10)
     res_marg = {}
-    for label, enc_mod in (("ms_per_step", wrap), ("ms_per_step_dense_candidates", _Opaque(wrap))):
+    for label, enc_mod in (("ms_per_step", wrap_b), ("ms_per_step_dense_candidates", _Opaque(wrap_b))):
         marg = TopKSparsemaxMarg(enc_mod, _dec, _loss, encoder_entropy_coeff=1.0)
 
         def marg_step():
-            x.grad = None
-            marg(x, dec_in, lab)["loss"].backward()
+            wrap_b.agent.bias.grad = None
+            marg(xin, dec_in, lab)["loss"].backward()
 
         ms, _, _ = timed(marg_step, 5, 2, world, device)
         res_marg[label] = ms / 5

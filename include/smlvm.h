@@ -165,6 +165,12 @@ int smlvm_bits_score_bwd(const uint32_t* bits, const float* dscores_k, float* dx
  * compacted candidate ids of smlvm_compact_fill) without materialising the dense [B,k,n] tensor. */
 int smlvm_bits_expand(const uint32_t* bits, const int64_t* index, float* out, int64_t n_out,
                       int32_t n, void* stream);
+/* out[e] = src[idx[e]] for n_out rows of row_bytes bytes (a multiple of 4; 16-byte rows and pointers
+ * take 128-bit accesses).  replaces: `x.unsqueeze(1).repeat(1,k,1).view(B*k,-1)[mask]`
+ * lvmhelpers/structmarg.py:95-124 (idx = the compacted row ids of smlvm_compact_fill) and
+ * `encoder_input[idxs]`, `decoder_input[idxs]`, `labels[idxs]` structmarg.py:236-240.               */
+int smlvm_gather_rows(const void* src, const int32_t* idx, void* out, int64_t n_out, int64_t row_bytes,
+                      void* stream);
 
 /* ------------------------------------------------------------------------- *
  * (3b) SparseMAP active-set solver, one CTA per sample

@@ -229,7 +229,41 @@ constexpr int64_t kTopkTileMinRows = 16384;
 
 // out[e, :] = the n bits of packed row index[e] (index == NULL: row e) as fp32 {0,1}: the
 // boolean-mask indexing `bit_vector_z.view(-1, n)[mask]` of structmarg.py:116-126 from packed bits,
-// so that the dense [B,k,n] fp32 tensor is never materialised.  One warp per output row.
+// so that the dense [B,k,n] fp32 tensor is never materialised.  A thread per float4 of the output
+// (four in flight), consecutive threads on consecutive float4s.
+__global__ void __launch_bounds__(256)
+bits_expand_vec_kernel(const uint32_t* __restrict__ bits, const int64_t* __restrict__ index, float* __restrict__ out,
+                       int64_t n_out, int n)
+{
+    const int W = (n + 31) >> 5, q4 = n >> 2;  // float4s per row (n % 4 == 0)
+    const int64_t total = n_out * q4, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t c0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c0 < total; c0 += 4 * stride) {
+        uint32_t word[4];
+        int col[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t c = c0 + u * stride;
+            word[u] = 0u;
+            col[u] = 0;
+            if (c < total) {
+                const int64_t e = c / q4;
+                col[u] = (int)(c - e * q4) * 4;
+                const int64_t src = index != nullptr ? __ldg(index + e) : e;
+                word[u] = __ldg(bits + src * W + (col[u] >> 5));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t c = c0 + u * stride;
+            if (c < total) {
+                const uint32_t nib = word[u] >> (col[u] & 31);
+                stg_stream4(out + c * 4, make_float4((float)(nib & 1u), (float)((nib >> 1) & 1u),
+                                                     (float)((nib >> 2) & 1u), (float)((nib >> 3) & 1u)));
+            }
+        }
+    }
+}
+// any n / alignment: one warp per output row
 __global__ void __launch_bounds__(256)
 bits_expand_kernel(const uint32_t* __restrict__ bits, const int64_t* __restrict__ index, float* __restrict__ out,
                    int64_t n_out, int n)
@@ -240,14 +274,33 @@ bits_expand_kernel(const uint32_t* __restrict__ bits, const int64_t* __restrict_
         const int64_t src = index != nullptr ? __ldg(index + e) : e;
         const uint32_t* bw = bits + src * W;
         float* o = out + e * n;
-        if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
-            for (int c = lane * 4; c < n; c += 128) {
-                const uint32_t nib = __ldg(bw + (c >> 5)) >> (c & 31);
-                stg_stream4(o + c, make_float4((float)(nib & 1u), (float)((nib >> 1) & 1u), (float)((nib >> 2) & 1u),
-                                               (float)((nib >> 3) & 1u)));
+        for (int c = lane; c < n; c += 32) stg_stream(o + c, (float)((__ldg(bw + (c >> 5)) >> (c & 31)) & 1u));
+    }
+}
+
+// out[e] = src[idx[e]] for rows of `row_chunks` chunks of sizeof(T) bytes: `encoder_input[idxs]`,
+// `x.unsqueeze(1).repeat(1,k,1).view(B*k,-1)[mask]` (structmarg.py:95-124, 236-240).  A thread per
+// chunk, four in flight, consecutive threads on consecutive chunks of the output.
+template <typename T>
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const T* __restrict__ src, const int32_t* __restrict__ idx, T* __restrict__ out, int64_t n_out,
+                   int64_t row_chunks)
+{
+    const int64_t total = n_out * row_chunks, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t c0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c0 < total; c0 += 4 * stride) {
+        T v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t c = c0 + u * stride;
+            if (c < total) {
+                const int64_t e = c / row_chunks;
+                v[u] = __ldg(src + (int64_t)__ldg(idx + e) * row_chunks + (c - e * row_chunks));
             }
-        } else {
-            for (int c = lane; c < n; c += 32) stg_stream(o + c, (float)((__ldg(bw + (c >> 5)) >> (c & 31)) & 1u));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t c = c0 + u * stride;
+            if (c < total) out[c] = v[u];
         }
     }
 }
@@ -322,9 +375,38 @@ extern "C" int smlvm_bits_expand(const uint32_t* bits, const int64_t* index, flo
     if (n_out < 0 || n < 1) return SMLVM_ERR_ARG;
     if (n_out == 0) return SMLVM_OK;
     if (bits == nullptr || out == nullptr) return SMLVM_ERR_ARG;
-    int64_t need = (n_out + 7) / 8;
-    int64_t cap = (int64_t)device_sm_count() * 16;
-    bits_expand_kernel<<<(int)(need < cap ? need : cap), 256, 0, as_stream(stream)>>>(bits, index, out, n_out, n);
+    const int64_t cap = (int64_t)device_sm_count() * 16;
+    if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
+        const int64_t need = (n_out * (n >> 2) + 1023) / 1024;
+        bits_expand_vec_kernel<<<(int)(need < cap ? need : cap), 256, 0, as_stream(stream)>>>(bits, index, out, n_out, n);
+    } else {
+        const int64_t need = (n_out + 7) / 8;
+        bits_expand_kernel<<<(int)(need < cap ? need : cap), 256, 0, as_stream(stream)>>>(bits, index, out, n_out, n);
+    }
+    SMLVM_LAUNCH_CHECK();
+    return SMLVM_OK;
+}
+
+extern "C" int smlvm_gather_rows(const void* src, const int32_t* idx, void* out, int64_t n_out, int64_t row_bytes,
+                                 void* stream)
+{
+    if (n_out < 0 || row_bytes < 1) return SMLVM_ERR_ARG;
+    if (n_out == 0) return SMLVM_OK;
+    if (src == nullptr || idx == nullptr || out == nullptr) return SMLVM_ERR_ARG;
+    const uintptr_t al = reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(out) | (uintptr_t)row_bytes;
+    const int chunk = (al & 15u) == 0 ? 16 : ((al & 7u) == 0 ? 8 : ((al & 3u) == 0 ? 4 : 0));
+    if (chunk == 0) return SMLVM_ERR_UNSUPPORTED;
+    const int64_t row_chunks = row_bytes / chunk;
+    const int64_t cap = (int64_t)device_sm_count() * 16;
+    const int64_t need = (n_out * row_chunks + 1023) / 1024;
+    const int grid = (int)(need < cap ? need : cap);
+    cudaStream_t st = as_stream(stream);
+    if (chunk == 16)
+        gather_rows_kernel<uint4><<<grid, 256, 0, st>>>((const uint4*)src, idx, (uint4*)out, n_out, row_chunks);
+    else if (chunk == 8)
+        gather_rows_kernel<uint2><<<grid, 256, 0, st>>>((const uint2*)src, idx, (uint2*)out, n_out, row_chunks);
+    else
+        gather_rows_kernel<uint32_t><<<grid, 256, 0, st>>>((const uint32_t*)src, idx, (uint32_t*)out, n_out, row_chunks);
     SMLVM_LAUNCH_CHECK();
     return SMLVM_OK;
 }

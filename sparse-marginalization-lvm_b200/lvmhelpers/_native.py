@@ -41,6 +41,7 @@ _PROTOTYPES = {
     "smlvm_bits_score_fwd": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     "smlvm_bits_score_bwd": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     "smlvm_bits_expand": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _vp]),
+    "smlvm_gather_rows": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
     "smlvm_sparsemap_capacity": (_i32, [_i32]),
     "smlvm_sparsemap_plan": (_i32, [_i32, _i32, _vp, _vp, _vp]),
     "smlvm_sparsemap_fwd": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i64, _i32,

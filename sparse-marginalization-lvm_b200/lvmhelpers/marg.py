@@ -190,8 +190,8 @@ class Marginalizer(torch.nn.Module):
         """decoder calls proportional to the support: one ragged batch of N = sum_b |supp(b)| rows."""
         batch_size = encoder_probs.shape[0]
         comp = ops.compact(encoder_probs.detach(), side["nnz"], slots=side["slots"])
-        rows, cols = comp["rows"].long(), comp["cols"].long()
-        take = lambda t: t.index_select(0, rows) if torch.is_tensor(t) else t
+        rows, cols = comp["rows"], comp["cols"].long()
+        take = lambda t: ops.gather_rows(t, rows)
         decoder_output = self.decoder(cols, take(decoder_input))
         loss_components, logs = self.loss(take(encoder_input), take(discrete_latent_z), take(decoder_input),
                                           decoder_output, take(labels))

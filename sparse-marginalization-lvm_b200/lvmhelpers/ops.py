@@ -376,6 +376,38 @@ def bits_score(x, bits):
     return _BitsScore.apply(_f32c(x, "scores"), bits)
 
 
+class _GatherRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, idx):
+        out = torch.empty((idx.numel(),) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+        row_bytes = (src.numel() // max(src.shape[0], 1)) * src.element_size()
+        check(lib.smlvm_gather_rows(ptr(src), ptr(idx), ptr(out), idx.numel(), row_bytes, stream()),
+              "smlvm_gather_rows")
+        ctx.save_for_backward(idx)
+        ctx.src_shape = src.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (idx,) = ctx.saved_tensors
+        d = torch.zeros(ctx.src_shape, dtype=dout.dtype, device=dout.device)
+        d.index_add_(0, idx.long(), dout)
+        return d, None
+
+
+def gather_rows(t, idx):
+    """``t[idx]`` along dim 0 for the compacted row ids (int32) of the support: the repeat-and-mask of
+    structmarg.py:95-124 and the ``[idxs]`` gathers of :236-240.  Rows whose size is not a multiple of
+    4 bytes, empty tensors and non-CUDA tensors go through ``index_select``."""
+    if not torch.is_tensor(t):
+        return t
+    row_bytes = (t.numel() // t.shape[0]) * t.element_size() if t.dim() > 0 and t.shape[0] > 0 else 0
+    if not t.is_cuda or row_bytes == 0 or row_bytes % 4 != 0 or idx.numel() == 0:
+        return t.index_select(0, idx.to(torch.int64) if idx.dtype != torch.int64 else idx)
+    idx = idx.to(device=t.device, dtype=torch.int32).contiguous()
+    return _GatherRows.apply(t.contiguous(), idx)
+
+
 def bits_expand(bits, index, n):
     """packed bits [..., W] int32 + candidate ids [N] int64 (None: every row) -> fp32 {0,1} [N, n]:
     ``bit_vector_z.view(-1, n)[mask]`` (structmarg.py:116-126) without the dense [B,k,n] tensor."""

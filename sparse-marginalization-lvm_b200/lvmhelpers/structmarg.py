@@ -148,9 +148,9 @@ class TopKSparsemaxMarg(torch.nn.Module):
             encoder_probs_flat = encoder_probs._smlvm_vals
         rows = comp["rows"]
         # x.unsqueeze(1).repeat(1,k,1).view(B*k,-1)[mask] == x[row of each survivor] (:95-124)
-        encoder_input_rep_flat = encoder_input.index_select(0, rows)
-        decoder_input_rep_flat = decoder_input.index_select(0, rows)
-        labels_rep_flat = labels.index_select(0, rows)
+        encoder_input_rep_flat = ops.gather_rows(encoder_input, rows)
+        decoder_input_rep_flat = ops.gather_rows(decoder_input, rows)
+        labels_rep_flat = ops.gather_rows(labels, rows)
         if isinstance(bit_vector_z, PackedBitVectors):
             bit_vector_z_flat = bit_vector_z.rows(comp["flat_idx"])
         else:
@@ -231,9 +231,9 @@ class SparseMAPMarg(torch.nn.Module):
         if gather is None:
             gather = torch.as_tensor(idxs, device=encoder_input.device)
         loss_components, logs = self.loss(
-            encoder_input.index_select(0, gather), bit_vector_z,
-            decoder_input.index_select(0, gather), decoder_output,
-            labels.index_select(0, gather))
+            ops.gather_rows(encoder_input, gather), bit_vector_z,
+            ops.gather_rows(decoder_input, gather), decoder_output,
+            ops.gather_rows(labels, gather))
 
         loss = ops.ragged_loss(encoder_probs, loss_components, 1.0 / batch_size)
         full_loss = loss + entropy_loss

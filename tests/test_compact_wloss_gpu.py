@@ -141,3 +141,32 @@ def test_segment_logsumexp_matches_reference_loop():
     fin = torch.isfinite(ref)
     assert torch.equal(fin, torch.isfinite(out))
     assert (out[fin] - ref[fin]).abs().max().item() <= 1e-3 * 1e-2 + 2e-4 * 1  # |v| ~ 2000: fp32 ulp 1.2e-4
+
+
+@pytest.mark.parametrize("shape,dtype", [((300, 128), torch.float32), ((257, 784), torch.float32), ((100,), torch.int64),
+                                         ((64, 3), torch.float32), ((50, 2, 6), torch.float32), ((40, 5), torch.int32),
+                                         ((33, 7), torch.float16), ((10, 1), torch.uint8)])
+def test_gather_rows_matches_index_select(shape, dtype):
+    """smlvm_gather_rows (`encoder_input[idxs]`, structmarg.py:95-124, 236-240): every chunk width (16 / 8 / 4
+    bytes), odd row sizes through the index_select route, repeated and unsorted ids, empty selection, and the
+    gradient of a differentiable source."""
+    from lvmhelpers import ops
+    g = torch.Generator().manual_seed(shape[0])
+    if dtype.is_floating_point:
+        t = torch.randn(shape, generator=g).to(dtype).cuda()
+    else:
+        t = torch.randint(0, 100, shape, generator=g).to(dtype).cuda()
+    idx = torch.randint(0, shape[0], (4 * shape[0] + 3,), generator=g).to(torch.int32).cuda()
+    assert torch.equal(ops.gather_rows(t, idx), t.index_select(0, idx.long()))
+    srt = torch.sort(idx).values
+    assert torch.equal(ops.gather_rows(t, srt), t.index_select(0, srt.long()))
+    assert ops.gather_rows(t, idx[:0]).shape == (0,) + tuple(shape[1:])
+    assert torch.equal(ops.gather_rows(t, idx.long()), t.index_select(0, idx.long()))       # int64 ids accepted
+    if dtype == torch.float32:
+        a = t.clone().requires_grad_(True)
+        b = t.clone().requires_grad_(True)
+        w = torch.randn((idx.numel(),) + tuple(shape[1:]), generator=g).cuda()
+        (ops.gather_rows(a, idx) * w).sum().backward()
+        (b.index_select(0, idx.long()) * w).sum().backward()
+        assert torch.allclose(a.grad, b.grad, rtol=1e-5, atol=1e-5)
+    assert ops.gather_rows(None, idx) is None and ops.gather_rows(3.5, idx) == 3.5
