@@ -502,6 +502,18 @@ def run_native(args, rank, local_rank, world):
     ms_per_step = ms / args.steps
     value = rows * world / (ms_per_step * 1e-3)
 
+    # the same step as a user runs it: no events between the kernels, the compaction branch on the step's side
+    # stream under the loss / backward kernels, and as one CUDA-graph replay (informational: `value` above stays
+    # the instrumented, serial region the roofline numbers come from)
+    ms_plain, _, _ = timed(lambda: step.run(x, losses), args.steps, args.warmup, world, device)
+    graph = step.capture(x, losses)
+    ms_graph, _, _ = timed(graph.replay, args.steps, args.warmup, world, device)
+    uninstrumented = {"ms_per_step": ms_plain / args.steps, "ms_per_step_cuda_graph": ms_graph / args.steps,
+                      "value": rows * world / (ms_plain / args.steps * 1e-3),
+                      "value_cuda_graph": rows * world / (ms_graph / args.steps * 1e-3), "unit": UNIT,
+                      "note": "no per-kernel events; scan + fill on a side stream (hotpath.SparsemaxMargStep.run)"}
+    del graph
+
     # end to end through host buffers: H2D of X and L, the step, D2H of gradient + loss, every
     # step, through the host-buffer entry point of the package (micro-batched over 3 streams)
     from lvmhelpers.hotpath import HostPipelinedMargStep
@@ -545,6 +557,7 @@ def run_native(args, rank, local_rank, world):
                                   "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,
                                   "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak}},
             "kernels": kernels,
+            "resident_uninstrumented": uninstrumented,
             "cpu_baseline": cpu,
             "paths": paths,
             "check": {"loss": loss_value, "support_mean": total_nnz / rows},

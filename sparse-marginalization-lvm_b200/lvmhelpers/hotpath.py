@@ -18,10 +18,14 @@ from . import _native as N
 from ._native import lib, check, ptr
 
 
+OVERLAP_MIN_ROWS = 65536
+
+
 class SparsemaxMargStep:
     KERNELS = ("sparsemax_fwd", "scan_counts", "compact_fill", "wloss_dense_fwd", "sparsemax_bwd")
 
-    def __init__(self, rows, cols, device, capacity, entropy_coeff=0.0, global_rows=None, use_slots=None):
+    def __init__(self, rows, cols, device, capacity, entropy_coeff=0.0, global_rows=None, use_slots=None,
+                 overlap_compaction=True):
         """``global_rows``: batch size B of the 1/B in the loss and entropy terms when this step
         owns only a shard / micro-batch of the batch (default: ``rows``).
         ``use_slots``: let the weighted loss and the backward read the losses only at the support
@@ -52,6 +56,9 @@ class SparsemaxMargStep:
             if self.entropy_coeff != 0.0 else None
         self.scan_ws = torch.zeros(max(lib.smlvm_scan_workspace_bytes(rows), 64), dtype=torch.uint8, device=device)
         self.red_ws = torch.zeros(lib.smlvm_reduce_workspace_bytes(), dtype=torch.uint8, device=device)
+        # side stream of the compaction branch (run()); small batches are launch-bound: one stream
+        self.side = torch.cuda.Stream(device=device) if (overlap_compaction and rows >= OVERLAP_MIN_ROWS) else None
+        self._ev_fwd, self._ev_side = torch.cuda.Event(), torch.cuda.Event()
 
     @staticmethod
     def size_capacity(x):
@@ -61,21 +68,34 @@ class SparsemaxMargStep:
         return int(out["nnz"].sum().item())
 
     def run(self, x, losses, rec=None):
-        """Launch the five kernels on the current stream.  ``rec(name)`` (optional) is called
-        before and after each launch so that a caller can bracket them with CUDA events."""
-        st = torch.cuda.current_stream().cuda_stream
+        """Launch the five kernels.  The compaction branch (scan -> fill) depends only on the forward,
+        like the loss branch (weighted loss -> backward): for large batches it goes to a side stream
+        between two events, so the latency-bound scan and the fill run under the HBM-bound loss /
+        backward kernels.  ``rec(name)`` (optional) is called before and after each launch so that a
+        caller can bracket the kernels with CUDA events; the launches are then serial on the current
+        stream."""
+        cur = torch.cuda.current_stream()
+        st = cur.cuda_stream
         rows, K = self.rows, self.cols
         mark = rec if rec is not None else (lambda name: None)
         mark("sparsemax_fwd")
         slots = ptr(self.slots) if self.use_slots else None
         check(lib.smlvm_sparsemax_fwd(ptr(x), ptr(self.p), ptr(self.supp), ptr(self.nnz), ptr(self.ent),
                                       ptr(self.amax), slots, rows, K, st), "smlvm_sparsemax_fwd")
+        fork = rec is None and self.side is not None
+        st_c = st
+        if fork:
+            self._ev_fwd.record(cur)
+            self.side.wait_event(self._ev_fwd)
+            st_c = self.side.cuda_stream
         mark("scan_counts")
         check(lib.smlvm_scan_counts(ptr(self.nnz), ptr(self.offsets), rows, ptr(self.scan_ws),
-                                    self.scan_ws.numel(), st), "smlvm_scan_counts")
+                                    self.scan_ws.numel(), st_c), "smlvm_scan_counts")
         mark("compact_fill")
         check(lib.smlvm_compact_fill(ptr(self.p), ptr(self.offsets), slots, ptr(self.vals), ptr(self.ri),
-                                     ptr(self.ci), rows, K, st), "smlvm_compact_fill")
+                                     ptr(self.ci), rows, K, st_c), "smlvm_compact_fill")
+        if fork:
+            self._ev_side.record(self.side)
         mark("wloss_dense_fwd")
         lslots = ptr(self.loss_slots) if self.use_slots else None
         check(lib.smlvm_wloss_dense_fwd(ptr(self.p), ptr(losses), slots, lslots, ptr(self.row_loss), ptr(self.total),
@@ -85,6 +105,8 @@ class SparsemaxMargStep:
         check(lib.smlvm_sparsemax_bwd(ptr(self.p), ptr(self.supp), None, ptr(losses), None, 1.0 / self.global_rows,
                                       ptr(self.dent), slots, lslots, ptr(self.dx), ptr(self.dloss), rows, K, st),
               "smlvm_sparsemax_bwd")
+        if fork:
+            cur.wait_event(self._ev_side)
         mark(None)
         return self.total
 

@@ -102,3 +102,40 @@ def test_compact_step_matches_oracle(oracle, rows, K):
     assert (step.base.dx.cpu() - xr.grad).abs().max().item() <= 4e-6 * max(1.0, xr.grad.abs().max().item())
     assert (step.dloss_ragged[:int(mask.sum())].cpu() - Lr.grad).abs().max().item() <= 1e-7
     assert (step.base.dx.cpu()[~mask] == 0).all()
+
+
+def test_compaction_branch_on_side_stream_matches_serial():
+    """rows >= 65536: scan + fill run on the step's side stream between two events; same results as the
+    serial (instrumented) launch order, eager and as a CUDA-graph replay, repeated back to back."""
+    from lvmhelpers import hotpath
+    rows, K = hotpath.OVERLAP_MIN_ROWS, 32
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(rows, K, generator=g).cuda()
+    L = torch.rand(rows, K, generator=g).cuda()
+    nnz = hotpath.SparsemaxMargStep.size_capacity(x)
+    serial = hotpath.SparsemaxMargStep(rows, K, x.device, nnz + 64, entropy_coeff=0.7, overlap_compaction=False)
+    forked = hotpath.SparsemaxMargStep(rows, K, x.device, nnz + 64, entropy_coeff=0.7)
+    assert serial.side is None and forked.side is not None
+    serial.run(x, L)
+    names = ("p", "offsets", "dx", "dloss", "row_loss", "total")
+
+    def same():
+        torch.cuda.synchronize()
+        for nme in names:
+            assert torch.equal(getattr(serial, nme), getattr(forked, nme)), nme
+        for nme in ("vals", "ri", "ci"):
+            assert torch.equal(getattr(serial, nme)[:nnz], getattr(forked, nme)[:nnz]), nme
+
+    for _ in range(3):
+        forked.run(x, L)
+    same()
+    marks = []
+    forked.run(x, L, rec=marks.append)          # instrumented: serial on the current stream
+    assert marks == list(hotpath.SparsemaxMargStep.KERNELS) + [None]
+    same()
+    graph = forked.capture(x, L)
+    for nme in names + ("vals", "ri", "ci"):
+        getattr(forked, nme).zero_()
+    graph.replay()
+    graph.replay()
+    same()
