@@ -96,7 +96,16 @@ def ptr(t):
     return None if t is None else t.data_ptr()
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_cur_device = getattr(torch._C, "_cuda_getDevice", None)
+
+
 def stream():
+    """cudaStream_t of torch's current stream on the current device.  The two C entry points cost well
+    under a microsecond; ``torch.cuda.current_stream()`` walks through a dozen Python frames (0.3 ms per
+    wrapper step at the launch-bound B = 64 shapes, 18 launches per step)."""
+    if _raw_stream is not None and _cur_device is not None:
+        return _raw_stream(_cur_device())
     return torch.cuda.current_stream().cuda_stream
 
 

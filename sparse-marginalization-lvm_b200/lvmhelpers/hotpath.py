@@ -74,15 +74,15 @@ class SparsemaxMargStep:
         backward kernels.  ``rec(name)`` (optional) is called before and after each launch so that a
         caller can bracket the kernels with CUDA events; the launches are then serial on the current
         stream."""
-        cur = torch.cuda.current_stream()
-        st = cur.cuda_stream
+        fork = rec is None and self.side is not None
+        cur = torch.cuda.current_stream() if fork else None
+        st = cur.cuda_stream if fork else N.stream()
         rows, K = self.rows, self.cols
         mark = rec if rec is not None else (lambda name: None)
         mark("sparsemax_fwd")
         slots = ptr(self.slots) if self.use_slots else None
         check(lib.smlvm_sparsemax_fwd(ptr(x), ptr(self.p), ptr(self.supp), ptr(self.nnz), ptr(self.ent),
                                       ptr(self.amax), slots, rows, K, st), "smlvm_sparsemax_fwd")
-        fork = rec is None and self.side is not None
         st_c = st
         if fork:
             self._ev_fwd.record(cur)
@@ -158,7 +158,7 @@ class SparsemaxMargCompactStep:
 
     def run(self, x, losses_ragged, n_items, rec=None):
         b = self.base
-        st = torch.cuda.current_stream().cuda_stream
+        st = N.stream()
         rows, K = b.rows, b.cols
         mark = rec if rec is not None else (lambda name: None)
         mark("sparsemax_fwd")
