@@ -105,6 +105,32 @@ def test_bits_score_fwd_bwd():
     assert (x.grad.double() - xr.grad.double()).abs().max().item() <= 1e-5
 
 
+@pytest.mark.parametrize("rows,n,k", [(2048, 128, 10), (1030, 32, 16), (1500, 100, 2), (4096, 4, 7), (1024, 64, 13),
+                                      (1100, 36, 3), (2000, 128, 17), (1200, 130, 4)])
+def test_bits_score_large_shapes(rows, n, k):
+    """Re-scoring einsum from packed bits at larger shapes, top-k patterns and arbitrary ones: fp64 sums
+    rounded once, so equal to the fp64 einsum to the last fp32 bit (1 ulp allowed for double rounding)."""
+    from lvmhelpers import ops
+    g = torch.Generator().manual_seed(n * 17 + k)
+    x = (torch.randn(rows, n, generator=g) * 3).cuda()
+    k_eff = min(k, 2 ** min(n, 20))
+    cfg, bits, _ = ops.topk_bits(x, k_eff)
+    sk = ops.bits_score(x, bits)
+    ref = torch.einsum("bkj,bj->bk", cfg.double(), x.double())
+    def close(a, b):
+        return bool(((a.double() - b).abs() <= 1.2e-7 * b.abs().clamp(min=1e-30)).all())
+
+    assert close(sk, ref)
+    # arbitrary (not top-k) bit patterns too
+    rb = torch.randint(-2 ** 31, 2 ** 31 - 1, bits.shape, generator=g, dtype=torch.int64).to(torch.int32).cuda()
+    W = (n + 31) // 32
+    if n % 32:
+        rb[..., W - 1] &= (1 << (n % 32)) - 1
+    idx = torch.arange(n, device="cuda")
+    dense = ((rb[..., idx // 32] >> (idx % 32)) & 1).double()
+    assert close(ops.bits_score(x, rb), torch.einsum("bkj,bj->bk", dense, x.double()))
+
+
 @pytest.mark.parametrize("rows,n,k", [(300, 128, 10), (64, 32, 10), (50, 33, 4), (20, 7, 5), (10, 200, 3)])
 def test_bits_expand_matches_dense_configs(rows, n, k):
     """smlvm_bits_expand: packed candidates -> fp32 rows, all of them and an arbitrary selection
