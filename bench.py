@@ -257,6 +257,42 @@ def small_config_latency(device):
             torch.cuda.synchronize()
             res[label] = e0.elapsed_time(e1) / 200 * 1e3
         out[name] = res
+
+    # configs 3-4 (bit-vector VAE, 32 bits, batch 64) through the public wrapper API, forward + backward
+    from lvmhelpers import ops
+    from lvmhelpers.structmarg import TopKSparsemaxWrapper
+    g = torch.Generator().manual_seed(43)
+    xb = torch.randn(64, 32, generator=g).to(device).requires_grad_(True)
+    wrap = TopKSparsemaxWrapper(torch.nn.Identity(), k=10)
+    cl = (torch.rand(640, generator=g) * 3).to(device)
+
+    def topk_step():
+        xb.grad = None
+        _, distr, ent = wrap(xb)
+        vals = distr._smlvm_vals
+        (ops.ragged_loss(vals, cl[:vals.numel()], 1.0 / 64) - ent).backward()
+
+    def smap_step(kind, budget):
+        def f():
+            xb.grad = None
+            p, _, _ = ops.sparsemap_batch(xb, kind, budget=budget, max_iter=300, only_positive=True)
+            (ops.ragged_loss(p, torch.ones_like(p), 1.0 / 64) - ops.ragged_entropy(p, 1.0 / 64)).backward()
+        return f
+
+    for name, fn in (("C3_topk_sparsemax_64x32_k10", topk_step), ("C4_sparsemap_bernoulli_64x32", smap_step(0, 0)),
+                     ("C4_sparsemap_budget16_64x32", smap_step(1, 16))):
+        for _ in range(10):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(100):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        out[name] = {"eager_us": e0.elapsed_time(e1) / 100 * 1e3, "host_wall_us": (time.perf_counter() - t0) / 100 * 1e6,
+                     "note": "public wrapper API, forward + backward, host-launch bound"}
     return out
 
 
