@@ -36,4 +36,4 @@ def test_fuzz_sparsemap_solver():
     included: n = 128 rows that outgrow a tier are re-solved), full solutions on a sample of rows."""
     if not torch.cuda.is_available():
         pytest.skip("needs a GPU")
-    assert _fuzz("fuzz_solver").run_solver(seed=5, n_cases=8, rows=256, verbose=False) == 0
+    assert _fuzz("fuzz_solver").run_solver(seed=5, n_cases=8, rows=320, verbose=False) == 0
