@@ -37,3 +37,9 @@ def test_fuzz_sparsemap_solver():
     if not torch.cuda.is_available():
         pytest.skip("needs a GPU")
     assert _fuzz("fuzz_solver").run_solver(seed=5, n_cases=8, rows=320, verbose=False) == 0
+
+
+def test_fuzz_sparsemap_sequence_factor():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    assert _fuzz("fuzz_solver").run_sequence(seed=5, n_cases=4, rows=32, verbose=False) == 0

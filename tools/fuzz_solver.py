@@ -44,6 +44,38 @@ def run_solver(seed=0, n_cases=24, rows=512, verbose=True):
     return bad
 
 
+def run_sequence(seed=0, n_cases=6, rows=48, verbose=True):
+    """Sequence-binary factor (transition scores t, 2-state Viterbi oracle): every row against the oracle."""
+    rng = np.random.default_rng(seed)
+    bad = 0
+    for case in range(n_cases):
+        n = int(rng.choice([2, 5, 20, 33, 64, 100]))
+        scale = float(10 ** rng.uniform(-0.7, 0.5))
+        x = (rng.standard_normal((rows, n)) * scale).astype(np.float32)
+        t = (rng.standard_normal((rows, n - 1)) * scale).astype(np.float32)
+        if case % 2 == 0:
+            x, t = np.round(x * 2) / 2, np.round(t * 2) / 2
+        st = ops.sparsemap_solve(torch.from_numpy(x).cuda(), 2, t=torch.from_numpy(t).cuda(), max_iter=100, keep_S=False)
+        torch.cuda.synchronize()
+        ok = True
+        for r in range(rows):
+            ref = oracle.sparsemap_fwd(x[r], 2, t=t[r], max_iter=100)
+            m = int(st["counts"][r])
+            p = st["p_pad"][r, :m].cpu().numpy()
+            b = st["bits"][r, :m].cpu().numpy().astype(np.uint32)
+            idx = np.arange(n)
+            aset = ((b[:, idx // 32] >> (idx % 32)) & 1).astype(np.int32)
+            ok = ok and aset.shape == ref["aset"].shape and np.array_equal(aset, ref["aset"]) \
+                and np.abs(p - ref["p"]).max() <= 1e-5 and int(st["status"][r]) == ref["status"] \
+                and int(st["iters"][r]) == ref["iters"]
+        if not ok:
+            bad += 1
+            print("SEQUENCE MISMATCH case", case, "n", n, "scale %.3g" % scale, flush=True)
+    if verbose:
+        print("sequence fuzz: %d cases, %d mismatches" % (n_cases, bad))
+    return bad
+
+
 def run_topk(seed=0, n_cases=40, verbose=True):
     rng = np.random.default_rng(seed)
     bad = 0
@@ -70,5 +102,5 @@ def run_topk(seed=0, n_cases=40, verbose=True):
 
 if __name__ == "__main__":
     seed = int(sys.argv[1]) if len(sys.argv) > 1 else 0
-    b = run_topk(seed) + run_solver(seed)
+    b = run_topk(seed) + run_solver(seed) + run_sequence(seed)
     sys.exit(1 if b else 0)
