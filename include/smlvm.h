@@ -221,10 +221,19 @@ int smlvm_sparsemap_expand(const float* p_pad, const uint32_t* aset_bits, const 
  * dp is ragged in the same layout smlvm_sparsemap_expand produced (same offsets,
  * same only_positive); dropped vertices get dp = 0.
  * replaces: SparseMAP.jv / dist_jacobian_vec lvmhelpers/sparsemap.py:38-44,80-87          */
+/* S of sample r is read at S_pad + r*cap*cap (the layout smlvm_sparsemap_fwd writes) or, when S_rows is
+ * not NULL, at the device address S_rows[r] (int64: the packed copies of smlvm_sparsemap_pack_inverse, possibly
+ * in several buffers).                                                                               */
 int smlvm_sparsemap_bwd(const float* dp, const int64_t* offsets, int32_t only_positive,
                         const float* p_pad, const uint32_t* aset_bits, const int32_t* counts,
-                        const double* S_pad, float* dx, float* dt, int64_t rows, int32_t n,
-                        void* stream);
+                        const double* S_pad, const int64_t* S_rows, float* dx, float* dt, int64_t rows,
+                        int32_t n, void* stream);
+
+/* S_packed[S_offsets[r] .. + counts[r]^2) = the |A|^2 doubles of sample r in S_pad: keeps 8|A|^2 bytes per
+ * sample for the backward instead of the padded 8(n+1)^2 (133 KB at n = 128; the reference keeps the whole
+ * factor object alive for this, sparsemap.py:19,42).                                                     */
+int smlvm_sparsemap_pack_inverse(const double* S_pad, const int32_t* counts, const int64_t* S_offsets,
+                           double* S_packed, int64_t rows, int32_t n, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * (4) probability-weighted loss, fused segmented reduce

@@ -689,8 +689,8 @@ __global__ void __launch_bounds__(128)
 sparsemap_bwd_kernel(const float* __restrict__ dp, const int64_t* __restrict__ offsets,
                      int only_positive, const float* __restrict__ p_pad,
                      const uint32_t* __restrict__ aset_bits, const int32_t* __restrict__ counts,
-                     const double* __restrict__ S_pad, float* __restrict__ dx,
-                     float* __restrict__ dt, int64_t rows, int n)
+                     const double* __restrict__ S_pad, const int64_t* __restrict__ S_rows,
+                     float* __restrict__ dx, float* __restrict__ dt, int64_t rows, int n)
 {
     extern __shared__ double sh[];
     const int cap = n + 1, W = (n + 31) / 32;
@@ -710,7 +710,8 @@ sparsemap_bwd_kernel(const float* __restrict__ dp, const int64_t* __restrict__ o
             }
         }
         __syncthreads();
-        const double* S = S_pad + row * (int64_t)cap * cap;
+        const double* S = S_rows != nullptr ? reinterpret_cast<const double*>(__ldg(S_rows + row))
+                                            : S_pad + row * (int64_t)cap * cap;
         for (int a = tid; a < m; a += T) {
             double acc = 0.0;
             for (int c = 0; c < m; ++c) acc += S[(int64_t)c * m + a] * g[c];  // S symmetric
@@ -732,6 +733,23 @@ sparsemap_bwd_kernel(const float* __restrict__ dp, const int64_t* __restrict__ o
             dx[row * n + i] = (float)on;
             if (dt != nullptr && i + 1 < n) dt[row * (int64_t)(n - 1) + i] = (float)edge;
         }
+    }
+}
+
+// S of every sample (|A|^2 doubles at the start of its (n+1)^2 slot) -> one packed buffer at S_offsets[row]:
+// the padded layout costs 133 KB per sample at n = 128 (139 GB for the 1M-sample point of the sweep), the
+// packed one 8 |A|^2 (15 KB on average).  One warp per sample.
+__global__ void __launch_bounds__(256)
+sparsemap_pack_S_kernel(const double* __restrict__ S_pad, const int32_t* __restrict__ counts,
+                        const int64_t* __restrict__ S_offsets, double* __restrict__ S_packed, int64_t rows, int n)
+{
+    const int cap = n + 1, lane = threadIdx.x & 31;
+    const int64_t warps_total = (int64_t)gridDim.x * 8;
+    for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += warps_total) {
+        const int m = __ldg(counts + row);
+        const double* src = S_pad + row * (int64_t)cap * cap;
+        double* dst = S_packed + __ldg(S_offsets + row);
+        for (int e = lane; e < m * m; e += 32) dst[e] = __ldg(src + e);
     }
 }
 
@@ -888,19 +906,33 @@ extern "C" int smlvm_sparsemap_expand(const float* p_pad, const uint32_t* aset_b
 
 extern "C" int smlvm_sparsemap_bwd(const float* dp, const int64_t* offsets, int32_t only_positive,
                                    const float* p_pad, const uint32_t* aset_bits,
-                                   const int32_t* counts, const double* S_pad, float* dx, float* dt,
-                                   int64_t rows, int32_t n, void* stream)
+                                   const int32_t* counts, const double* S_pad, const int64_t* S_rows,
+                                   float* dx, float* dt, int64_t rows, int32_t n, void* stream)
 {
     if (rows < 0 || n < 1) return SMLVM_ERR_ARG;
     if (rows == 0) return SMLVM_OK;
     if (dp == nullptr || offsets == nullptr || p_pad == nullptr || aset_bits == nullptr ||
-        counts == nullptr || S_pad == nullptr || dx == nullptr)
+        counts == nullptr || (S_pad == nullptr && S_rows == nullptr) || dx == nullptr)
         return SMLVM_ERR_ARG;
     if (n > SMLVM_SPARSEMAP_MAX_BITS) return SMLVM_ERR_UNSUPPORTED;
     const size_t smem = 2 * (size_t)(n + 1) * sizeof(double);
     int64_t cap = (int64_t)device_sm_count() * 32;
     sparsemap_bwd_kernel<<<(int)(rows < cap ? rows : cap), 128, smem, as_stream(stream)>>>(
-        dp, offsets, only_positive, p_pad, aset_bits, counts, S_pad, dx, dt, rows, n);
+        dp, offsets, only_positive, p_pad, aset_bits, counts, S_pad, S_rows, dx, dt, rows, n);
+    SMLVM_LAUNCH_CHECK();
+    return SMLVM_OK;
+}
+
+extern "C" int smlvm_sparsemap_pack_inverse(const double* S_pad, const int32_t* counts, const int64_t* S_offsets,
+                                      double* S_packed, int64_t rows, int32_t n, void* stream)
+{
+    if (rows < 0 || n < 1) return SMLVM_ERR_ARG;
+    if (rows == 0) return SMLVM_OK;
+    if (S_pad == nullptr || counts == nullptr || S_offsets == nullptr || S_packed == nullptr) return SMLVM_ERR_ARG;
+    if (n > SMLVM_SPARSEMAP_MAX_BITS) return SMLVM_ERR_UNSUPPORTED;
+    const int64_t need = (rows + 7) / 8, cap = (int64_t)device_sm_count() * 16;
+    sparsemap_pack_S_kernel<<<(int)(need < cap ? need : cap), 256, 0, as_stream(stream)>>>(S_pad, counts, S_offsets,
+                                                                                         S_packed, rows, n);
     SMLVM_LAUNCH_CHECK();
     return SMLVM_OK;
 }

@@ -434,8 +434,17 @@ def sparsemap_plan(n, kind=0):
     return [(caps[i], smem[i], ctas[i]) for i in range(nt)]
 
 
+# The padded S of the solver (8 (n+1)^2 bytes per sample) is written as such only up to this many bytes per
+# call; larger batches are solved in chunks of that size whose S is packed to 8 |A|^2 bytes per sample
+# (smlvm_sparsemap_pack_inverse) -- 1M samples at n = 128: 139 GB padded, ~16 GB packed.
+S_PAD_MAX_BYTES = 1 << 30
+
+
 def sparsemap_solve(x, kind, budget=0, t=None, init_scores=None, max_iter=100, keep_S=True):
-    """Batched active-set solve.  x [rows, n] -> padded solver state (dict), no host sync."""
+    """Batched active-set solve.  x [rows, n] -> padded solver state (dict).  No host sync unless S has to be
+    packed (one read of the packed size per chunk).  ``state["S"]`` is the padded [rows, cap*cap] tensor or
+    None; ``state["S_rows"]`` the per-sample device addresses of the packed copies (kept alive in
+    ``state["S_chunks"]``)."""
     x = _f32c(x, "scores")
     rows, n = x.shape
     dev = x.device
@@ -451,12 +460,38 @@ def sparsemap_solve(x, kind, budget=0, t=None, init_scores=None, max_iter=100, k
     kept = torch.empty(rows, dtype=torch.int32, device=dev)
     iters = torch.empty(rows, dtype=torch.int32, device=dev)
     status = torch.empty(rows, dtype=torch.int32, device=dev)
-    S = torch.empty((rows, cap * cap), dtype=torch.float64, device=dev) if keep_S else None
-    check(lib.smlvm_sparsemap_fwd(ptr(x), ptr(t), ptr(init_scores), kind, budget, max_iter, rows, n,
-                                  ptr(p_pad), ptr(bits), ptr(counts), ptr(kept), ptr(iters),
-                                  ptr(status), ptr(S), stream()), "smlvm_sparsemap_fwd")
-    return dict(p_pad=p_pad, bits=bits, counts=counts, kept=kept, iters=iters, status=status, S=S,
-                n=n, rows=rows, kind=kind)
+    state = dict(p_pad=p_pad, bits=bits, counts=counts, kept=kept, iters=iters, status=status, S=None,
+                 S_rows=None, S_chunks=None, n=n, rows=rows, kind=kind)
+
+    def solve(r0, r1, S):
+        sl = slice(r0, r1)
+        check(lib.smlvm_sparsemap_fwd(ptr(x[sl]), ptr(None if t is None else t[sl]),
+                                      ptr(None if init_scores is None else init_scores[sl]), kind, budget, max_iter,
+                                      r1 - r0, n, ptr(p_pad[sl]), ptr(bits[sl]), ptr(counts[sl]), ptr(kept[sl]),
+                                      ptr(iters[sl]), ptr(status[sl]), ptr(S), stream()), "smlvm_sparsemap_fwd")
+
+    slot = cap * cap * 8
+    if not keep_S or rows * slot <= S_PAD_MAX_BYTES:
+        S = torch.empty((rows, cap * cap), dtype=torch.float64, device=dev) if keep_S else None
+        solve(0, rows, S)
+        state["S"] = S
+        return state
+    chunk = max(1, S_PAD_MAX_BYTES // slot)
+    S_tmp = torch.empty((min(chunk, rows), cap * cap), dtype=torch.float64, device=dev)
+    S_rows = torch.empty(rows, dtype=torch.int64, device=dev)
+    chunks = []
+    for r0 in range(0, rows, chunk):
+        r1 = min(rows, r0 + chunk)
+        solve(r0, r1, S_tmp)
+        m = counts[r0:r1]
+        offs = scan_counts(m * m)                       # doubles before each sample's S in the packed buffer
+        packed = torch.empty(max(int(offs[-1].item()), 1), dtype=torch.float64, device=dev)
+        check(lib.smlvm_sparsemap_pack_inverse(ptr(S_tmp), ptr(m), ptr(offs), ptr(packed), r1 - r0, n, stream()),
+              "smlvm_sparsemap_pack_inverse")
+        S_rows[r0:r1] = offs[:-1] * 8 + packed.data_ptr()
+        chunks.append(packed)
+    state["S_rows"], state["S_chunks"] = S_rows, chunks
+    return state
 
 
 def sparsemap_expand(state, only_positive, offsets, total, want_aset=True, want_idx=True):
@@ -478,8 +513,8 @@ def sparsemap_bwd(state, dp, offsets, only_positive, want_dt=False):
     dx = torch.empty((rows, n), dtype=torch.float32, device=dev)
     dt = torch.empty((rows, max(n - 1, 1)), dtype=torch.float32, device=dev) if want_dt else None
     check(lib.smlvm_sparsemap_bwd(ptr(dp), ptr(offsets), int(only_positive), ptr(state["p_pad"]),
-                                  ptr(state["bits"]), ptr(state["counts"]), ptr(state["S"]), ptr(dx),
-                                  ptr(dt), rows, n, stream()), "smlvm_sparsemap_bwd")
+                                  ptr(state["bits"]), ptr(state["counts"]), ptr(state["S"]), ptr(state.get("S_rows")),
+                                  ptr(dx), ptr(dt), rows, n, stream()), "smlvm_sparsemap_bwd")
     if want_dt:
         dt = dt[:, :n - 1]
     return dx, dt

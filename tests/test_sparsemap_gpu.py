@@ -190,3 +190,35 @@ def test_demo_vector(oracle):
     e0 = np.zeros(len(ref["p"])); e0[0] = 1
     dx_ref, _ = oracle.sparsemap_bwd(x.numpy(), e0, 1, 3, max_iter=100)
     assert np.abs(g0.cpu().numpy() - dx_ref).max() <= 1e-5
+
+
+@pytest.mark.parametrize("n,kind,budget", [(32, BERN, 0), (33, BUDGET, 9), (20, 2, 0)])
+def test_packed_S_chunks_equal_padded(n, kind, budget):
+    """Large batches keep 8|A|^2 bytes of S per sample (solved in chunks, smlvm_sparsemap_pack_inverse) instead of the
+    padded 8(n+1)^2: same forward state, same backward, chunk boundaries included."""
+    from lvmhelpers import ops
+    rows = 101
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(rows, n, generator=g).cuda()
+    t = torch.randn(rows, n - 1, generator=g).cuda() if kind == 2 else None
+    ref = ops.sparsemap_solve(x, kind, budget=budget, t=t, max_iter=100)
+    assert ref["S"] is not None and ref["S_rows"] is None
+    old = ops.S_PAD_MAX_BYTES
+    ops.S_PAD_MAX_BYTES = 7 * (n + 1) * (n + 1) * 8          # chunks of 7 samples
+    try:
+        st = ops.sparsemap_solve(x, kind, budget=budget, t=t, max_iter=100)
+    finally:
+        ops.S_PAD_MAX_BYTES = old
+    assert st["S"] is None and st["S_rows"] is not None and len(st["S_chunks"]) == (rows + 6) // 7
+    for key in ("p_pad", "bits", "counts", "kept", "iters", "status"):
+        assert torch.equal(st[key], ref[key]), key
+    m = ref["counts"].long()
+    assert sum(c.numel() for c in st["S_chunks"]) >= int((m * m).sum())
+    offsets = ops.scan_counts(ref["kept"])
+    total = int(offsets[-1])
+    dp = torch.randn(total, generator=g).cuda()
+    dx_ref, dt_ref = ops.sparsemap_bwd(ref, dp, offsets, True, want_dt=kind == 2)
+    dx, dt = ops.sparsemap_bwd(st, dp, offsets, True, want_dt=kind == 2)
+    assert torch.equal(dx, dx_ref)
+    if kind == 2:
+        assert torch.equal(dt, dt_ref)
