@@ -437,7 +437,7 @@ def sparsemap_plan(n, kind=0):
 # The padded S of the solver (8 (n+1)^2 bytes per sample) is written as such only up to this many bytes per
 # call; larger batches are solved in chunks of that size whose S is packed to 8 |A|^2 bytes per sample
 # (smlvm_sparsemap_pack_inverse) -- 1M samples at n = 128: 139 GB padded, ~16 GB packed.
-S_PAD_MAX_BYTES = 1 << 30
+S_PAD_MAX_BYTES = 4 << 30
 
 
 def sparsemap_solve(x, kind, budget=0, t=None, init_scores=None, max_iter=100, keep_S=True):
