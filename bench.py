@@ -610,7 +610,7 @@ def main():
     ap.add_argument("--rows", type=int, default=1 << 20, help="rows per GPU")
     ap.add_argument("--cols", type=int, default=128)
     ap.add_argument("--path-rows-topk", type=int, default=1 << 18)
-    ap.add_argument("--path-rows-smap", type=int, default=1 << 14)
+    ap.add_argument("--path-rows-smap", type=int, default=1 << 16)
     ap.add_argument("--e2e-chunks", type=int, default=8)
     ap.add_argument("--no-paths", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
