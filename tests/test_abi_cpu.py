@@ -78,6 +78,13 @@ def test_argument_validation_needs_no_device():
     assert lib.smlvm_sparsemap_fwd(1 << 20, None, None, 0, 0, 10, 4, 4096, 1 << 21, 1 << 22, 1 << 23,
                                    None, None, None, None, None) == -2               # n too large
     assert lib.smlvm_scan_workspace_bytes(1 << 20) > 0 and lib.smlvm_reduce_workspace_bytes() > 0
+    assert lib.smlvm_gather_rows(None, None, None, 4, 16, None) == -1                 # NULL buffers
+    assert lib.smlvm_gather_rows(None, None, None, 0, 16, None) == 0                  # empty selection
+    assert lib.smlvm_gather_rows(1 << 20, 1 << 21, 1 << 22, 4, 6, None) == -2         # rows not a multiple of 4 bytes
+    assert lib.smlvm_bits_expand(None, None, None, 4, 32, None) == -1
+    assert lib.smlvm_bits_expand(None, None, None, 0, 32, None) == 0
+    assert lib.smlvm_sparsemap_pack_inverse(None, None, None, None, 4, 32, None) == -1
+    assert lib.smlvm_sparsemap_pack_inverse(1 << 20, 1 << 21, 1 << 22, 1 << 23, 4, 4096, None) == -2
 
 
 def test_host_side_refuses_cpu_tensors():
