@@ -222,7 +222,7 @@ __device__ __forceinline__ double factor_map(const SolverSmem& sm, int n, int bu
 // within rounding, so WHICH vertex the MAP oracle returns is decided by the last bits of z.  To
 // follow the reference's pivoting the sums that feed z must be rounded in its order.  Row-wise
 // sums (z, tau, d, u) are sequential per thread anyway; the two whole-matrix / whole-vector sums
-// below are chains: warp 0 forms 32 terms at a time in parallel and folds them in sequence.
+// below are chains: their terms are formed in parallel into shared memory and folded by ONE thread.
 
 // acc = (((acc -+ t_0) -+ t_1) -+ ...) over `total` doubles of a 16-byte aligned shared array, by ONE
 // thread.  The next eight terms are loaded (128-bit) while the current eight are folded, so the chain
@@ -288,10 +288,10 @@ __device__ double evaluate_warp(const SolverSmem& sm, int n)
 
 // Schur complement s = r0 - sum_{i<=j} c_ij r_i r_j inv_ij in libad3's order (rows in solver
 // order, c_ii = 1, c_ij = 2; libad3 skips r_i == 0 / r_j == 0, whose terms are exact zeros).
-// Two steps: every thread of the CTA forms terms into sm.terms (row-major upper triangle), then
-// ONE thread folds them in sequence -- the fold is a pure DSUB dependency chain fed by
-// independent 64-bit shared loads (ncu r01: the shuffle-fed version cost ~45 cycles per term and
-// kept the other 7 warps at the barrier 60 % of the time).
+// Two steps: the terms are formed in parallel into one half of sm.terms (row-major upper triangle,
+// rounds of whole rows), then ONE thread folds them in sequence -- a pure DSUB dependency chain fed by
+// 128-bit shared loads issued a batch ahead (ncu r01: a shuffle-fed chain cost ~45 cycles per term and
+// kept the other 7 warps at the barrier 60 % of the time; this one runs at ~11).
 // rows [a0, a1) of the upper triangle -> out (row-major, packed), by warps w0 .. nw-1 of the CTA
 __device__ __forceinline__ void schur_terms_fill(const SolverSmem& sm, double* dst, int m, int LD, int a0, int a1,
                                                  int w0)
