@@ -413,29 +413,43 @@ __global__ void __launch_bounds__(256, 4) sparsemap_fwd_kernel(const float* __re
                 if (tid < 32) {
                     double best = CUDART_INF;
                     int besti = 0x7fffffff;
-                    int anyneg = 0;
-                    for (int a = tid; a < m; a += 32) {
-                        const double zz = sm.z[a], pp = sm.p[a];
-                        if (zz >= pp) continue;
-                        if (zz < 0.0) anyneg = 1;
-                        const double ratio = __ddiv_rn(pp, __dsub_rn(pp, zz));
-                        if (ratio < best) { best = ratio; besti = a; }
-                    }
+                    bool neg = false;
+                    // four candidates per lane and pass: their divisions are independent and overlap
+                    for (int a0 = tid; a0 < m; a0 += 128) {
+                        double ratio[4];
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const double ob = __shfl_xor_sync(kFull, best, o);
-                        const int oi = __shfl_xor_sync(kFull, besti, o);
-                        anyneg |= __shfl_xor_sync(kFull, anyneg, o);
-                        if (oi != 0x7fffffff &&
-                            (besti == 0x7fffffff || ob < best || (ob == best && oi < besti))) {
-                            best = ob;
-                            besti = oi;
+                        for (int u = 0; u < 4; ++u) {
+                            const int a = a0 + 32 * u;
+                            ratio[u] = CUDART_INF;
+                            if (a < m) {
+                                const double zz = sm.z[a], pp = sm.p[a];
+                                if (zz < pp) {
+                                    neg = neg || zz < 0.0;
+                                    ratio[u] = __ddiv_rn(pp, __dsub_rn(pp, zz));
+                                }
+                            }
                         }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)    // ascending index: the first minimum wins
+                            if (ratio[u] < best) { best = ratio[u]; besti = a0 + 32 * u; }
                     }
+                    const int anyneg = __any_sync(kFull, neg) ? 1 : 0;
+                    // lexicographic minimum of (ratio, index) over the warp: order-preserving 64-bit key of
+                    // the double (sign flip), reduced as two 32-bit halves, then the lowest index holding it
+                    const long long bb = __double_as_longlong(__dadd_rn(best, 0.0));  // (-0.0 -> +0.0: numeric ties)
+                    const unsigned long long key = (unsigned long long)bb ^ ((unsigned long long)(bb >> 63) | 0x8000000000000000ull);
+                    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+                    const bool cand = besti != 0x7fffffff;
+                    const unsigned mhi = __reduce_min_sync(kFull, cand ? hi : 0xffffffffu);
+                    const bool e1 = cand && hi == mhi;
+                    const unsigned mlo = __reduce_min_sync(kFull, e1 ? lo : 0xffffffffu);
+                    const bool e2 = e1 && lo == mlo;
+                    const unsigned mi = __reduce_min_sync(kFull, e2 ? (unsigned)besti : 0x7fffffffu);
+                    const double gbest = __shfl_sync(kFull, best, mi & 31);  // lane (index mod 32) owns that candidate
                     if (tid == 0) {
                         sm.misc[0] = anyneg;
-                        sm.misc[1] = besti;
-                        sm.red[37] = best;
+                        sm.misc[1] = (int)mi;
+                        sm.red[37] = gbest;
                     }
                 }
                 __syncthreads();
