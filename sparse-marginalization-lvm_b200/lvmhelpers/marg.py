@@ -192,8 +192,9 @@ class Marginalizer(torch.nn.Module):
         comp = ops.compact(encoder_probs.detach(), side["nnz"], slots=side["slots"])
         rows, cols = comp["rows"], comp["cols"].long()
         take = lambda t: ops.gather_rows(t, rows)
-        decoder_output = self.decoder(cols, take(decoder_input))
-        loss_components, logs = self.loss(take(encoder_input), take(discrete_latent_z), take(decoder_input),
+        decoder_input_rep = take(decoder_input)
+        decoder_output = self.decoder(cols, decoder_input_rep)
+        loss_components, logs = self.loss(take(encoder_input), take(discrete_latent_z), decoder_input_rep,
                                           decoder_output, take(labels))
         p_vals = comp["vals"]
         full_loss, loss_mean = _CompactMarginalObjective.apply(

@@ -404,8 +404,15 @@ def gather_rows(t, idx):
     row_bytes = (t.numel() // t.shape[0]) * t.element_size() if t.dim() > 0 and t.shape[0] > 0 else 0
     if not t.is_cuda or row_bytes == 0 or row_bytes % 4 != 0 or idx.numel() == 0:
         return t.index_select(0, idx.to(torch.int64) if idx.dtype != torch.int64 else idx)
-    idx = idx.to(device=t.device, dtype=torch.int32).contiguous()
-    return _GatherRows.apply(t.contiguous(), idx)
+    if idx.dtype != torch.int32 or idx.device != t.device:
+        idx = idx.to(device=t.device, dtype=torch.int32)
+    idx, t = idx.contiguous(), t.contiguous()
+    if t.requires_grad and torch.is_grad_enabled():
+        return _GatherRows.apply(t, idx)
+    # data (no gradient): skip the autograd node, one launch
+    out = torch.empty((idx.numel(),) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    check(lib.smlvm_gather_rows(ptr(t), ptr(idx), ptr(out), idx.numel(), row_bytes, stream()), "smlvm_gather_rows")
+    return out
 
 
 def bits_expand(bits, index, n):
