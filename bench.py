@@ -382,8 +382,13 @@ def extra_paths(args, world, device, rank):
         loss.backward()
 
     ms, _, _ = timed(topk_step, 5, 2, world, device)
+    # k-best search 4n + k(4n+4) B/row (scores in, fp32 configurations + scores out), sparsemax over
+    # the k scores fwd+bwd 20k B/row, gradient of the scores 4n B/row
+    topk_bytes = rows * (4 * 128 + 10 * (4 * 128 + 4) + 20 * 10 + 4 * 128)
     out["topk_sparsemax_n128_k10"] = {"rows_per_gpu": rows, "ms_per_step": ms / 5,
-                                     "value": rows * world / (ms / 5 * 1e-3), "unit": UNIT}
+                                     "value": rows * world / (ms / 5 * 1e-3), "unit": UNIT,
+                                     "hbm_frac_of_algorithmic_bytes": topk_bytes / (ms / 5 * 1e-3) / 1e9
+                                     / measured_hbm_peak()[0]}
 
     # the same branch through its consumer, TopKSparsemaxMarg (structmarg.py:82-153): candidates handed over
     # packed, only the support expanded to fp32 for the (dummy) decoder -- against the dense [B,k,n] hand-over
