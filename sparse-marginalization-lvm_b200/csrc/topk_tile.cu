@@ -10,8 +10,8 @@
 // warp run in lockstep without divergence, and the lists live in shared memory as
 // [slot][lane] so that every access is conflict-free whatever slot a lane points at.
 //
-//   shared memory per warp: 32 bits x 32 rows of scores transposed as xs[32][33] (coalesced
-//   global reads, conflict-free column reads; restaged every 32 bits), two score lists
+//   shared memory per warp: STAGE bits x 32 rows of scores transposed as xs[STAGE][33] (sector-sized
+//   global reads, conflict-free column reads; restaged every STAGE bits), two score lists
 //   S[2][k][32] and two configuration lists C[2][k][32] of W-word vectors (ping-pong; one
 //   64/128-bit access moves a configuration, the new bit is OR-ed in with one LOP3 per word).
 //   The fp32 {0,1} output (4*k*n B/row, the API's format) and the packed bits are written by the
@@ -21,6 +21,10 @@
 namespace smlvm {
 
 // a configuration = W 32-bit words moved as ONE shared-memory access ([slot][lane] of Cfg<W>)
+// STAGE = bits of the scores staged per round (transposed, [STAGE][33] floats per warp): 32, or 8 when the
+// shorter stage buys >= 25 % more resident warps (k = 10, n = 128: 14 KB per warp, 14 warps per SM instead of
+// 11 -- throughput follows the resident warps almost linearly; otherwise the extra rounds cost more)
+
 template <int W> struct Cfg;
 template <> struct Cfg<1> { uint32_t w[1]; };
 template <> struct __align__(8) Cfg<2> { uint32_t w[2]; };
@@ -52,11 +56,11 @@ __device__ __forceinline__ void move_cfg(const char* src, Cfg<W>* dst, bool on, 
 // run out: the loop is compare / select / move, with the new bit OR-ed into word WQ only.
 template <int W, int WQ>
 __device__ __forceinline__ void topk_merge_block(Cfg<W>* C, float* S, const float* xs, int lane, int k, int ib0,
-                                                 int iend, int& cur, int& len)
+                                                 int iend, int shift0, int& cur, int& len)
 {
     for (int ib = ib0; ib < iend; ++ib) {
         const float v = xs[ib * 33 + lane];
-        const uint32_t bit = 1u << ib;
+        const uint32_t bit = 1u << (shift0 + ib);
         const char* ScB = reinterpret_cast<const char*>(S + (cur * k) * 32 + lane);
         float* Sn = S + ((cur ^ 1) * k) * 32 + lane;
         const char* CcB = reinterpret_cast<const char*>(C + (cur * k) * 32 + lane);
@@ -93,7 +97,7 @@ __device__ __forceinline__ void topk_merge_block(Cfg<W>* C, float* S, const floa
     }
 }
 
-template <int W>
+template <int W, int STAGE>
 __global__ void __launch_bounds__(512)
 topk_tile_kernel(const float* __restrict__ x, float* __restrict__ configs, uint32_t* __restrict__ bits,
                  float* __restrict__ dp_scores, int64_t rows, int n, int k)
@@ -101,32 +105,32 @@ topk_tile_kernel(const float* __restrict__ x, float* __restrict__ configs, uint3
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int words_n = (n + 31) >> 5;
-    const size_t per_warp = ((size_t)2 * k * W * 32 + 32 * 33 + (2 * k + 1) * 32) * 4;
+    const size_t per_warp = ((size_t)2 * k * W * 32 + STAGE * 33 + (2 * k + 1) * 32) * 4;
     Cfg<W>* C = reinterpret_cast<Cfg<W>*>(smem_raw + warp * per_warp);        // [2][k][32]
-    float* xs = reinterpret_cast<float*>(C + 2 * k * 32);                     // [32][33]: 32 bits x 32 rows
-    float* S = xs + 32 * 33;                                                  // [2][k][32] (+ one slot of slack)
+    float* xs = reinterpret_cast<float*>(C + 2 * k * 32);                     // [STAGE][33]: STAGE bits x 32 rows
+    float* S = xs + STAGE * 33;                                                // [2][k][32] (+ one slot of slack)
 
     const int64_t ntiles = (rows + 31) / 32;
     for (int64_t t = (int64_t)blockIdx.x * nwarps + warp; t < ntiles; t += (int64_t)gridDim.x * nwarps) {
         const int64_t row0 = t * 32;
         const int trows = (int)min((int64_t)32, rows - row0);
         int cur = 0, len = 2;
-        for (int i0 = 0; i0 < n; i0 += 32) {
-            // ---- stage bits i0..i0+31 of the 32 score rows, transposed (coalesced reads, 8 rows of
-            //      loads in flight per lane before the first dependent store) ---------------------
+        for (int i0 = 0; i0 < n; i0 += STAGE) {
+            // ---- stage bits i0..i0+STAGE-1 of the 32 score rows, transposed: lane -> (column l & 7, rows
+            //      (l >> 3) + 4j), one 32-byte sector per row and load, 8 loads in flight per lane ----------
             __syncwarp();
             {
-                const int c = i0 + lane;
-                for (int r0 = 0; r0 < 32; r0 += 8) {
-                    float tmp[8];
+                const int col = lane & (STAGE - 1), rb = lane / STAGE;
+                const int c = i0 + col;
+                constexpr int kRowsPerLoad = 32 / STAGE, kLoads = 32 / kRowsPerLoad;
+                float tmp[kLoads];
 #pragma unroll
-                    for (int rr = 0; rr < 8; ++rr) {
-                        const int r = r0 + rr;
-                        tmp[rr] = (r < trows && c < n) ? __ldcs(x + (row0 + r) * n + c) : 0.f;
-                    }
-#pragma unroll
-                    for (int rr = 0; rr < 8; ++rr) xs[lane * 33 + r0 + rr] = tmp[rr];
+                for (int j = 0; j < kLoads; ++j) {
+                    const int r = rb + kRowsPerLoad * j;
+                    tmp[j] = (r < trows && c < n) ? __ldcs(x + (row0 + r) * n + c) : 0.f;
                 }
+#pragma unroll
+                for (int j = 0; j < kLoads; ++j) xs[col * 33 + rb + kRowsPerLoad * j] = tmp[j];
             }
             __syncwarp();
             int ib = 0;
@@ -147,18 +151,19 @@ topk_tile_kernel(const float* __restrict__ x, float* __restrict__ configs, uint3
                 C[1 * 32 + lane] = c1;
                 ib = 1;
             }
-            const int iend = min(32, n - i0);
+            const int iend = min(STAGE, n - i0);
+            const int sh0 = i0 & 31;
             if (W == 1) {
-                topk_merge_block<W, 0>(C, S, xs, lane, k, ib, iend, cur, len);
+                topk_merge_block<W, 0>(C, S, xs, lane, k, ib, iend, sh0, cur, len);
             } else if (W == 2) {
-                if (i0 == 0) topk_merge_block<W, 0>(C, S, xs, lane, k, ib, iend, cur, len);
-                else topk_merge_block<W, (W > 1 ? 1 : 0)>(C, S, xs, lane, k, ib, iend, cur, len);
+                if (i0 < 32) topk_merge_block<W, 0>(C, S, xs, lane, k, ib, iend, sh0, cur, len);
+                else topk_merge_block<W, (W > 1 ? 1 : 0)>(C, S, xs, lane, k, ib, iend, sh0, cur, len);
             } else {
                 switch (i0 >> 5) {
-                    case 0: topk_merge_block<W, 0>(C, S, xs, lane, k, ib, iend, cur, len); break;
-                    case 1: topk_merge_block<W, (W > 1 ? 1 : 0)>(C, S, xs, lane, k, ib, iend, cur, len); break;
-                    case 2: topk_merge_block<W, (W > 2 ? 2 : 0)>(C, S, xs, lane, k, ib, iend, cur, len); break;
-                    default: topk_merge_block<W, (W > 3 ? 3 : 0)>(C, S, xs, lane, k, ib, iend, cur, len); break;
+                    case 0: topk_merge_block<W, 0>(C, S, xs, lane, k, ib, iend, sh0, cur, len); break;
+                    case 1: topk_merge_block<W, (W > 1 ? 1 : 0)>(C, S, xs, lane, k, ib, iend, sh0, cur, len); break;
+                    case 2: topk_merge_block<W, (W > 2 ? 2 : 0)>(C, S, xs, lane, k, ib, iend, sh0, cur, len); break;
+                    default: topk_merge_block<W, (W > 3 ? 3 : 0)>(C, S, xs, lane, k, ib, iend, sh0, cur, len); break;
                 }
             }
         }
@@ -217,32 +222,45 @@ int topk_tile_launch(const float* x, float* configs, uint32_t* bits, float* dp_s
 {
     const int words_n = (n + 31) >> 5;
     const int W = words_n <= 1 ? 1 : (words_n <= 2 ? 2 : 4);
-    const size_t per_warp = ((size_t)2 * k * W * 32 + 32 * 33 + (2 * k + 1) * 32) * 4;
-    int warps = (int)((200 * 1024) / per_warp);
-    warps = warps > 16 ? 16 : (warps < 1 ? 1 : warps);
+    auto per_warp_bytes = [&](int stage) { return ((size_t)2 * k * W * 32 + stage * 33 + (2 * k + 1) * 32) * 4; };
+    // resident warps per SM: 200 KB of lists, at most 32 (two CTAs of <= 16 warps)
+    auto warps_per_sm = [&](int stage) {
+        const int w = (int)((200 * 1024) / per_warp_bytes(stage));
+        return w > 32 ? 32 : (w < 1 ? 1 : w);
+    };
+    const int stage = (4 * warps_per_sm(8) >= 5 * warps_per_sm(32)) ? 8 : 32;
+    const size_t per_warp = per_warp_bytes(stage);
+    const int wsm = warps_per_sm(stage);
+    const int ctas_per_sm = wsm > 16 ? 2 : 1;
+    int warps = wsm / ctas_per_sm;
     const int64_t ntiles = (rows + 31) / 32;
-    if (ntiles < (int64_t)warps * device_sm_count()) {  // small batches: spread the tiles over the SMs
-        const int w2 = (int)((ntiles + device_sm_count() - 1) / device_sm_count());
+    const int64_t slots = (int64_t)device_sm_count() * ctas_per_sm;
+    if (ntiles < (int64_t)warps * slots) {  // small batches: spread the tiles over the SMs
+        const int w2 = (int)((ntiles + slots - 1) / slots);
         warps = w2 < 1 ? 1 : (w2 < warps ? w2 : warps);
     }
     const size_t smem = per_warp * warps;
     const int64_t need = (ntiles + warps - 1) / warps;
-    const int64_t cap = (int64_t)device_sm_count();
-    const int grid = (int)(need < cap ? need : cap);
-#define SMLVM_TOPK_TILE_CASE(WW)                                                                          \
-    case WW: {                                                                                            \
-        cudaError_t e = cudaFuncSetAttribute(topk_tile_kernel<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                             200 * 1024);                                                 \
-        if (e != cudaSuccess) return (int)e;                                                              \
-        topk_tile_kernel<WW><<<grid, warps * 32, smem, st>>>(x, configs, bits, dp_scores, rows, n, k);    \
-        break;                                                                                            \
-    }
+    const int grid = (int)(need < slots ? need : slots);
+#define SMLVM_TOPK_TILE_LAUNCH(WW, SS)                                                                        \
+    do {                                                                                                      \
+        cudaError_t e = cudaFuncSetAttribute(topk_tile_kernel<WW, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             200 * 1024);                                                     \
+        if (e != cudaSuccess) return (int)e;                                                                  \
+        topk_tile_kernel<WW, SS><<<grid, warps * 32, smem, st>>>(x, configs, bits, dp_scores, rows, n, k);    \
+    } while (0)
+#define SMLVM_TOPK_TILE_CASE(WW)                                                                              \
+    case WW:                                                                                                  \
+        if (stage == 8) SMLVM_TOPK_TILE_LAUNCH(WW, 8);                                                        \
+        else SMLVM_TOPK_TILE_LAUNCH(WW, 32);                                                                  \
+        break;
     switch (W) {
         SMLVM_TOPK_TILE_CASE(1)
         SMLVM_TOPK_TILE_CASE(2)
         SMLVM_TOPK_TILE_CASE(4)
     }
 #undef SMLVM_TOPK_TILE_CASE
+#undef SMLVM_TOPK_TILE_LAUNCH
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? SMLVM_OK : (int)e;
 }
