@@ -222,6 +222,35 @@ bits_score_bwd_kernel(const uint32_t* __restrict__ bits, const float* __restrict
     }
 }
 
+// Same sums for n % 4 == 0, straight from global memory: a thread per float4 of dx (four columns of one
+// row), its k configuration words and k upstream gradients are independent loads (L1 hits: a row's k*W
+// words and k floats are shared by the n/4 threads of the row), no staging and no warp barrier.
+__global__ void __launch_bounds__(256)
+bits_score_bwd_vec_kernel(const uint32_t* __restrict__ bits, const float* __restrict__ ds, float* __restrict__ dx,
+                          int64_t rows, int n, int k)
+{
+    const int words_n = (n + 31) >> 5, q4 = n >> 2;
+    const int64_t total = rows * q4, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const int64_t r = t / q4;
+        const int c = (int)(t - r * q4) * 4;
+        const uint32_t* b = bits + r * (int64_t)k * words_n + (c >> 5);
+        const float* d = ds + r * k;
+        const int sh = c & 31;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 5
+        for (int j = 0; j < k; ++j) {
+            const uint32_t nib = __ldg(b + j * words_n) >> sh;
+            const float dj = __ldg(d + j);
+            a0 += (nib & 1u) ? dj : 0.f;
+            a1 += (nib & 2u) ? dj : 0.f;
+            a2 += (nib & 4u) ? dj : 0.f;
+            a3 += (nib & 8u) ? dj : 0.f;
+        }
+        stg_stream4(dx + t * 4, make_float4(a0, a1, a2, a3));
+    }
+}
+
 template <int G>
 static void launch_topk_w(int W, int grid, size_t smem, cudaStream_t st, const float* x,
                           float* configs, uint32_t* bits, float* dp_scores, int64_t rows, int n,
@@ -402,6 +431,13 @@ extern "C" int smlvm_bits_score_bwd(const uint32_t* bits, const float* dscores_k
     int64_t need = (rows + 7) / 8;
     int64_t cap = (int64_t)device_sm_count() * 8;
     const size_t smem = (size_t)(kThreads / kWarp) * (((k + 3) & ~3) + ((k * ((n + 31) / 32) + 3) & ~3)) * sizeof(float);
+    if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(dx) & 15u) == 0) {
+        const int64_t need_v = (rows * (n >> 2) + 255) / 256, cap_v = (int64_t)device_sm_count() * 16;
+        bits_score_bwd_vec_kernel<<<(int)(need_v < cap_v ? need_v : cap_v), 256, 0, as_stream(stream)>>>(
+            bits, dscores_k, dx, rows, n, k);
+        SMLVM_LAUNCH_CHECK();
+        return SMLVM_OK;
+    }
     bits_score_bwd_kernel<<<(int)(need < cap ? need : cap), kThreads, smem, as_stream(stream)>>>(
         bits, dscores_k, dx, rows, n, k);
     SMLVM_LAUNCH_CHECK();
