@@ -222,32 +222,36 @@ bits_score_bwd_kernel(const uint32_t* __restrict__ bits, const float* __restrict
     }
 }
 
-// Same sums for n % 4 == 0, straight from global memory: a thread per float4 of dx (four columns of one
-// row), its k configuration words and k upstream gradients are independent loads (L1 hits: a row's k*W
-// words and k floats are shared by the n/4 threads of the row), no staging and no warp barrier.
+// Same sums for n % CPT == 0, straight from global memory: a thread per CPT (8 / 16 / 32) columns of one row
+// of dx, its k configuration words and k upstream gradients are independent loads (L1 hits: a row's k*W
+// words and k floats are shared by the n/CPT threads of the row), no staging and no warp barrier.  The
+// loads bound this kernel (4 columns per thread: 0.38 ms, 8: 0.26 ms at 1M x 128, k = 10).
+template <int CPT>
 __global__ void __launch_bounds__(256)
 bits_score_bwd_vec_kernel(const uint32_t* __restrict__ bits, const float* __restrict__ ds, float* __restrict__ dx,
                           int64_t rows, int n, int k)
 {
-    const int words_n = (n + 31) >> 5, q4 = n >> 2;
-    const int64_t total = rows * q4, stride = (int64_t)gridDim.x * blockDim.x;
+    const int words_n = (n + 31) >> 5, qn = n / CPT;
+    const int64_t total = rows * qn, stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
-        const int64_t r = t / q4;
-        const int c = (int)(t - r * q4) * 4;
+        const int64_t r = t / qn;
+        const int c = (int)(t - r * qn) * CPT;
         const uint32_t* b = bits + r * (int64_t)k * words_n + (c >> 5);
         const float* d = ds + r * k;
         const int sh = c & 31;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 5
+        float a[CPT];
+#pragma unroll
+        for (int e = 0; e < CPT; ++e) a[e] = 0.f;
+#pragma unroll 2
         for (int j = 0; j < k; ++j) {
-            const uint32_t nib = __ldg(b + j * words_n) >> sh;
+            const uint32_t w = __ldg(b + j * words_n) >> sh;
             const float dj = __ldg(d + j);
-            a0 += (nib & 1u) ? dj : 0.f;
-            a1 += (nib & 2u) ? dj : 0.f;
-            a2 += (nib & 4u) ? dj : 0.f;
-            a3 += (nib & 8u) ? dj : 0.f;
+#pragma unroll
+            for (int e = 0; e < CPT; ++e) a[e] += ((w >> e) & 1u) ? dj : 0.f;
         }
-        stg_stream4(dx + t * 4, make_float4(a0, a1, a2, a3));
+#pragma unroll
+        for (int e = 0; e < CPT; e += 4)
+            stg_stream4(dx + t * CPT + e, make_float4(a[e], a[e + 1], a[e + 2], a[e + 3]));
     }
 }
 
@@ -431,10 +435,20 @@ extern "C" int smlvm_bits_score_bwd(const uint32_t* bits, const float* dscores_k
     int64_t need = (rows + 7) / 8;
     int64_t cap = (int64_t)device_sm_count() * 8;
     const size_t smem = (size_t)(kThreads / kWarp) * (((k + 3) & ~3) + ((k * ((n + 31) / 32) + 3) & ~3)) * sizeof(float);
-    if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(dx) & 15u) == 0) {
-        const int64_t need_v = (rows * (n >> 2) + 255) / 256, cap_v = (int64_t)device_sm_count() * 16;
-        bits_score_bwd_vec_kernel<<<(int)(need_v < cap_v ? need_v : cap_v), 256, 0, as_stream(stream)>>>(
-            bits, dscores_k, dx, rows, n, k);
+    if ((n & 7) == 0 && (reinterpret_cast<uintptr_t>(dx) & 15u) == 0) {
+        static int cpt_env = -1;
+        if (cpt_env < 0) {
+            const char* e = getenv("SMLVM_BITS_BWD_CPT");
+            cpt_env = e ? atoi(e) : 0;
+        }
+        int cpt = (n & 31) == 0 ? 32 : ((n & 15) == 0 ? 16 : 8);
+        if (cpt_env == 8 || (cpt_env == 16 && (n & 15) == 0) || (cpt_env == 32 && (n & 31) == 0)) cpt = cpt_env;
+        const int64_t need_v = (rows * (n / cpt) + 255) / 256, cap_v = (int64_t)device_sm_count() * 16;
+        const int grid_v = (int)(need_v < cap_v ? need_v : cap_v);
+        cudaStream_t st = as_stream(stream);
+        if (cpt == 32) bits_score_bwd_vec_kernel<32><<<grid_v, 256, 0, st>>>(bits, dscores_k, dx, rows, n, k);
+        else if (cpt == 16) bits_score_bwd_vec_kernel<16><<<grid_v, 256, 0, st>>>(bits, dscores_k, dx, rows, n, k);
+        else bits_score_bwd_vec_kernel<8><<<grid_v, 256, 0, st>>>(bits, dscores_k, dx, rows, n, k);
         SMLVM_LAUNCH_CHECK();
         return SMLVM_OK;
     }
