@@ -496,9 +496,20 @@ def run_native(args, rank, local_rank, world):
     peak, peak_src = measured_hbm_peak()
     rows, K = args.rows, args.cols
 
-    numa_cpus = bind_to_gpu_numa_node(physical_gpu_index(local_rank)) if world > 1 else None
+    # pinned host buffers are allocated while bound to the GPU's NUMA node; a single rank gets its CPUs back
+    # afterwards (the CPU baseline of the same run uses every host thread), sharded ranks stay bound
+    affinity0 = os.sched_getaffinity(0)
+    if world == 1:
+        torch.ones(1 << 22).add_(1.0).sum()  # start the intra-op thread pool BEFORE binding: its threads keep every CPU
+    numa_cpus = bind_to_gpu_numa_node(physical_gpu_index(local_rank))
     x_host, l_host = make_inputs(rows, K, 42 + rank)
     x_pin, l_pin = x_host.pin_memory(), l_host.pin_memory()
+    dx_pin = torch.empty(rows, K).pin_memory()
+    if world == 1:
+        try:
+            os.sched_setaffinity(0, affinity0)
+        except Exception:
+            pass
     x, losses = x_pin.to(device), l_pin.to(device)
     total_nnz = SparsemaxMargStep.size_capacity(x)
     step = SparsemaxMargStep(rows, K, device, capacity=total_nnz + 1024, entropy_coeff=1.0)
@@ -558,7 +569,6 @@ def run_native(args, rank, local_rank, world):
     # end to end through host buffers: H2D of X and L, the step, D2H of gradient + loss, every
     # step, through the host-buffer entry point of the package (micro-batched over 3 streams)
     from lvmhelpers.hotpath import HostPipelinedMargStep
-    dx_pin = torch.empty(rows, K).pin_memory()
     e2e_steps = max(3, min(args.steps, 20))
     pipe = HostPipelinedMargStep(rows, K, device, capacity_per_row=total_nnz / rows * 1.05 + 0.5,
                                  entropy_coeff=1.0, chunks=args.e2e_chunks)

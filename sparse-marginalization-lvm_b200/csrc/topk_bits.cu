@@ -175,6 +175,91 @@ bits_score_fwd_vec_kernel(const uint32_t* __restrict__ bits, const float* __rest
     }
 }
 
+// Re-scoring for k-best lists (n % 4 == 0, n <= 128).  The vec kernel above converts every score k times
+// (k*n F2F.F64.F32 per row on the quarter-rate conversion pipe: what bounds it) although the k
+// configurations of a k-best list differ from the best one in a handful of bits.  Here a warp takes 8 rows
+// at a time: (1) 4 lanes per row stream the row once (float4s, kept in shared memory) and sum it under the
+// bits of configuration 0 in fp64 (lane partials + butterfly); (2) a lane per (row, j) walks the set bits
+// of cfg_j ^ cfg_0 (one loop over the 128-bit difference: the warp runs max-over-lanes iterations) and adds
+// +-x to that base -- or, when the configuration has fewer set bits than its difference (arbitrary
+// patterns), or the base is not finite, the set bits of cfg_j from zero.
+// Any order of the fp64 sum is within 1e-16 of any other, rounded once to fp32.
+constexpr int kScoreRows = 8;
+constexpr int kScorePad = 16;  // floats between staged rows: the two rows of a 128-bit store phase hit disjoint banks
+
+__global__ void __launch_bounds__(kThreads)
+bits_score_fwd_delta_kernel(const uint32_t* __restrict__ bits, const float* __restrict__ x,
+                            float* __restrict__ scores_k, int64_t rows, int n, int k, uint32_t k_magic)
+{
+    extern __shared__ __align__(16) float xs_all[];
+    constexpr int kWarps = kThreads / kWarp;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int words_n = (n + 31) >> 5, n4 = n >> 2, ns = n + kScorePad;
+    float* xs = xs_all + warp * kScoreRows * ns;
+    double* base_s = reinterpret_cast<double*>(xs_all + kWarps * kScoreRows * ns) + warp * kScoreRows;
+    const int g = lane & 3, rr1 = lane >> 2;
+    const int64_t warps_total = (int64_t)gridDim.x * kWarps;
+    for (int64_t blk = (int64_t)blockIdx.x * kWarps + warp; blk * kScoreRows < rows; blk += warps_total) {
+        const int64_t r0 = blk * kScoreRows;
+        const int cnt = (int)((rows - r0) < (int64_t)kScoreRows ? (rows - r0) : (int64_t)kScoreRows);
+        __syncwarp();
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        if (rr1 < cnt) {
+            const float4* xr = reinterpret_cast<const float4*>(x + (r0 + rr1) * (int64_t)n);
+            const uint32_t* b0 = bits + (r0 + rr1) * (int64_t)k * words_n;
+            float4* xo = reinterpret_cast<float4*>(xs + rr1 * ns);
+#pragma unroll 8
+            for (int c = g; c < n4; c += 4) {
+                const float4 f = __ldg(xr + c);
+                xo[c] = f;
+                const uint32_t nib = __ldg(b0 + (c >> 3)) >> (4 * (c & 7));
+                if (nib & 1u) a0 += (double)f.x;
+                if (nib & 2u) a1 += (double)f.y;
+                if (nib & 4u) a2 += (double)f.z;
+                if (nib & 8u) a3 += (double)f.w;
+            }
+        }
+        double a = (a0 + a1) + (a2 + a3);
+        a += __shfl_xor_sync(kFull, a, 2);
+        a += __shfl_xor_sync(kFull, a, 1);
+        if (g == 0 && rr1 < cnt) base_s[rr1] = a;
+        __syncwarp();
+        const int tasks = cnt * k;
+        for (int t = lane; t < tasks; t += 32) {
+            const int rr = k == 1 ? t : (int)__umulhi((uint32_t)t, k_magic);  // t / k, k_magic = ceil(2^32 / k)
+            const int j = t - rr * k;
+            const uint32_t* b0 = bits + (r0 + rr) * (int64_t)k * words_n;
+            const uint32_t* bj = b0 + j * words_n;
+            uint32_t cw[4], dw[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                cw[q] = q < words_n ? __ldg(bj + q) : 0u;
+                dw[q] = q < words_n ? (cw[q] ^ __ldg(b0 + q)) : 0u;
+            }
+            const int pc = __popc(cw[0]) + __popc(cw[1]) + __popc(cw[2]) + __popc(cw[3]);
+            const int pd = __popc(dw[0]) + __popc(dw[1]) + __popc(dw[2]) + __popc(dw[3]);
+            const double base = base_s[rr];
+            const bool use_diff = pd < pc && fabs(base) <= 1.7976931348623157e308;
+            const uint64_t c_lo = cw[0] | ((uint64_t)cw[1] << 32), c_hi = cw[2] | ((uint64_t)cw[3] << 32);
+            uint64_t m_lo = use_diff ? (dw[0] | ((uint64_t)dw[1] << 32)) : c_lo;
+            uint64_t m_hi = use_diff ? (dw[2] | ((uint64_t)dw[3] << 32)) : c_hi;
+            double acc = use_diff ? base : 0.0;
+            const float* xrow = xs + rr * ns;
+            while ((m_lo | m_hi) != 0ull) {
+                const bool lo = m_lo != 0ull;
+                const uint64_t cur = lo ? m_lo : m_hi;
+                const int i = __ffsll((long long)cur) - 1;
+                const uint64_t rest = cur & (cur - 1ull);
+                m_lo = lo ? rest : m_lo;
+                m_hi = lo ? m_hi : rest;
+                const double v = (double)xrow[i + (lo ? 0 : 64)];
+                acc += (((lo ? c_lo : c_hi) >> i) & 1ull) ? v : -v;
+            }
+            scores_k[r0 * k + t] = (float)acc;
+        }
+    }
+}
+
 // dx[r,i] = sum_j ds[r,j] * bit(r,j,i).  One warp per row: ds and the k*W words are staged in
 // shared memory, lane l owns columns l, l+32, ...; every shared read is a broadcast.
 __global__ void __launch_bounds__(kThreads)
@@ -416,7 +501,19 @@ extern "C" int smlvm_bits_score_fwd(const uint32_t* bits, const float* x, float*
     if (bits == nullptr || x == nullptr || scores_k == nullptr) return SMLVM_ERR_ARG;
     int64_t need = (rows * k + kThreads - 1) / kThreads;
     int64_t cap = (int64_t)device_sm_count() * 16;
-    if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0)
+    static int fwd_env = -1;  // SMLVM_BITS_FWD=vec keeps the per-configuration streaming kernel (A/B runs)
+    if (fwd_env < 0) {
+        const char* e = getenv("SMLVM_BITS_FWD");
+        fwd_env = (e && strcmp(e, "vec") == 0) ? 1 : 0;
+    }
+    if ((n & 3) == 0 && n <= 128 && fwd_env == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0) {
+        constexpr int kWarps = kThreads / kWarp;
+        const int64_t need_d = (rows + kWarps * kScoreRows - 1) / (kWarps * kScoreRows), cap_d = (int64_t)device_sm_count() * 8;
+        const size_t smem = (size_t)kWarps * kScoreRows * ((n + kScorePad) * sizeof(float) + sizeof(double));
+        const uint32_t k_magic = (uint32_t)((0x100000000ull + (uint64_t)k - 1) / (uint64_t)k);
+        bits_score_fwd_delta_kernel<<<(int)(need_d < cap_d ? need_d : cap_d), kThreads, smem, as_stream(stream)>>>(
+            bits, x, scores_k, rows, n, k, k_magic);
+    } else if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15u) == 0)
         bits_score_fwd_vec_kernel<<<(int)(need < cap ? need : cap), kThreads, 0, as_stream(stream)>>>(
             bits, x, scores_k, rows, n, k);
     else

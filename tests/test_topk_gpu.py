@@ -131,6 +131,29 @@ def test_bits_score_large_shapes(rows, n, k):
     assert close(ops.bits_score(x, rb), torch.einsum("bkj,bj->bk", dense, x.double()))
 
 
+@pytest.mark.parametrize("rows,n,k", [(1000, 128, 10), (333, 64, 5), (200, 32, 10)])
+def test_bits_score_non_finite_scores(rows, n, k):
+    """Masked (-inf) and +inf scores: the re-scoring that starts from configuration 0's sum must fall back to
+    the plain sum when that base is not finite, and -inf entries outside every configuration must not leak."""
+    from lvmhelpers import ops
+    g = torch.Generator().manual_seed(n + k)
+    x = torch.randn(rows, n, generator=g) * 2
+    x[torch.rand(rows, n, generator=g) < 0.1] = float("-inf")
+    x[::7, 3] = float("inf")
+    x = x.cuda()
+    _, bits, _ = ops.topk_bits(x, k, want_configs=False)
+    rb = torch.randint(-2 ** 31, 2 ** 31 - 1, bits.shape, generator=g, dtype=torch.int64).to(torch.int32).cuda()
+    idx = torch.arange(n, device="cuda")
+    for b in (bits, rb):
+        dense = ((b[..., idx // 32] >> (idx % 32)) & 1).bool()
+        ref = torch.where(dense, x.double()[:, None, :], torch.zeros((), device="cuda", dtype=torch.float64)).sum(-1)
+        got = ops.bits_score(x, b).double()
+        fin = torch.isfinite(ref)
+        assert torch.equal(torch.isnan(got), torch.isnan(ref))
+        assert torch.equal(got[~fin & ~torch.isnan(ref)], ref[~fin & ~torch.isnan(ref)])
+        assert bool(((got[fin] - ref[fin]).abs() <= 1.2e-7 * ref[fin].abs().clamp(min=1e-30)).all())
+
+
 @pytest.mark.parametrize("rows,n,k", [(300, 128, 10), (64, 32, 10), (50, 33, 4), (20, 7, 5), (10, 200, 3)])
 def test_bits_expand_matches_dense_configs(rows, n, k):
     """smlvm_bits_expand: packed candidates -> fp32 rows, all of them and an arbitrary selection
