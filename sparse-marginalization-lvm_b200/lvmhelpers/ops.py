@@ -14,6 +14,7 @@ from ._native import lib, check, ptr, stream
 
 
 SLOTS_MIN_ROWS = 4096
+SLOTS_MIN_COLS = 16
 
 
 def _slots_or_none(slots):
@@ -110,8 +111,9 @@ class _SparsemaxStats(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
         # support slots only pay on large batches (rows that do not fit them are processed one by one
-        # inside a warp); small batches are launch-bound and keep the plain kernels
-        big = x.shape[0] >= SLOTS_MIN_ROWS
+        # inside a warp); small batches are launch-bound and keep the plain kernels.  Rows of <= 16
+        # columns are no longer than their 64 bytes of slots: the consumers read them directly
+        big = x.shape[0] >= SLOTS_MIN_ROWS and x.shape[1] > SLOTS_MIN_COLS
         out = sparsemax_fwd(x, want_entropy=True, want_argmax=True, want_nnz=True, want_slots=big)
         ctx.save_for_backward(out["supp"], out["p"])
         slots = out["slots"] if big else torch.empty(0, device=x.device)

@@ -52,7 +52,10 @@ class _CompactValues(torch.autograd.Function):
 
 def _compact_with_flat(p, nnz, slots=None):
     comp = ops.compact(p.detach(), nnz, slots=slots)
-    comp["flat_idx"] = comp["rows"].to(torch.int64) * p.shape[-1] + comp["cols"].to(torch.int64)
+    if p.numel() < 2 ** 31:  # two launches (int32 multiply-add, widen) instead of four
+        comp["flat_idx"] = torch.add(comp["cols"], comp["rows"], alpha=p.shape[-1]).to(torch.int64)
+    else:
+        comp["flat_idx"] = comp["rows"].to(torch.int64) * p.shape[-1] + comp["cols"].to(torch.int64)
     return comp
 
 
