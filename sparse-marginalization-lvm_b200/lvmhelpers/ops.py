@@ -447,6 +447,7 @@ def sparsemap_plan(n, kind=0):
 # call; larger batches are solved in chunks of that size whose S is packed to 8 |A|^2 bytes per sample
 # (smlvm_sparsemap_pack_inverse) -- 1M samples at n = 128: 139 GB padded, ~16 GB packed.
 S_PAD_MAX_BYTES = 4 << 30
+SMAP_CHUNK_LANES = 2   # streams the solve chunks alternate between (1 = serial chunks)
 
 
 def sparsemap_solve(x, kind, budget=0, t=None, init_scores=None, max_iter=100, keep_S=True):
@@ -486,19 +487,46 @@ def sparsemap_solve(x, kind, budget=0, t=None, init_scores=None, max_iter=100, k
         state["S"] = S
         return state
     chunk = max(1, S_PAD_MAX_BYTES // slot)
-    S_tmp = torch.empty((min(chunk, rows), cap * cap), dtype=torch.float64, device=dev)
+    nchunks = (rows + chunk - 1) // chunk
+    # Chunks alternate between the current stream and a side stream over two padded buffers: a chunk ends with
+    # a latency-bound tail (the few samples that outgrew the first capacity tier are re-solved from scratch by
+    # small launches, ~3 ms after 16 ms at n = 128) and with the host read of its packed size; the next chunk's
+    # first-tier launch is already queued on the other stream and fills the SMs the tail leaves idle.
+    # The current stream waits for the side stream before returning.
+    cur = torch.cuda.current_stream(dev)
+    lanes = [cur, torch.cuda.Stream(device=dev)] if (nchunks > 1 and SMAP_CHUNK_LANES > 1) else [cur]
+    S_tmp = [torch.empty((min(chunk, rows), cap * cap), dtype=torch.float64, device=dev) for _ in lanes]
     S_rows = torch.empty(rows, dtype=torch.int64, device=dev)
     chunks = []
-    for r0 in range(0, rows, chunk):
-        r1 = min(rows, r0 + chunk)
-        solve(r0, r1, S_tmp)
-        m = counts[r0:r1]
-        offs = scan_counts(m * m)                       # doubles before each sample's S in the packed buffer
-        packed = torch.empty(max(int(offs[-1].item()), 1), dtype=torch.float64, device=dev)
-        check(lib.smlvm_sparsemap_pack_inverse(ptr(S_tmp), ptr(m), ptr(offs), ptr(packed), r1 - r0, n, stream()),
-              "smlvm_sparsemap_pack_inverse")
-        S_rows[r0:r1] = offs[:-1] * 8 + packed.data_ptr()
+    if len(lanes) > 1:
+        lanes[1].wait_stream(cur)
+
+    def finish(i, r0, r1, m, offs):
+        lane = lanes[i % len(lanes)]
+        with torch.cuda.stream(lane):
+            total = max(int(offs[-1].item()), 1)         # host read: waits for this chunk's solve only
+            packed = torch.empty(total, dtype=torch.float64, device=dev)
+            check(lib.smlvm_sparsemap_pack_inverse(ptr(S_tmp[i % len(lanes)]), ptr(m), ptr(offs), ptr(packed), r1 - r0, n,
+                                                   stream()), "smlvm_sparsemap_pack_inverse")
+            S_rows[r0:r1] = offs[:-1] * 8 + packed.data_ptr()
+        if lane is not cur:
+            packed.record_stream(cur)                    # born on the side stream, read by the backward on this one
         chunks.append(packed)
+
+    pending = None
+    for i, r0 in enumerate(range(0, rows, chunk)):
+        r1 = min(rows, r0 + chunk)
+        with torch.cuda.stream(lanes[i % len(lanes)]):
+            solve(r0, r1, S_tmp[i % len(lanes)])
+            m = counts[r0:r1]
+            offs = scan_counts(m * m)                   # doubles before each sample's S in the packed buffer
+        if pending is not None:
+            finish(*pending)
+        pending = (i, r0, r1, m, offs)
+    finish(*pending)
+    if len(lanes) > 1:
+        cur.wait_stream(lanes[1])
+        # temporaries born on the side stream (m * m, offsets) die here: the side stream is idle by now
     state["S_rows"], state["S_chunks"] = S_rows, chunks
     return state
 
