@@ -448,7 +448,7 @@ def extra_paths(args, world, device, rank):
             stats["N"] = int(p.numel())
             stats["st"] = aux["state"]
 
-        ms, _, _ = timed(smap_step, 3, 1, world, device)
+        ms, _, _ = timed(smap_step, 3, 3, world, device)
         st = stats["st"]
         n_items = stats["N"]
         fwd_bytes = rows * 4 * 128 + n_items * (4 * 128 + 8) + 4 * rows

@@ -450,6 +450,18 @@ S_PAD_MAX_BYTES = 4 << 30
 SMAP_CHUNK_LANES = 2   # streams the solve chunks alternate between (1 = serial chunks)
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev):
+    """One side stream per device for the life of the process: the caching allocator keeps a pool per stream,
+    so a fresh stream per call would send every call's temporaries to cudaMalloc."""
+    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _SIDE_STREAMS[key]
+
+
 def sparsemap_solve(x, kind, budget=0, t=None, init_scores=None, max_iter=100, keep_S=True):
     """Batched active-set solve.  x [rows, n] -> padded solver state (dict).  No host sync unless S has to be
     packed (one read of the packed size per chunk).  ``state["S"]`` is the padded [rows, cap*cap] tensor or
@@ -494,7 +506,7 @@ def sparsemap_solve(x, kind, budget=0, t=None, init_scores=None, max_iter=100, k
     # first-tier launch is already queued on the other stream and fills the SMs the tail leaves idle.
     # The current stream waits for the side stream before returning.
     cur = torch.cuda.current_stream(dev)
-    lanes = [cur, torch.cuda.Stream(device=dev)] if (nchunks > 1 and SMAP_CHUNK_LANES > 1) else [cur]
+    lanes = [cur, _side_stream(dev)] if (nchunks > 1 and SMAP_CHUNK_LANES > 1) else [cur]
     S_tmp = [torch.empty((min(chunk, rows), cap * cap), dtype=torch.float64, device=dev) for _ in lanes]
     S_rows = torch.empty(rows, dtype=torch.int64, device=dev)
     chunks = []
