@@ -878,6 +878,14 @@ extern "C" int smlvm_sparsemap_fwd(const float* x, const float* t, const double*
     }
     const int grid = (int)(rows < cap_grid ? rows : cap_grid);
     cudaStream_t st = as_stream(stream);
+    // The later tiers re-solve the few samples that outgrew the first one: most SMs idle, pure latency,
+    // so they get the widest CTA like a small batch (SMLVM_SMAP_TAIL_THREADS=0: same CTA as the first tier).
+    static int tail_threads = -1;
+    if (tail_threads < 0) {
+        const char* e = getenv("SMLVM_SMAP_TAIL_THREADS");
+        const int v = e ? atoi(e) : 256;
+        tail_threads = (v >= 32 && v <= 256 && v % 32 == 0) ? v : 0;
+    }
 #define SMLVM_SMAP_LAUNCH(K)                                                                       \
     do {                                                                                           \
         cudaError_t e =                                                                            \
@@ -888,7 +896,8 @@ extern "C" int smlvm_sparsemap_fwd(const float* x, const float* t, const double*
                                  (int)cudaSharedmemCarveoutMaxShared);                             \
         if (e != cudaSuccess) return (int)e;                                                       \
         for (int ti = 0; ti < ntier; ++ti) {                                                       \
-            sparsemap_fwd_kernel<K><<<grid, threads, solver_smem_bytes(n, tiers[ti]), st>>>(       \
+            const int th = (ti == 0 || tail_threads == 0) ? threads : tail_threads;                \
+            sparsemap_fwd_kernel<K><<<grid, th, solver_smem_bytes(n, tiers[ti]), st>>>(            \
                 x, t, init_scores, budget, max_iter, rows, n, tiers[ti], ti == 0, ti == ntier - 1, \
                 p_pad, aset_bits, counts, kept, iters, status, S_pad);                             \
         }                                                                                          \

@@ -590,6 +590,7 @@ class _SparseMAPBatch(torch.autograd.Function):
         ctx.only_positive = only_positive
         ctx.has_t = t is not None
         ctx.mark_non_differentiable(aset)
+        ctx.set_materialize_grads(False)  # no [N, n] zeros for the non-differentiable vertices in backward
         aux["sizes"] = host[1:]
         aux["idx"] = idx
         aux["offsets"] = offsets
@@ -598,6 +599,8 @@ class _SparseMAPBatch(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dp, _daset):
+        if dp is None:
+            return None, None, None, None, None, None, None, None
         dx, dt = sparsemap_bwd(ctx.state, dp, ctx.offsets, ctx.only_positive, want_dt=ctx.has_t)
         return dx, dt, None, None, None, None, None, None
 
