@@ -34,6 +34,29 @@ METRIC = "latent-marginalized samples/sec fwd+bwd"
 UNIT = "samples/s"
 
 
+_JSON_FD = None
+
+
+def keep_stdout_for_the_json_line():
+    """Only the JSON line may reach stdout: native libraries print there too (NCCL's version banner under
+    torchrun).  File descriptor 1 is pointed at stderr for the run; emit() writes to the saved descriptor."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
+
+
 def measured_hbm_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -186,7 +209,7 @@ def run_reference(args, rank, world):
         "note": "entmax is not installable offline; the CPU arm is the oracle's torch-CPU "
                 "restatement of entmax.sparsemax + the reference's own torch expressions",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, world):
@@ -613,7 +636,7 @@ def run_native(args, rank, local_rank, world):
             "paths": paths,
             "check": {"loss": loss_value, "support_mean": total_nnz / rows},
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
 
 
 def main():
@@ -630,6 +653,7 @@ def main():
     ap.add_argument("--no-paths", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    keep_stdout_for_the_json_line()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
