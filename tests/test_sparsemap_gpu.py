@@ -192,8 +192,9 @@ def test_demo_vector(oracle):
     assert np.abs(g0.cpu().numpy() - dx_ref).max() <= 1e-5
 
 
+@pytest.mark.parametrize("lanes", [1, 2])
 @pytest.mark.parametrize("n,kind,budget", [(32, BERN, 0), (33, BUDGET, 9), (20, 2, 0)])
-def test_packed_S_chunks_equal_padded(n, kind, budget):
+def test_packed_S_chunks_equal_padded(n, kind, budget, lanes):
     """Large batches keep 8|A|^2 bytes of S per sample (solved in chunks, smlvm_sparsemap_pack_inverse) instead of the
     padded 8(n+1)^2: same forward state, same backward, chunk boundaries included."""
     from lvmhelpers import ops
@@ -203,12 +204,13 @@ def test_packed_S_chunks_equal_padded(n, kind, budget):
     t = torch.randn(rows, n - 1, generator=g).cuda() if kind == 2 else None
     ref = ops.sparsemap_solve(x, kind, budget=budget, t=t, max_iter=100)
     assert ref["S"] is not None and ref["S_rows"] is None
-    old = ops.S_PAD_MAX_BYTES
+    old, old_lanes = ops.S_PAD_MAX_BYTES, ops.SMAP_CHUNK_LANES
     ops.S_PAD_MAX_BYTES = 7 * (n + 1) * (n + 1) * 8          # chunks of 7 samples
+    ops.SMAP_CHUNK_LANES = lanes                               # serial chunks / chunks alternating between two streams
     try:
         st = ops.sparsemap_solve(x, kind, budget=budget, t=t, max_iter=100)
     finally:
-        ops.S_PAD_MAX_BYTES = old
+        ops.S_PAD_MAX_BYTES, ops.SMAP_CHUNK_LANES = old, old_lanes
     assert st["S"] is None and st["S_rows"] is not None and len(st["S_chunks"]) == (rows + 6) // 7
     for key in ("p_pad", "bits", "counts", "kept", "iters", "status"):
         assert torch.equal(st[key], ref[key]), key
