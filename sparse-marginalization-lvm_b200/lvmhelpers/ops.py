@@ -532,10 +532,14 @@ def sparsemap_solve(x, kind, budget=0, t=None, init_scores=None, max_iter=100, k
             solve(r0, r1, S_tmp[i % len(lanes)])
             m = counts[r0:r1]
             offs = scan_counts(m * m)                   # doubles before each sample's S in the packed buffer
+        if len(lanes) == 1:                             # one padded buffer: pack before the next solve overwrites it
+            finish(i, r0, r1, m, offs)
+            continue
         if pending is not None:
             finish(*pending)
         pending = (i, r0, r1, m, offs)
-    finish(*pending)
+    if pending is not None:
+        finish(*pending)
     if len(lanes) > 1:
         cur.wait_stream(lanes[1])
         # temporaries born on the side stream (m * m, offsets) die here: the side stream is idle by now
