@@ -208,8 +208,7 @@ bits_score_fwd_delta_kernel(const uint32_t* __restrict__ bits, const float* __re
             const float4* xr = reinterpret_cast<const float4*>(x + (r0 + rr1) * (int64_t)n);
             const uint32_t* b0 = bits + (r0 + rr1) * (int64_t)k * words_n;
             float4* xo = reinterpret_cast<float4*>(xs + rr1 * ns);
-#pragma unroll 8
-            for (int c = g; c < n4; c += 4) {
+            auto take = [&](int c) {
                 const float4 f = __ldg(xr + c);
                 xo[c] = f;
                 const uint32_t nib = __ldg(b0 + (c >> 3)) >> (4 * (c & 7));
@@ -217,6 +216,13 @@ bits_score_fwd_delta_kernel(const uint32_t* __restrict__ bits, const float* __re
                 if (nib & 2u) a1 += (double)f.y;
                 if (nib & 4u) a2 += (double)f.z;
                 if (nib & 8u) a3 += (double)f.w;
+            };
+            if (n4 == 32) {  // n = 128: eight float4s per lane, no loop control
+#pragma unroll
+                for (int it = 0; it < 8; ++it) take(g + 4 * it);
+            } else {
+#pragma unroll 4
+                for (int c = g; c < n4; c += 4) take(c);
             }
         }
         double a = (a0 + a1) + (a2 + a3);
