@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libsmlvm.so")
 
 ABI_VERSION = 3
 
-FACTOR_BERNOULLI, FACTOR_BUDGET, FACTOR_SEQUENCE_BINARY = 0, 1, 2
+FACTOR_BERNOULLI, FACTOR_BUDGET, FACTOR_SEQUENCE_BINARY, FACTOR_SEQUENCE = 0, 1, 2, 3
 SOLVE_STATUS = {0: "converged", 1: "max_iter", 2: "repeated_config", 3: "singular"}
 
 SPARSEMAX_MAX_COLS = 8192

@@ -1,22 +1,27 @@
 """lvmhelpers.sparsemap counterpart: SparseMAP as ``torch.autograd.Function``s.
 
-Reference: lvmhelpers/sparsemap.py.  ``bernoulli_smap`` / ``budget_smap`` /
-``sequence_smap`` keep their signatures and return ``(p, aset)`` -- a distribution
-over the active vertices (fp32 ``[|A|]``) and the vertices themselves (fp32
-``[|A|, n]``, non-differentiable) in the solver's order.  The factor graph, the
-libad3 active-set QP and its Jacobian-vector product run in one CTA of the
-``smlvm_sparsemap_*`` kernels; there is no per-sample host round trip
+Reference: lvmhelpers/sparsemap.py.  Same class tree -- ``SparseMAP`` / ``SequenceSparseMAP`` with
+``run_sparsemap`` / ``jv`` and a ``make_factor`` hook per subclass (sparsemap.py:10-87), the three
+concrete functions (:90-148) and ``bernoulli_smap`` / ``budget_smap`` / ``sequence_smap`` (:151-160),
+which return ``(p, aset)``: a distribution over the active vertices (fp32 ``[|A|]``) and the
+vertices themselves (fp32 ``[|A|, n]``, non-differentiable) in the solver's order.
+
+What changed underneath: ``make_factor`` returns a plain handle (``lvmhelpers._factors``) that
+names the MAP oracle; the factor graph, the libad3 active-set QP and its Jacobian-vector product
+run in one CTA of the ``smlvm_sparsemap_*`` kernels, and there is no per-sample host round trip
 (reference: sparsemap.py:21,33-34,42-43).
 
-``init=True`` draws the same ``torch.rand(2n, dtype=double)`` from the CPU
-generator as sparsemap.py:26 and seeds the active set with the factor's MAP of
-those scores.  (``sequence_smap(init=True)`` raises in the reference,
-sparsemap.py:68; here it does what that line intended: zero edge scores.)
+``init=True`` draws the same ``torch.rand(2n, dtype=double)`` from the CPU generator as
+sparsemap.py:26 and seeds the active set with the factor's MAP of those scores.
+(``sequence_smap(init=True)`` raises in the reference, sparsemap.py:68; here it does what that
+line intended: zero edge scores.)
 """
 import torch
 
 from . import ops
-from ._native import FACTOR_BERNOULLI, FACTOR_BUDGET, FACTOR_SEQUENCE_BINARY
+from .pbernoulli import PFactorBernoulli
+from .pbudget import PFactorBudget
+from .psequence import PFactorSequenceBinary
 
 
 def draw_init_scores(rows, n):
@@ -25,70 +30,128 @@ def draw_init_scores(rows, n):
     return torch.rand(rows, 2 * n, dtype=torch.double)
 
 
-class _SingleSparseMAP(torch.autograd.Function):
-    kind = None
+def _solve_one(ctx, x, t):
+    """One sample through the batched solver (rows = 1) with the factor ``ctx.f``."""
+    if x.dim() != 1:
+        raise ValueError("expected a 1-D score vector, got shape %s" % (tuple(x.shape),))
+    f = ctx.f
+    f._require_initialized()
+    n = x.shape[0]
+    if f.length != n:
+        raise ValueError("factor initialised for %d variables, scores have %d" % (f.length, n))
+    xb = x.detach().reshape(1, n)
+    tb = None if t is None else t.detach().reshape(1, n - 1)
+    init_scores = draw_init_scores(1, n) if ctx.init else None
+    state = ops.sparsemap_solve(xb, f.kind, budget=f.budget, t=tb, init_scores=init_scores,
+                                max_iter=ctx.max_iter, keep_S=True)
+    offsets = ops.scan_counts(state["counts"])
+    total = int(offsets[-1].item())
+    p, aset, _ = ops.sparsemap_expand(state, False, offsets, total, want_idx=False)
+    ctx.state, ctx.offsets = state, offsets
+    ctx.mark_non_differentiable(aset)
+    return p, aset
+
+
+class SparseMAP(torch.autograd.Function):
+    """reference sparsemap.py:10-44: factors over 2n binary variables (on / off halves)."""
 
     @classmethod
-    def _solve(cls, ctx, x, t, budget, max_iter, init):
-        if x.dim() != 1:
-            raise ValueError("expected a 1-D score vector, got shape %s" % (tuple(x.shape),))
-        n = x.shape[0]
-        xb = x.detach().reshape(1, n)
-        tb = None if t is None else t.detach().reshape(1, n - 1)
-        init_scores = draw_init_scores(1, n) if init else None
-        state = ops.sparsemap_solve(xb, cls.kind, budget=budget, t=tb, init_scores=init_scores,
-                                    max_iter=max_iter, keep_S=True)
-        offsets = ops.scan_counts(state["counts"])
-        total = int(offsets[-1].item())
-        p, aset, _ = ops.sparsemap_expand(state, False, offsets, total, want_idx=False)
-        ctx.state, ctx.offsets, ctx.n = state, offsets, n
-        ctx.mark_non_differentiable(aset)
-        return p, aset
+    def make_factor(cls, ctx):
+        raise NotImplementedError
 
     @classmethod
-    def _jv(cls, ctx, dp, want_dt):
-        dx, dt = ops.sparsemap_bwd(ctx.state, dp, ctx.offsets, False, want_dt=want_dt)
-        return dx.reshape(ctx.n), (None if dt is None else dt.reshape(ctx.n - 1))
+    def run_sparsemap(cls, ctx, x):
+        ctx.n = x.shape[0]
+        ctx.f = cls.make_factor(ctx)
+        return _solve_one(ctx, x, None)
+
+    @classmethod
+    def jv(cls, ctx, dp):
+        dx, _ = ops.sparsemap_bwd(ctx.state, dp, ctx.offsets, False, want_dt=False)
+        return dx.reshape(ctx.n)
 
 
-class BernSparseMAP(_SingleSparseMAP):
+class SequenceSparseMAP(torch.autograd.Function):
+    """reference sparsemap.py:47-87: the same with edge potentials ``t`` as additional scores."""
+
+    @classmethod
+    def make_factor(cls, ctx):
+        raise NotImplementedError
+
+    @classmethod
+    def run_sparsemap(cls, ctx, x, t):
+        ctx.n = x.shape[0]
+        ctx.f = cls.make_factor(ctx)
+        return _solve_one(ctx, x, t)
+
+    @classmethod
+    def jv(cls, ctx, dp):
+        dx, dt = ops.sparsemap_bwd(ctx.state, dp, ctx.offsets, False, want_dt=True)
+        return dx.reshape(ctx.n), dt.reshape(ctx.n - 1)
+
+
+class BernSparseMAP(SparseMAP):
     """reference sparsemap.py:90-106"""
-    kind = FACTOR_BERNOULLI
+
+    @classmethod
+    def make_factor(cls, ctx):
+        f = PFactorBernoulli()
+        f.initialize(ctx.n)
+        return f
 
     @classmethod
     def forward(cls, ctx, x, max_iter, init):
-        return cls._solve(ctx, x, None, 0, max_iter, init)
+        ctx.max_iter = max_iter
+        ctx.init = init
+        return cls.run_sparsemap(ctx, x)
 
     @classmethod
     def backward(cls, ctx, dp, daset):
-        return cls._jv(ctx, dp, False)[0], None, None
+        return cls.jv(ctx, dp), None, None
 
 
-class BudgetSparseMAP(_SingleSparseMAP):
+class BudgetSparseMAP(SparseMAP):
     """reference sparsemap.py:109-127"""
-    kind = FACTOR_BUDGET
+
+    @classmethod
+    def make_factor(cls, ctx):
+        f = PFactorBudget()
+        f.initialize(ctx.n, ctx.budget)
+        return f
 
     @classmethod
     def forward(cls, ctx, x, budget, max_iter, init):
-        return cls._solve(ctx, x, None, budget, max_iter, init)
+        ctx.n = x.shape[0]
+        ctx.init = init
+        ctx.max_iter = max_iter
+        ctx.budget = budget
+        return cls.run_sparsemap(ctx, x)
 
     @classmethod
     def backward(cls, ctx, dp, daset):
-        return cls._jv(ctx, dp, False)[0], None, None, None
+        return cls.jv(ctx, dp), None, None, None
 
 
-class SequenceBinarySparseMAP(_SingleSparseMAP):
+class SequenceBinarySparseMAP(SequenceSparseMAP):
     """reference sparsemap.py:130-148"""
-    kind = FACTOR_SEQUENCE_BINARY
+
+    @classmethod
+    def make_factor(cls, ctx):
+        f = PFactorSequenceBinary()
+        f.initialize(ctx.n)
+        return f
 
     @classmethod
     def forward(cls, ctx, x, t, max_iter, init):
-        return cls._solve(ctx, x, t, 0, max_iter, init)
+        ctx.n = x.shape[0]
+        ctx.init = init
+        ctx.max_iter = max_iter
+        return cls.run_sparsemap(ctx, x, t)
 
     @classmethod
     def backward(cls, ctx, dp, daset):
-        dx, dt = cls._jv(ctx, dp, True)
-        return dx, dt, None, None
+        d_eta_u, d_eta_v = cls.jv(ctx, dp)
+        return d_eta_u, d_eta_v, None, None
 
 
 def bernoulli_smap(x, max_iter=100, init=True):

@@ -1,4 +1,7 @@
 """lvmhelpers/utils.py counterpart: the decoder side of the drop-in boundary."""
+import importlib.util
+import os
+
 import torch.nn as nn
 
 
@@ -15,3 +18,35 @@ class DeterministicWrapper(nn.Module):
 
     def forward(self, *args, **kwargs):
         return self.agent(*args, **kwargs)
+
+
+_reference_utils = None
+
+
+def _load_reference_utils():
+    """The ``utils.py`` of another ``lvmhelpers`` portion on the package path (the reference checkout),
+    loaded under a private name; None when there is none."""
+    global _reference_utils
+    if _reference_utils is None:
+        from . import __path__ as portions
+        here = os.path.dirname(os.path.abspath(__file__))
+        for d in portions:
+            cand = os.path.join(d, "utils.py")
+            if os.path.abspath(d) != here and os.path.isfile(cand):
+                spec = importlib.util.spec_from_file_location("lvmhelpers._reference_utils", cand)
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+                _reference_utils = mod
+                break
+    return _reference_utils
+
+
+def __getattr__(name):
+    # Everything off the hot path (``populate_common_params``: the experiments' argparse options,
+    # reference lvmhelpers/utils.py:20-98) stays the reference's own code.
+    ref = _load_reference_utils()
+    if ref is not None and hasattr(ref, name):
+        return getattr(ref, name)
+    raise AttributeError(
+        "lvmhelpers.utils has no attribute %r: it is not part of the sparse-marginalization hot path; put the "
+        "reference checkout on sys.path AFTER this package to fall through to its lvmhelpers/utils.py" % name)
