@@ -240,6 +240,22 @@ def main():
     run(dict(name="topk", **prob), m, {"enc_w": enc.weight, "enc_b": enc.bias, "dec": dec.weight},
         ("loss_output",))
 
+    # the same case with the reference's re-scoring einsum (structmarg.py:47) accumulated in fp64 and rounded
+    # once: how far the REFERENCE's own results move under the rounding of that one fp32 contraction.  The GPU
+    # path accumulates the re-scoring in fp64; tests/test_golden_gpu.py holds it to this variant tightly and to
+    # the fp32 one within the band between the two.
+    prob = toy_problem(2, 64, 20, 32, 6)
+    enc, dec = make_modules(prob, categorical=False)
+    m = TopKSparsemaxMarg(TopKSparsemaxWrapper(enc, k=10), DeterministicWrapper(BitDecoder(dec)), loss_fun,
+                          encoder_entropy_coeff=1.0)
+    einsum32 = torch.einsum
+    torch.einsum = lambda eq, *ops: einsum32(eq, *[o.double() for o in ops]).float()
+    try:
+        run(dict(name="topk64", **prob), m, {"enc_w": enc.weight, "enc_b": enc.bias, "dec": dec.weight},
+            ("loss_output",))
+    finally:
+        torch.einsum = einsum32
+
     # SparseMAP, bernoulli and budget 16, init off and on (config 4 shape: n = 32, B = 64)
     for nm, budget, init in (("smap_bern", 0, False), ("smap_budget", 16, False), ("smap_budget_init", 16, True)):
         prob = toy_problem(3, 64, 20, 32, 6)

@@ -150,18 +150,30 @@ def test_topk_marg_vs_reference_wrapper(wrap):
     res["loss"].backward()
     distr = res["log"]["distr"].detach().cpu().numpy()
     assert np.array_equal(distr > 0, wrap["topk_log_distr"] > 0)                  # compaction mask bit-exact
-    # the sparsemax INPUTS differ here: scores_k = einsum(bits, Linear(x)) has |scores_k| ~ 10-30
-    # (fp32 ulp ~ 2e-6) and is accumulated in another order than the reference's CPU bmm, so the
-    # end-to-end bar is a few ulps of the scores; the kernel-level 1e-6 bar is held above
-    assert np.abs(distr - wrap["topk_log_distr"]).max() <= 1e-5
+    # The sparsemax INPUTS differ from the reference's by the rounding of ONE contraction: scores_k =
+    # einsum(bits, Linear(x)) (structmarg.py:47) has |scores_k| ~ 10-46 (fp32 ulp ~ 4e-6); the reference
+    # accumulates it in fp32 on the CPU, the re-scoring kernel in fp64 with one final rounding.  The goldens hold
+    # the reference's own pipeline BOTH ways (tests/golden/make_golden.py: `topk` = as shipped, `topk64` = its
+    # einsum accumulated in fp64), so the tolerance is measured, not asserted in a comment:
+    #   * against the fp64-einsum reference the usual bars hold (probabilities 1e-6 of kernel-level parity plus
+    #     one ulp of the scores, gradients 1e-5 of their scale);
+    #   * against the shipped fp32-einsum reference the result lies inside the band the reference itself spans
+    #     between its two variants (x1.5 + the bar above).
+    d32, d64 = wrap["topk_log_distr"], wrap["topk64_log_distr"]
+    assert np.array_equal(d32 > 0, d64 > 0)
+    assert np.abs(distr - d64).max() <= 2e-6
+    assert np.abs(distr - d32).max() <= 1.5 * np.abs(d32 - d64).max() + 2e-6
     lo = res["log"]["loss_output"].detach().cpu().numpy()
     assert lo.shape == wrap["topk_log_loss_output"].shape                         # same ragged total, same order
     assert np.allclose(lo, wrap["topk_log_loss_output"], rtol=1e-5, atol=1e-5)
-    # gradient bar 1e-3: with entropy coeff 1 the gradient holds -(log p + 1) of probabilities
-    # down to ~1e-5, so it is ill-conditioned in the sparsemax inputs -- the REFERENCE pipeline
-    # itself moves by 2.2e-4 in enc_w.grad when its einsum is accumulated in fp64 instead of fp32
-    # (|scores_k| up to 46, ulp 3.8e-6; measured with the oracle in the build container)
-    _check(wrap, "topk", res, {"enc_w": enc.weight, "enc_b": enc.bias, "dec": dec.weight}, gtol=1e-3)
+    params = {"enc_w": enc.weight, "enc_b": enc.bias, "dec": dec.weight}
+    _check(wrap, "topk64", res, params, gtol=2e-5)
+    for pname, prm in params.items():
+        r32, r64 = wrap[f"topk_grad_{pname}"], wrap[f"topk64_grad_{pname}"]
+        band = 1.5 * np.abs(r32 - r64).max() + 2e-5 * max(1.0, np.abs(r32).max())
+        assert np.abs(prm.grad.cpu().numpy() - r32).max() <= band, pname
+    # the band itself is what the old hand-set 1e-3 stood for: the reference moves ~2e-4 in enc_w.grad
+    assert 1e-5 < np.abs(wrap["topk_grad_enc_w"] - wrap["topk64_grad_enc_w"]).max() < 1e-3
 
 
 @pytest.mark.parametrize("name,budget,init", [("smap_bern", 0, False), ("smap_budget", 16, False),

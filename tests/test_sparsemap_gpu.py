@@ -60,7 +60,8 @@ def test_forward_matches_oracle(oracle, n, kind, budget, scale):
             assert abs(p.sum() - 1) <= 1e-4 and p.min() >= -1e-7
         if kind == BUDGET:
             assert aset.sum(1).max() <= budget
-    assert flagged == 0  # repeated-config / singular branches never fire on random inputs
+    assert flagged == 0  # no repeated-config / singular exit among these few rows (they do occur: a few per 10^5
+    # samples at n = 128, see test_n128_flagged_samples_match_oracle)
 
 
 @pytest.mark.parametrize("n,kind,budget", [(32, BERN, 0), (32, BUDGET, 16), (128, BUDGET, 64)])
@@ -224,3 +225,42 @@ def test_packed_S_chunks_equal_padded(n, kind, budget, lanes):
     assert torch.equal(dx, dx_ref)
     if kind == 2:
         assert torch.equal(dt, dt_ref)
+
+
+@pytest.mark.parametrize("kind,budget,lo_hi_maxiter", [(BUDGET, 64, (0.03, 0.09)), (BERN, 0, (0.0, 0.005))])
+def test_n128_flagged_samples_match_oracle(oracle, kind, budget, lo_hi_maxiter):
+    """The samples that do NOT end in plain convergence at the benchmark shape (n = 128, max_iter = 300,
+    N(0,1) scores, structmarg.py:172-196): every sample with status >= 2 (repeated configuration / singular
+    insertion) of a 131072-sample batch, and every max_iter sample of its first 16384 rows, compared with the
+    oracle in full -- (p, aset, iters, status).  Round 1 measured status_hist = [61844, 3690, 2, 0] on 65536
+    budget-64 samples and [65498, 38, 0, 0] for Bernoulli: about 5.6 % / 0.06 % of the samples stop at max_iter
+    and a handful per 10^5 stop because the oracle returns a vertex that is already active (libad3 would clear
+    its cache there and the reference trip `assert supp > 0`, structmarg.py:192; we keep the solution -- the
+    oracle restates exactly that, oracle/ad3_min/GenericFactor.cpp:9-16)."""
+    rows, head = 131072, 16384
+    g = torch.Generator().manual_seed(20261020 + kind)
+    x = torch.randn(rows, 128, generator=g)
+    from lvmhelpers import ops
+    st = ops.sparsemap_solve(x.cuda(), kind, budget=budget, max_iter=300, keep_S=False)
+    status = st["status"].cpu().numpy()
+    hist = np.bincount(status, minlength=4)
+    assert hist.sum() == rows and hist[3] == 0                      # no singular insertion on random scores
+    assert lo_hi_maxiter[0] * rows <= hist[1] <= lo_hi_maxiter[1] * rows, hist
+    assert hist[2] <= 40, hist                                      # repeated configurations: a few per 10^5
+    pick = np.concatenate([np.nonzero(status >= 2)[0], np.nonzero(status[:head] == 1)[0]])
+    pick = pick[:1500]
+    assert len(pick) > 0
+    xn = x.numpy()
+    for r in pick:
+        ref = oracle.sparsemap_fwd(xn[r], kind, budget, max_iter=300)
+        p, aset = _unpack(st, int(r))
+        assert int(status[r]) == ref["status"], (r, status[r], ref["status"])
+        assert int(st["iters"][r]) == ref["iters"]
+        assert aset.shape == ref["aset"].shape and np.array_equal(aset, ref["aset"]), r
+        assert np.abs(p - ref["p"]).max() <= 1e-5
+        assert int(st["kept"][r]) == int((ref["p"].astype(np.float32) > 0).sum()) >= 1
+    # and the cheap invariants on ALL samples: a max_iter / repeated-config sample still carries a usable
+    # distribution (what SparseMAPWrapper hands on after dropping p <= 0, structmarg.py:189-192)
+    assert int(st["kept"].min()) >= 1
+    cnt = st["counts"].cpu().numpy()
+    assert cnt.min() >= 1 and cnt.max() <= 129
