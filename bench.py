@@ -151,7 +151,7 @@ def cpu_step(x, losses, coeff=ENTROPY_COEFF):
     idx = torch.nonzero(mask)
     loss = P.unsqueeze(1).bmm(lr.unsqueeze(-1)).squeeze().mean()
     (loss - coeff * ent.mean()).backward()
-    return {"loss": float(loss), "P": P.detach(), "entropy": ent.detach(), "dx": xr.grad, "dl": lr.grad,
+    return {"loss": float(loss.detach()), "P": P.detach(), "entropy": ent.detach(), "dx": xr.grad, "dl": lr.grad,
             "vals": vals, "idx": idx}
 
 

@@ -236,7 +236,8 @@ def test_n128_flagged_samples_match_oracle(oracle, kind, budget, lo_hi_maxiter):
     budget-64 samples and [65498, 38, 0, 0] for Bernoulli: about 5.6 % / 0.06 % of the samples stop at max_iter
     and a handful per 10^5 stop because the oracle returns a vertex that is already active (libad3 would clear
     its cache there and the reference trip `assert supp > 0`, structmarg.py:192; we keep the solution -- the
-    oracle restates exactly that, oracle/ad3_min/GenericFactor.cpp:9-16)."""
+    oracle restates exactly that, oracle/ad3_min/GenericFactor.cpp:9-16).  First run of THIS test on the B200, 131072
+    budget-64 samples: [123714, 7348, 7, 3] -- three singular insertions as well."""
     rows, head = 131072, 16384
     g = torch.Generator().manual_seed(20261020 + kind)
     x = torch.randn(rows, 128, generator=g)
@@ -244,7 +245,10 @@ def test_n128_flagged_samples_match_oracle(oracle, kind, budget, lo_hi_maxiter):
     st = ops.sparsemap_solve(x.cuda(), kind, budget=budget, max_iter=300, keep_S=False)
     status = st["status"].cpu().numpy()
     hist = np.bincount(status, minlength=4)
-    assert hist.sum() == rows and hist[3] == 0                      # no singular insertion on random scores
+    # singular insertions (|Schur complement| < 1e-9) do occur at the budget factor: 3 of 131072 samples when this
+    # test was first run on the B200.  libad3 evicts a vertex there through an eigendecomposition (third-party
+    # code, absent here); kernel and oracle both stop with the current iterate and flag the sample
+    assert hist.sum() == rows and hist[3] <= 20, hist
     assert lo_hi_maxiter[0] * rows <= hist[1] <= lo_hi_maxiter[1] * rows, hist
     assert hist[2] <= 40, hist                                      # repeated configurations: a few per 10^5
     pick = np.concatenate([np.nonzero(status >= 2)[0], np.nonzero(status[:head] == 1)[0]])
