@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SMLVM_ABI_VERSION 3
+#define SMLVM_ABI_VERSION 4
 
 #define SMLVM_OK 0
 #define SMLVM_ERR_ARG (-1)         /* null pointer, negative size, bad enum        */
@@ -202,12 +202,22 @@ int32_t smlvm_sparsemap_plan(int32_t n, int32_t kind, int32_t* caps, int32_t* sm
  *   counts[rows]               int32  |A|
  *   kept[rows]                 int32  number of p_pad > 0 (NULL to skip)
  *   iters[rows], status[rows]  int32  (NULL to skip)
- *   S_pad[rows,cap*cap]        fp64   inverse_A[1:,1:], packed with row stride |A|
- *                                     (NULL to skip; needed by smlvm_sparsemap_bwd)       */
+ * The inverse needed by smlvm_sparsemap_bwd, S = inverse_A[1:,1:] (|A|^2 doubles per sample, row stride |A|; the
+ * reference keeps the whole factor object alive for this, sparsemap.py:19,42), is bump-allocated from a caller-owned
+ * arena (NULL to skip):
+ *   S_arena[S_capacity]        fp64
+ *   S_offsets[rows]            int64  element offset of sample r's S in the arena, or -1 if it did not fit
+ *   S_cursor[1]                uint64 device counter, ZEROED BY THE CALLER before the (first) call that shares the
+ *                                     arena; ends at the number of doubles all samples needed -- > S_capacity means
+ *                                     some samples got offset -1 (re-solve with an arena of that size).  Padded to
+ *                                     (n+1)^2 per sample the arena cannot overflow.
+ * workspace: smlvm_sparsemap_workspace_bytes(rows) bytes (worklists of the capacity tiers); rows < 2^31.          */
+size_t smlvm_sparsemap_workspace_bytes(int64_t rows);
 int smlvm_sparsemap_fwd(const float* x, const float* t, const double* init_scores, int32_t kind,
                         int32_t budget, int32_t max_iter, int64_t rows, int32_t n, float* p_pad,
                         uint32_t* aset_bits, int32_t* counts, int32_t* kept, int32_t* iters,
-                        int32_t* status, double* S_pad, void* stream);
+                        int32_t* status, double* S_arena, int64_t S_capacity, int64_t* S_offsets,
+                        uint64_t* S_cursor, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Ragged expansion in sample order (structmarg.py:181-198): for every kept vertex
  * (all of them if only_positive == 0, those with p_pad > 0 otherwise) at
@@ -221,19 +231,12 @@ int smlvm_sparsemap_expand(const float* p_pad, const uint32_t* aset_bits, const 
  * dp is ragged in the same layout smlvm_sparsemap_expand produced (same offsets,
  * same only_positive); dropped vertices get dp = 0.
  * replaces: SparseMAP.jv / dist_jacobian_vec lvmhelpers/sparsemap.py:38-44,80-87          */
-/* S of sample r is read at S_pad + r*cap*cap (the layout smlvm_sparsemap_fwd writes) or, when S_rows is
- * not NULL, at the device address S_rows[r] (int64: the packed copies of smlvm_sparsemap_pack_inverse, possibly
- * in several buffers).                                                                               */
+/* S of sample r is read at S_arena + S_offsets[r] (what smlvm_sparsemap_fwd wrote); a sample whose offset is -1
+ * gets NaN gradients (its inverse did not fit the forward's arena: the caller should have re-solved).             */
 int smlvm_sparsemap_bwd(const float* dp, const int64_t* offsets, int32_t only_positive,
                         const float* p_pad, const uint32_t* aset_bits, const int32_t* counts,
-                        const double* S_pad, const int64_t* S_rows, float* dx, float* dt, int64_t rows,
+                        const double* S_arena, const int64_t* S_offsets, float* dx, float* dt, int64_t rows,
                         int32_t n, void* stream);
-
-/* S_packed[S_offsets[r] .. + counts[r]^2) = the |A|^2 doubles of sample r in S_pad: keeps 8|A|^2 bytes per
- * sample for the backward instead of the padded 8(n+1)^2 (133 KB at n = 128; the reference keeps the whole
- * factor object alive for this, sparsemap.py:19,42).                                                     */
-int smlvm_sparsemap_pack_inverse(const double* S_pad, const int32_t* counts, const int64_t* S_offsets,
-                           double* S_packed, int64_t rows, int32_t n, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * (4) probability-weighted loss, fused segmented reduce

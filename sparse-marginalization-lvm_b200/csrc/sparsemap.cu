@@ -22,10 +22,28 @@
 #include <math_constants.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
 namespace smlvm {
+
+// Development aid (make timing -> tools/_dev/libsmlvm_timing.so, never shipped): cycle totals of selected solver
+// phases (SMLVM_TIMING_MASK: one bit per phase; a recorded phase collects everything since the previous recorded
+// point, so few live counters -- no spills), accumulated by thread 0 of every CTA; smlvm_debug_phase_cycles().
+#ifdef SMLVM_SMAP_TIMING
+#ifndef SMLVM_TIMING_MASK
+#define SMLVM_TIMING_MASK 0xffff
+#endif
+__device__ unsigned long long g_phase_cycles[16];
+#define PHASE_BEGIN() long long ph_last = clock64(); unsigned long long ph_acc[16] = {0}
+#define PHASE(k) do { if (((SMLVM_TIMING_MASK >> (k)) & 1) && threadIdx.x == 0) { const long long ph_now = clock64(); ph_acc[k] += (unsigned long long)(ph_now - ph_last); ph_last = ph_now; } } while (0)
+#define PHASE_END() do { if (threadIdx.x == 0) for (int k = 0; k < 16; ++k) if ((SMLVM_TIMING_MASK >> k) & 1) atomicAdd(&g_phase_cycles[k], ph_acc[k]); } while (0)
+#else
+#define PHASE_BEGIN()
+#define PHASE(k)
+#define PHASE_END()
+#endif
 
 struct SolverSmem {
     double* inv;    // [LD*LD]  index 0 = constraint row, vertex a -> a + 1
@@ -149,7 +167,8 @@ __device__ double map_budget(const SolverSmem& sm, int n, int budget)
         const unsigned b = __ballot_sync(kFull, y);
         if (lane == 0) sm.ynew[i >> 5] = b;
     }
-    const int active = block_sum_int(cnt, sm.red);  // also orders the sm.d / sm.ynew writes
+    // (one barrier-with-count when every thread owns at most one coordinate; also orders the sm.d / sm.ynew writes)
+    const int active = n <= (int)blockDim.x ? __syncthreads_count(cnt) : block_sum_int(cnt, sm.red);
     if (active > budget) {
         // keep the `budget` largest gains, ties towards the lower index (sort of (-gain, i))
         sum = 0.0;
@@ -159,7 +178,15 @@ __device__ double map_budget(const SolverSmem& sm, int n, int budget)
             if (valid) {
                 const double gi = sm.d[i];
                 int rank = 0;
-                for (int j = 0; j < n; ++j) {
+                int j = 0;
+                for (; j + 8 <= n; j += 8) {   // eight gains loaded ahead of their compares (this loop ran at one
+                    double gj[8];              // shared-memory latency per element: 17 % of the budget-64 solve)
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) gj[u] = sm.d[j + u];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) rank += (gj[u] > gi || (gj[u] == gi && j + u < i)) ? 1 : 0;
+                }
+                for (; j < n; ++j) {
                     const double gj = sm.d[j];
                     rank += (gj > gi || (gj == gi && j < i)) ? 1 : 0;
                 }
@@ -310,21 +337,20 @@ __device__ __forceinline__ void schur_terms_fill(const SolverSmem& sm, double* d
         }
     }
 }
-// rows [a0, a1) that fit one round of the terms buffer (at least one row: a row has <= cap+1 terms)
+// rows [a0, a1) that go into one round of the terms buffer: row a has m + 1 - a terms, so chunk / (m + 1 - a0) rows
+// from a0 on hold at most `chunk` terms (at least one row: a row has <= cap + 1 <= chunk terms).  Closed form: this
+// runs on the fold thread's critical path once per round (a search loop here cost 8 % of the kernel's instructions).
 __device__ __forceinline__ int schur_round_end(int m, int a0, int chunk, int& count)
 {
-    // common case (|A| <= 46): everything that is left fits one round
     const int rest = ((m + 1 - a0) * (m + 2 - a0)) / 2;
-    if (rest <= chunk) {
+    if (rest <= chunk) {  // everything that is left fits (|A| <= 18: the only round)
         count = rest;
         return m + 1;
     }
-    int a1 = a0, c = 0;
-    while (a1 <= m && c + (m + 1 - a1) <= chunk) {
-        c += m + 1 - a1;
-        ++a1;
-    }
-    count = c;
+    const int len = m + 1 - a0;
+    const int rows = chunk / len;
+    const int a1 = a0 + rows;  // < m + 1 because rest > chunk
+    count = rows * len - (rows * (rows - 1)) / 2;
     return a1;
 }
 
@@ -338,11 +364,15 @@ __device__ __forceinline__ int common_values(const uint32_t* a, const uint32_t* 
 template <int KIND>
 __global__ void __launch_bounds__(256, 4) sparsemap_fwd_kernel(const float* __restrict__ x, const float* __restrict__ t,
                                      const double* __restrict__ init_scores, int budget,
-                                     int max_iter, int64_t rows, int n, int cap, int first_tier,
-                                     int last_tier, float* __restrict__ p_pad,
+                                     int max_iter, int64_t rows, int n, int cap, int last_tier,
+                                     const int32_t* __restrict__ wl_in, const int32_t* __restrict__ wl_in_count,
+                                     int32_t* __restrict__ wl_out, int32_t* __restrict__ wl_out_count,
+                                     float* __restrict__ p_pad,
                                      uint32_t* __restrict__ aset_bits, int32_t* __restrict__ counts,
                                      int32_t* __restrict__ kept, int32_t* __restrict__ iters,
-                                     int32_t* __restrict__ status, double* __restrict__ S_pad)
+                                     int32_t* __restrict__ status, double* __restrict__ S_arena,
+                                     long long S_capacity, long long* __restrict__ S_offsets,
+                                     unsigned long long* __restrict__ S_cursor)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int cap_out = n + 1;                    // layout of the padded outputs (ABI)
@@ -350,10 +380,22 @@ __global__ void __launch_bounds__(256, 4) sparsemap_fwd_kernel(const float* __re
     const SolverSmem sm = carve(smem_raw, n, cap);
     const int tid = threadIdx.x, T = blockDim.x;
 
-    for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+    // the first capacity tier takes every sample; later tiers only the samples an earlier tier could not hold,
+    // from the worklist that tier appended them to (a small persistent grid: no empty CTAs)
+    // (a later tier's CTAs pull the next entry with an atomic ticket: its few samples are the long ones, a static
+    // assignment would leave most CTAs idle behind the unlucky one)
+    const int64_t work = wl_in != nullptr ? (int64_t)__ldg(wl_in_count) : rows;
+    int* ticket = wl_in != nullptr ? const_cast<int*>(wl_in_count) + 1 : nullptr;
+    for (int64_t wi = blockIdx.x;; wi += gridDim.x) {
         __syncthreads();
-        // later capacity tiers only re-solve the samples an earlier tier could not hold
-        if (!first_tier && counts[row] != -1) continue;
+        if (wl_in != nullptr) {
+            if (threadIdx.x == 0) sm.misc[7] = atomicAdd(ticket, 1);
+            __syncthreads();
+            wi = sm.misc[7];
+        }
+        if (wi >= work) break;
+        const int64_t row = wl_in != nullptr ? (int64_t)__ldg(wl_in + wi) : wi;
+        PHASE_BEGIN();
         // ---- load the sample -----------------------------------------------------------
         for (int i = tid; i < n; i += T) {
             sm.eta[i] = (double)x[row * n + i];
@@ -398,67 +440,68 @@ __global__ void __launch_bounds__(256, 4) sparsemap_fwd_kernel(const float* __re
         // before the previous barrier, what it writes is not read by anyone inside the same phase.
         for (it = 0; it < max_iter; ++it) {
             if (changed) {
-                // ---- [tau; z] = inv * [1; score] -----------------------------------------------
+                // ---- [tau; z] = inv * [1; score]; a blocking constraint exists iff some z_a < p_a is negative:
+                //      the test rides on the barrier that publishes z, so the common pass (none) computes no
+                //      ratios and needs no second barrier ------------------------------------------------------
+                int neg = 0;
                 for (int a = tid; a <= m; a += T) {
                     const double* row = sm.inv + a * LD;
                     double acc = row[0];  // column 0 times b_0 = 1
 #pragma unroll 8
                     for (int j = 1; j <= m; ++j) acc = __dadd_rn(acc, __dmul_rn(row[j], sm.score[j - 1]));
-                    if (a == 0) sm.red[38] = acc; else sm.z[a - 1] = acc;
+                    if (a == 0) {
+                        sm.red[38] = acc;
+                    } else {
+                        sm.z[a - 1] = acc;
+                        neg |= (acc < sm.p[a - 1] && acc < 0.0) ? 1 : 0;
+                    }
                 }
-                __syncthreads();
+                const bool exist_blocking = __syncthreads_or(neg) != 0;
+                PHASE(0);
                 tau = sm.red[38];
-
-                // ---- line search: first minimal ratio p/(p-z) over z < p -----------------
-                if (tid < 32) {
-                    double best = CUDART_INF;
-                    int besti = 0x7fffffff;
-                    bool neg = false;
-                    // four candidates per lane and pass: their divisions are independent and overlap
-                    for (int a0 = tid; a0 < m; a0 += 128) {
-                        double ratio[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int a = a0 + 32 * u;
-                            ratio[u] = CUDART_INF;
-                            if (a < m) {
-                                const double zz = sm.z[a], pp = sm.p[a];
-                                if (zz < pp) {
-                                    neg = neg || zz < 0.0;
-                                    ratio[u] = __ddiv_rn(pp, __dsub_rn(pp, zz));
-                                }
-                            }
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)    // ascending index: the first minimum wins
-                            if (ratio[u] < best) { best = ratio[u]; besti = a0 + 32 * u; }
-                    }
-                    const int anyneg = __any_sync(kFull, neg) ? 1 : 0;
-                    // lexicographic minimum of (ratio, index) over the warp: order-preserving 64-bit key of
-                    // the double (sign flip), reduced as two 32-bit halves, then the lowest index holding it
-                    const long long bb = __double_as_longlong(__dadd_rn(best, 0.0));  // (-0.0 -> +0.0: numeric ties)
-                    const unsigned long long key = (unsigned long long)bb ^ ((unsigned long long)(bb >> 63) | 0x8000000000000000ull);
-                    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
-                    const bool cand = besti != 0x7fffffff;
-                    const unsigned mhi = __reduce_min_sync(kFull, cand ? hi : 0xffffffffu);
-                    const bool e1 = cand && hi == mhi;
-                    const unsigned mlo = __reduce_min_sync(kFull, e1 ? lo : 0xffffffffu);
-                    const bool e2 = e1 && lo == mlo;
-                    const unsigned mi = __reduce_min_sync(kFull, e2 ? (unsigned)besti : 0x7fffffffu);
-                    const double gbest = __shfl_sync(kFull, best, mi & 31);  // lane (index mod 32) owns that candidate
-                    if (tid == 0) {
-                        sm.misc[0] = anyneg;
-                        sm.misc[1] = (int)mi;
-                        sm.red[37] = gbest;
-                    }
-                }
-                __syncthreads();
-                const bool exist_blocking = sm.misc[0] != 0;
                 if (!exist_blocking) {
-                    // p is next read by a later line search (barriers in between): no barrier here
+                    // p is next read by a later blocking test (barriers in between): no barrier here
                     for (int a = tid; a < m; a += T) sm.p[a] = sm.z[a];
                     changed = false;
                 } else {
+                    // ---- line search: first minimal ratio p/(p-z) over z < p -----------------
+                    if (tid < 32) {
+                        double best = CUDART_INF;
+                        int besti = 0x7fffffff;
+                        // four candidates per lane and pass: their divisions are independent and overlap
+                        for (int a0 = tid; a0 < m; a0 += 128) {
+                            double ratio[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int a = a0 + 32 * u;
+                                ratio[u] = CUDART_INF;
+                                if (a < m) {
+                                    const double zz = sm.z[a], pp = sm.p[a];
+                                    if (zz < pp) ratio[u] = __ddiv_rn(pp, __dsub_rn(pp, zz));
+                                }
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)    // ascending index: the first minimum wins
+                                if (ratio[u] < best) { best = ratio[u]; besti = a0 + 32 * u; }
+                        }
+                        // lexicographic minimum of (ratio, index) over the warp: order-preserving 64-bit key of
+                        // the double (sign flip), reduced as two 32-bit halves, then the lowest index holding it
+                        const long long bb = __double_as_longlong(__dadd_rn(best, 0.0));  // (-0.0 -> +0.0: numeric ties)
+                        const unsigned long long key = (unsigned long long)bb ^ ((unsigned long long)(bb >> 63) | 0x8000000000000000ull);
+                        const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+                        const bool cand = besti != 0x7fffffff;
+                        const unsigned mhi = __reduce_min_sync(kFull, cand ? hi : 0xffffffffu);
+                        const bool e1 = cand && hi == mhi;
+                        const unsigned mlo = __reduce_min_sync(kFull, e1 ? lo : 0xffffffffu);
+                        const bool e2 = e1 && lo == mlo;
+                        const unsigned mi = __reduce_min_sync(kFull, e2 ? (unsigned)besti : 0x7fffffffu);
+                        const double gbest = __shfl_sync(kFull, best, mi & 31);  // lane (index mod 32) owns that candidate
+                        if (tid == 0) {
+                            sm.misc[1] = (int)mi;
+                            sm.red[37] = gbest;
+                        }
+                    }
+                    __syncthreads();
                     const int blocking = sm.misc[1];
                     double alpha = sm.red[37];
                     if (alpha > 1.0) alpha = 1.0;
@@ -531,7 +574,9 @@ __global__ void __launch_bounds__(256, 4) sparsemap_fwd_kernel(const float* __re
                 }
                 // Bernoulli / budget oracles read, per thread, the scores that thread wrote
                 if (KIND == SMLVM_FACTOR_SEQUENCE_BINARY) __syncthreads();
+                PHASE(3);
                 const double value = factor_map<KIND>(sm, n, budget, sm.t);  // ends behind a barrier
+                PHASE(4);
                 if (value <= tau + 1e-9) {
                     st = SMLVM_SOLVE_CONVERGED;
                     ++it;
@@ -547,6 +592,7 @@ __global__ void __launch_bounds__(256, 4) sparsemap_fwd_kernel(const float* __re
                     same |= (c == n) ? 1 : 0;
                 }
                 same = __syncthreads_or(same);
+                PHASE(5);
                 if (same) {
                     st = SMLVM_SOLVE_REPEATED_CONFIG;
                     ++it;
@@ -560,6 +606,7 @@ __global__ void __launch_bounds__(256, 4) sparsemap_fwd_kernel(const float* __re
                 int a_end = schur_round_end(m, 0, kTermsChunk, cnt_cur);
                 schur_terms_fill(sm, sm.terms, m, LD, 0, a_end, 0);
                 __syncthreads();
+                PHASE(6);
                 double sfold = (double)n;
                 const int fill_w0 = T > 32 ? 1 : 0;  // warp 0 folds: the others fill the next round meanwhile
                 for (int half = 0, first = 1;; half ^= 1, first = 0) {
@@ -568,7 +615,9 @@ __global__ void __launch_bounds__(256, 4) sparsemap_fwd_kernel(const float* __re
                         a_nxt = schur_round_end(m, a_end, kTermsChunk, cnt_nxt);
                         schur_terms_fill(sm, sm.terms + (half ^ 1) * kTermsChunk, m, LD, a_end, a_nxt, fill_w0);
                     }
+                    PHASE(13);
                     if (tid == 0) sfold = fold_serial<true>(sm.terms + half * kTermsChunk, cnt_cur, sfold);
+                    PHASE(12);
                     if (first) {
                         if ((tid >> 5) == eval_warp) {
                             const double scn = evaluate_warp<KIND>(sm, n);
@@ -591,6 +640,7 @@ __global__ void __launch_bounds__(256, 4) sparsemap_fwd_kernel(const float* __re
                 }
                 if (tid == 0) sm.red[36] = sfold;
                 __syncthreads();
+                PHASE(7);
                 const double sval = sm.red[36];
                 if (sval > -1e-9 && sval < 1e-9) {
                     st = SMLVM_SOLVE_SINGULAR;
@@ -625,6 +675,7 @@ __global__ void __launch_bounds__(256, 4) sparsemap_fwd_kernel(const float* __re
                 ++m;
                 changed = true;
                 __syncthreads();
+                PHASE(8);
             }
         }
         if (it > max_iter) it = max_iter;
@@ -632,7 +683,7 @@ __global__ void __launch_bounds__(256, 4) sparsemap_fwd_kernel(const float* __re
         // ---- outputs (solver order) -----------------------------------------------------
         __syncthreads();
         if (st == -1) {  // hand the sample to the next capacity tier
-            if (tid == 0) counts[row] = -1;
+            if (tid == 0) wl_out[atomicAdd(wl_out_count, 1)] = (int32_t)row;
             continue;
         }
         int kp = 0;
@@ -648,11 +699,23 @@ __global__ void __launch_bounds__(256, 4) sparsemap_fwd_kernel(const float* __re
             const int a = e / W, q = e - a * W;
             aset_bits[(row * cap_out + a) * W + q] = (a < m) ? sm.bits[a * W + q] : 0u;
         }
-        if (S_pad != nullptr) {
-            double* S = S_pad + row * (int64_t)cap_out * cap_out;
-            for (int e = tid; e < m * m; e += T) {
-                const int a = e / m, c = e - a * m;
-                S[e] = sm.inv[(a + 1) * LD + c + 1];
+        if (S_arena != nullptr) {
+            // |A|^2 doubles of this sample, bump-allocated from the caller's arena; a sample that does not fit
+            // gets offset -1 (the cursor still advances: it ends at the size the arena should have had)
+            if (tid == 0) {
+                const long long off = (long long)atomicAdd(S_cursor, (unsigned long long)(m * m));
+                const long long ok = (off + (long long)m * m <= S_capacity) ? off : -1;
+                S_offsets[row] = ok;
+                reinterpret_cast<long long*>(sm.red)[34] = ok;
+            }
+            __syncthreads();
+            const long long off = reinterpret_cast<const long long*>(sm.red)[34];
+            if (off >= 0) {
+                double* S = S_arena + off;
+                for (int e = tid; e < m * m; e += T) {
+                    const int a = e / m, c = e - a * m;
+                    S[e] = sm.inv[(a + 1) * LD + c + 1];
+                }
             }
         }
         if (kept != nullptr) {
@@ -664,8 +727,11 @@ __global__ void __launch_bounds__(256, 4) sparsemap_fwd_kernel(const float* __re
             if (iters != nullptr) iters[row] = it;
             if (status != nullptr) status[row] = st;
         }
+        PHASE(11);
+        PHASE_END();
     }
 }
+
 
 // Ragged expansion: one warp per sample.
 __global__ void __launch_bounds__(256)
@@ -703,7 +769,7 @@ __global__ void __launch_bounds__(128)
 sparsemap_bwd_kernel(const float* __restrict__ dp, const int64_t* __restrict__ offsets,
                      int only_positive, const float* __restrict__ p_pad,
                      const uint32_t* __restrict__ aset_bits, const int32_t* __restrict__ counts,
-                     const double* __restrict__ S_pad, const int64_t* __restrict__ S_rows,
+                     const double* __restrict__ S_arena, const long long* __restrict__ S_offsets,
                      float* __restrict__ dx, float* __restrict__ dt, int64_t rows, int n)
 {
     extern __shared__ double sh[];
@@ -724,8 +790,15 @@ sparsemap_bwd_kernel(const float* __restrict__ dp, const int64_t* __restrict__ o
             }
         }
         __syncthreads();
-        const double* S = S_rows != nullptr ? reinterpret_cast<const double*>(__ldg(S_rows + row))
-                                            : S_pad + row * (int64_t)cap * cap;
+        const long long soff = __ldg(S_offsets + row);
+        if (soff < 0) {  // this sample's inverse did not fit the arena of the forward call: fail loudly
+            for (int i = tid; i < n; i += T) {
+                dx[row * n + i] = __int_as_float(0x7fc00000);
+                if (dt != nullptr && i + 1 < n) dt[row * (int64_t)(n - 1) + i] = __int_as_float(0x7fc00000);
+            }
+            continue;
+        }
+        const double* S = S_arena + soff;
         for (int a = tid; a < m; a += T) {
             double acc = 0.0;
             for (int c = 0; c < m; ++c) acc += S[(int64_t)c * m + a] * g[c];  // S symmetric
@@ -747,23 +820,6 @@ sparsemap_bwd_kernel(const float* __restrict__ dp, const int64_t* __restrict__ o
             dx[row * n + i] = (float)on;
             if (dt != nullptr && i + 1 < n) dt[row * (int64_t)(n - 1) + i] = (float)edge;
         }
-    }
-}
-
-// S of every sample (|A|^2 doubles at the start of its (n+1)^2 slot) -> one packed buffer at S_offsets[row]:
-// the padded layout costs 133 KB per sample at n = 128 (139 GB for the 1M-sample point of the sweep), the
-// packed one 8 |A|^2 (15 KB on average).  One warp per sample.
-__global__ void __launch_bounds__(256)
-sparsemap_pack_S_kernel(const double* __restrict__ S_pad, const int32_t* __restrict__ counts,
-                        const int64_t* __restrict__ S_offsets, double* __restrict__ S_packed, int64_t rows, int n)
-{
-    const int cap = n + 1, lane = threadIdx.x & 31;
-    const int64_t warps_total = (int64_t)gridDim.x * 8;
-    for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += warps_total) {
-        const int m = __ldg(counts + row);
-        const double* src = S_pad + row * (int64_t)cap * cap;
-        double* dst = S_packed + __ldg(S_offsets + row);
-        for (int e = lane; e < m * m; e += 32) dst[e] = __ldg(src + e);
     }
 }
 
@@ -807,10 +863,10 @@ static int plan_tiers(int n, int kind, int (&tiers)[3])
     };
     int ntier = 0;
     if (!single) {
-        int c1 = cap_for(kind == SMLVM_FACTOR_BUDGET ? 4 : 5), c2 = cap_for(2);
+        int c1 = cap_for(kind == SMLVM_FACTOR_BUDGET ? 4 : 6), c2 = cap_for(2);
         if (forced[0] > 0) c1 = forced[0];
         if (forced[1] > 0) c2 = forced[1];
-        if (c1 < n + 1 && 5 * c1 >= 2 * n) tiers[ntier++] = c1;          // useful only if >= 0.4 n
+        if (c1 < n + 1 && (5 * c1 >= 2 * n || forced[0] > 0)) tiers[ntier++] = c1;  // useful only if >= 0.4 n
         if (c2 < n + 1 && (ntier == 0 || c2 > tiers[ntier - 1])) tiers[ntier++] = c2;
     }
     tiers[ntier++] = n + 1;
@@ -820,6 +876,19 @@ static int plan_tiers(int n, int kind, int (&tiers)[3])
 }  // namespace smlvm
 
 using namespace smlvm;
+
+#ifdef SMLVM_SMAP_TIMING
+// out_host[16]: cycles per solver phase summed over all CTAs since the last call (then reset)
+extern "C" int smlvm_debug_phase_cycles(unsigned long long* out_host)
+{
+    cudaDeviceSynchronize();
+    cudaError_t e = cudaMemcpyFromSymbol(out_host, g_phase_cycles, sizeof(unsigned long long) * 16);
+    if (e != cudaSuccess) return (int)e;
+    unsigned long long zero[16] = {0};
+    e = cudaMemcpyToSymbol(g_phase_cycles, zero, sizeof(zero));
+    return (int)e;
+}
+#endif
 
 extern "C" int32_t smlvm_sparsemap_capacity(int32_t n) { return n + 1; }
 
@@ -844,11 +913,19 @@ extern "C" int32_t smlvm_sparsemap_plan(int32_t n, int32_t kind, int32_t* caps, 
     return nt;
 }
 
+extern "C" size_t smlvm_sparsemap_workspace_bytes(int64_t rows)
+{
+    // per later tier (at most 2): one counter (64 B slot) + a worklist of sample ids
+    if (rows < 0) return 0;
+    return 2 * (64 + (size_t)rows * sizeof(int32_t)) + 64;
+}
+
 extern "C" int smlvm_sparsemap_fwd(const float* x, const float* t, const double* init_scores,
                                    int32_t kind, int32_t budget, int32_t max_iter, int64_t rows,
                                    int32_t n, float* p_pad, uint32_t* aset_bits, int32_t* counts,
-                                   int32_t* kept, int32_t* iters, int32_t* status, double* S_pad,
-                                   void* stream)
+                                   int32_t* kept, int32_t* iters, int32_t* status, double* S_arena,
+                                   int64_t S_capacity, int64_t* S_offsets, uint64_t* S_cursor,
+                                   void* workspace, size_t workspace_bytes, void* stream)
 {
     if (rows < 0 || n < 1 || max_iter < 0 || budget < 0) return SMLVM_ERR_ARG;
     if (kind < SMLVM_FACTOR_BERNOULLI || kind > SMLVM_FACTOR_SEQUENCE_BINARY) return SMLVM_ERR_ARG;
@@ -856,16 +933,19 @@ extern "C" int smlvm_sparsemap_fwd(const float* x, const float* t, const double*
     if (rows == 0) return SMLVM_OK;
     if (x == nullptr || p_pad == nullptr || aset_bits == nullptr || counts == nullptr)
         return SMLVM_ERR_ARG;
+    if (S_arena != nullptr && (S_offsets == nullptr || S_cursor == nullptr || S_capacity < 0)) return SMLVM_ERR_ARG;
+    if (rows > 0x7fffffff) return SMLVM_ERR_UNSUPPORTED;  // worklists hold int32 sample ids
+    if (workspace == nullptr || workspace_bytes < smlvm_sparsemap_workspace_bytes(rows)) return SMLVM_ERR_WORKSPACE;
     const int threads = solver_threads(n, kind, rows);
     // Capacity tiers.  The (|A|+1)^2 fp64 inverse dominates shared memory: sized for the worst case
     // |A| = n + 1 it allows ONE sample per SM at n = 128, although typical active sets hold 40-60
-    // vertices.  Samples are first solved with the capacities that let 5 (budget: 4), then 2, CTAs
-    // share an SM (62 / 72 and 110 vertices at n = 128); a sample
-    // whose active set outgrows its tier is flagged (counts = -1) and re-solved from scratch by the
-    // next tier.  Same stream, no host synchronisation; an empty tier costs one trivial launch.
+    // vertices.  Samples are first solved with the capacity that lets 6 (budget: 4) CTAs share an SM, then 2
+    // (54 / 72 and 110 vertices at n = 128); a sample whose active set outgrows its tier is appended to the next
+    // tier's worklist and re-solved from scratch there by a small persistent grid.  Same stream, no host
+    // synchronisation; an empty tier costs one launch of CTAs that read a zero and exit.
     int tiers[3];
     const int ntier = plan_tiers(n, kind, tiers);
-    // one CTA per sample: the hardware scheduler evens out the data-dependent solve lengths
+    // first tier: one CTA per sample, the hardware scheduler evens out the data-dependent solve lengths
     // (measured best against persistent grids of 16/64/256 CTAs per SM at n = 32 and n = 128)
     int64_t cap_grid = 0x7fffffff;
     {
@@ -886,6 +966,16 @@ extern "C" int smlvm_sparsemap_fwd(const float* x, const float* t, const double*
         const int v = e ? atoi(e) : 256;
         tail_threads = (v >= 32 && v <= 256 && v % 32 == 0) ? v : 0;
     }
+    // workspace: [count_1 (64 B)] [list_1: rows x int32] [count_2 (64 B)] [list_2: rows x int32]
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    const size_t list_bytes = ((size_t)rows * sizeof(int32_t) + 63) & ~(size_t)63;
+    int32_t* wl_count[3] = {nullptr, reinterpret_cast<int32_t*>(ws), reinterpret_cast<int32_t*>(ws + 64 + list_bytes)};
+    int32_t* wl_list[3] = {nullptr, reinterpret_cast<int32_t*>(ws + 64), reinterpret_cast<int32_t*>(ws + 128 + list_bytes)};
+    if (ntier > 1) {
+        cudaError_t e = cudaMemsetAsync(wl_count[1], 0, 64, st);
+        if (e == cudaSuccess && ntier > 2) e = cudaMemsetAsync(wl_count[2], 0, 64, st);
+        if (e != cudaSuccess) return (int)e;
+    }
 #define SMLVM_SMAP_LAUNCH(K)                                                                       \
     do {                                                                                           \
         cudaError_t e =                                                                            \
@@ -897,9 +987,20 @@ extern "C" int smlvm_sparsemap_fwd(const float* x, const float* t, const double*
         if (e != cudaSuccess) return (int)e;                                                       \
         for (int ti = 0; ti < ntier; ++ti) {                                                       \
             const int th = (ti == 0 || tail_threads == 0) ? threads : tail_threads;                \
-            sparsemap_fwd_kernel<K><<<grid, th, solver_smem_bytes(n, tiers[ti]), st>>>(            \
-                x, t, init_scores, budget, max_iter, rows, n, tiers[ti], ti == 0, ti == ntier - 1, \
-                p_pad, aset_bits, counts, kept, iters, status, S_pad);                             \
+            const size_t smem = solver_smem_bytes(n, tiers[ti]);                                   \
+            int g = grid;                                                                          \
+            if (ti > 0) {  /* persistent: as many CTAs as fit the device at this tier's footprint */ \
+                int per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));                          \
+                per_sm = per_sm < 1 ? 1 : per_sm;                                                  \
+                const int64_t fit = (int64_t)device_sm_count() * per_sm;                           \
+                g = (int)(rows < fit ? rows : fit);                                                \
+            }                                                                                      \
+            sparsemap_fwd_kernel<K><<<g, th, smem, st>>>(                                          \
+                x, t, init_scores, budget, max_iter, rows, n, tiers[ti], ti == ntier - 1,          \
+                wl_list[ti], wl_count[ti], ti + 1 < ntier ? wl_list[ti + 1] : nullptr,             \
+                ti + 1 < ntier ? wl_count[ti + 1] : nullptr, p_pad, aset_bits, counts, kept, iters, \
+                status, S_arena, (long long)S_capacity, reinterpret_cast<long long*>(S_offsets),   \
+                reinterpret_cast<unsigned long long*>(S_cursor));                                  \
         }                                                                                          \
     } while (0)
     if (kind == SMLVM_FACTOR_BERNOULLI) SMLVM_SMAP_LAUNCH(SMLVM_FACTOR_BERNOULLI);
@@ -929,33 +1030,20 @@ extern "C" int smlvm_sparsemap_expand(const float* p_pad, const uint32_t* aset_b
 
 extern "C" int smlvm_sparsemap_bwd(const float* dp, const int64_t* offsets, int32_t only_positive,
                                    const float* p_pad, const uint32_t* aset_bits,
-                                   const int32_t* counts, const double* S_pad, const int64_t* S_rows,
+                                   const int32_t* counts, const double* S_arena, const int64_t* S_offsets,
                                    float* dx, float* dt, int64_t rows, int32_t n, void* stream)
 {
     if (rows < 0 || n < 1) return SMLVM_ERR_ARG;
     if (rows == 0) return SMLVM_OK;
     if (dp == nullptr || offsets == nullptr || p_pad == nullptr || aset_bits == nullptr ||
-        counts == nullptr || (S_pad == nullptr && S_rows == nullptr) || dx == nullptr)
+        counts == nullptr || S_arena == nullptr || S_offsets == nullptr || dx == nullptr)
         return SMLVM_ERR_ARG;
     if (n > SMLVM_SPARSEMAP_MAX_BITS) return SMLVM_ERR_UNSUPPORTED;
     const size_t smem = 2 * (size_t)(n + 1) * sizeof(double);
     int64_t cap = (int64_t)device_sm_count() * 32;
     sparsemap_bwd_kernel<<<(int)(rows < cap ? rows : cap), 128, smem, as_stream(stream)>>>(
-        dp, offsets, only_positive, p_pad, aset_bits, counts, S_pad, S_rows, dx, dt, rows, n);
-    SMLVM_LAUNCH_CHECK();
-    return SMLVM_OK;
-}
-
-extern "C" int smlvm_sparsemap_pack_inverse(const double* S_pad, const int32_t* counts, const int64_t* S_offsets,
-                                      double* S_packed, int64_t rows, int32_t n, void* stream)
-{
-    if (rows < 0 || n < 1) return SMLVM_ERR_ARG;
-    if (rows == 0) return SMLVM_OK;
-    if (S_pad == nullptr || counts == nullptr || S_offsets == nullptr || S_packed == nullptr) return SMLVM_ERR_ARG;
-    if (n > SMLVM_SPARSEMAP_MAX_BITS) return SMLVM_ERR_UNSUPPORTED;
-    const int64_t need = (rows + 7) / 8, cap = (int64_t)device_sm_count() * 16;
-    sparsemap_pack_S_kernel<<<(int)(need < cap ? need : cap), 256, 0, as_stream(stream)>>>(S_pad, counts, S_offsets,
-                                                                                         S_packed, rows, n);
+        dp, offsets, only_positive, p_pad, aset_bits, counts, S_arena,
+        reinterpret_cast<const long long*>(S_offsets), dx, dt, rows, n);
     SMLVM_LAUNCH_CHECK();
     return SMLVM_OK;
 }

@@ -10,9 +10,9 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsmlvm.so")
+LIB_PATH = os.environ.get("SMLVM_LIB_PATH") or os.path.join(_HERE, "libsmlvm.so")   # override: development builds only
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 FACTOR_BERNOULLI, FACTOR_BUDGET, FACTOR_SEQUENCE_BINARY, FACTOR_SEQUENCE = 0, 1, 2, 3
 SOLVE_STATUS = {0: "converged", 1: "max_iter", 2: "repeated_config", 3: "singular"}
@@ -44,11 +44,11 @@ _PROTOTYPES = {
     "smlvm_gather_rows": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
     "smlvm_sparsemap_capacity": (_i32, [_i32]),
     "smlvm_sparsemap_plan": (_i32, [_i32, _i32, _vp, _vp, _vp]),
+    "smlvm_sparsemap_workspace_bytes": (_sz, [_i64]),
     "smlvm_sparsemap_fwd": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i64, _i32,
-                                           _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+                                           _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "smlvm_sparsemap_expand": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _i32, _vp]),
     "smlvm_sparsemap_bwd": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
-    "smlvm_sparsemap_pack_inverse": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "smlvm_reduce_workspace_bytes": (_sz, []),
     "smlvm_wloss_dense_fwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _i32, _vp, _sz, _vp]),
     "smlvm_wloss_ragged_fwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _i64, _vp, _sz, _vp]),

@@ -443,11 +443,15 @@ def sparsemap_plan(n, kind=0):
     return [(caps[i], smem[i], ctas[i]) for i in range(nt)]
 
 
-# The padded S of the solver (8 (n+1)^2 bytes per sample) is written as such only up to this many bytes per
-# call; larger batches are solved in chunks of that size whose S is packed to 8 |A|^2 bytes per sample
-# (smlvm_sparsemap_pack_inverse) -- 1M samples at n = 128: 139 GB padded, ~16 GB packed.
-S_PAD_MAX_BYTES = 4 << 30
-SMAP_CHUNK_LANES = 2   # streams the solve chunks alternate between (1 = serial chunks)
+# The inverses the backward needs (|A|^2 doubles per sample) are bump-allocated by the solver from ONE arena.  Up to
+# this many bytes the arena is sized for the worst case, (n+1)^2 per sample, and cannot overflow; beyond it (the
+# sweep's 65536+ samples at n = 128: 133 KB per sample padded, ~16-28 KB used) it is sized from the largest per-sample
+# need seen so far for this (n, factor, budget), and a caller that reads the solver's cursor (one scalar, together
+# with the ragged sizes it reads anyway) re-solves with the exact size on overflow.
+S_WORST_CASE_MAX_BYTES = 2 << 30
+SMAP_CHUNK_LANES = 1      # streams a large batch is split over (1 = one launch sequence; 2 measured slower)
+SMAP_SPLIT_MIN_ROWS = 16384
+_S_NEED = {}              # (n, kind, budget) -> doubles per sample (largest mean seen)
 
 
 _SIDE_STREAMS = {}
@@ -462,11 +466,20 @@ def _side_stream(dev):
     return _SIDE_STREAMS[key]
 
 
-def sparsemap_solve(x, kind, budget=0, t=None, init_scores=None, max_iter=100, keep_S=True):
-    """Batched active-set solve.  x [rows, n] -> padded solver state (dict).  No host sync unless S has to be
-    packed (one read of the packed size per chunk).  ``state["S"]`` is the padded [rows, cap*cap] tensor or
-    None; ``state["S_rows"]`` the per-sample device addresses of the packed copies (kept alive in
-    ``state["S_chunks"]``)."""
+def sparsemap_arena_doubles(rows, n, kind, budget=0):
+    """Size (in doubles) of the arena ``sparsemap_solve`` allocates for the inverses of ``rows`` samples."""
+    worst = rows * (n + 1) ** 2
+    if worst * 8 <= S_WORST_CASE_MAX_BYTES:
+        return worst
+    per_sample = _S_NEED.get((n, kind, budget), 0.45 * (n + 1) ** 2)
+    return int(min(worst, max(S_WORST_CASE_MAX_BYTES // 8, rows * per_sample * 1.25 + 65536)))
+
+
+def sparsemap_solve(x, kind, budget=0, t=None, init_scores=None, max_iter=100, keep_S=True, arena_doubles=None):
+    """Batched active-set solve.  x [rows, n] -> padded solver state (dict).  Asynchronous: no host read, no
+    allocation inside the library.  ``state["S"]`` is the arena of the inverses (or None), ``state["S_offsets"]``
+    each sample's offset in it (-1: did not fit), ``state["S_cursor"]`` the device counter that ends at the number
+    of doubles needed, ``state["S_capacity"]`` the arena size; ``sparsemap_arena_overflow(state)`` compares them."""
     x = _f32c(x, "scores")
     rows, n = x.shape
     dev = x.device
@@ -482,69 +495,56 @@ def sparsemap_solve(x, kind, budget=0, t=None, init_scores=None, max_iter=100, k
     kept = torch.empty(rows, dtype=torch.int32, device=dev)
     iters = torch.empty(rows, dtype=torch.int32, device=dev)
     status = torch.empty(rows, dtype=torch.int32, device=dev)
-    state = dict(p_pad=p_pad, bits=bits, counts=counts, kept=kept, iters=iters, status=status, S=None,
-                 S_rows=None, S_chunks=None, n=n, rows=rows, kind=kind)
+    S = S_off = cursor = None
+    capacity = 0
+    if keep_S:
+        capacity = int(arena_doubles) if arena_doubles is not None else sparsemap_arena_doubles(rows, n, kind, budget)
+        S = torch.empty(max(capacity, 1), dtype=torch.float64, device=dev)
+        S_off = torch.empty(rows, dtype=torch.int64, device=dev)
+        cursor = torch.zeros(1, dtype=torch.int64, device=dev)
+    state = dict(p_pad=p_pad, bits=bits, counts=counts, kept=kept, iters=iters, status=status, S=S, S_offsets=S_off,
+                 S_cursor=cursor, S_capacity=capacity, n=n, rows=rows, kind=kind, budget=budget)
+    if rows == 0:
+        return state
 
-    def solve(r0, r1, S):
+    def solve(r0, r1):
         sl = slice(r0, r1)
+        ws = torch.empty(lib.smlvm_sparsemap_workspace_bytes(r1 - r0), dtype=torch.uint8, device=dev)
         check(lib.smlvm_sparsemap_fwd(ptr(x[sl]), ptr(None if t is None else t[sl]),
                                       ptr(None if init_scores is None else init_scores[sl]), kind, budget, max_iter,
                                       r1 - r0, n, ptr(p_pad[sl]), ptr(bits[sl]), ptr(counts[sl]), ptr(kept[sl]),
-                                      ptr(iters[sl]), ptr(status[sl]), ptr(S), stream()), "smlvm_sparsemap_fwd")
+                                      ptr(iters[sl]), ptr(status[sl]), ptr(S), capacity,
+                                      ptr(None if S_off is None else S_off[sl]), ptr(cursor), ptr(ws), ws.numel(),
+                                      stream()), "smlvm_sparsemap_fwd")
+        return ws
 
-    slot = cap * cap * 8
-    if not keep_S or rows * slot <= S_PAD_MAX_BYTES:
-        S = torch.empty((rows, cap * cap), dtype=torch.float64, device=dev) if keep_S else None
-        solve(0, rows, S)
-        state["S"] = S
+    if rows < SMAP_SPLIT_MIN_ROWS or SMAP_CHUNK_LANES < 2:
+        solve(0, rows)
         return state
-    chunk = max(1, S_PAD_MAX_BYTES // slot)
-    nchunks = (rows + chunk - 1) // chunk
-    # Chunks alternate between the current stream and a side stream over two padded buffers: a chunk ends with
-    # a latency-bound tail (the few samples that outgrew the first capacity tier are re-solved from scratch by
-    # small launches, ~3 ms after 16 ms at n = 128) and with the host read of its packed size; the next chunk's
-    # first-tier launch is already queued on the other stream and fills the SMs the tail leaves idle.
-    # The current stream waits for the side stream before returning.
+    # Two halves on two streams over the same arena: a launch sequence ends with a latency-bound tail (the few
+    # samples that outgrew the first capacity tier are re-solved from scratch by a small persistent grid; they are the
+    # LARGE ones, ~3 ms each at n = 128) under which the other half's first tier keeps the SMs busy.
     cur = torch.cuda.current_stream(dev)
-    lanes = [cur, _side_stream(dev)] if (nchunks > 1 and SMAP_CHUNK_LANES > 1) else [cur]
-    S_tmp = [torch.empty((min(chunk, rows), cap * cap), dtype=torch.float64, device=dev) for _ in lanes]
-    S_rows = torch.empty(rows, dtype=torch.int64, device=dev)
-    chunks = []
-    if len(lanes) > 1:
-        lanes[1].wait_stream(cur)
-
-    def finish(i, r0, r1, m, offs):
-        lane = lanes[i % len(lanes)]
-        with torch.cuda.stream(lane):
-            total = max(int(offs[-1].item()), 1)         # host read: waits for this chunk's solve only
-            packed = torch.empty(total, dtype=torch.float64, device=dev)
-            check(lib.smlvm_sparsemap_pack_inverse(ptr(S_tmp[i % len(lanes)]), ptr(m), ptr(offs), ptr(packed), r1 - r0, n,
-                                                   stream()), "smlvm_sparsemap_pack_inverse")
-            S_rows[r0:r1] = offs[:-1] * 8 + packed.data_ptr()
-        if lane is not cur:
-            packed.record_stream(cur)                    # born on the side stream, read by the backward on this one
-        chunks.append(packed)
-
-    pending = None
-    for i, r0 in enumerate(range(0, rows, chunk)):
-        r1 = min(rows, r0 + chunk)
-        with torch.cuda.stream(lanes[i % len(lanes)]):
-            solve(r0, r1, S_tmp[i % len(lanes)])
-            m = counts[r0:r1]
-            offs = scan_counts(m * m)                   # doubles before each sample's S in the packed buffer
-        if len(lanes) == 1:                             # one padded buffer: pack before the next solve overwrites it
-            finish(i, r0, r1, m, offs)
-            continue
-        if pending is not None:
-            finish(*pending)
-        pending = (i, r0, r1, m, offs)
-    if pending is not None:
-        finish(*pending)
-    if len(lanes) > 1:
-        cur.wait_stream(lanes[1])
-        # temporaries born on the side stream (m * m, offsets) die here: the side stream is idle by now
-    state["S_rows"], state["S_chunks"] = S_rows, chunks
+    side = _side_stream(dev)
+    half = (rows + 1) // 2
+    solve(0, half)
+    side.wait_stream(cur)            # inputs, the zeroed cursor
+    with torch.cuda.stream(side):
+        ws = solve(half, rows)
+    ws.record_stream(side)
+    cur.wait_stream(side)
     return state
+
+
+def sparsemap_arena_overflow(state, needed=None):
+    """Doubles the arena should have had if some inverse did not fit, else 0.  Reads the solver's cursor (a host
+    synchronisation) unless the caller already has it (``needed``); remembers the per-sample need."""
+    if state["S"] is None or state["rows"] == 0:
+        return 0
+    needed = int(state["S_cursor"].item()) if needed is None else int(needed)
+    key = (state["n"], state["kind"], state["budget"])
+    _S_NEED[key] = max(_S_NEED.get(key, 0.0), needed / state["rows"])
+    return needed if needed > state["S_capacity"] else 0
 
 
 def sparsemap_expand(state, only_positive, offsets, total, want_aset=True, want_idx=True):
@@ -565,8 +565,10 @@ def sparsemap_bwd(state, dp, offsets, only_positive, want_dt=False):
     dp = dp.contiguous().float()
     dx = torch.empty((rows, n), dtype=torch.float32, device=dev)
     dt = torch.empty((rows, max(n - 1, 1)), dtype=torch.float32, device=dev) if want_dt else None
+    if state["S"] is None:
+        raise RuntimeError("sparsemap_bwd: the forward solve was run with keep_S=False")
     check(lib.smlvm_sparsemap_bwd(ptr(dp), ptr(offsets), int(only_positive), ptr(state["p_pad"]),
-                                  ptr(state["bits"]), ptr(state["counts"]), ptr(state["S"]), ptr(state.get("S_rows")),
+                                  ptr(state["bits"]), ptr(state["counts"]), ptr(state["S"]), ptr(state["S_offsets"]),
                                   ptr(dx), ptr(dt), rows, n, stream()), "smlvm_sparsemap_bwd")
     if want_dt:
         dt = dt[:, :n - 1]
@@ -586,7 +588,13 @@ class _SparseMAPBatch(torch.autograd.Function):
                                 max_iter=max_iter, keep_S=True)
         sizes = state["kept"] if only_positive else state["counts"]
         offsets = scan_counts(sizes)
-        host = torch.cat([offsets[-1:], sizes.to(torch.int64)]).cpu()  # the one D2H per batch
+        host = torch.cat([offsets[-1:], state["S_cursor"], sizes.to(torch.int64)]).cpu()  # the one D2H per batch
+        needed = sparsemap_arena_overflow(state, int(host[1]))
+        if needed:   # first large batch of this shape: the inverses did not fit the estimated arena -- exact size now
+            state = sparsemap_solve(x, kind, budget=budget, t=t, init_scores=init_scores, max_iter=max_iter,
+                                    keep_S=True, arena_doubles=needed)
+            sizes = state["kept"] if only_positive else state["counts"]
+        host = torch.cat([host[:1], host[2:]])
         total = int(host[0])
         p, aset, idx = sparsemap_expand(state, only_positive, offsets, total)
         ctx.state = state

@@ -53,7 +53,7 @@ def test_library_is_sm100a_only():
 def test_version_and_error_strings():
     from lvmhelpers import _native
     lib = _native.lib
-    assert lib.smlvm_version() == _native.ABI_VERSION == 3
+    assert lib.smlvm_version() == _native.ABI_VERSION == 4
     assert b"argument" in lib.smlvm_error_string(-1).lower()
     for code in (0, -1, -2, -3, 1, 700, 12345):
         assert lib.smlvm_error_string(code) is not None
@@ -73,18 +73,21 @@ def test_argument_validation_needs_no_device():
     assert lib.smlvm_topk_bits(1 << 20, 1 << 21, None, None, 4, 8, 1, None) == -1   # k < 2 (binary_topk.h:102)
     assert lib.smlvm_topk_bits(1 << 20, 1 << 21, None, None, 4, 600, 4, None) == -2  # n > CODE_MAX_SIZE
     assert lib.smlvm_sparsemap_capacity(32) == 33
-    assert lib.smlvm_sparsemap_fwd(1 << 20, None, None, 7, 0, 10, 4, 32, 1 << 21, 1 << 22, 1 << 23,
-                                   None, None, None, None, None) == -1               # bad factor kind
-    assert lib.smlvm_sparsemap_fwd(1 << 20, None, None, 0, 0, 10, 4, 4096, 1 << 21, 1 << 22, 1 << 23,
-                                   None, None, None, None, None) == -2               # n too large
+    tail = (None, None, None, None, 0, None, None, 1 << 24, 1 << 20, None)
+    assert lib.smlvm_sparsemap_fwd(1 << 20, None, None, 7, 0, 10, 4, 32, 1 << 21, 1 << 22, 1 << 23, *tail) == -1   # bad factor kind
+    assert lib.smlvm_sparsemap_fwd(1 << 20, None, None, 0, 0, 10, 4, 4096, 1 << 21, 1 << 22, 1 << 23, *tail) == -2  # n too large
+    assert lib.smlvm_sparsemap_fwd(1 << 20, None, None, 0, 0, 10, 4, 32, 1 << 21, 1 << 22, 1 << 23,
+                                   None, None, None, None, 0, None, None, 1 << 24, 8, None) == -3                  # workspace too small
+    assert lib.smlvm_sparsemap_fwd(1 << 20, None, None, 0, 0, 10, 4, 32, 1 << 21, 1 << 22, 1 << 23,
+                                   None, None, None, 1 << 25, 100, None, None, 1 << 24, 1 << 20, None) == -1       # arena without offsets
+    assert lib.smlvm_sparsemap_workspace_bytes(1000) >= 2 * 4 * 1000
     assert lib.smlvm_scan_workspace_bytes(1 << 20) > 0 and lib.smlvm_reduce_workspace_bytes() > 0
     assert lib.smlvm_gather_rows(None, None, None, 4, 16, None) == -1                 # NULL buffers
     assert lib.smlvm_gather_rows(None, None, None, 0, 16, None) == 0                  # empty selection
     assert lib.smlvm_gather_rows(1 << 20, 1 << 21, 1 << 22, 4, 6, None) == -2         # rows not a multiple of 4 bytes
     assert lib.smlvm_bits_expand(None, None, None, 4, 32, None) == -1
     assert lib.smlvm_bits_expand(None, None, None, 0, 32, None) == 0
-    assert lib.smlvm_sparsemap_pack_inverse(None, None, None, None, 4, 32, None) == -1
-    assert lib.smlvm_sparsemap_pack_inverse(1 << 20, 1 << 21, 1 << 22, 1 << 23, 4, 4096, None) == -2
+    assert lib.smlvm_sparsemap_bwd(1 << 20, 1 << 21, 1, 1 << 22, 1 << 23, 1 << 24, None, None, 1 << 25, None, 4, 32, None) == -1
 
 
 def test_host_side_refuses_cpu_tensors():
@@ -165,5 +168,5 @@ def test_sparsemap_plan_needs_no_device():
                 assert 0 < smem <= 227 * 1024 and 1 <= ctas <= 32
                 assert ctas * (smem + 1024) <= 228 * 1024
     assert ops.sparsemap_plan(128, 1)[0][0] > ops.sparsemap_plan(128, 0)[0][0]
-    assert ops.sparsemap_plan(128, 0)[0][2] == 5 and ops.sparsemap_plan(128, 1)[0][2] == 4
+    assert ops.sparsemap_plan(128, 0)[0][2] == 6 and ops.sparsemap_plan(128, 1)[0][2] == 4
     assert ops.sparsemap_plan(129, 0) == [] and ops.sparsemap_plan(8, 7) == []

@@ -195,28 +195,35 @@ def test_demo_vector(oracle):
 
 @pytest.mark.parametrize("lanes", [1, 2])
 @pytest.mark.parametrize("n,kind,budget", [(32, BERN, 0), (33, BUDGET, 9), (20, 2, 0)])
-def test_packed_S_chunks_equal_padded(n, kind, budget, lanes):
-    """Large batches keep 8|A|^2 bytes of S per sample (solved in chunks, smlvm_sparsemap_pack_inverse) instead of the
-    padded 8(n+1)^2: same forward state, same backward, chunk boundaries included."""
+def test_arena_of_inverses(n, kind, budget, lanes):
+    """The inverses of the backward are bump-allocated from one arena (8|A|^2 bytes per sample instead of the padded
+    8(n+1)^2), also when the batch is split over two streams: same forward state and the same backward whatever the
+    arena layout; a too-small arena is reported through the cursor, the samples that did not fit get offset -1 and
+    NaN gradients, and re-solving with the reported size fits exactly."""
     from lvmhelpers import ops
     rows = 101
     g = torch.Generator().manual_seed(n)
     x = torch.randn(rows, n, generator=g).cuda()
     t = torch.randn(rows, n - 1, generator=g).cuda() if kind == 2 else None
-    ref = ops.sparsemap_solve(x, kind, budget=budget, t=t, max_iter=100)
-    assert ref["S"] is not None and ref["S_rows"] is None
-    old, old_lanes = ops.S_PAD_MAX_BYTES, ops.SMAP_CHUNK_LANES
-    ops.S_PAD_MAX_BYTES = 7 * (n + 1) * (n + 1) * 8          # chunks of 7 samples
-    ops.SMAP_CHUNK_LANES = lanes                               # serial chunks / chunks alternating between two streams
-    try:
-        st = ops.sparsemap_solve(x, kind, budget=budget, t=t, max_iter=100)
-    finally:
-        ops.S_PAD_MAX_BYTES, ops.SMAP_CHUNK_LANES = old, old_lanes
-    assert st["S"] is None and st["S_rows"] is not None and len(st["S_chunks"]) == (rows + 6) // 7
-    for key in ("p_pad", "bits", "counts", "kept", "iters", "status"):
-        assert torch.equal(st[key], ref[key]), key
+    ref = ops.sparsemap_solve(x, kind, budget=budget, t=t, max_iter=100)     # worst-case arena, one launch sequence
     m = ref["counts"].long()
-    assert sum(c.numel() for c in st["S_chunks"]) >= int((m * m).sum())
+    need = int((m * m).sum())
+    assert ops.sparsemap_arena_overflow(ref) == 0 and int(ref["S_cursor"]) == need
+    assert int(ref["S_offsets"].min()) >= 0
+    old = (ops.SMAP_SPLIT_MIN_ROWS, ops.SMAP_CHUNK_LANES)
+    ops.SMAP_SPLIT_MIN_ROWS, ops.SMAP_CHUNK_LANES = 8, lanes
+    try:
+        st = ops.sparsemap_solve(x, kind, budget=budget, t=t, max_iter=100, arena_doubles=need)     # exact fit
+        small = ops.sparsemap_solve(x, kind, budget=budget, t=t, max_iter=100, arena_doubles=need // 2)
+    finally:
+        ops.SMAP_SPLIT_MIN_ROWS, ops.SMAP_CHUNK_LANES = old
+    for key in ("p_pad", "bits", "counts", "kept", "iters", "status"):
+        assert torch.equal(st[key], ref[key]) and torch.equal(small[key], ref[key]), key
+    assert ops.sparsemap_arena_overflow(st) == 0 and int(st["S_offsets"].min()) >= 0
+    # every sample owns a disjoint |A|^2 slice
+    o = st["S_offsets"].cpu().numpy(); mm = (m * m).cpu().numpy()
+    order = np.argsort(o)
+    assert np.all(o[order][1:] >= (o[order] + mm[order])[:-1]) and o.max() + mm[np.argmax(o)] <= need
     offsets = ops.scan_counts(ref["kept"])
     total = int(offsets[-1])
     dp = torch.randn(total, generator=g).cuda()
@@ -225,6 +232,31 @@ def test_packed_S_chunks_equal_padded(n, kind, budget, lanes):
     assert torch.equal(dx, dx_ref)
     if kind == 2:
         assert torch.equal(dt, dt_ref)
+    # overflow: reported, flagged per sample, loud in the backward
+    assert ops.sparsemap_arena_overflow(small) == need
+    lost = small["S_offsets"] < 0
+    assert 0 < int(lost.sum()) < rows
+    dx_s, _ = ops.sparsemap_bwd(small, dp, offsets, True, want_dt=kind == 2)
+    assert torch.isnan(dx_s[lost]).all() and torch.equal(dx_s[~lost], dx_ref[~lost])
+
+
+def test_batch_autograd_resolves_on_arena_overflow():
+    """ops.sparsemap_batch: when the estimated arena is too small the batch is solved again with the exact size."""
+    from lvmhelpers import ops
+    x = torch.randn(300, 32, generator=torch.Generator().manual_seed(3)).cuda().requires_grad_(True)
+    p, aset, aux = ops.sparsemap_batch(x, BERN, max_iter=100)
+    p.sum().backward()
+    g_ref = x.grad.clone()
+    old = ops.sparsemap_arena_doubles
+    ops.sparsemap_arena_doubles = lambda rows, n, kind, budget=0: 64        # far too small
+    try:
+        x.grad = None
+        p2, aset2, aux2 = ops.sparsemap_batch(x, BERN, max_iter=100)
+        p2.sum().backward()
+    finally:
+        ops.sparsemap_arena_doubles = old
+    assert torch.equal(p2, p) and torch.equal(aset2, aset) and torch.equal(x.grad, g_ref)
+    assert int(aux2["state"]["S_offsets"].min()) >= 0
 
 
 @pytest.mark.parametrize("kind,budget,lo_hi_maxiter", [(BUDGET, 64, (0.03, 0.09)), (BERN, 0, (0.0, 0.005))])
