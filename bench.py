@@ -639,9 +639,9 @@ def run_native(args, rank, local_rank, world):
     clocks = sampler.summary(th0, th1)
 
     # kernel durations over the timed steps only (drop the warm-up marks)
-    per_step = len(SparsemaxMargStep.KERNELS) + 1
+    per_step = len(step.kernels) + 1
     marks = marks[args.warmup * per_step:]
-    dur = {k: 0.0 for k in SparsemaxMargStep.KERNELS}
+    dur = {k: 0.0 for k in step.kernels}
     for i in range(len(marks) - 1):
         name, ev = marks[i]
         if name is not None:
@@ -723,7 +723,7 @@ def run_native(args, rank, local_rank, world):
             "config": workload_config(args, world),
             "clocks": clocks,
             "e2e": e2e,
-            "gpu_launches": args.steps * len(SparsemaxMargStep.KERNELS),
+            "gpu_launches": args.steps * len(step.kernels),
             "roofline": {"bound": "hbm", "kernel": top, "achieved": kernels[top]["gbs"], "peak": peak,
                          "unit": "GB/s", "frac": kernels[top]["frac"], "traffic": traffic,
                          "peak_source": peak_src,

@@ -108,10 +108,31 @@ int smlvm_sparsemax_bwd(const float* p, const int32_t* supp_size, const float* d
  * = loss_scale * vals.  Reads O(N) instead of O(rows*cols).
  * replaces: SparsemaxFunction.backward composed with the boolean-mask indexing backward of
  *           lvmhelpers/structmarg.py:116-126,140 (`p_flat[mask] @ loss`).                          */
+/* n_items = entries the ragged arrays hold; offsets beyond it (a compaction that overflowed its capacity) are
+ * clamped, so the kernel never reads past the caller's lists.                                              */
 int smlvm_sparsemax_bwd_ragged(const int64_t* offsets, const int32_t* col_idx, const float* vals,
                                const int32_t* supp_size, const float* dp, const float* loss,
                                const float* loss_scale_dev, float loss_scale_host, const float* dent,
-                               float* dx, float* dloss, int64_t rows, int32_t cols, void* stream);
+                               float* dx, float* dloss, int64_t rows, int32_t cols, int64_t n_items,
+                               void* stream);
+
+/* The categorical step behind the forward, in ONE launch, driven by the forward's support slots (required):
+ *   weighted loss      row_loss[r] = sum_c p[r,c]*loss[r,c] (NULL to skip), total[0] = scale * sum_r row_loss[r]
+ *                      (NULL to skip; fp64, fixed order; workspace: smlvm_reduce_workspace_bytes())
+ *   its backward       dx = sparsemax Jacobian of (scale * loss + dent[row] * d entropy / d p), dloss = scale * p
+ *                      (dent, dloss may be NULL) -- upstream gradient 1, as after loss.backward()
+ *   support compaction (vals, row_idx, col_idx) of p > 0 at offsets[r] + rank in column order, at most `capacity`
+ *                      entries written (offsets NULL: skipped; each list may be NULL)
+ * One read of the 64 B of slots and one gather of loss per non-zero serve all three.  SMLVM_ERR_UNSUPPORTED when the
+ * slot-driven tile kernel does not cover the shape (cols % 4, cols <= 512, 16-byte aligned dx / dloss): use the
+ * separate entry points.
+ * replaces: marg.py:125-126 forward + autograd backward, entropy() backward marg.py:6-28, and the mask indexing of
+ *           structmarg.py:116-126.                                                                              */
+int smlvm_marg_step_fused(const float* p, const int32_t* supp_size, const float* loss, float scale,
+                          const float* dent, const float* support_slots, const int64_t* offsets, float* vals,
+                          int32_t* row_idx, int32_t* col_idx, int64_t capacity, float* row_loss, float* total,
+                          float* dx, float* dloss, int64_t rows, int32_t cols, void* workspace,
+                          size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * (2) support compaction
@@ -132,11 +153,13 @@ int smlvm_compact_count(const float* p, int32_t* counts, int64_t rows, int32_t c
 
 /* Emits, for every p[r,c] > 0 in row-major order at position offsets[r] + rank:
  *   vals (fp32), row_idx (int32), col_idx (int32); each output may be NULL.
+ * capacity = entries each list can hold: positions >= capacity are NOT written (never out of bounds); the caller
+ * detects the overflow as offsets[rows] > capacity.
  * support_slots (NULL = scan p): the pairs written by smlvm_sparsemax_fwd; with them the kernel
  * streams 64 B per row instead of the whole row of p (rows that did not fit are scanned).       */
 int smlvm_compact_fill(const float* p, const int64_t* offsets, const float* support_slots,
                        float* vals, int32_t* row_idx, int32_t* col_idx, int64_t rows, int32_t cols,
-                       void* stream);
+                       int64_t capacity, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * (3a) k-best bit-vectors

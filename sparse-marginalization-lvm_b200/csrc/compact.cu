@@ -147,7 +147,7 @@ template <int E, int G, bool VEC, bool FILL>
 __global__ void __launch_bounds__(kThreads)
 compact_kernel(const float* __restrict__ p, const int64_t* __restrict__ offsets,
                int32_t* __restrict__ counts, float* __restrict__ vals, int32_t* __restrict__ row_idx,
-               int32_t* __restrict__ col_idx, int64_t rows, int K)
+               int32_t* __restrict__ col_idx, int64_t rows, int K, int64_t capacity)
 {
     constexpr int RPW = kWarp / G;
     constexpr int SPAN = E * G;
@@ -183,9 +183,11 @@ compact_kernel(const float* __restrict__ p, const int64_t* __restrict__ offsets,
                         for (int q = 0; q < 4; ++q) {
                             if (f & (1u << q)) {
                                 const int64_t o = out + rank;
-                                if (vals != nullptr) vals[o] = v[4 * c + q];
-                                if (row_idx != nullptr) row_idx[o] = (int32_t)row;
-                                if (col_idx != nullptr) col_idx[o] = c0 + 4 * (c * G + l) + q;
+                                if (o < capacity) {
+                                    if (vals != nullptr) vals[o] = v[4 * c + q];
+                                    if (row_idx != nullptr) row_idx[o] = (int32_t)row;
+                                    if (col_idx != nullptr) col_idx[o] = c0 + 4 * (c * G + l) + q;
+                                }
                                 ++rank;
                             }
                         }
@@ -200,7 +202,7 @@ compact_kernel(const float* __restrict__ p, const int64_t* __restrict__ offsets,
                 for (int e = 0; e < E; ++e) {
                     const bool nz = v[e] > 0.f;
                     unsigned b = __ballot_sync(kFull, nz);
-                    if (FILL && nz) {
+                    if (FILL && nz && out + __popc(b & lt) < capacity) {
                         const int64_t o = out + __popc(b & lt);
                         if (vals != nullptr) vals[o] = v[e];
                         if (row_idx != nullptr) row_idx[o] = (int32_t)row;
@@ -225,7 +227,7 @@ static int group_lanes(int K)
 
 template <bool FILL>
 static int launch_compact(const float* p, const int64_t* offsets, int32_t* counts, float* vals,
-                          int32_t* row_idx, int32_t* col_idx, int64_t rows, int K, cudaStream_t st)
+                          int32_t* row_idx, int32_t* col_idx, int64_t rows, int K, int64_t capacity, cudaStream_t st)
 {
     const int G = group_lanes(K);
     const bool vec = (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(p) & 15u) == 0);
@@ -237,10 +239,10 @@ static int launch_compact(const float* p, const int64_t* offsets, int32_t* count
     case GG:                                                                                       \
         if (vec)                                                                                   \
             compact_kernel<4, GG, true, FILL><<<grid, kThreads, 0, st>>>(p, offsets, counts, vals, \
-                                                                         row_idx, col_idx, rows, K); \
+                                                                         row_idx, col_idx, rows, K, capacity); \
         else                                                                                       \
             compact_kernel<4, GG, false, FILL><<<grid, kThreads, 0, st>>>(p, offsets, counts, vals, \
-                                                                          row_idx, col_idx, rows, K); \
+                                                                          row_idx, col_idx, rows, K, capacity); \
         break;
     switch (G) {
         SMLVM_COMPACT_CASE(1)
@@ -257,10 +259,10 @@ static int launch_compact(const float* p, const int64_t* offsets, int32_t* count
 
 // compact_tile.cu
 int compact_fill_slots_launch(const float* p, const float* slots, const int64_t* offsets, float* vals,
-                              int32_t* row_idx, int32_t* col_idx, int64_t rows, int cols, cudaStream_t st);
+                              int32_t* row_idx, int32_t* col_idx, int64_t rows, int cols, int64_t capacity, cudaStream_t st);
 bool compact_tile_supported(int cols);
 int compact_fill_tile_launch(const float* p, const int64_t* offsets, float* vals, int32_t* row_idx,
-                             int32_t* col_idx, int64_t rows, int cols, cudaStream_t st);
+                             int32_t* col_idx, int64_t rows, int cols, int64_t capacity, cudaStream_t st);
 
 // SMLVM_COMPACT=reg|tile overrides the path choice (tests run both).
 static int compact_path_override()
@@ -315,24 +317,24 @@ extern "C" int smlvm_compact_count(const float* p, int32_t* counts, int64_t rows
     if (rows < 0 || cols < 1) return SMLVM_ERR_ARG;
     if (rows == 0) return SMLVM_OK;
     if (p == nullptr || counts == nullptr) return SMLVM_ERR_ARG;
-    return launch_compact<false>(p, nullptr, counts, nullptr, nullptr, nullptr, rows, cols,
+    return launch_compact<false>(p, nullptr, counts, nullptr, nullptr, nullptr, rows, cols, 0,
                                  as_stream(stream));
 }
 
 extern "C" int smlvm_compact_fill(const float* p, const int64_t* offsets, const float* support_slots,
                                   float* vals, int32_t* row_idx, int32_t* col_idx, int64_t rows,
-                                  int32_t cols, void* stream)
+                                  int32_t cols, int64_t capacity, void* stream)
 {
-    if (rows < 0 || cols < 1) return SMLVM_ERR_ARG;
+    if (rows < 0 || cols < 1 || capacity < 0) return SMLVM_ERR_ARG;
     if (rows == 0) return SMLVM_OK;
     if (p == nullptr || offsets == nullptr) return SMLVM_ERR_ARG;
     if (support_slots != nullptr)
-        return compact_fill_slots_launch(p, support_slots, offsets, vals, row_idx, col_idx, rows, cols,
+        return compact_fill_slots_launch(p, support_slots, offsets, vals, row_idx, col_idx, rows, cols, capacity,
                                          as_stream(stream));
     const int ovr = compact_path_override();
     if (compact_tile_supported(cols) && (reinterpret_cast<uintptr_t>(p) & 15u) == 0 && ovr != 1 &&
         (rows >= kCompactTileMinRows || ovr == 2))
-        return compact_fill_tile_launch(p, offsets, vals, row_idx, col_idx, rows, cols, as_stream(stream));
-    return launch_compact<true>(p, offsets, nullptr, vals, row_idx, col_idx, rows, cols,
+        return compact_fill_tile_launch(p, offsets, vals, row_idx, col_idx, rows, cols, capacity, as_stream(stream));
+    return launch_compact<true>(p, offsets, nullptr, vals, row_idx, col_idx, rows, cols, capacity,
                                 as_stream(stream));
 }

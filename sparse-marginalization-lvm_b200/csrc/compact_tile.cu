@@ -20,7 +20,7 @@ namespace smlvm {
 template <int K, int W>
 __global__ void __launch_bounds__(W * 32, 1)
 compact_fill_tile(const float* __restrict__ p, const int64_t* __restrict__ offsets, float* __restrict__ vals,
-                  int32_t* __restrict__ row_idx, int32_t* __restrict__ col_idx, int64_t rows)
+                  int32_t* __restrict__ row_idx, int32_t* __restrict__ col_idx, int64_t rows, int64_t capacity)
 {
     constexpr int S = 2;
     constexpr int NC = K / 4;
@@ -90,9 +90,11 @@ compact_fill_tile(const float* __restrict__ p, const int64_t* __restrict__ offse
                 if (mw) {
                     const int col = w * 32 + __ffs(mw) - 1;
                     mw &= mw - 1;
-                    if (vals != nullptr) vals[out] = lds32(rowa + (col << 2));
-                    if (row_idx != nullptr) row_idx[out] = (int32_t)row;
-                    if (col_idx != nullptr) col_idx[out] = col;
+                    if (out < capacity) {
+                        if (vals != nullptr) vals[out] = lds32(rowa + (col << 2));
+                        if (row_idx != nullptr) row_idx[out] = (int32_t)row;
+                        if (col_idx != nullptr) col_idx[out] = col;
+                    }
                     ++out;
                 }
             }
@@ -107,7 +109,7 @@ compact_fill_tile(const float* __restrict__ p, const int64_t* __restrict__ offse
 
 template <int K, int W>
 static int launch_compact_tile(const float* p, const int64_t* offsets, float* vals, int32_t* row_idx,
-                               int32_t* col_idx, int64_t rows, cudaStream_t st)
+                               int32_t* col_idx, int64_t rows, int64_t capacity, cudaStream_t st)
 {
     auto kern = compact_fill_tile<K, W>;
     const size_t smem = (size_t)W * 2 * kTileRows * K * 4 + (size_t)W * 2 * 8;
@@ -128,7 +130,7 @@ static int launch_compact_tile(const float* p, const int64_t* offsets, float* va
     const int64_t need = (ntiles + W - 1) / W;
     const int64_t cap = (int64_t)device_sm_count() * ctas_per_sm;
     const int grid = (int)(need < cap ? need : cap);
-    kern<<<grid, W * 32, smem, st>>>(p, offsets, vals, row_idx, col_idx, rows);
+    kern<<<grid, W * 32, smem, st>>>(p, offsets, vals, row_idx, col_idx, rows, capacity);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? SMLVM_OK : (int)e;
 }
@@ -141,7 +143,8 @@ static int launch_compact_tile(const float* p, const int64_t* offsets, float* va
 __global__ void __launch_bounds__(256)
 compact_fill_slots_kernel(const float* __restrict__ p, const float* __restrict__ slots,
                           const int64_t* __restrict__ offsets, float* __restrict__ vals,
-                          int32_t* __restrict__ row_idx, int32_t* __restrict__ col_idx, int64_t rows, int K)
+                          int32_t* __restrict__ row_idx, int32_t* __restrict__ col_idx, int64_t rows, int K,
+                          int64_t capacity)
 {
     constexpr int NS = SMLVM_SUPPORT_SLOTS;
     const int lane = threadIdx.x & 31;
@@ -177,7 +180,7 @@ compact_fill_slots_kernel(const float* __restrict__ p, const float* __restrict__
             }
 #pragma unroll
             for (int j = 0; j < NS; ++j) {
-                if (j < cnt) {
+                if (j < cnt && b + j < capacity) {
                     if (vals != nullptr) vals[b + j] = v[j];
                     if (row_idx != nullptr) row_idx[b + j] = (int32_t)r;
                     if (col_idx != nullptr) col_idx[b + j] = c[j];
@@ -196,7 +199,7 @@ compact_fill_slots_kernel(const float* __restrict__ p, const float* __restrict__
                 const int col = c0 + lane;
                 const float pv = col < K ? __ldg(pr + col) : 0.f;
                 const unsigned bal = __ballot_sync(kFull, pv > 0.f);
-                if (pv > 0.f) {
+                if (pv > 0.f && out + __popc(bal & ((1u << lane) - 1u)) < capacity) {
                     const int64_t o = out + __popc(bal & ((1u << lane) - 1u));
                     if (vals != nullptr) vals[o] = pv;
                     if (row_idx != nullptr) row_idx[o] = (int32_t)rr;
@@ -209,12 +212,12 @@ compact_fill_slots_kernel(const float* __restrict__ p, const float* __restrict__
 }
 
 int compact_fill_slots_launch(const float* p, const float* slots, const int64_t* offsets, float* vals,
-                              int32_t* row_idx, int32_t* col_idx, int64_t rows, int cols, cudaStream_t st)
+                              int32_t* row_idx, int32_t* col_idx, int64_t rows, int cols, int64_t capacity, cudaStream_t st)
 {
     int64_t need = (rows + 255) / 256;
     int64_t cap = (int64_t)device_sm_count() * 16;
     compact_fill_slots_kernel<<<(int)(need < cap ? need : cap), 256, 0, st>>>(p, slots, offsets, vals, row_idx,
-                                                                            col_idx, rows, cols);
+                                                                            col_idx, rows, cols, capacity);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? SMLVM_OK : (int)e;
 }
@@ -263,13 +266,13 @@ int support_slots_launch(const float* p, float* slots, int64_t rows, int cols, c
 bool compact_tile_supported(int cols) { return cols == 32 || cols == 64 || cols == 128 || cols == 256; }
 
 int compact_fill_tile_launch(const float* p, const int64_t* offsets, float* vals, int32_t* row_idx,
-                             int32_t* col_idx, int64_t rows, int cols, cudaStream_t st)
+                             int32_t* col_idx, int64_t rows, int cols, int64_t capacity, cudaStream_t st)
 {
     switch (cols) {
-        case 32: return launch_compact_tile<32, 8>(p, offsets, vals, row_idx, col_idx, rows, st);
-        case 64: return launch_compact_tile<64, 8>(p, offsets, vals, row_idx, col_idx, rows, st);
-        case 128: return launch_compact_tile<128, 7>(p, offsets, vals, row_idx, col_idx, rows, st);
-        case 256: return launch_compact_tile<256, 3>(p, offsets, vals, row_idx, col_idx, rows, st);
+        case 32: return launch_compact_tile<32, 8>(p, offsets, vals, row_idx, col_idx, rows, capacity, st);
+        case 64: return launch_compact_tile<64, 8>(p, offsets, vals, row_idx, col_idx, rows, capacity, st);
+        case 128: return launch_compact_tile<128, 7>(p, offsets, vals, row_idx, col_idx, rows, capacity, st);
+        case 256: return launch_compact_tile<256, 3>(p, offsets, vals, row_idx, col_idx, rows, capacity, st);
         default: return SMLVM_ERR_UNSUPPORTED;
     }
 }

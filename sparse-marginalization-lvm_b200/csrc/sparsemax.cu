@@ -477,12 +477,12 @@ sparsemax_bwd_ragged_kernel(const int64_t* __restrict__ offsets, const int32_t* 
                             const float* __restrict__ dp, const float* __restrict__ loss,
                             const float* __restrict__ loss_scale_dev, float loss_scale_host,
                             const float* __restrict__ dent, float* __restrict__ dx, float* __restrict__ dloss,
-                            int64_t rows, int K)
+                            int64_t rows, int K, int64_t n_items)
 {
     float ls = loss_scale_host;
     if (loss_scale_dev != nullptr) ls *= __ldg(loss_scale_dev);
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t b = __ldg(offsets + r), e = __ldg(offsets + r + 1);
+        const int64_t b = min(__ldg(offsets + r), n_items), e = min(__ldg(offsets + r + 1), n_items);
         const float de = dent != nullptr ? __ldg(dent + r) : 0.f;
         float sum = 0.f;
         for (int64_t j = b; j < e; ++j) {
@@ -580,7 +580,7 @@ int bwd_slots_launch(const float* p, const int32_t* supp, const float* dp, const
 bool bwd_ragged_tile_supported(int cols);
 int bwd_ragged_tile_launch(const int64_t* offsets, const int32_t* cols_idx, const float* vals, const int32_t* supp,
                            const float* dp, const float* loss, const float* lsd, float lsh, const float* dent,
-                           float* dx, float* dloss, int64_t rows, int K, cudaStream_t st);
+                           float* dx, float* dloss, int64_t rows, int K, int64_t n_items, cudaStream_t st);
 
 // sparsemax_tile.cu
 bool sparsemax_tile_supported(int cols);
@@ -678,25 +678,52 @@ extern "C" int smlvm_sparsemax_bwd(const float* p, const int32_t* supp_size, con
     return SMLVM_OK;
 }
 
+// sparsemax_bwd_tile.cu
+namespace smlvm {
+int step_fused_launch(const float* p, const int32_t* supp, const float* loss, float scale, const float* dent,
+                      const float* slots, const int64_t* offsets, float* vals, int32_t* row_idx, int32_t* col_idx,
+                      int64_t capacity, float* row_loss, float* total, void* workspace, float* dx, float* dloss,
+                      int64_t rows, int K, cudaStream_t st);
+}
+
+extern "C" int smlvm_marg_step_fused(const float* p, const int32_t* supp_size, const float* loss, float scale,
+                                     const float* dent, const float* support_slots, const int64_t* offsets,
+                                     float* vals, int32_t* row_idx, int32_t* col_idx, int64_t capacity,
+                                     float* row_loss, float* total, float* dx, float* dloss, int64_t rows,
+                                     int32_t cols, void* workspace, size_t workspace_bytes, void* stream)
+{
+    if (rows < 0 || cols < 1 || capacity < 0) return SMLVM_ERR_ARG;
+    if (rows == 0) return SMLVM_OK;
+    if (p == nullptr || supp_size == nullptr || loss == nullptr || support_slots == nullptr || dx == nullptr)
+        return SMLVM_ERR_ARG;
+    if (total != nullptr && (workspace == nullptr || workspace_bytes < smlvm_reduce_workspace_bytes()))
+        return SMLVM_ERR_WORKSPACE;
+    if (!bwd_slots_supported(cols) || !aligned16(dx) || (dloss != nullptr && !aligned16(dloss)))
+        return SMLVM_ERR_UNSUPPORTED;
+    return step_fused_launch(p, supp_size, loss, scale, dent, support_slots, offsets, vals, row_idx, col_idx, capacity,
+                             row_loss, total, workspace, dx, dloss, rows, cols, as_stream(stream));
+}
+
 extern "C" int smlvm_sparsemax_bwd_ragged(const int64_t* offsets, const int32_t* col_idx, const float* vals,
                                           const int32_t* supp_size, const float* dp, const float* loss,
                                           const float* loss_scale_dev, float loss_scale_host, const float* dent,
-                                          float* dx, float* dloss, int64_t rows, int32_t cols, void* stream)
+                                          float* dx, float* dloss, int64_t rows, int32_t cols, int64_t n_items,
+                                          void* stream)
 {
-    if (rows < 0 || cols < 1) return SMLVM_ERR_ARG;
+    if (rows < 0 || cols < 1 || n_items < 0) return SMLVM_ERR_ARG;
     if (rows == 0) return SMLVM_OK;
     if (offsets == nullptr || col_idx == nullptr || vals == nullptr || supp_size == nullptr || dx == nullptr)
         return SMLVM_ERR_ARG;
     cudaStream_t st = as_stream(stream);
     if (bwd_ragged_tile_supported(cols) && aligned16(dx))
         return bwd_ragged_tile_launch(offsets, col_idx, vals, supp_size, dp, loss, loss_scale_dev, loss_scale_host,
-                                      dent, dx, dloss, rows, cols, st);
+                                      dent, dx, dloss, rows, cols, n_items, st);
     cudaError_t e = cudaMemsetAsync(dx, 0, (size_t)rows * cols * sizeof(float), st);
     if (e != cudaSuccess) return (int)e;
     int64_t need = (rows + 255) / 256;
     int64_t cap = (int64_t)device_sm_count() * 16;
     sparsemax_bwd_ragged_kernel<<<(int)(need < cap ? need : cap), 256, 0, st>>>(
-        offsets, col_idx, vals, supp_size, dp, loss, loss_scale_dev, loss_scale_host, dent, dx, dloss, rows, cols);
+        offsets, col_idx, vals, supp_size, dp, loss, loss_scale_dev, loss_scale_host, dent, dx, dloss, rows, cols, n_items);
     SMLVM_LAUNCH_CHECK();
     return SMLVM_OK;
 }

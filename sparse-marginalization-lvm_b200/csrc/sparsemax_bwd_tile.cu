@@ -9,6 +9,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "reduce_ws.cuh"
 #include "sparsemax_exact.cuh"
 #include "tile_ptx.cuh"
 
@@ -23,7 +24,7 @@ bwd_ragged_tile_kernel(const int64_t* __restrict__ offsets, const int32_t* __res
                        const float* __restrict__ dp, const float* __restrict__ loss,
                        const float* __restrict__ loss_scale_dev, float loss_scale_host,
                        const float* __restrict__ dent, float* __restrict__ dx, float* __restrict__ dloss,
-                       int64_t rows, int K, bool clear)
+                       int64_t rows, int K, bool clear, int64_t n_items)
 {
     __shared__ float s_all[kBwdWarps][4][kStage];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -41,7 +42,8 @@ bwd_ragged_tile_kernel(const int64_t* __restrict__ offsets, const int32_t* __res
         const int trows = (int)min((int64_t)32, rows - row0);
         const bool live = lane < trows;
         const int64_t row = row0 + lane;
-        const int64_t b = live ? __ldg(offsets + row) : 0, e = live ? __ldg(offsets + row + 1) : 0;
+        // (entries beyond the caller's lists -- a compaction that overflowed its capacity -- are ignored)
+        const int64_t b = live ? min(__ldg(offsets + row), n_items) : 0, e = live ? min(__ldg(offsets + row + 1), n_items) : 0;
         const float kf = live ? (float)__ldg(supp + row) : 1.f;
         const float de = (dent != nullptr && live) ? __ldg(dent + row) : 0.f;
 
@@ -108,7 +110,7 @@ bwd_ragged_tma_kernel(const int64_t* __restrict__ offsets, const int32_t* __rest
                       const float* __restrict__ dp, const float* __restrict__ loss,
                       const float* __restrict__ loss_scale_dev, float loss_scale_host,
                       const float* __restrict__ dent, float* __restrict__ dx, float* __restrict__ dloss,
-                      int64_t rows, int K)
+                      int64_t rows, int K, int64_t n_items)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -128,7 +130,8 @@ bwd_ragged_tma_kernel(const int64_t* __restrict__ offsets, const int32_t* __rest
         const int trows = (int)min((int64_t)kTileRows, rows - row0);
         const bool live = lane < trows;
         const int64_t row = row0 + lane;
-        const int64_t b = live ? __ldg(offsets + row) : 0, e = live ? __ldg(offsets + row + 1) : 0;
+        // (entries beyond the caller's lists -- a compaction that overflowed its capacity -- are ignored)
+        const int64_t b = live ? min(__ldg(offsets + row), n_items) : 0, e = live ? min(__ldg(offsets + row + 1), n_items) : 0;
         const float kf = live ? (float)__ldg(supp + row) : 1.f;
         const float de = (dent != nullptr && live) ? __ldg(dent + row) : 0.f;
         const int64_t tb = __shfl_sync(kFull, b, 0);
@@ -215,13 +218,33 @@ bwd_ragged_tma_kernel(const int64_t* __restrict__ offsets, const int32_t* __rest
 // densely by the whole warp straight into the tile.  One 16 KB tile per warp keeps 12 warps per SM
 // (two tiles per warp: 6 warps, 0.28 ms -- the kernel is bound by the latency of the two dependent
 // load rounds, slots then gathers, which more warps hide).
+// FUSED: the same launch also produces what the step needs from the same slots -- the weighted loss itself
+// (row_loss[r] = sum_j val_j L[r, col_j], total = total_scale * sum_r row_loss, fp64, fixed order: marg.py:125-126) and
+// the support compaction (value, row, col) at offsets[r] in column order (structmarg.py:116-126), both clamped to the
+// caller's capacity.  One read of the slots and ONE random gather of L per non-zero serve loss, gradient and lists
+// (separately: wloss 0.088 ms + fill 0.040 ms + backward 0.214 ms at 1M x 128; the gather cost ~2x its bytes each time).
+struct FusedExtras {
+    float* row_loss;          // [rows] or NULL
+    float* total;             // device scalar or NULL
+    float total_scale;
+    ReduceWs ws;
+    const int64_t* offsets;   // [rows + 1] or NULL: no compaction
+    float* vals;
+    int32_t* row_idx;
+    int32_t* col_idx;
+    int64_t capacity;         // entries the three lists can hold (writes beyond are dropped)
+};
+
+template <bool FUSED>
 __global__ void __launch_bounds__(512, 1)
 bwd_slots_tma_kernel(const float* __restrict__ p, const int32_t* __restrict__ supp, const float* __restrict__ dp,
                      const float* __restrict__ loss, const float* __restrict__ loss_scale_dev,
                      float loss_scale_host, const float* __restrict__ dent, const float* __restrict__ slots,
                      const float* __restrict__ loss_slots, float* __restrict__ dx, float* __restrict__ dloss,
-                     int64_t rows, int K)
+                     int64_t rows, int K, FusedExtras fx)
 {
+    __shared__ double red[20];
+    double acc_total = 0.0;
     constexpr int NS = SMLVM_SUPPORT_SLOTS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -278,6 +301,75 @@ bwd_slots_tma_kernel(const float* __restrict__ p, const int32_t* __restrict__ su
         }
         const unsigned scan_rows = __ballot_sync(kFull, scan);
 
+        if (FUSED) {
+            // ---- weighted loss of the row, in slot order (the arithmetic of wloss_slots_kernel) -------------------
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < NS; ++j) s = fmaf(v[j], (live && !scan && c[j] >= 0) ? lv[j] : 0.f, s);
+            if (scan) s = 0.f;
+            unsigned todo = scan_rows;
+            while (todo) {
+                const int rl = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int64_t rr = row0 + rl;
+                float part = 0.f;
+                for (int col = lane; col < K; col += 32) part = fmaf(__ldg(p + rr * K + col), __ldg(loss + rr * K + col), part);
+                part = group_sum<32>(part);
+                if (lane == rl) s = part;
+            }
+            if (live) {
+                if (fx.row_loss != nullptr) fx.row_loss[row] = s;
+                acc_total += (double)s;
+            }
+            // ---- support compaction: the row's pairs sorted by column at offsets[row] --------------------------
+            if (fx.offsets != nullptr) {
+                const int64_t ob = live ? __ldg(fx.offsets + row) : 0;
+                if (live && !scan) {
+                    float sv[NS];
+                    int sc[NS];
+#pragma unroll
+                    for (int j = 0; j < NS; ++j) { sv[j] = v[j]; sc[j] = (c[j] < 0) ? 0x7fffffff : c[j]; }
+#pragma unroll
+                    for (int pass = 0; pass < NS; ++pass) {
+#pragma unroll
+                        for (int j = pass & 1; j + 1 < NS; j += 2) {
+                            const bool sw = sc[j] > sc[j + 1];
+                            const int ca = sw ? sc[j + 1] : sc[j], cb = sw ? sc[j] : sc[j + 1];
+                            const float va = sw ? sv[j + 1] : sv[j], vb = sw ? sv[j] : sv[j + 1];
+                            sc[j] = ca; sc[j + 1] = cb; sv[j] = va; sv[j + 1] = vb;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < NS; ++j) {
+                        if (sc[j] != 0x7fffffff && ob + j < fx.capacity) {
+                            if (fx.vals != nullptr) fx.vals[ob + j] = sv[j];
+                            if (fx.row_idx != nullptr) fx.row_idx[ob + j] = (int32_t)row;
+                            if (fx.col_idx != nullptr) fx.col_idx[ob + j] = sc[j];
+                        }
+                    }
+                }
+                unsigned todo2 = scan_rows;
+                while (todo2) {   // rows that did not fit the slots: the warp scans P, 32 columns at a time
+                    const int rl = __ffs(todo2) - 1;
+                    todo2 &= todo2 - 1;
+                    const int64_t rr = row0 + rl;
+                    int64_t out = __shfl_sync(kFull, ob, rl);
+                    for (int c0 = 0; c0 < K; c0 += 32) {
+                        const int col = c0 + lane;
+                        const float pv = col < K ? __ldg(p + rr * K + col) : 0.f;
+                        const unsigned bal = __ballot_sync(kFull, pv > 0.f);
+                        const int64_t o = out + __popc(bal & ((1u << lane) - 1u));
+                        if (pv > 0.f && o < fx.capacity) {
+                            if (fx.vals != nullptr) fx.vals[o] = pv;
+                            if (fx.row_idx != nullptr) fx.row_idx[o] = (int32_t)rr;
+                            if (fx.col_idx != nullptr) fx.col_idx[o] = col;
+                        }
+                        out += __popc(bal);
+                    }
+                }
+            }
+        }
+
         for (int phase = 0; phase < (dloss != nullptr ? 2 : 1); ++phase) {
             // the previous store of this warp must have finished READING the tile
             if (lane == 0) bulk_wait_read0();
@@ -326,13 +418,15 @@ bwd_slots_tma_kernel(const float* __restrict__ p, const int32_t* __restrict__ su
         }
     }
     if (lane == 0) bulk_wait_read0();
+    if (FUSED && fx.total != nullptr) finish_totals(fx.ws, acc_total, 0.0, fx.total_scale, fx.total, nullptr, red);
 }
 
 bool bwd_slots_supported(int cols) { return cols % 4 == 0 && cols >= 4 && cols <= 512; }
 
-int bwd_slots_launch(const float* p, const int32_t* supp, const float* dp, const float* loss, const float* lsd,
-                     float lsh, const float* dent, const float* slots, const float* loss_slots, float* dx,
-                     float* dloss, int64_t rows, int K, cudaStream_t st)
+template <bool FUSED>
+static int bwd_slots_launch_t(const float* p, const int32_t* supp, const float* dp, const float* loss, const float* lsd,
+                              float lsh, const float* dent, const float* slots, const float* loss_slots, float* dx,
+                              float* dloss, int64_t rows, int K, const FusedExtras& fx, cudaStream_t st)
 {
     const size_t per_warp = (size_t)kTileRows * K * 4;
     int warps = (int)((200 * 1024) / per_warp);
@@ -342,7 +436,7 @@ int bwd_slots_launch(const float* p, const int32_t* supp, const float* dp, const
     int dev = 0;
     cudaGetDevice(&dev);
     if (!configured_dev[dev & 63]) {
-        cudaError_t ea = cudaFuncSetAttribute(bwd_slots_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t ea = cudaFuncSetAttribute(bwd_slots_tma_kernel<FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               200 * 1024);
         if (ea != cudaSuccess) return (int)ea;
         configured_dev[dev & 63] = true;
@@ -350,17 +444,44 @@ int bwd_slots_launch(const float* p, const int32_t* supp, const float* dp, const
     const int64_t nt = (rows + kTileRows - 1) / kTileRows;
     const int64_t nd = (nt + warps - 1) / warps;
     const int64_t cp = (int64_t)device_sm_count();
-    bwd_slots_tma_kernel<<<(int)(nd < cp ? nd : cp), warps * 32, smem, st>>>(p, supp, dp, loss, lsd, lsh, dent, slots,
-                                                                              loss_slots, dx, dloss, rows, K);
+    bwd_slots_tma_kernel<FUSED><<<(int)(nd < cp ? nd : cp), warps * 32, smem, st>>>(p, supp, dp, loss, lsd, lsh, dent, slots,
+                                                                                     loss_slots, dx, dloss, rows, K, fx);
     cudaError_t e2 = cudaGetLastError();
     return e2 == cudaSuccess ? SMLVM_OK : (int)e2;
+}
+
+int bwd_slots_launch(const float* p, const int32_t* supp, const float* dp, const float* loss, const float* lsd,
+                     float lsh, const float* dent, const float* slots, const float* loss_slots, float* dx,
+                     float* dloss, int64_t rows, int K, cudaStream_t st)
+{
+    FusedExtras none = {};
+    return bwd_slots_launch_t<false>(p, supp, dp, loss, lsd, lsh, dent, slots, loss_slots, dx, dloss, rows, K, none, st);
+}
+
+// loss forward + backward (+ compaction) of the categorical step in one launch; see FusedExtras
+int step_fused_launch(const float* p, const int32_t* supp, const float* loss, float scale, const float* dent,
+                      const float* slots, const int64_t* offsets, float* vals, int32_t* row_idx, int32_t* col_idx,
+                      int64_t capacity, float* row_loss, float* total, void* workspace, float* dx, float* dloss,
+                      int64_t rows, int K, cudaStream_t st)
+{
+    FusedExtras fx;
+    fx.row_loss = row_loss;
+    fx.total = total;
+    fx.total_scale = scale;
+    fx.ws = ws_view(workspace);
+    fx.offsets = offsets;
+    fx.vals = vals;
+    fx.row_idx = row_idx;
+    fx.col_idx = col_idx;
+    fx.capacity = capacity;
+    return bwd_slots_launch_t<true>(p, supp, nullptr, loss, nullptr, scale, dent, slots, nullptr, dx, dloss, rows, K, fx, st);
 }
 
 bool bwd_ragged_tile_supported(int cols) { return cols % 4 == 0 && cols >= 4; }
 
 int bwd_ragged_tile_launch(const int64_t* offsets, const int32_t* cols_idx, const float* vals, const int32_t* supp,
                            const float* dp, const float* loss, const float* lsd, float lsh, const float* dent,
-                           float* dx, float* dloss, int64_t rows, int K, cudaStream_t st)
+                           float* dx, float* dloss, int64_t rows, int K, int64_t n_items, cudaStream_t st)
 {
     const int64_t ngroups = (rows + 31) / 32;
     const int64_t need = (ngroups + kBwdWarps - 1) / kBwdWarps;
@@ -389,7 +510,7 @@ int bwd_ragged_tile_launch(const int64_t* offsets, const int32_t* cols_idx, cons
         const int64_t nd = (nt + warps - 1) / warps;
         const int64_t cp = (int64_t)device_sm_count();
         bwd_ragged_tma_kernel<<<(int)(nd < cp ? nd : cp), warps * 32, smem, st>>>(offsets, cols_idx, vals, supp, dp, loss,
-                                                                                   lsd, lsh, dent, dx, dloss, rows, K);
+                                                                                   lsd, lsh, dent, dx, dloss, rows, K, n_items);
         cudaError_t e2 = cudaGetLastError();
         return e2 == cudaSuccess ? SMLVM_OK : (int)e2;
     }
@@ -405,7 +526,7 @@ int bwd_ragged_tile_launch(const int64_t* offsets, const int32_t* cols_idx, cons
         if (em != cudaSuccess) return (int)em;
     }
     bwd_ragged_tile_kernel<<<grid, kBwdWarps * 32, 0, st>>>(offsets, cols_idx, vals, supp, dp, loss, lsd, lsh, dent, dx,
-                                                           dloss, rows, K, fused != 0);
+                                                           dloss, rows, K, fused != 0, n_items);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? SMLVM_OK : (int)e;
 }

@@ -32,11 +32,13 @@ _PROTOTYPES = {
     "smlvm_error_string": (ctypes.c_char_p, [ctypes.c_int]),
     "smlvm_sparsemax_fwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "smlvm_sparsemax_bwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
-    "smlvm_sparsemax_bwd_ragged": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "smlvm_sparsemax_bwd_ragged": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _i64, _i32, _i64, _vp]),
+    "smlvm_marg_step_fused": (ctypes.c_int, [_vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp,
+                                             _i64, _i32, _vp, _sz, _vp]),
     "smlvm_scan_workspace_bytes": (_sz, [_i64]),
     "smlvm_scan_counts": (ctypes.c_int, [_vp, _vp, _i64, _vp, _sz, _vp]),
     "smlvm_compact_count": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp]),
-    "smlvm_compact_fill": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "smlvm_compact_fill": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i64, _vp]),
     "smlvm_topk_bits": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     "smlvm_bits_score_fwd": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     "smlvm_bits_score_bwd": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp]),

@@ -11,6 +11,13 @@ so a step can be replayed back to back or captured in a CUDA graph.
     P, losses     --weighted loss-->  per-row loss, mean loss                     (kernel 4)
     P, losses     --fused bwd------>  dscores (sparsemax Jacobian of g*L/B + entropy term),
                                       dlosses = g*P/B                             (kernel 1')
+
+With the forward's support slots (large batches of peaked rows) kernels 2b, 4 and 1' are ONE launch
+(``smlvm_marg_step_fused``): fwd -> scan -> {loss, lists, gradients}.
+
+Capacity contract: the ragged lists are pre-allocated for ``capacity`` entries.  The fill never writes past them
+(entries beyond the capacity are dropped) and the ragged consumers never read past them; a batch whose support is
+larger than the capacity leaves ``offsets[-1] > capacity`` -- ``overflowed()`` reads that one scalar.
 """
 import torch
 
@@ -25,7 +32,7 @@ class SparsemaxMargStep:
     KERNELS = ("sparsemax_fwd", "scan_counts", "compact_fill", "wloss_dense_fwd", "sparsemax_bwd")
 
     def __init__(self, rows, cols, device, capacity, entropy_coeff=0.0, global_rows=None, use_slots=None,
-                 overlap_compaction=True):
+                 overlap_compaction=True, fused=None):
         """``global_rows``: batch size B of the 1/B in the loss and entropy terms when this step
         owns only a shard / micro-batch of the batch (default: ``rows``).
         ``use_slots``: let the weighted loss and the backward read the losses only at the support
@@ -33,7 +40,10 @@ class SparsemaxMargStep:
         of P and L), and the compaction read the slots instead of P.  Default: on for large batches
         (>= 4096 rows) whose expected support (``capacity / rows``) is at most 6 entries per row -- rows
         that do not fit the 8 slots fall back to dense processing one by one inside a warp, which only
-        pays when they are rare and there are many warps."""
+        pays when they are rare and there are many warps.
+        ``fused``: loss, lists and gradients in one launch (``smlvm_marg_step_fused``); default: whenever the
+        slots are on and the shape is covered.  ``False`` keeps the separate kernels (compaction on a side stream).
+        """
         if use_slots is None:
             use_slots = capacity <= 6 * rows and rows >= 4096
         self.use_slots = bool(use_slots)
@@ -59,6 +69,14 @@ class SparsemaxMargStep:
         # side stream of the compaction branch (run()); small batches are launch-bound: one stream
         self.side = torch.cuda.Stream(device=device) if (overlap_compaction and rows >= OVERLAP_MIN_ROWS) else None
         self._ev_fwd, self._ev_side = torch.cuda.Event(), torch.cuda.Event()
+        # loss, lists and gradients in one launch behind the scan (needs the slots; tile kernel shapes only)
+        self.fused = self.use_slots and cols % 4 == 0 and cols <= 512 and (fused is None or bool(fused))
+        self.kernels = ("sparsemax_fwd", "scan_counts", "marg_step_fused") if self.fused else self.KERNELS
+
+    def overflowed(self):
+        """True when the last batch had more non-zeros than ``capacity`` (the lists then hold the first ``capacity``
+        entries only; loss and gradients are complete -- they do not depend on the lists).  One host read."""
+        return int(self.offsets[-1].item()) > self.capacity
 
     @staticmethod
     def size_capacity(x):
@@ -74,7 +92,7 @@ class SparsemaxMargStep:
         backward kernels.  ``rec(name)`` (optional) is called before and after each launch so that a
         caller can bracket the kernels with CUDA events; the launches are then serial on the current
         stream."""
-        fork = rec is None and self.side is not None
+        fork = rec is None and self.side is not None and not self.fused
         cur = torch.cuda.current_stream() if fork else None
         st = cur.cuda_stream if fork else N.stream()
         rows, K = self.rows, self.cols
@@ -83,6 +101,18 @@ class SparsemaxMargStep:
         slots = ptr(self.slots) if self.use_slots else None
         check(lib.smlvm_sparsemax_fwd(ptr(x), ptr(self.p), ptr(self.supp), ptr(self.nnz), ptr(self.ent),
                                       ptr(self.amax), slots, rows, K, st), "smlvm_sparsemax_fwd")
+        if self.fused:
+            mark("scan_counts")
+            check(lib.smlvm_scan_counts(ptr(self.nnz), ptr(self.offsets), rows, ptr(self.scan_ws),
+                                        self.scan_ws.numel(), st), "smlvm_scan_counts")
+            mark("marg_step_fused")
+            check(lib.smlvm_marg_step_fused(ptr(self.p), ptr(self.supp), ptr(losses), 1.0 / self.global_rows,
+                                            ptr(self.dent), slots, ptr(self.offsets), ptr(self.vals), ptr(self.ri),
+                                            ptr(self.ci), self.capacity, ptr(self.row_loss), ptr(self.total),
+                                            ptr(self.dx), ptr(self.dloss), rows, K, ptr(self.red_ws),
+                                            self.red_ws.numel(), st), "smlvm_marg_step_fused")
+            mark(None)
+            return self.total
         st_c = st
         if fork:
             self._ev_fwd.record(cur)
@@ -93,7 +123,7 @@ class SparsemaxMargStep:
                                     self.scan_ws.numel(), st_c), "smlvm_scan_counts")
         mark("compact_fill")
         check(lib.smlvm_compact_fill(ptr(self.p), ptr(self.offsets), slots, ptr(self.vals), ptr(self.ri),
-                                     ptr(self.ci), rows, K, st_c), "smlvm_compact_fill")
+                                     ptr(self.ci), rows, K, self.capacity, st_c), "smlvm_compact_fill")
         if fork:
             self._ev_side.record(self.side)
         mark("wloss_dense_fwd")
@@ -125,7 +155,7 @@ class SparsemaxMargStep:
     def algorithmic_bytes(self, total_nnz):
         """Bytes each kernel must move per launch (fp32 = 4 B)."""
         r, K, N_ = self.rows, self.cols, total_nnz
-        return {
+        d = {
             # X in, P out, supp/nnz/entropy/argmax (+ 64 B of support slots)
             "sparsemax_fwd": r * (8 * K + 4 + 4 + 4 + 8 + (64 if self.use_slots else 0)),
             "scan_counts": r * (4 + 8),                         # counts in, offsets out
@@ -137,7 +167,11 @@ class SparsemaxMargStep:
             "wloss_dense_fwd": (r * (64 + 32 + 4) + 32 * N_) if self.use_slots else r * (8 * K + 4),
             "sparsemax_bwd": (r * (64 + 32 + 4 + 8 * K) if self.use_slots else r * (8 * K + 4 + 8 * K))
                              + (4 * r if self.dent is not None else 0),
+            # the three above in one launch: slots + offsets + supp (+dent) in, one sector of L per non-zero,
+            # row loss, dX, dL and 12 B of lists per non-zero out
+            "marg_step_fused": r * (64 + 16 + 4 + 4 + 8 * K) + (4 * r if self.dent is not None else 0) + (32 + 12) * N_,
         }
+        return {k: d[k] for k in self.kernels}
 
 
 class SparsemaxMargCompactStep:
@@ -170,21 +204,25 @@ class SparsemaxMargCompactStep:
               "smlvm_scan_counts")
         mark("compact_fill")
         check(lib.smlvm_compact_fill(ptr(b.p), ptr(b.offsets), slots, ptr(b.vals), ptr(b.ri), ptr(b.ci), rows, K,
-                                     st), "smlvm_compact_fill")
+                                     b.capacity, st), "smlvm_compact_fill")
         mark("wloss_ragged_fwd")
         check(lib.smlvm_wloss_ragged_fwd(ptr(b.vals), ptr(losses_ragged), None, None, ptr(b.total), None,
-                                         1.0 / b.global_rows, 0, n_items, ptr(b.red_ws), b.red_ws.numel(), st),
+                                         1.0 / b.global_rows, 0, min(int(n_items), b.capacity), ptr(b.red_ws),
+                                         b.red_ws.numel(), st),
               "smlvm_wloss_ragged_fwd")
         mark("sparsemax_bwd_ragged")
         check(lib.smlvm_sparsemax_bwd_ragged(ptr(b.offsets), ptr(b.ci), ptr(b.vals), ptr(b.supp), None,
                                              ptr(losses_ragged), None, 1.0 / b.global_rows, ptr(b.dent), ptr(b.dx),
-                                             ptr(self.dloss_ragged), rows, K, st), "smlvm_sparsemax_bwd_ragged")
+                                             ptr(self.dloss_ragged), rows, K, min(int(n_items), b.capacity), st),
+              "smlvm_sparsemax_bwd_ragged")
         mark(None)
         return b.total
 
     def algorithmic_bytes(self, total_nnz):
         r, K, N_ = self.base.rows, self.base.cols, total_nnz
-        d = self.base.algorithmic_bytes(total_nnz)
+        rr = r
+        d = {"sparsemax_fwd": rr * (8 * K + 4 + 4 + 4 + 8 + (64 if self.base.use_slots else 0)), "scan_counts": rr * 12,
+             "compact_fill": (rr * (64 + 16) if self.base.use_slots else rr * (4 * K + 8)) + 12 * N_}
         return {"sparsemax_fwd": d["sparsemax_fwd"], "scan_counts": d["scan_counts"], "compact_fill": d["compact_fill"],
                 "wloss_ragged_fwd": 8 * N_ + 4,
                 "sparsemax_bwd_ragged": 4 * r * K + r * (8 + 4 + 4) + N_ * (4 + 4 + 4 + 4)}

@@ -86,7 +86,8 @@ def sparsemax_bwd_ragged(comp, supp, shape, dp=None, loss=None, loss_scale=None,
     dent = None if dent is None else _f32c(dent, "dent")
     check(lib.smlvm_sparsemax_bwd_ragged(ptr(comp["offsets"]), ptr(comp["cols"]), ptr(comp["vals"]), ptr(supp),
                                          ptr(dp), ptr(loss), ptr(loss_scale), float(loss_scale_host), ptr(dent),
-                                         ptr(dx), ptr(dloss), rows, K, stream()), "smlvm_sparsemax_bwd_ragged")
+                                         ptr(dx), ptr(dloss), rows, K, comp["vals"].numel(), stream()),
+          "smlvm_sparsemax_bwd_ragged")
     return (dx, dloss) if want_dloss else dx
 
 
@@ -174,7 +175,7 @@ def compact_fill(p, offsets, total, want_vals=True, want_rows=True, want_cols=Tr
     vals = torch.empty(total, dtype=torch.float32, device=dev) if want_vals else None
     ri = torch.empty(total, dtype=torch.int32, device=dev) if want_rows else None
     ci = torch.empty(total, dtype=torch.int32, device=dev) if want_cols else None
-    check(lib.smlvm_compact_fill(ptr(p), ptr(offsets), ptr(slots), ptr(vals), ptr(ri), ptr(ci), rows, K,
+    check(lib.smlvm_compact_fill(ptr(p), ptr(offsets), ptr(slots), ptr(vals), ptr(ri), ptr(ci), rows, K, int(total),
                                  stream()), "smlvm_compact_fill")
     return vals, ri, ci
 

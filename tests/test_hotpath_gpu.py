@@ -113,9 +113,10 @@ def test_compaction_branch_on_side_stream_matches_serial():
     x = torch.randn(rows, K, generator=g).cuda()
     L = torch.rand(rows, K, generator=g).cuda()
     nnz = hotpath.SparsemaxMargStep.size_capacity(x)
-    serial = hotpath.SparsemaxMargStep(rows, K, x.device, nnz + 64, entropy_coeff=0.7, overlap_compaction=False)
-    forked = hotpath.SparsemaxMargStep(rows, K, x.device, nnz + 64, entropy_coeff=0.7)
-    assert serial.side is None and forked.side is not None
+    serial = hotpath.SparsemaxMargStep(rows, K, x.device, nnz + 64, entropy_coeff=0.7, overlap_compaction=False,
+                                       fused=False)
+    forked = hotpath.SparsemaxMargStep(rows, K, x.device, nnz + 64, entropy_coeff=0.7, fused=False)
+    assert serial.side is None and forked.side is not None and not forked.fused
     serial.run(x, L)
     names = ("p", "offsets", "dx", "dloss", "row_loss", "total")
 
@@ -139,3 +140,68 @@ def test_compaction_branch_on_side_stream_matches_serial():
     graph.replay()
     graph.replay()
     same()
+
+
+@pytest.mark.parametrize("rows,K,scale", [(8192, 128, 1.0), (8192, 64, 0.5), (4096 + 17, 32, 1.0), (65536, 128, 1.0)])
+def test_fused_step_equals_separate_kernels(rows, K, scale):
+    """smlvm_marg_step_fused (loss + lists + gradients in one launch behind the scan) against the three separate
+    kernels: row losses, lists, dX and dL bit-equal (same arithmetic in the same order), the fp64-accumulated total
+    to one fp32 ulp (another partition of the same sum); rows whose support does not fit the slots included."""
+    from lvmhelpers import hotpath
+    g = torch.Generator().manual_seed(rows + K)
+    x = (torch.randn(rows, K, generator=g) * scale).cuda()
+    x[5] = 0.0                      # a constant row: K non-zeros, does not fit the slots
+    x[rows - 1, :20] = 3.0          # 20 tied maxima
+    L = (torch.rand(rows, K, generator=g) * 3).cuda()
+    nnz = hotpath.SparsemaxMargStep.size_capacity(x)
+    a = hotpath.SparsemaxMargStep(rows, K, x.device, nnz + 64, entropy_coeff=0.7, use_slots=True, fused=False,
+                                  overlap_compaction=False)
+    b = hotpath.SparsemaxMargStep(rows, K, x.device, nnz + 64, entropy_coeff=0.7, use_slots=True)
+    assert b.fused and not a.fused and b.kernels == ("sparsemax_fwd", "scan_counts", "marg_step_fused")
+    a.run(x, L); b.run(x, L)
+    torch.cuda.synchronize()
+    for nme in ("p", "offsets", "dx", "dloss", "row_loss"):
+        assert torch.equal(getattr(a, nme), getattr(b, nme)), nme
+    for nme in ("vals", "ri", "ci"):
+        assert torch.equal(getattr(a, nme)[:nnz], getattr(b, nme)[:nnz]), nme
+    assert abs(a.total.item() - b.total.item()) <= 2e-7 * max(1.0, abs(a.total.item()))
+    assert not b.overflowed()
+    # as a CUDA-graph replay
+    graph = b.capture(x, L)
+    for nme in ("dx", "dloss", "row_loss", "vals", "ri", "ci"):
+        getattr(b, nme).zero_()
+    graph.replay(); graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(a.dx, b.dx) and torch.equal(a.ri[:nnz], b.ri[:nnz])
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_capacity_overflow_is_clamped_and_reported(fused):
+    """A batch with more non-zeros than the pre-allocated capacity: nothing is written past the lists (guard words
+    behind them stay intact), loss and gradients are unaffected, overflowed() says so."""
+    from lvmhelpers import hotpath
+    rows, K = 8192, 128
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(rows, K, generator=g).cuda()
+    L = (torch.rand(rows, K, generator=g) * 3).cuda()
+    nnz = hotpath.SparsemaxMargStep.size_capacity(x)
+    ref = hotpath.SparsemaxMargStep(rows, K, x.device, nnz + 64, entropy_coeff=1.0, use_slots=True, fused=fused)
+    ref.run(x, L)
+    cap = nnz // 2
+    small = hotpath.SparsemaxMargStep(rows, K, x.device, cap + 256, entropy_coeff=1.0, use_slots=True, fused=fused)
+    small.capacity = cap                      # the last 256 entries of each list are guard words
+    for t in (small.vals, small.ri, small.ci):
+        t[cap:] = 12345
+    small.run(x, L)
+    torch.cuda.synchronize()
+    assert small.overflowed() and not ref.overflowed()
+    for t in (small.vals, small.ri, small.ci):
+        assert (t[cap:] == 12345).all()
+    assert torch.equal(small.ri[:cap], ref.ri[:cap]) and torch.equal(small.ci[:cap], ref.ci[:cap])
+    assert torch.equal(small.dx, ref.dx) and torch.equal(small.total, ref.total)
+    # the ragged consumers never read past the lists either
+    cs = hotpath.SparsemaxMargCompactStep(rows, K, x.device, cap + 256, entropy_coeff=1.0)
+    cs.base.capacity = cap
+    cs.run(x, torch.rand(cap + 256, device=x.device), nnz)      # caller claims nnz items: clamped to the capacity
+    torch.cuda.synchronize()
+    assert torch.isfinite(cs.base.dx).all()
