@@ -331,8 +331,7 @@ def small_config_latency(device):
     def topk_step():
         xb.grad = None
         _, distr, ent = wrap(xb)
-        vals = distr._smlvm_vals
-        (ops.ragged_loss(vals, cl[:vals.numel()], 1.0 / 64) - ent).backward()
+        (torch.dot(distr.view(-1), cl) * (1.0 / 64) - ent).backward()   # (p . loss) / B - entropy, structmarg.py:140-142
 
     def smap_step(kind, budget):
         def f():
@@ -399,37 +398,106 @@ def extra_paths(args, world, device, rank):
                     for k in dur}}
     del cstep, xc, lr
 
-    # (e) the one collective the path has in training: the sum-all-reduce of the wrapped encoder's parameter
-    # gradients (lvmhelpers/dist.py::GradAllReducer over NCCL), launched asynchronously behind the sharded step.
-    # A dummy Linear(cols, cols) encoder feeds the categorical step; rows sharded, losses scaled by 1 / B_global.
+    # (e) the one collective the path has in training: the all-reduce of the wrapped encoder's parameter gradients
+    # (lvmhelpers/dist.py::GradAllReducer over NCCL).  The encoder is the bit-vector VAE's inference net shape,
+    # Linear(784, 128) -> ReLU -> Linear(128, n) (experiments/bit_vector-vae/train.py:56-60), feeding the sharded
+    # categorical step; rows sharded, losses scaled by 1 / B_global.  Three timings: no collective, all-reduce
+    # launched after backward, all-reduce launched from backward's own hooks (the last layer's bucket goes out
+    # while the first layer's gradients are still being computed).
     from lvmhelpers.dist import GradAllReducer
     erow = min(args.rows, 262144)
-    enc = torch.nn.Linear(args.cols, args.cols).to(device)
+    enc = torch.nn.Sequential(torch.nn.Linear(784, 128), torch.nn.ReLU(), torch.nn.Linear(128, args.cols)).to(device)
     with torch.no_grad():
-        for prm in enc.parameters():     # same weights on every rank
-            prm.copy_(torch.randn(prm.shape, generator=torch.Generator().manual_seed(5)) * 0.1)
-    einp = torch.randn(erow, args.cols, generator=g).to(device)
+        for i, prm in enumerate(enc.parameters()):     # same weights on every rank
+            prm.copy_(torch.randn(prm.shape, generator=torch.Generator().manual_seed(5 + i)) * 0.05)
+    einp = torch.randn(erow, 784, generator=g).to(device)
     eloss = (torch.rand(erow, args.cols, generator=g) * 3).to(device)
-    estep = SparsemaxMargStep(erow, args.cols, device, 6 * erow, entropy_coeff=1.0, global_rows=erow * world)
-    reducer = GradAllReducer(enc.parameters())
+    estep = SparsemaxMargStep(erow, args.cols, device, 8 * erow, entropy_coeff=1.0, global_rows=erow * world,
+                              use_slots=True)
+    reducer = GradAllReducer(enc.parameters(), bucket_bytes=1 << 17)     # two buckets: one per layer
 
-    def enc_step(reduce):
+    def enc_step(mode):
         enc.zero_grad(set_to_none=True)
         scores = enc(einp)
         estep.run(scores.detach(), eloss)
         scores.backward(estep.dx)
-        if reduce:
+        if mode == "after":
             reducer.start()
+        if mode != "none":
             reducer.finish()
 
-    ms_local, _, _ = timed(lambda: enc_step(False), 10, 3, world, device)
-    ms_red, _, _ = timed(lambda: enc_step(True), 10, 3, world, device)
+    ms_local, _, _ = timed(lambda: enc_step("none"), 10, 3, world, device)
+    ms_red, _, _ = timed(lambda: enc_step("after"), 10, 3, world, device)
+    reducer.attach()
+    ms_hook, _, _ = timed(lambda: enc_step("hooks"), 10, 3, world, device)
+    reducer.detach()
     out["sharded_step_with_encoder_allreduce"] = {
-        "rows_per_gpu": erow, "encoder": "Linear(%d, %d), fp32" % (args.cols, args.cols),
-        "allreduce_bytes": sum(prm.numel() * 4 for prm in enc.parameters()), "backend": "nccl" if world > 1 else "none",
-        "ms_per_step_without_allreduce": ms_local / 10, "ms_per_step": ms_red / 10,
-        "value": erow * world / (ms_red / 10 * 1e-3), "unit": UNIT}
-    del estep, einp, eloss
+        "rows_per_gpu": erow, "encoder": "Linear(784, 128) -> ReLU -> Linear(128, %d), fp32" % args.cols,
+        "allreduce_bytes": sum(prm.numel() * 4 for prm in enc.parameters()), "buckets": len(reducer.buckets),
+        "backend": "nccl" if world > 1 else "none (1 rank: the reducer is a no-op)",
+        "ms_per_step_without_allreduce": ms_local / 10, "ms_per_step_allreduce_after_backward": ms_red / 10,
+        "ms_per_step": ms_hook / 10,
+        "note": "ms_per_step = all-reduce launched from backward hooks (overlapped)",
+        "value": erow * world / (ms_hook / 10 * 1e-3), "unit": UNIT}
+    del estep, einp, eloss, enc
+
+    # multi-rank correctness on the GPU: per-rank partial losses with 1 / B_global SUM (NCCL all-reduce) to the
+    # single-process CPU loss over the concatenated shards (rank 0 regenerates every shard from its seed)
+    if world > 1:
+        from lvmhelpers.dist import allreduce_stats
+        crow_chk = 8192
+        xk, lk = make_inputs(crow_chk, args.cols, 900 + rank)
+        kstep = SparsemaxMargStep(crow_chk, args.cols, device, 8 * crow_chk, entropy_coeff=1.0,
+                                  global_rows=crow_chk * world, use_slots=True)
+        part = kstep.run(xk.to(device), lk.to(device))
+        tot = allreduce_stats({"loss": part, "nnz": kstep.nnz.sum()})
+        if rank == 0:
+            import oracle
+            xs, ls = zip(*[make_inputs(crow_chk, args.cols, 900 + r) for r in range(world)])
+            Pc, _ = oracle.sparsemax_fwd(torch.cat(xs))
+            ref_loss = float((Pc * torch.cat(ls)).sum(-1).mean())
+            out.setdefault("_parity", {})["rank_sum"] = {
+                "ranks": world, "rows_per_rank": crow_chk, "loss_sum_over_ranks": tot["loss"], "loss_single_process_cpu": ref_loss,
+                "support_total_equal": int(tot["nnz"]) == int((Pc > 0).sum()),
+                "ok": bool(abs(tot["loss"] - ref_loss) <= 1e-5 and int(tot["nnz"]) == int((Pc > 0).sum()))}
+        del kstep
+
+    # the work of the categorical step depends on the score scale (support size).  The contract line is
+    # N(0,1) scores (support 3.5 of 128); here the same step at scales 0.3 / 0.1 / 3 and at the signal game's regime
+    # (K = 256, scores / tau_s = 10 -> scale 0.1, experiments/signal-game/archs.py:42), per kernel, plus a batch sweep.
+    def categorical_variant(vrows, K, scale, steps=10):
+        gv = torch.Generator().manual_seed(77)
+        xv = (torch.randn(vrows, K, generator=gv) * scale).to(device)
+        lv = (torch.rand(vrows, K, generator=gv) * 3).to(device)
+        nn_ = SparsemaxMargStep.size_capacity(xv)
+        stp = SparsemaxMargStep(vrows, K, device, nn_ + 1024, entropy_coeff=1.0)
+        mk = []
+
+        def rec_v(name):
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            mk.append((name, ev))
+
+        msv, _, _ = timed(lambda: stp.run(xv, lv, rec_v), steps, 3, world, device)
+        per = len(stp.kernels) + 1
+        mk = mk[3 * per:]
+        dv = {k: 0.0 for k in stp.kernels}
+        for i in range(len(mk) - 1):
+            if mk[i][0] is not None:
+                dv[mk[i][0]] += mk[i][1].elapsed_time(mk[i + 1][1]) / steps
+        abv = stp.algorithmic_bytes(nn_)
+        pk = measured_hbm_peak()[0]
+        return {"rows_per_gpu": vrows, "cols": K, "score_scale": scale, "support_mean": nn_ / vrows,
+                "support_slots": stp.use_slots, "ms_per_step": msv / steps, "value": vrows * world / (msv / steps * 1e-3),
+                "unit": UNIT, "step_frac": sum(abv.values()) / (msv / steps * 1e-3) / 1e9 / pk,
+                "kernels": {k: {"ms": dv[k], "frac": abv[k] / (dv[k] * 1e-3) / 1e9 / pk if dv[k] > 0 else None} for k in dv}}
+
+    out["score_scale_variants"] = [categorical_variant(args.rows, args.cols, sc) for sc in (3.0, 0.3, 0.1)]
+    out["signal_game_regime_K256"] = categorical_variant(min(args.rows, 262144), 256, 0.1)
+    if rank == 0 and world == 1:
+        out["batch_sweep"] = [{k: v for k, v in categorical_variant(b, args.cols, 1.0, steps=20).items()
+                               if k in ("rows_per_gpu", "ms_per_step", "value", "step_frac")}
+                              for b in (4096, 16384, 65536, 262144) if b <= args.rows]
 
     rows = args.path_rows_topk
     x = torch.randn(rows, 128, generator=g).to(device).requires_grad_(True)
@@ -439,8 +507,7 @@ def extra_paths(args, world, device, rank):
     def topk_step():
         x.grad = None
         bits, distr, ent = wrap(x)
-        vals = distr._smlvm_vals
-        loss = ops.ragged_loss(vals, cand_loss[:vals.numel()], 1.0 / rows) - ent
+        loss = torch.dot(distr.view(-1), cand_loss) * (1.0 / rows) - ent   # (p . loss) / B - entropy, structmarg.py:140-142
         loss.backward()
 
     ms, _, _ = timed(topk_step, 5, 2, world, device)
@@ -685,7 +752,14 @@ def run_native(args, rank, local_rank, world):
                                  entropy_coeff=1.0, chunks=args.e2e_chunks)
     ms_e2e, _, _ = timed(lambda: pipe.run(x_pin, l_pin, dx_pin), e2e_steps, 3, world, device)
     loss_value = pipe.loss()
+    # the ceiling of an upload-bound step: a plain pinned-memory H2D copy of the same two inputs, nothing else
+    ms_copy, _, _ = timed(lambda: (x.copy_(x_pin, non_blocking=True), losses.copy_(l_pin, non_blocking=True)), 5, 2,
+                          world, device)
     e2e = {"value": rows * world / (ms_e2e / e2e_steps * 1e-3), "unit": UNIT,
+           "h2d_gbs_achieved_per_rank": pipe.h2d_bytes / (ms_e2e / e2e_steps * 1e-3) / 1e9,
+           "h2d_gbs_plain_pinned_copy_per_rank": pipe.h2d_bytes / (ms_copy / 5 * 1e-3) / 1e9,
+           "bound": "PCIe / host memory: every rank uploads 2 x rows x K x 4 B per step; all ranks of a box share "
+                    "the host's DRAM and PCIe root complexes, so e2e scales with host bandwidth, not with GPUs",
            "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
            "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
            "api": "lvmhelpers.hotpath.HostPipelinedMargStep.run over pinned host buffers, "
@@ -713,7 +787,10 @@ def run_native(args, rank, local_rank, world):
             parity.update(paths.pop("_parity", {}))
         parity["ok"] = all(v.get("ok", False) for v in parity.values() if isinstance(v, dict))
     elif paths is not None:
-        paths.pop("_parity", None)
+        extra_par = paths.pop("_parity", None)
+        if rank == 0 and extra_par:
+            parity = dict(extra_par)
+            parity["ok"] = all(v.get("ok", False) for v in parity.values() if isinstance(v, dict))
 
     if rank == 0:
         line = {

@@ -183,6 +183,23 @@ int smlvm_bits_score_fwd(const uint32_t* bits, const float* x, float* scores_k, 
 /* dx[rows,n] = sum_k dscores_k[r,k] * bits[r,k,j]  (autograd of the einsum w.r.t. scores)   */
 int smlvm_bits_score_bwd(const uint32_t* bits, const float* dscores_k, float* dx, int64_t rows,
                          int32_t n, int32_t k, void* stream);
+/* Sparsemax over the k <= 16 re-scored candidates of every row, with what the callers take from it:
+ *   distr[rows,k]  = entmax.sparsemax(scores_k, dim=-1)                       lvmhelpers/structmarg.py:48
+ *   supp_size, nnz [rows] int32 (NULL to skip), row_entropy[rows] = -sum_{p>0} p log p (NULL to skip)
+ *   entropy_total[0] = scale * sum_r row_entropy[r]  (fp64, fixed order; NULL to skip): the structured entropy
+ *                      -(distr[mask] @ log distr[mask]) / B of structmarg.py:51-58 with scale = 1 / B
+ * workspace: smlvm_reduce_workspace_bytes().  SMLVM_ERR_UNSUPPORTED for k > 16 (use smlvm_sparsemax_fwd). */
+int smlvm_ksparsemax_fwd(const float* scores_k, float* distr, int32_t* supp_size, int32_t* nnz,
+                         float* row_entropy, float* entropy_total, float scale, int64_t rows, int32_t k,
+                         void* workspace, size_t workspace_bytes, void* stream);
+/* Backward of the two above and of smlvm_bits_score_fwd in one launch:
+ *   g_j  = ddistr[r,j] - dentropy_total[0] * scale * (log p_j + 1)   on the support (either source may be NULL)
+ *   ds   = where(p != 0, g - sum_{p != 0} g / supp_size, 0)           SparsemaxFunction.backward over the k candidates
+ *   dx[r,c] = sum_j ds_j * bits[r,j,c]                                autograd of the einsum, structmarg.py:47
+ * Needs k <= 16, n % 8 == 0 and a 16-byte aligned dx (else SMLVM_ERR_UNSUPPORTED: compose the separate calls). */
+int smlvm_topk_sparsemax_bwd(const uint32_t* bits, const float* distr, const int32_t* supp_size,
+                             const float* ddistr, const float* dentropy_total, float scale, float* dx,
+                             int64_t rows, int32_t n, int32_t k, void* stream);
 /* out[n_out,n] fp32 {0,1} = the n bits of packed row index[e] of bits[*,W] (index NULL: row e).
  * replaces: `bit_vector_z.view(-1, n)[mask]` lvmhelpers/structmarg.py:116-126 (with index = the
  * compacted candidate ids of smlvm_compact_fill) without materialising the dense [B,k,n] tensor. */

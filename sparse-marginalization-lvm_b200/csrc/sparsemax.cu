@@ -629,11 +629,14 @@ extern "C" int smlvm_sparsemax_fwd(const float* x, float* p, int32_t* supp_size,
         int N = 2048;
         while (N < cols) N <<= 1;
         size_t smem = (size_t)N * 8 + (kWideThreads + 32) * sizeof(double);
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(sparsemax_fwd_wide, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 8192 * 8 + (kWideThreads + 32) * (int)sizeof(double));
-            attr_set = true;
+        static bool attr_set_dev[64] = {false};   // function attributes are per device
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!attr_set_dev[dev & 63]) {
+            cudaError_t ea = cudaFuncSetAttribute(sparsemax_fwd_wide, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  8192 * 8 + (kWideThreads + 32) * (int)sizeof(double));
+            if (ea != cudaSuccess) return (int)ea;
+            attr_set_dev[dev & 63] = true;
         }
         int64_t cap = (int64_t)device_sm_count() * 8;
         int grid = (int)(rows < cap ? rows : cap);

@@ -34,6 +34,7 @@
 
 #include "common.cuh"
 #include "sparsemax_exact.cuh"
+#include "sparsemax_list.cuh"
 #include "tile_ptx.cuh"
 
 namespace smlvm {
@@ -41,28 +42,6 @@ namespace smlvm {
 constexpr int kCap = 32;        // candidate-list entries per row
 constexpr int kSupportSlots = SMLVM_SUPPORT_SLOTS;
 constexpr int kMaxPasses = 3;   // bound-tightening passes before a row is treated as wide
-
-// Descending bitonic network over a register array (compile-time indices, no divergence).
-template <int N>
-__device__ __forceinline__ void sort_desc_regs(float (&v)[N])
-{
-#pragma unroll
-    for (int k = 2; k <= N; k <<= 1) {
-#pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                const int l = i ^ j;
-                if (l > i) {
-                    const bool desc = (i & k) == 0;
-                    const float hi = fmaxf(v[i], v[l]), lo = fminf(v[i], v[l]);
-                    v[i] = desc ? hi : lo;
-                    v[l] = desc ? lo : hi;
-                }
-            }
-        }
-    }
-}
 
 // per-warp shared memory of the tile kernel
 template <int K, int S>
@@ -132,47 +111,6 @@ __device__ __forceinline__ void warp_row_exact(float* srow, int lane, int& k_out
     h_out = group_sum<32>(h);
 }
 
-
-// (k, tau) of the reference from the candidate list of one row (thread-private column `lv` of
-// the [slot][lane] shared-memory list, n <= N entries): the candidates are loaded into
-// registers, sorted descending by a bitonic network (compile-time indices, no divergence) and
-// the reference's own support test is evaluated position by position -- fp64 cumulative sum in
-// sorted order, C_r = fl32(fl32(cumsum_r) - 1), support where fl32(r * S_r) > C_r, k = number
-// of such r, tau = C_k / k.  Padding is -inf: it sorts last and fails the test.
-template <int N>
-__device__ __forceinline__ void list_threshold(const float* lv, int n, int& k_out, float& tau_out)
-{
-    float v[N];
-#pragma unroll
-    for (int j = 0; j < N; ++j) v[j] = (j < n) ? lv[j * 32] : -CUDART_INF_F;
-    sort_desc_regs<N>(v);
-    double cs = 0.0;
-    float c_last = -1.f;
-    int kk = 0, last_true = -1;
-#pragma unroll
-    for (int r = 0; r < N; ++r) {
-        cs += (double)v[r];
-        const float C = __fsub_rn((float)cs, 1.0f);
-        if (__fmul_rn((float)(r + 1), v[r]) > C) {
-            ++kk;
-            c_last = C;
-            last_true = r;
-        }
-    }
-    if (__any_sync(kFull, last_true + 1 != kk && kk > 0)) {
-        // trues not contiguous (rounding): the reference takes C at index k, not at the last true
-        if (last_true + 1 != kk && kk > 0) {
-            cs = 0.0;
-#pragma unroll
-            for (int r = 0; r < N; ++r)
-                if (r < kk) cs += (double)v[r];
-            c_last = __fsub_rn((float)cs, 1.0f);
-        }
-    }
-    kk = max(kk, 1);
-    k_out = kk;
-    tau_out = __fdiv_rn(c_last, (float)kk);
-}
 
 template <int K, int S, int W>
 __global__ void __launch_bounds__(W * 32, 1)

@@ -42,6 +42,8 @@ _PROTOTYPES = {
     "smlvm_topk_bits": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     "smlvm_bits_score_fwd": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     "smlvm_bits_score_bwd": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp]),
+    "smlvm_ksparsemax_fwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _i32, _vp, _sz, _vp]),
+    "smlvm_topk_sparsemax_bwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _f32, _vp, _i64, _i32, _i32, _vp]),
     "smlvm_bits_expand": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _vp]),
     "smlvm_gather_rows": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
     "smlvm_sparsemap_capacity": (_i32, [_i32]),
@@ -113,10 +115,18 @@ def stream():
 
 
 def require_cuda(t, name):
+    """Every op funnels its primary operand through here: CUDA tensors only, and on the CURRENT device -- the
+    kernels are launched on the current device's stream, so an operand of another GPU would be read by the wrong
+    device (or fault without peer access).  Wrap the call in ``torch.cuda.device(t.device)``."""
     if not t.is_cuda:
         raise RuntimeError(
             "%s must live on a CUDA device: the sparse-marginalization path has no CPU "
             "implementation (got device=%s)" % (name, t.device))
+    cur = _cur_device() if _cur_device is not None else torch.cuda.current_device()
+    if t.device.index != cur:
+        raise RuntimeError(
+            "%s lives on %s but the current CUDA device is cuda:%d: the kernels launch on the current device's "
+            "stream -- wrap the call in `with torch.cuda.device(%r):`" % (name, t.device, cur, str(t.device)))
 
 
 # A small cache of zero-initialised reduction / scan workspaces per (device, stream).

@@ -47,19 +47,32 @@ def to_global_rows(local_idx, rank, world_size, global_rows):
 
 
 class GradAllReducer:
-    """Sum-all-reduce of parameter gradients in flat buckets, launched asynchronously so the
-    collective overlaps whatever the caller does next (the decoder's backward in training).
+    """All-reduce of parameter gradients in flat buckets, launched asynchronously so the collective overlaps
+    whatever runs next.
 
-    Buckets are sized for launch latency, not link count (NVSwitch gives every GPU full
-    bandwidth to every peer): one bucket of up to ``bucket_bytes`` per all-reduce.
+    Buckets are sized for launch latency, not link count (NVSwitch gives every GPU full bandwidth to every
+    peer): one bucket of up to ``bucket_bytes`` per all-reduce, in REVERSE parameter order (the order in which
+    backward produces the gradients).
+
+    ``average``: which 1/B the sharded losses carry.
+      * ``False`` (sum): every rank scaled its loss by 1/B_GLOBAL (``hotpath.SparsemaxMargStep(global_rows=...)``,
+        ``loss_scale``) -- summed gradients are the single-process gradients.
+      * ``True`` (mean): every rank used its LOCAL 1/B, which is what the reference-API wrappers ``Marginalizer``,
+        ``TopKSparsemaxMarg`` and ``SparseMAPMarg`` hard-code (marg.py:126, structmarg.py:140,242).  With equal
+        shards the mean over ranks is the single-process gradient (the DDP convention).
+
+    ``attach()`` registers post-accumulate hooks: a bucket's all-reduce is launched from inside ``backward()`` the
+    moment its last gradient has been written, so it runs under the rest of the backward pass; ``finish()`` then
+    only waits.  Without ``attach()``, call ``start()`` after backward.
     """
 
-    def __init__(self, params, bucket_bytes=64 << 20, group=None):
+    def __init__(self, params, bucket_bytes=64 << 20, group=None, average=False):
         self.params = [p for p in params if p.requires_grad]
         self.group = group
+        self.average = bool(average)
         self.buckets = []
         cur, size = [], 0
-        for p in self.params:
+        for p in reversed(self.params):
             nbytes = p.numel() * p.element_size()
             if cur and (size + nbytes > bucket_bytes or p.dtype != cur[0].dtype or p.device != cur[0].device):
                 self.buckets.append(cur)
@@ -69,6 +82,13 @@ class GradAllReducer:
         if cur:
             self.buckets.append(cur)
         self._pending = []
+        self._hooks = []
+        self._ready = None
+
+    def _launch(self, bucket):
+        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in bucket])
+        work = td.all_reduce(flat, op=td.ReduceOp.SUM, group=self.group, async_op=True)
+        self._pending.append((bucket, flat, work))
 
     def start(self):
         """Flatten + launch one async all-reduce per bucket.  Gradients that are None count as 0."""
@@ -77,16 +97,42 @@ class GradAllReducer:
         if ws == 1:
             return self
         for bucket in self.buckets:
-            flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1)
-                              for p in bucket])
-            work = td.all_reduce(flat, op=td.ReduceOp.SUM, group=self.group, async_op=True)
-            self._pending.append((bucket, flat, work))
+            self._launch(bucket)
         return self
+
+    def attach(self):
+        """Launch each bucket from backward itself (``register_post_accumulate_grad_hook``)."""
+        if self._hooks:
+            return self
+        self._ready = [0] * len(self.buckets)
+        where = {id(p): bi for bi, b in enumerate(self.buckets) for p in b}
+
+        def hook(p):
+            _, ws = world()
+            if ws == 1:
+                return
+            bi = where[id(p)]
+            self._ready[bi] += 1
+            if self._ready[bi] == len(self.buckets[bi]):
+                self._ready[bi] = 0
+                self._launch(self.buckets[bi])
+
+        for p in self.params:
+            self._hooks.append(p.register_post_accumulate_grad_hook(hook))
+        return self
+
+    def detach(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
 
     def finish(self):
         """Wait and scatter the reduced buckets back into ``.grad``."""
+        _, ws = world()
         for bucket, flat, work in self._pending:
             work.wait()
+            if self.average:
+                flat.div_(ws)
             off = 0
             for p in bucket:
                 n = p.numel()

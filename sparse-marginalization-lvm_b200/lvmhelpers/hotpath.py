@@ -92,6 +92,9 @@ class SparsemaxMargStep:
         backward kernels.  ``rec(name)`` (optional) is called before and after each launch so that a
         caller can bracket the kernels with CUDA events; the launches are then serial on the current
         stream."""
+        N.require_cuda(x, "scores")      # also: on the current device (the launches go to its stream)
+        if x.device != self.p.device or losses.device != self.p.device:
+            raise RuntimeError("SparsemaxMargStep was built for %s, got inputs on %s / %s" % (self.p.device, x.device, losses.device))
         fork = rec is None and self.side is not None and not self.fused
         cur = torch.cuda.current_stream() if fork else None
         st = cur.cuda_stream if fork else N.stream()

@@ -379,6 +379,62 @@ def bits_score(x, bits):
     return _BitsScore.apply(_f32c(x, "scores"), bits)
 
 
+KSPARSEMAX_MAX_K = 16
+
+
+class _TopKSparsemax(torch.autograd.Function):
+    """scores [B, n] -> (distr [B, k], structured entropy / B, packed candidates, ...) for k <= 16 and n % 8 == 0:
+    k-best search, re-scoring, sparsemax over k with the entropy -- three launches, no host read, no support
+    compaction (structmarg.py:38-58); backward ONE launch (``smlvm_topk_sparsemax_bwd``)."""
+
+    @staticmethod
+    def forward(ctx, scores, k, want_configs):
+        rows, n = scores.shape
+        dev = scores.device
+        cfg, bits, _ = topk_bits(scores, k, want_configs=want_configs, want_bits=True)
+        sk = torch.empty((rows, k), dtype=torch.float32, device=dev)
+        check(lib.smlvm_bits_score_fwd(ptr(bits), ptr(scores), ptr(sk), rows, n, k, stream()), "smlvm_bits_score_fwd")
+        distr = torch.empty_like(sk)
+        supp = torch.empty(rows, dtype=torch.int32, device=dev)
+        nnz = torch.empty(rows, dtype=torch.int32, device=dev)
+        ent = torch.empty((), dtype=torch.float32, device=dev)
+        ws = N.reduce_workspace(dev)
+        scale = 1.0 / rows
+        check(lib.smlvm_ksparsemax_fwd(ptr(sk), ptr(distr), ptr(supp), ptr(nnz), None, ptr(ent), scale, rows, k,
+                                       ptr(ws), ws.numel(), stream()), "smlvm_ksparsemax_fwd")
+        ctx.save_for_backward(bits, distr, supp)
+        ctx.n, ctx.scale = n, scale
+        if cfg is None:
+            cfg = torch.empty(0, device=dev)
+        ctx.mark_non_differentiable(bits, cfg, nnz, supp)
+        ctx.set_materialize_grads(False)
+        return distr, ent, bits, cfg, nnz, supp
+
+    @staticmethod
+    def backward(ctx, ddistr, dent, _db, _dc, _dn, _ds):
+        bits, distr, supp = ctx.saved_tensors
+        rows, k = distr.shape
+        dx = torch.empty((rows, ctx.n), dtype=torch.float32, device=distr.device)
+        if ddistr is None and dent is None:
+            return dx.zero_(), None, None
+        ddistr = None if ddistr is None else ddistr.contiguous().float()
+        dent = None if dent is None else dent.contiguous().float()
+        check(lib.smlvm_topk_sparsemax_bwd(ptr(bits), ptr(distr), ptr(supp), ptr(ddistr), ptr(dent), ctx.scale, ptr(dx),
+                                           rows, ctx.n, k, stream()), "smlvm_topk_sparsemax_bwd")
+        return dx, None, None
+
+
+def topk_sparsemax_supported(n, k):
+    return 2 <= k <= KSPARSEMAX_MAX_K and n % 8 == 0
+
+
+def topk_sparsemax(scores, k, want_configs=False):
+    """(distr [B,k], entropy scalar, bits [B,k,W] int32, configs [B,k,n] | None, nnz [B] int32, supp [B] int32)."""
+    scores = _f32c(scores, "scores")
+    distr, ent, bits, cfg, nnz, supp = _TopKSparsemax.apply(scores, int(k), bool(want_configs))
+    return distr, ent, bits, (cfg if want_configs else None), nnz, supp
+
+
 class _GatherRows(torch.autograd.Function):
     @staticmethod
     def forward(ctx, src, idx):

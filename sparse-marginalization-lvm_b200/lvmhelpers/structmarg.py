@@ -95,7 +95,15 @@ class TopKSparsemaxWrapper(nn.Module):
     def forward(self, *args, **kwargs):
         scores = self.agent(*args, **kwargs)
         batch_size, latent_size = scores.shape
-        # the top-k bit-vectors (detached, as the numpy round trip of structmarg.py:43)
+        if ops.topk_sparsemax_supported(latent_size, self.k):
+            # k-best search (detached, as the numpy round trip of structmarg.py:43), re-scoring (:47), sparsemax over
+            # k (:48) and the entropy over the support (:51-58): three launches, no host read.  The support
+            # compaction the reference needs further down (TopKSparsemaxMarg, :116-126) is built there, on demand.
+            distr, entropy_distr, bits, cfg, nnz, _ = ops.topk_sparsemax(scores, self.k, want_configs=not self.packed_output)
+            bit_vector_z = PackedBitVectors(bits, latent_size) if self.packed_output else cfg
+            distr._smlvm_nnz = nnz
+            return bit_vector_z, distr, entropy_distr
+        # general shapes (k > 16 or n % 8 != 0): the separate kernels
         bit_vector_z, bits, _ = ops.topk_bits(scores.detach(), self.k, want_configs=not self.packed_output)
         if self.packed_output:
             bit_vector_z = PackedBitVectors(bits, latent_size)
@@ -145,7 +153,7 @@ class TopKSparsemaxMarg(torch.nn.Module):
         # support compaction (:116-126): row-major order of encoder_probs > 0
         comp = getattr(encoder_probs, "_smlvm_compact", None)
         if comp is None:
-            comp = _compact_with_flat(encoder_probs, None)
+            comp = _compact_with_flat(encoder_probs, getattr(encoder_probs, "_smlvm_nnz", None))
             encoder_probs_flat = _CompactValues.apply(encoder_probs, comp)
         else:
             encoder_probs_flat = encoder_probs._smlvm_vals

@@ -95,3 +95,45 @@ def test_grad_allreducer_single_process_is_identity():
     GradAllReducer(m.parameters())()
     assert all(torch.equal(a, p.grad) for a, p in zip(before, m.parameters()))
     assert allreduce_stats({"a": 2.0}) == {"a": 2.0}
+
+
+def _worker_mean_hooks(rank, ws, port, rows, out_path):
+    """Local 1/B on every rank (what the reference-API wrappers hard-code), mean all-reduce launched from backward."""
+    for p in (ROOT, os.path.join(ROOT, "sparse-marginalization-lvm_b200")):
+        sys.path.insert(0, p)
+    import oracle
+    from lvmhelpers.dist import shard_bounds, GradAllReducer
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    td.init_process_group("gloo", rank=rank, world_size=ws)
+    try:
+        g = torch.Generator().manual_seed(0)
+        x, L = torch.randn(rows, 12, generator=g), torch.rand(rows, 10, generator=g) * 3
+        a, b = shard_bounds(rows, rank, ws)
+        model = _model(1)
+        red = GradAllReducer(model.parameters(), bucket_bytes=512, average=True).attach()
+        launched = []
+        for step in range(2):                       # hooks survive across steps
+            model.zero_grad(set_to_none=True)
+            loss = _loss(model, x[a:b], L[a:b], 1.0 / (b - a), oracle)
+            loss.backward()
+            launched.append(len(red._pending))      # every bucket was launched from inside backward()
+            red.finish()
+        if rank == 0:
+            torch.save({"launched": launched, "buckets": len(red.buckets),
+                        "grads": [p.grad.clone() for p in model.parameters()]}, out_path)
+    finally:
+        td.destroy_process_group()
+
+
+def test_mean_allreduce_from_backward_hooks_matches_single_process(oracle, tmp_path):
+    rows = 64                                        # equal shards: the mean of local-1/B gradients is the global one
+    out = str(tmp_path / "r0.pt")
+    mp.spawn(_worker_mean_hooks, args=(2, _free_port(), rows, out), nprocs=2, join=True)
+    got = torch.load(out)
+    assert got["buckets"] >= 2 and got["launched"] == [got["buckets"]] * 2
+    g = torch.Generator().manual_seed(0)
+    x, L = torch.randn(rows, 12, generator=g), torch.rand(rows, 10, generator=g) * 3
+    model = _model(1)
+    _loss(model, x, L, 1.0 / rows, oracle).backward()
+    for ga, p in zip(got["grads"], model.parameters()):
+        assert torch.allclose(ga, p.grad, atol=1e-6)

@@ -225,3 +225,73 @@ def test_topk_marg_packed_candidates_equal_dense_path():
     for a, b in zip(g_packed, [p.grad for p in list(enc.parameters()) + list(dec.parameters())]):
         assert torch.equal(a, b)
     assert torch.equal(res["log"]["loss_output"], res2["log"]["loss_output"])
+
+
+@pytest.mark.parametrize("rows,k,scale", [(64, 10, 1.0), (5000, 10, 0.1), (5000, 16, 3.0), (333, 2, 1.0), (40000, 7, 0.3),
+                                          (1, 3, 1.0)])
+def test_ksparsemax_fwd_matches_oracle(oracle, rows, k, scale):
+    """smlvm_ksparsemax_fwd: sparsemax over the k <= 16 re-scored candidates (structmarg.py:48), bit-equal to the
+    oracle's restatement of entmax.sparsemax, with supp / nnz / entropy over the support (:51-58)."""
+    from lvmhelpers import ops, _native as N
+    g = torch.Generator().manual_seed(rows + k)
+    s = torch.randn(rows, k, generator=g) * scale
+    s[::5] = torch.round(s[::5] * 4) / 4          # exact ties
+    if rows > 10:
+        s[3] = 0.0                                # constant row
+        s[4, 0] = s[4, 1:].max() + 1.0            # gap of exactly 1
+        s[7, 1] = float("-inf")
+    P_ref, k_ref = oracle.sparsemax_fwd(s)
+    sk = s.cuda()
+    distr = torch.empty_like(sk)
+    supp = torch.empty(rows, dtype=torch.int32, device="cuda")
+    nnz = torch.empty(rows, dtype=torch.int32, device="cuda")
+    rent = torch.empty(rows, dtype=torch.float32, device="cuda")
+    tot = torch.empty((), dtype=torch.float32, device="cuda")
+    ws = N.reduce_workspace(sk.device)
+    N.check(N.lib.smlvm_ksparsemax_fwd(N.ptr(sk), N.ptr(distr), N.ptr(supp), N.ptr(nnz), N.ptr(rent), N.ptr(tot), 1.0 / rows,
+                                       rows, k, N.ptr(ws), ws.numel(), N.stream()), "smlvm_ksparsemax_fwd")
+    assert torch.equal(distr.cpu(), P_ref)
+    assert torch.equal(supp.cpu().long(), k_ref)
+    assert torch.equal(nnz.cpu().long(), (P_ref > 0).sum(-1))
+    pd = P_ref.double()
+    h_ref = -torch.where(pd > 0, pd * pd.clamp(min=1e-300).log(), torch.zeros_like(pd)).sum(-1)
+    assert (rent.cpu().double() - h_ref).abs().max().item() < 2e-6
+    assert abs(tot.item() - h_ref.sum().item() / rows) < 1e-5 * max(1.0, abs(h_ref.sum().item() / rows))
+
+
+@pytest.mark.parametrize("rows,n,k", [(64, 32, 10), (3000, 128, 10), (500, 40, 16), (20000, 64, 4), (100, 8, 2), (70, 96, 5)])
+def test_topk_sparsemax_fused_equals_composed(rows, n, k):
+    """ops.topk_sparsemax (k-best -> re-score -> k-sparsemax + entropy; backward in one launch) against the separate
+    kernels composed with autograd: same candidates, same distribution bits, gradients within 1e-6."""
+    from lvmhelpers import ops
+    g = torch.Generator().manual_seed(n * 7 + k)
+    x0 = (torch.randn(rows, n, generator=g) * 0.7).cuda()
+    w = torch.randn(rows, k, generator=g).cuda()
+    x1 = x0.clone().requires_grad_(True)
+    distr, ent, bits, cfg, nnz, supp = ops.topk_sparsemax(x1, k, want_configs=True)
+    (distr.mul(w).sum() + 0.37 * ent).backward()
+
+    x2 = x0.clone().requires_grad_(True)
+    cfg2, bits2, _ = ops.topk_bits(x2.detach(), k)
+    assert torch.equal(bits, bits2) and torch.equal(cfg, cfg2)
+    sk = ops.bits_score(x2, bits2)
+    out = ops.sparsemax_fwd(sk.detach())
+    assert torch.equal(distr.detach(), out["p"]) and torch.equal(supp, out["supp"]) and torch.equal(nnz, out["nnz"])
+    # reference composition in torch autograd (fp64): einsum -> sparsemax Jacobian -> masked entropy
+    P = out["p"].double()
+    on = P > 0
+    ent_ref = -(P[on] * P[on].log()).sum() / rows
+    assert abs(ent.item() - ent_ref.item()) < 1e-5 * max(1.0, abs(ent_ref.item()))
+    gd = w.double() - 0.37 / rows * torch.where(on, P.clamp(min=1e-300).log() + 1.0, torch.zeros_like(P))
+    gd = torch.where(on, gd, torch.zeros_like(gd))
+    ds = torch.where(on, gd - gd.sum(-1, keepdim=True) / on.sum(-1, keepdim=True), torch.zeros_like(gd))
+    dx_ref = torch.einsum("bk,bkj->bj", ds, cfg2.double())
+    tol = 1e-6 * max(1.0, dx_ref.abs().max().item())
+    assert (x1.grad.double() - dx_ref).abs().max().item() <= tol
+    # only one of the two gradient sources
+    x3 = x0.clone().requires_grad_(True)
+    d3, e3, *_ = ops.topk_sparsemax(x3, k)
+    e3.backward()
+    gd = torch.where(on, -(1.0 / rows) * (P.clamp(min=1e-300).log() + 1.0), torch.zeros_like(P))
+    ds = torch.where(on, gd - gd.sum(-1, keepdim=True) / on.sum(-1, keepdim=True), torch.zeros_like(gd))
+    assert (x3.grad.double() - torch.einsum("bk,bkj->bj", ds, cfg2.double())).abs().max().item() <= 1e-6
