@@ -492,7 +492,7 @@ def extra_paths(args, world, device, rank):
                 "unit": UNIT, "step_frac": sum(abv.values()) / (msv / steps * 1e-3) / 1e9 / pk,
                 "kernels": {k: {"ms": dv[k], "frac": abv[k] / (dv[k] * 1e-3) / 1e9 / pk if dv[k] > 0 else None} for k in dv}}
 
-    out["score_scale_variants"] = [categorical_variant(args.rows, args.cols, sc) for sc in (3.0, 0.3, 0.1)]
+    out["score_scale_variants"] = [categorical_variant(args.rows, args.cols, sc) for sc in (3.0, 0.3, 0.1, 0.03)]
     out["signal_game_regime_K256"] = categorical_variant(min(args.rows, 262144), 256, 0.1)
     if rank == 0 and world == 1:
         out["batch_sweep"] = [{k: v for k, v in categorical_variant(b, args.cols, 1.0, steps=20).items()

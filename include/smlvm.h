@@ -116,7 +116,9 @@ int smlvm_sparsemax_bwd_ragged(const int64_t* offsets, const int32_t* col_idx, c
                                float* dx, float* dloss, int64_t rows, int32_t cols, int64_t n_items,
                                void* stream);
 
-/* The categorical step behind the forward, in ONE launch, driven by the forward's support slots (required):
+/* The categorical step behind the forward, in ONE launch, driven by the forward's support slots -- or, with
+ * support_slots == NULL (rows with wide supports: 32 < cols <= 512, cols % 4 == 0, 16-byte aligned p / loss / dx /
+ * dloss), by ONE dense read of p and loss:
  *   weighted loss      row_loss[r] = sum_c p[r,c]*loss[r,c] (NULL to skip), total[0] = scale * sum_r row_loss[r]
  *                      (NULL to skip; fp64, fixed order; workspace: smlvm_reduce_workspace_bytes())
  *   its backward       dx = sparsemax Jacobian of (scale * loss + dent[row] * d entropy / d p), dloss = scale * p

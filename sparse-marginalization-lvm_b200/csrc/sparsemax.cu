@@ -32,47 +32,6 @@ constexpr int kThreads = 256;
 // ---- register path ---------------------------------------------------------
 
 template <int E, int G, bool VEC>
-__device__ __forceinline__ void load_row(const float* __restrict__ base, int K, int l, float fill,
-                                         float (&v)[E])
-{
-    if (VEC) {
-#pragma unroll
-        for (int c = 0; c < E / 4; ++c) {
-            int col = 4 * (c * G + l);
-            float4 q = make_float4(fill, fill, fill, fill);
-            if (col < K) q = ldg_stream4(base + col);
-            v[4 * c + 0] = q.x; v[4 * c + 1] = q.y; v[4 * c + 2] = q.z; v[4 * c + 3] = q.w;
-        }
-    } else {
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-            int col = e * G + l;
-            v[e] = (col < K) ? ldg_stream(base + col) : fill;
-        }
-    }
-}
-
-template <int E, int G, bool VEC>
-__device__ __forceinline__ void store_row(float* __restrict__ base, int K, int l,
-                                          const float (&v)[E])
-{
-    if (VEC) {
-#pragma unroll
-        for (int c = 0; c < E / 4; ++c) {
-            int col = 4 * (c * G + l);
-            if (col < K)
-                stg_stream4(base + col, make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
-        }
-    } else {
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-            int col = e * G + l;
-            if (col < K) stg_stream(base + col, v[e]);
-        }
-    }
-}
-
-template <int E, int G, bool VEC>
 __global__ void __launch_bounds__(kThreads)
 sparsemax_fwd_reg(const float* __restrict__ x, float* __restrict__ p, int32_t* __restrict__ supp,
                   int32_t* __restrict__ nnz, float* __restrict__ ent, int64_t* __restrict__ amax,
@@ -586,18 +545,22 @@ int bwd_ragged_tile_launch(const int64_t* offsets, const int32_t* cols_idx, cons
 bool sparsemax_tile_supported(int cols);
 int sparsemax_fwd_tile_launch(const float* x, float* p, int32_t* supp, int32_t* nnz, float* ent, int64_t* amax,
                               float* support_slots, int64_t rows, int cols, cudaStream_t st);
+// sparsemax_coop.cu
+bool sparsemax_coop_supported(int cols);
+int sparsemax_fwd_coop_launch(const float* x, float* p, int32_t* supp, int32_t* nnz, float* ent, int64_t* amax,
+                              int64_t rows, int cols, bool vec, cudaStream_t st);
 // compact_tile.cu
 int support_slots_launch(const float* p, float* slots, int64_t rows, int cols, cudaStream_t st);
 
 // Forward path selection.  The TMA-staged tile kernel wins once there are enough 32-row tiles to
 // occupy the SMs; tiny batches (the B = 64 experiment shapes) are launch-bound and stay on the
-// register kernel.  SMLVM_SPARSEMAX_FWD=reg|tile overrides (tests exercise both on every shape).
+// register kernel.  SMLVM_SPARSEMAX_FWD=reg|tile|coop overrides (tests/test_sparsemax_gpu.py runs every path in a subprocess).
 static int fwd_path_override()
 {
     static int cached = -1;
     if (cached < 0) {
         const char* e = getenv("SMLVM_SPARSEMAX_FWD");
-        cached = (e == nullptr) ? 0 : (strcmp(e, "reg") == 0 ? 1 : (strcmp(e, "tile") == 0 ? 2 : 0));
+        cached = (e == nullptr) ? 0 : (strcmp(e, "reg") == 0 ? 1 : (strcmp(e, "tile") == 0 ? 2 : (strcmp(e, "coop") == 0 ? 3 : 0)));
     }
     return cached;
 }
@@ -617,10 +580,21 @@ extern "C" int smlvm_sparsemax_fwd(const float* x, float* p, int32_t* supp_size,
     if (cols > SMLVM_SPARSEMAX_MAX_COLS) return SMLVM_ERR_UNSUPPORTED;
     cudaStream_t st = as_stream(stream);
     const int ovr = fwd_path_override();
-    if (sparsemax_tile_supported(cols) && aligned16(x) && aligned16(p) && ovr != 1 &&
-        (rows >= kTileMinRows || ovr == 2))
+    // Three forward kernels.  Large batches: the cooperative register kernel (G lanes per row, cost
+    // independent of the support size) unless the caller wants the support slots -- a caller asks for those when it
+    // expects peaked rows (supports of a few entries), where the thread-per-row tile kernel is the fastest and the
+    // only one that emits them.  Small batches are launch-bound and stay on the warp-per-row register kernel.
+    const bool big = rows >= kTileMinRows;
+    const bool coop_ok = sparsemax_coop_supported(cols) && ovr != 1 && ovr != 2 && (big || ovr == 3);
+    const bool tile_ok = sparsemax_tile_supported(cols) && aligned16(x) && aligned16(p) && ovr != 1 && ovr != 3 &&
+                         (big || ovr == 2);
+    if (tile_ok && (support_slots != nullptr || !coop_ok))
         return sparsemax_fwd_tile_launch(x, p, supp_size, nnz, entropy, argmax, support_slots, rows, cols, st);
-    if (cols <= 1024) {
+    if (coop_ok) {
+        const bool vec = (cols % 4 == 0) && aligned16(x) && aligned16(p);
+        const int rc = sparsemax_fwd_coop_launch(x, p, supp_size, nnz, entropy, argmax, rows, cols, vec, st);
+        if (rc != SMLVM_OK) return rc;
+    } else if (cols <= 1024) {
         RegShape sh = pick_shape(cols);
         const bool vec = (cols % 4 == 0) && aligned16(x) && aligned16(p);
         const int grid = grid_for(rows, sh.G);
@@ -687,6 +661,12 @@ int step_fused_launch(const float* p, const int32_t* supp, const float* loss, fl
                       const float* slots, const int64_t* offsets, float* vals, int32_t* row_idx, int32_t* col_idx,
                       int64_t capacity, float* row_loss, float* total, void* workspace, float* dx, float* dloss,
                       int64_t rows, int K, cudaStream_t st);
+// marg_step_dense.cu
+bool step_dense_supported(int cols);
+int step_dense_launch(const float* p, const int32_t* supp, const float* loss, float scale, const float* dent,
+                      const int64_t* offsets, float* vals, int32_t* row_idx, int32_t* col_idx, int64_t capacity,
+                      float* row_loss, float* total, void* workspace, float* dx, float* dloss, int64_t rows, int K,
+                      cudaStream_t st);
 }
 
 extern "C" int smlvm_marg_step_fused(const float* p, const int32_t* supp_size, const float* loss, float scale,
@@ -697,10 +677,16 @@ extern "C" int smlvm_marg_step_fused(const float* p, const int32_t* supp_size, c
 {
     if (rows < 0 || cols < 1 || capacity < 0) return SMLVM_ERR_ARG;
     if (rows == 0) return SMLVM_OK;
-    if (p == nullptr || supp_size == nullptr || loss == nullptr || support_slots == nullptr || dx == nullptr)
-        return SMLVM_ERR_ARG;
+    if (p == nullptr || supp_size == nullptr || loss == nullptr || dx == nullptr) return SMLVM_ERR_ARG;
     if (total != nullptr && (workspace == nullptr || workspace_bytes < smlvm_reduce_workspace_bytes()))
         return SMLVM_ERR_WORKSPACE;
+    if (support_slots == nullptr) {   // wide supports: one dense read of P and L (marg_step_dense.cu)
+        if (!step_dense_supported(cols) || !aligned16(p) || !aligned16(loss) || !aligned16(dx) ||
+            (dloss != nullptr && !aligned16(dloss)))
+            return SMLVM_ERR_UNSUPPORTED;
+        return step_dense_launch(p, supp_size, loss, scale, dent, offsets, vals, row_idx, col_idx, capacity, row_loss,
+                                 total, workspace, dx, dloss, rows, cols, as_stream(stream));
+    }
     if (!bwd_slots_supported(cols) || !aligned16(dx) || (dloss != nullptr && !aligned16(dloss)))
         return SMLVM_ERR_UNSUPPORTED;
     return step_fused_launch(p, supp_size, loss, scale, dent, support_slots, offsets, vals, row_idx, col_idx, capacity,

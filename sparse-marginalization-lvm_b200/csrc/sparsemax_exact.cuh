@@ -18,6 +18,48 @@ __device__ __forceinline__ int col_of(int e, int l)
     return e * G + l;
 }
 
+// A row of K fp32 in the registers of a G-lane group (E values per lane, E*G >= K; columns >= K read `fill`).
+template <int E, int G, bool VEC>
+__device__ __forceinline__ void load_row(const float* __restrict__ base, int K, int l, float fill,
+                                         float (&v)[E])
+{
+    if (VEC) {
+#pragma unroll
+        for (int c = 0; c < E / 4; ++c) {
+            int col = 4 * (c * G + l);
+            float4 q = make_float4(fill, fill, fill, fill);
+            if (col < K) q = ldg_stream4(base + col);
+            v[4 * c + 0] = q.x; v[4 * c + 1] = q.y; v[4 * c + 2] = q.z; v[4 * c + 3] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            int col = e * G + l;
+            v[e] = (col < K) ? ldg_stream(base + col) : fill;
+        }
+    }
+}
+
+template <int E, int G, bool VEC>
+__device__ __forceinline__ void store_row(float* __restrict__ base, int K, int l,
+                                          const float (&v)[E])
+{
+    if (VEC) {
+#pragma unroll
+        for (int c = 0; c < E / 4; ++c) {
+            int col = 4 * (c * G + l);
+            if (col < K)
+                stg_stream4(base + col, make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            int col = e * G + l;
+            if (col < K) stg_stream(base + col, v[e]);
+        }
+    }
+}
+
 // Descending bitonic sort of the E*G values of a group; sorted position of
 // slot e in lane l is l*E + e.
 template <int E, int G>

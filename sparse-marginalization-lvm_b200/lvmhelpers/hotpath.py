@@ -12,8 +12,8 @@ so a step can be replayed back to back or captured in a CUDA graph.
     P, losses     --fused bwd------>  dscores (sparsemax Jacobian of g*L/B + entropy term),
                                       dlosses = g*P/B                             (kernel 1')
 
-With the forward's support slots (large batches of peaked rows) kernels 2b, 4 and 1' are ONE launch
-(``smlvm_marg_step_fused``): fwd -> scan -> {loss, lists, gradients}.
+Kernels 2b, 4 and 1' are ONE launch (``smlvm_marg_step_fused``): fwd -> scan -> {loss, lists, gradients} -- driven by
+the forward's support slots for large batches of peaked rows, by one dense read of P and L otherwise (32 < K <= 512).
 
 Capacity contract: the ragged lists are pre-allocated for ``capacity`` entries.  The fill never writes past them
 (entries beyond the capacity are dropped) and the ragged consumers never read past them; a batch whose support is
@@ -69,8 +69,10 @@ class SparsemaxMargStep:
         # side stream of the compaction branch (run()); small batches are launch-bound: one stream
         self.side = torch.cuda.Stream(device=device) if (overlap_compaction and rows >= OVERLAP_MIN_ROWS) else None
         self._ev_fwd, self._ev_side = torch.cuda.Event(), torch.cuda.Event()
-        # loss, lists and gradients in one launch behind the scan (needs the slots; tile kernel shapes only)
-        self.fused = self.use_slots and cols % 4 == 0 and cols <= 512 and (fused is None or bool(fused))
+        # loss, lists and gradients in one launch behind the scan: from the support slots (peaked rows) or from one
+        # dense read of P and L (wide supports, 32 < K <= 512: smlvm_marg_step_fused with slots = NULL)
+        covered = cols % 4 == 0 and cols <= 512 and (self.use_slots or cols > 32)
+        self.fused = covered and (fused is None or bool(fused))
         self.kernels = ("sparsemax_fwd", "scan_counts", "marg_step_fused") if self.fused else self.KERNELS
 
     def overflowed(self):
@@ -171,8 +173,9 @@ class SparsemaxMargStep:
             "sparsemax_bwd": (r * (64 + 32 + 4 + 8 * K) if self.use_slots else r * (8 * K + 4 + 8 * K))
                              + (4 * r if self.dent is not None else 0),
             # the three above in one launch: slots + offsets + supp (+dent) in, one sector of L per non-zero,
-            # row loss, dX, dL and 12 B of lists per non-zero out
-            "marg_step_fused": r * (64 + 16 + 4 + 4 + 8 * K) + (4 * r if self.dent is not None else 0) + (32 + 12) * N_,
+            # row loss, dX, dL and 12 B of lists per non-zero out; without slots P and L are read densely (8K B/row)
+            "marg_step_fused": (r * (64 + 16 + 4 + 4 + 8 * K) + (32 + 12) * N_ if self.use_slots
+                                else r * (8 * K + 16 + 4 + 4 + 8 * K) + 12 * N_) + (4 * r if self.dent is not None else 0),
         }
         return {k: d[k] for k in self.kernels}
 

@@ -35,6 +35,47 @@ def test_resident_step_matches_oracle(oracle, rows, K):
     assert (step.dloss.cpu() - Lr.grad).abs().max().item() <= 1e-7
 
 
+@pytest.mark.parametrize("rows,K,scale", [(64, 256, 0.1), (4099, 128, 0.1), (4096, 128, 0.03), (4100, 64, 0.3), (5000, 256, 0.1),
+                                          (4097, 512, 0.05), (300, 36, 1.0), (4096, 100, 0.1)])
+@pytest.mark.parametrize("fused", [True, False])
+def test_wide_support_step_matches_oracle(oracle, rows, K, scale, fused):
+    """Flat score rows (supports of 10-60 entries: no support slots): forward by the cooperative kernel, then loss,
+    lists and gradients from ONE dense read of P and L (smlvm_marg_step_fused with slots = NULL) -- against the oracle
+    and against the three separate dense-read kernels (fused=False)."""
+    from lvmhelpers.hotpath import SparsemaxMargStep
+    g = torch.Generator().manual_seed(rows + K)
+    x, L = torch.randn(rows, K, generator=g) * scale, torch.rand(rows, K, generator=g) * 3
+    x[1] = 0.0                                  # constant row: full support
+    x[2, 1:] = x[2, 0] - 2.0                    # one-hot row: p = 1, upper clamp of the entropy
+    xd, Ld = x.cuda(), L.cuda()
+    nnz = SparsemaxMargStep.size_capacity(xd)
+    step = SparsemaxMargStep(rows, K, xd.device, nnz + 16, entropy_coeff=0.5, use_slots=False, fused=fused)
+    assert step.fused == fused
+    total = step.run(xd, Ld)
+    torch.cuda.synchronize()
+    xr, Lr = x.clone().requires_grad_(True), L.clone().requires_grad_(True)
+    P = oracle.sparsemax(xr)
+    ((P * Lr).sum(-1).mean() - 0.5 * oracle.entropy(P).mean()).backward()
+    assert torch.equal(step.p.cpu(), P.detach())
+    assert abs(total.item() - (P * L).sum(-1).mean().item()) <= 1e-5
+    assert (step.row_loss.cpu() - (P.detach() * L).sum(-1)).abs().max().item() <= 1e-5
+    nz = torch.nonzero(P.detach() > 0)
+    n = nz.shape[0]
+    assert int(step.offsets[-1]) == n
+    assert torch.equal(step.ri[:n].cpu().long(), nz[:, 0]) and torch.equal(step.ci[:n].cpu().long(), nz[:, 1])
+    assert torch.equal(step.vals[:n].cpu(), P.detach()[P.detach() > 0])
+    assert (step.dx.cpu() - xr.grad).abs().max().item() <= 1e-6 * max(1.0, xr.grad.abs().max().item()) * 4
+    assert (step.dloss.cpu() - Lr.grad).abs().max().item() <= 1e-7
+    # capacity: the lists are clamped, the overflow is reported, loss and gradients do not depend on them
+    small = SparsemaxMargStep(rows, K, xd.device, n // 2, entropy_coeff=0.5, use_slots=False, fused=fused)
+    guard = torch.full((64,), -7.0, device="cuda")
+    small.vals = torch.cat([small.vals, guard])[: n // 2]   # (view of a larger buffer: writes past n // 2 would land in guard)
+    t2 = small.run(xd, Ld)
+    torch.cuda.synchronize()
+    assert small.overflowed() and torch.equal(small.dx, step.dx) and t2.item() == total.item()
+    assert torch.equal(small.ri.cpu().long(), nz[: n // 2, 0])
+
+
 @pytest.mark.parametrize("chunks", [1, 4, 8])
 def test_host_pipelined_step_equals_resident(chunks):
     from lvmhelpers.hotpath import SparsemaxMargStep, HostPipelinedMargStep

@@ -78,12 +78,15 @@ def test_edge_rows(oracle):
 TILE_SHAPES = [(4096, 32), (4113, 64), (4096 + 31, 128), (8192, 128), (4097, 256), (5000, 512)]
 
 
-@pytest.mark.parametrize("rows,K", TILE_SHAPES)
+@pytest.mark.parametrize("rows,K", TILE_SHAPES + [(4100, 100), (4096, 36), (4099, 300)])
 @pytest.mark.parametrize("scale", [0.01, 0.1, 0.3, 1.0, 3.0])
-def test_tile_kernel_parity(oracle, rows, K, scale):
-    """rows >= 4096 and K in {32..512}: the TMA-staged tile kernel (sparsemax_tile.cu).  Small
-    scales give supports wider than the 32-entry candidate list (whole-warp path), large scales
-    the per-thread path; a partial last tile is included.  Bit-exact against the oracle."""
+@pytest.mark.parametrize("want_slots", [False, True])
+def test_tile_kernel_parity(oracle, rows, K, scale, want_slots):
+    """rows >= 4096: the two throughput kernels.  Without support slots the cooperative register kernel
+    (sparsemax_coop.cu: G lanes per row, Michelot + checked reference tau, 32 < K <= 512); with them (K in
+    {32, 64, 128}) the TMA-staged tile kernel (sparsemax_tile.cu).  Small scales give supports wider than the tile
+    kernel's 32-entry candidate list (whole-row / whole-warp paths), large scales the per-thread path; a partial last
+    tile, unaligned widths and structured rows are included.  Bit-exact against the oracle."""
     from lvmhelpers import ops
     x = _inputs(rows, K, scale, 1000 + K)
     # structured rows inside the batch: ties, one-hot with gap exactly 1, constants, masked
@@ -94,7 +97,7 @@ def test_tile_kernel_parity(oracle, rows, K, scale):
     x[9] = 1e4 * torch.sign(x[9])
     x[rows - 1] = torch.linspace(-1e-3, 1e-3, K)
     P_ref, k_ref = oracle.sparsemax_fwd(x)
-    out = ops.sparsemax_fwd(x.cuda(), want_entropy=True, want_argmax=True)
+    out = ops.sparsemax_fwd(x.cuda(), want_entropy=True, want_argmax=True, want_slots=want_slots)
     P = out["p"].cpu()
     assert torch.equal(P > 0, P_ref > 0)
     assert torch.equal(out["supp"].cpu().long(), k_ref)
@@ -103,6 +106,57 @@ def test_tile_kernel_parity(oracle, rows, K, scale):
     assert torch.equal(P, P_ref)
     assert torch.equal(out["argmax"].cpu(), x.argmax(-1))
     assert torch.allclose(out["entropy"].cpu(), oracle.entropy(P_ref), rtol=1e-5, atol=1e-6)
+    if want_slots:   # rows the slots describe: the support pairs are those of P
+        sl = out["slots"].cpu()
+        cols = sl[..., 1].contiguous().view(torch.int32)
+        fits = cols[:, 0] != -2
+        assert bool((((P_ref > 0).sum(-1) <= 8) | ~fits).all())
+        for r in torch.nonzero(fits)[:64, 0].tolist():
+            on = cols[r] >= 0
+            got = sorted(zip(cols[r][on].tolist(), sl[r, :, 0][on].tolist()))
+            ref = [(c, P_ref[r, c].item()) for c in torch.nonzero(P_ref[r] > 0)[:, 0].tolist()]
+            assert got == ref
+
+
+_PATH_SCRIPT = r"""
+import sys, torch
+sys.path[:0] = [%r, %r]
+import oracle
+from lvmhelpers import ops
+bad = []
+for rows, K in [(64, 10), (64, 256), (300, 128), (4099, 128), (4100, 64), (4097, 256), (130, 100), (4096, 32), (5000, 500)]:
+    for scale in (0.03, 0.3, 3.0):
+        g = torch.Generator().manual_seed(rows + K)
+        x = torch.randn(rows, K, generator=g) * scale
+        x[1] = 0.0
+        x[2, 1:] = x[2, 0] - 1.0
+        x[3] = torch.round(x[3] * 4) / 4
+        x[4, ::2] = float("-inf")
+        P_ref, k_ref = oracle.sparsemax_fwd(x)
+        out = ops.sparsemax_fwd(x.cuda(), want_entropy=True, want_argmax=True)
+        ok = torch.equal(out["p"].cpu(), P_ref) and torch.equal(out["supp"].cpu().long(), k_ref) \
+            and torch.equal(out["nnz"].cpu().long(), (P_ref > 0).sum(-1)) and torch.equal(out["argmax"].cpu(), x.argmax(-1)) \
+            and torch.allclose(out["entropy"].cpu(), oracle.entropy(P_ref), rtol=1e-5, atol=1e-6)
+        if not ok:
+            bad.append((rows, K, scale))
+print("BAD", bad) if bad else print("ALL-OK")
+"""
+
+
+@pytest.mark.parametrize("path", ["reg", "tile", "coop"])
+def test_every_forward_path_in_a_subprocess(path):
+    """SMLVM_SPARSEMAX_FWD pins the forward to ONE of its three kernels (read once per process, hence a subprocess):
+    each must be bit-exact against the oracle on every shape it accepts (shapes a pinned kernel does not cover fall
+    through to the register kernel)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SMLVM_SPARSEMAX_FWD=path)
+    script = _PATH_SCRIPT % (root, os.path.join(root, "sparse-marginalization-lvm_b200"))
+    res = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert "ALL-OK" in res.stdout, res.stdout[-2000:]
 
 
 def test_tile_kernel_optional_outputs():
