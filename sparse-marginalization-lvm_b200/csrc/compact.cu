@@ -265,6 +265,11 @@ int compact_fill_tile_launch(const float* p, const int64_t* offsets, float* vals
                              int32_t* col_idx, int64_t rows, int cols, int64_t capacity, cudaStream_t st);
 
 // SMLVM_COMPACT=reg|tile overrides the path choice (tests run both).
+// marg_step_dense.cu
+bool step_dense_supported(int cols);
+int compact_fill_coop_launch(const float* p, const int64_t* offsets, float* vals, int32_t* row_idx, int32_t* col_idx,
+                             int64_t rows, int K, int64_t capacity, cudaStream_t st);
+
 static int compact_path_override()
 {
     static int cached = -1;
@@ -332,6 +337,9 @@ extern "C" int smlvm_compact_fill(const float* p, const int64_t* offsets, const 
         return compact_fill_slots_launch(p, support_slots, offsets, vals, row_idx, col_idx, rows, cols, capacity,
                                          as_stream(stream));
     const int ovr = compact_path_override();
+    // wide rows of a large batch: G lanes per row, the run of 32 / G rows staged and stored coalesced (marg_step_dense.cu)
+    if (ovr == 0 && step_dense_supported(cols) && rows >= kCompactTileMinRows && (reinterpret_cast<uintptr_t>(p) & 15u) == 0)
+        return compact_fill_coop_launch(p, offsets, vals, row_idx, col_idx, rows, cols, capacity, as_stream(stream));
     if (compact_tile_supported(cols) && (reinterpret_cast<uintptr_t>(p) & 15u) == 0 && ovr != 1 &&
         (rows >= kCompactTileMinRows || ovr == 2))
         return compact_fill_tile_launch(p, offsets, vals, row_idx, col_idx, rows, cols, capacity, as_stream(stream));

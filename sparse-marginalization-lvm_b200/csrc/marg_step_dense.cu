@@ -22,7 +22,8 @@ namespace smlvm {
 
 constexpr int kDenseThreads = 256;
 
-template <int G, bool LISTS>
+// GRAD = false: the compaction alone (smlvm_compact_fill without support slots on large batches).
+template <int G, bool LISTS, bool GRAD>
 __global__ void __launch_bounds__(kDenseThreads, 2)
 marg_step_dense_kernel(const float* __restrict__ p, const int32_t* __restrict__ supp, const float* __restrict__ loss,
                        float scale, const float* __restrict__ dent, const int64_t* __restrict__ offsets,
@@ -48,11 +49,13 @@ marg_step_dense_kernel(const float* __restrict__ p, const int32_t* __restrict__ 
         const int64_t off = (live ? row : 0) * (int64_t)K;
         float pv[E], gv[E];
         load_row<E, G, true>(p + off, Kr, l, 0.f, pv);
+        int64_t obase = 0;
+        if (LISTS && live) obase = __ldg(offsets + row);
+        unsigned mask = 0u;
+        if (GRAD) {
         load_row<E, G, true>(loss + off, Kr, l, 0.f, gv);
         const int kk = live ? __ldg(supp + row) : 1;
         const float de = (dent != nullptr && live) ? __ldg(dent + row) : 0.f;
-        int64_t obase = 0;
-        if (LISTS && live) obase = __ldg(offsets + row);
 
         // ---- weighted loss of the row; dL = scale * P ----------------------------------------------
         float s0 = 0.f, s1 = 0.f;
@@ -74,7 +77,6 @@ marg_step_dense_kernel(const float* __restrict__ p, const int32_t* __restrict__ 
         }
 
         // ---- gradient w.r.t. the scores (the operation order of sparsemax_bwd_reg) -----------------
-        unsigned mask = 0u;
         float g0 = 0.f, g1 = 0.f;
 #pragma unroll
         for (int e = 0; e < E; ++e) {
@@ -90,6 +92,10 @@ marg_step_dense_kernel(const float* __restrict__ p, const int32_t* __restrict__ 
 #pragma unroll
         for (int e = 0; e < E; ++e) gv[e] = (pv[e] != 0.f) ? __fsub_rn(gv[e], vhat) : 0.f;
         if (live) store_row<E, G, true>(dx + off, K, l, gv);
+        } else {
+#pragma unroll
+            for (int e = 0; e < E; ++e) mask |= (pv[e] > 0.f) ? (1u << e) : 0u;
+        }
 
         // ---- support compaction -----------------------------------------------------------------------
         // The entries of the warp's 32 / G consecutive rows are one contiguous run of the lists.  Each lane ranks
@@ -150,7 +156,7 @@ marg_step_dense_kernel(const float* __restrict__ p, const int32_t* __restrict__ 
             __syncwarp();
         }
     }
-    if (total != nullptr) finish_totals(ws, acc_total, 0.0, scale, total, nullptr, red);
+    if (GRAD && total != nullptr) finish_totals(ws, acc_total, 0.0, scale, total, nullptr, red);
 }
 
 bool step_dense_supported(int cols) { return cols > 32 && cols <= 512 && cols % 4 == 0; }
@@ -172,23 +178,34 @@ static int launch_dense(const float* p, const int32_t* supp, const float* loss, 
         int dev = 0;
         cudaGetDevice(&dev);
         if (!configured_dev[dev & 63]) {
-            cudaError_t ea = cudaFuncSetAttribute(marg_step_dense_kernel<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                  (int)smem);
+            cudaError_t ea = cudaFuncSetAttribute(marg_step_dense_kernel<G, true, true>,
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (ea == cudaSuccess)
+                ea = cudaFuncSetAttribute(marg_step_dense_kernel<G, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem);
             if (ea != cudaSuccess) return (int)ea;
             configured_dev[dev & 63] = true;
         }
     }
-    if (offsets != nullptr)
-        marg_step_dense_kernel<G, true><<<grid, kDenseThreads, smem, st>>>(p, supp, loss, scale, dent, offsets, vals, row_idx,
+    if (loss == nullptr)
+        marg_step_dense_kernel<G, true, false><<<grid, kDenseThreads, smem, st>>>(p, supp, loss, scale, dent, offsets, vals,
+                                                                               row_idx, col_idx, capacity, row_loss, total,
+                                                                               ws_view(workspace), dx, dloss, rows, K);
+    else if (offsets != nullptr)
+        marg_step_dense_kernel<G, true, true><<<grid, kDenseThreads, smem, st>>>(p, supp, loss, scale, dent, offsets, vals, row_idx,
                                                                        col_idx, capacity, row_loss, total,
                                                                        ws_view(workspace), dx, dloss, rows, K);
     else
-        marg_step_dense_kernel<G, false><<<grid, kDenseThreads, 0, st>>>(p, supp, loss, scale, dent, offsets, vals, row_idx,
+        marg_step_dense_kernel<G, false, true><<<grid, kDenseThreads, 0, st>>>(p, supp, loss, scale, dent, offsets, vals, row_idx,
                                                                         col_idx, capacity, row_loss, total,
                                                                         ws_view(workspace), dx, dloss, rows, K);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? SMLVM_OK : (int)e;
 }
+
+// the compaction alone: (value, row, col) of p > 0 from a dense read of p, coalesced stores
+int compact_fill_coop_launch(const float* p, const int64_t* offsets, float* vals, int32_t* row_idx, int32_t* col_idx,
+                             int64_t rows, int K, int64_t capacity, cudaStream_t st);
 
 int step_dense_launch(const float* p, const int32_t* supp, const float* loss, float scale, const float* dent,
                       const int64_t* offsets, float* vals, int32_t* row_idx, int32_t* col_idx, int64_t capacity,
@@ -201,6 +218,13 @@ int step_dense_launch(const float* p, const int32_t* supp, const float* loss, fl
     if (K <= 256) return launch_dense<8>(SMLVM_DENSE_ARGS);
     return launch_dense<16>(SMLVM_DENSE_ARGS);
 #undef SMLVM_DENSE_ARGS
+}
+
+int compact_fill_coop_launch(const float* p, const int64_t* offsets, float* vals, int32_t* row_idx, int32_t* col_idx,
+                             int64_t rows, int K, int64_t capacity, cudaStream_t st)
+{
+    return step_dense_launch(p, nullptr, nullptr, 0.f, nullptr, offsets, vals, row_idx, col_idx, capacity, nullptr, nullptr,
+                             nullptr, nullptr, nullptr, rows, K, st);
 }
 
 }  // namespace smlvm
