@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SMLVM_ABI_VERSION 4
+#define SMLVM_ABI_VERSION 5
 
 #define SMLVM_OK 0
 #define SMLVM_ERR_ARG (-1)         /* null pointer, negative size, bad enum        */
@@ -319,6 +319,25 @@ int smlvm_wloss_ragged_bwd(const float* p, const float* loss, const float* g, co
  *           v = loss_output, sign = -1, shift = logp_z.                                         */
 int smlvm_segment_logsumexp(const float* v, const int64_t* offsets, float sign, float shift,
                             float* out, int64_t rows, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * (f)4 the remaining `entmax` call sites
+ * ------------------------------------------------------------------------- */
+/* p[rows,cols] = entmax.entmax15(x, dim=-1): X' = (x - max x) / 2, p = [(X' - tau)_+]^2 with sum p = 1 -- the
+ * reference's DEFAULT normalizer, lvmhelpers/marg.py:39,46.  entropy[rows] = entropy(p) of marg.py:6-28 and
+ * argmax[rows] = x.argmax(-1) of marg.py:53 (either may be NULL).  cols <= 1024, else SMLVM_ERR_UNSUPPORTED.    */
+int smlvm_entmax15_fwd(const float* x, float* p, float* entropy, int64_t* argmax, int64_t rows, int32_t cols,
+                       void* stream);
+/* Entmax15Function.backward: g = sqrt(p); dx = dp * g - (sum(dp * g) / sum(g)) * g                              */
+int smlvm_entmax15_bwd(const float* p, const float* dp, float* dx, int64_t rows, int32_t cols, void* stream);
+/* Fenchel-Young loss of entmax.SparsemaxLoss (alpha15 = 0) / Entmax15Loss (alpha15 = 1),
+ * experiments/semi_supervised-vae/train.py:9,312-325, given p = normalizer(x):
+ *   loss[r] = (1 - sum_j p^alpha) / (alpha (alpha - 1)) + <p - e_target, x>;   p_minus_y[rows,cols] = p - e_target
+ * (the gradient w.r.t. x; NULL to skip).  target int64 [rows] in [0, cols).                                     */
+int smlvm_fy_loss_fwd(const float* x, const float* p, const int64_t* target, int32_t alpha15, float* loss,
+                      float* p_minus_y, int64_t rows, int32_t cols, void* stream);
+/* out[r,:] = scale[r] * a[r,:]  (the loss's backward: grad_output[r] * (p - e_target))                          */
+int smlvm_row_scale(const float* a, const float* scale, float* out, int64_t rows, int32_t cols, void* stream);
 
 #ifdef __cplusplus
 }

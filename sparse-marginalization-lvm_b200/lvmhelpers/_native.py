@@ -12,7 +12,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SMLVM_LIB_PATH") or os.path.join(_HERE, "libsmlvm.so")   # override: development builds only
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 FACTOR_BERNOULLI, FACTOR_BUDGET, FACTOR_SEQUENCE_BINARY, FACTOR_SEQUENCE = 0, 1, 2, 3
 SOLVE_STATUS = {0: "converged", 1: "max_iter", 2: "repeated_config", 3: "singular"}
@@ -44,6 +44,10 @@ _PROTOTYPES = {
     "smlvm_bits_score_bwd": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     "smlvm_ksparsemax_fwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _i32, _vp, _sz, _vp]),
     "smlvm_topk_sparsemax_bwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _f32, _vp, _i64, _i32, _i32, _vp]),
+    "smlvm_entmax15_fwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "smlvm_entmax15_bwd": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _vp]),
+    "smlvm_fy_loss_fwd": (ctypes.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _i64, _i32, _vp]),
+    "smlvm_row_scale": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _vp]),
     "smlvm_bits_expand": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _vp]),
     "smlvm_gather_rows": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
     "smlvm_sparsemap_capacity": (_i32, [_i32]),

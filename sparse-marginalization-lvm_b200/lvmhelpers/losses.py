@@ -7,8 +7,9 @@ SURVEY.md §8(f) rank 4 -- outside the hot path proper, provided so that the exp
     L(X, y) = Omega(p*) + <p* - e_y, X>,       dL/dX = p* - e_y,
 
 Omega(p) = (1 - sum_j p_j^alpha) / (alpha (alpha - 1)), alpha = 2 (sparsemax) or 1.5 (entmax15).
-The sparsemax forward is the sm_100a kernel (``ops.sparsemax_fwd``) on CUDA tensors; entmax15 is the
-torch-op restatement of ``marg.entmax15``.
+fp32 CUDA scores with at most 1024 classes run as kernels: the normalizer (``smlvm_sparsemax_fwd`` /
+``smlvm_entmax15_fwd``), the loss rows with p - e_y (``smlvm_fy_loss_fwd``) and the backward (``smlvm_row_scale``).
+Other tensors (fp64 checks) take the torch-op form below.
 """
 import torch
 import torch.nn as nn
@@ -49,7 +50,10 @@ class _FYLoss(nn.Module):
         self.ignore_index, self.reduction = ignore_index, reduction   # k: accepted for API parity, unused
 
     def forward(self, X, target):
-        loss = _FYLossFunction.apply(X, target.clamp(min=0), self.alpha)
+        if X.is_cuda and X.dtype == torch.float32 and X.dim() == 2 and X.shape[-1] <= ops.ENTMAX15_MAX_COLS:
+            loss = ops.fy_loss(X, target.clamp(min=0), self.alpha == 1.5)
+        else:
+            loss = _FYLossFunction.apply(X, target.clamp(min=0), self.alpha)
         size = float(X.shape[0])
         if self.ignore_index >= 0:
             ignored = target == self.ignore_index

@@ -29,10 +29,8 @@ def entropy(p: torch.Tensor):
 class _Entmax15(torch.autograd.Function):
     """1.5-entmax (``entmax.entmax15``, the reference's DEFAULT normalizer argument at
     marg.py:39,46) restated with torch ops: exact sort-based threshold, closed-form backward.
-    Outside the hot path this package replaces with kernels (the north star names sparsemax
-    only; 'entmax' is not reachable from the experiments' CLI, lvmhelpers/utils.py:36-37) -- kept
-    so that ``ExplicitWrapper(agent)`` with its default argument still works.  Runs on whatever
-    device the scores live on."""
+    The definition the kernel (``ops.entmax15``) is tested against, and the path of tensors the
+    kernel does not take (fp64, CPU, more than 1024 columns)."""
 
     @staticmethod
     def forward(ctx, X):
@@ -61,8 +59,12 @@ class _Entmax15(torch.autograd.Function):
 
 
 def entmax15(X, dim=-1):
+    """``entmax.entmax15``: the sm_100a kernel (``smlvm_entmax15_fwd/_bwd``) for fp32 CUDA scores with at most 1024
+    columns; other tensors (fp64 checks, CPU) take the torch-op restatement above."""
     if dim not in (-1, X.dim() - 1):
         return entmax15(X.transpose(dim, -1), -1).transpose(dim, -1)
+    if X.is_cuda and X.dtype == torch.float32 and X.shape[-1] <= ops.ENTMAX15_MAX_COLS:
+        return ops.entmax15(X)
     return _Entmax15.apply(X)
 
 
@@ -156,6 +158,9 @@ class ExplicitWrapper(nn.Module):
         if self.normalizer_name == 'softmax':
             distr = torch.softmax(scores, dim=-1)
             return scores.argmax(dim=-1), distr, entropy(distr)
+        if scores.is_cuda and scores.dtype == torch.float32 and scores.shape[-1] <= ops.ENTMAX15_MAX_COLS:
+            distr, entropy_distr, sample = ops.entmax15(scores, want_stats=True)   # one launch
+            return sample, distr, entropy_distr
         distr = entmax15(scores, dim=-1)
         return scores.argmax(dim=-1), distr, entropy(distr)
 

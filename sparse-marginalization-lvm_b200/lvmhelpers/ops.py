@@ -145,6 +145,85 @@ def sparsemax_stats(X):
     return _SparsemaxStats.apply(X)
 
 
+ENTMAX15_MAX_COLS = 1024
+
+
+class _Entmax15(torch.autograd.Function):
+    """P = entmax15(X) over the last dimension of a [rows, K] fp32 CUDA tensor (K <= 1024) -> (P, entropy, argmax)."""
+
+    @staticmethod
+    def forward(ctx, x, want_stats):
+        rows, K = x.shape
+        p = torch.empty_like(x)
+        ent = torch.empty(rows, dtype=torch.float32, device=x.device) if want_stats else None
+        amax = torch.empty(rows, dtype=torch.int64, device=x.device) if want_stats else None
+        check(lib.smlvm_entmax15_fwd(ptr(x), ptr(p), ptr(ent), ptr(amax), rows, K, stream()), "smlvm_entmax15_fwd")
+        ctx.save_for_backward(p)
+        if not want_stats:
+            return p
+        ctx.mark_non_differentiable(amax)
+        ctx.ent_needs_p = True
+        return p, ent, amax
+
+    @staticmethod
+    def backward(ctx, dp, dent=None, _damax=None):
+        (p,) = ctx.saved_tensors
+        if dent is not None:
+            # d entropy / d p of marg.py:6-28 on the support (the clamp passes gradient inside [eps, 1 - eps])
+            eps = torch.finfo(torch.float32).eps
+            inside = (p >= eps) & (p <= 1 - eps)
+            de = torch.where(inside, -(torch.log(p.clamp(min=eps)) + 1.0), torch.zeros_like(p)) * dent.unsqueeze(-1)
+            dp = de if dp is None else dp + de
+        if dp is None:
+            return torch.zeros_like(p), None
+        dp = dp.contiguous().float()
+        dx = torch.empty_like(p)
+        check(lib.smlvm_entmax15_bwd(ptr(p), ptr(dp), ptr(dx), p.shape[0], p.shape[1], stream()), "smlvm_entmax15_bwd")
+        return dx, None
+
+
+def entmax15(X, want_stats=False):
+    """Drop-in for ``entmax.entmax15(X, dim=-1)`` on fp32 CUDA tensors with at most 1024 columns
+    (lvmhelpers/marg.py:46); ``want_stats``: also entropy() of marg.py:6-28 and X.argmax(-1) from the same launch."""
+    shp = X.shape
+    flat = _f32c(X.reshape(-1, shp[-1]), "scores")
+    if not want_stats:
+        return _Entmax15.apply(flat, False).reshape(shp)
+    p, ent, amax = _Entmax15.apply(flat, True)
+    return p.reshape(shp), ent.reshape(shp[:-1]), amax.reshape(shp[:-1])
+
+
+class _FYLoss(torch.autograd.Function):
+    """Fenchel-Young loss rows (entmax.SparsemaxLoss / Entmax15Loss) from scores and the normalizer's output."""
+
+    @staticmethod
+    def forward(ctx, x, p, target, alpha15):
+        rows, K = x.shape
+        loss = torch.empty(rows, dtype=torch.float32, device=x.device)
+        pm = torch.empty_like(x)
+        check(lib.smlvm_fy_loss_fwd(ptr(x), ptr(p), ptr(target), int(alpha15), ptr(loss), ptr(pm), rows, K, stream()),
+              "smlvm_fy_loss_fwd")
+        ctx.save_for_backward(pm)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (pm,) = ctx.saved_tensors
+        g = g.contiguous().float()
+        dx = torch.empty_like(pm)
+        check(lib.smlvm_row_scale(ptr(pm), ptr(g), ptr(dx), pm.shape[0], pm.shape[1], stream()), "smlvm_row_scale")
+        return dx, None, None, None
+
+
+def fy_loss(x, target, alpha15):
+    """[rows] Fenchel-Young losses of scores x [rows, K] against int64 targets; alpha15: entmax15 (else sparsemax)."""
+    x = _f32c(x, "scores")
+    target = target.to(device=x.device, dtype=torch.int64).contiguous()
+    with torch.no_grad():
+        p = (_Entmax15.apply(x.detach(), False) if alpha15 else sparsemax_fwd(x.detach(), want_nnz=False)["p"])
+    return _FYLoss.apply(x, p, target, bool(alpha15))
+
+
 # --------------------------------------------------------------------------------------
 # (2) compaction
 # --------------------------------------------------------------------------------------

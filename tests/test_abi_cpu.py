@@ -53,7 +53,7 @@ def test_library_is_sm100a_only():
 def test_version_and_error_strings():
     from lvmhelpers import _native
     lib = _native.lib
-    assert lib.smlvm_version() == _native.ABI_VERSION == 4
+    assert lib.smlvm_version() == _native.ABI_VERSION == 5
     assert b"argument" in lib.smlvm_error_string(-1).lower()
     for code in (0, -1, -2, -3, 1, 700, 12345):
         assert lib.smlvm_error_string(code) is not None

@@ -17,7 +17,8 @@ def test_sparsemax_loss_matches_definition(oracle):
     Xc = X.cuda().requires_grad_(True)
     for red, want in (("none", ref), ("sum", ref.sum()), ("elementwise_mean", ref.mean())):
         out = SparsemaxLoss(reduction=red)(Xc, y.cuda())
-        assert (out.detach().cpu().double() - want).abs().max() < 1e-5
+        # fp32 rows (|loss| ~ 10) and their fp32 sum (~200): a few ulp of the result
+        assert (out.detach().cpu().double() - want).abs().max() <= 4e-7 * max(1.0, want.abs().max().item())
     SparsemaxLoss()(Xc, y.cuda()).backward()
     onehot = torch.zeros(64, 10).scatter_(1, y[:, None], 1.0)
     assert (Xc.grad.cpu() - (P - onehot) / 64).abs().max() < 1e-6
