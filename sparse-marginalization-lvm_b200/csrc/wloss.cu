@@ -70,7 +70,7 @@ wloss_ragged_kernel(const float* __restrict__ p, const float* __restrict__ loss,
         for (int64_t i = tid; i < n_items; i += nthreads) {
             const float pi = __ldg(p + i);
             if (loss != nullptr) acc += (double)(pi * __ldg(loss + i));
-            if (neg_plogp != nullptr) ent -= (double)(pi * logf(pi));
+            if (neg_plogp != nullptr && pi > 0.f) ent -= (double)(pi * logf(pi));   // (p = 0: padding entries)
         }
     }
     if (row_loss != nullptr) {
@@ -106,7 +106,7 @@ wloss_ragged_bwd_kernel(const float* __restrict__ p, const float* __restrict__ l
         const float pi = __ldg(p + i);
         if (dp != nullptr) {
             float d = (loss != nullptr) ? gs * __ldg(loss + i) : 0.f;
-            if (gent != nullptr) d -= ge * (logf(pi) + 1.f);
+            if (gent != nullptr && pi > 0.f) d -= ge * (logf(pi) + 1.f);
             dp[i] = d;
         }
         if (dloss != nullptr) dloss[i] = gs * pi;

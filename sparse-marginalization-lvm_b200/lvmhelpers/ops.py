@@ -720,6 +720,8 @@ class _SparseMAPBatch(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, t, kind, budget, max_iter, init_scores, only_positive, aux):
+        if aux.get("static"):
+            return _SparseMAPBatch._forward_static(ctx, x, t, kind, budget, max_iter, init_scores, only_positive, aux)
         state = sparsemap_solve(x, kind, budget=budget, t=t, init_scores=init_scores,
                                 max_iter=max_iter, keep_S=True)
         sizes = state["kept"] if only_positive else state["counts"]
@@ -746,6 +748,32 @@ class _SparseMAPBatch(torch.autograd.Function):
         return p, aset
 
     @staticmethod
+    def _forward_static(ctx, x, t, kind, budget, max_iter, init_scores, only_positive, aux):
+        """No host read: the ragged outputs are allocated for the worst case, rows * (n + 1) entries -- the
+        reference's (p, aset) in sample order, followed by zeros (p = 0: no weight in the loss, none in the entropy).
+        Fixed shapes and no synchronisation: the whole forward + backward can be captured in a CUDA graph."""
+        rows, n = x.shape
+        if rows * (n + 1) ** 2 * 8 > S_WORST_CASE_MAX_BYTES:
+            raise ValueError("static SparseMAP outputs need the worst-case arena (rows * (n+1)^2 doubles <= 2 GB)")
+        state = sparsemap_solve(x, kind, budget=budget, t=t, init_scores=init_scores, max_iter=max_iter, keep_S=True,
+                                arena_doubles=rows * (n + 1) ** 2)
+        sizes = state["kept"] if only_positive else state["counts"]
+        offsets = scan_counts(sizes)
+        total = rows * (n + 1)
+        dev = x.device
+        p = torch.zeros(total, dtype=torch.float32, device=dev)
+        aset = torch.zeros((total, n), dtype=torch.float32, device=dev)
+        idx = torch.zeros(total, dtype=torch.int32, device=dev)
+        check(lib.smlvm_sparsemap_expand(ptr(state["p_pad"]), ptr(state["bits"]), ptr(state["counts"]), ptr(offsets),
+                                         int(only_positive), ptr(p), ptr(aset), ptr(idx), rows, n, stream()),
+              "smlvm_sparsemap_expand")
+        ctx.state, ctx.offsets, ctx.only_positive, ctx.has_t = state, offsets, only_positive, t is not None
+        ctx.mark_non_differentiable(aset)
+        ctx.set_materialize_grads(False)
+        aux.update(sizes=sizes, idx=idx, offsets=offsets, state=state)
+        return p, aset
+
+    @staticmethod
     def backward(ctx, dp, _daset):
         if dp is None:
             return None, None, None, None, None, None, None, None
@@ -753,10 +781,11 @@ class _SparseMAPBatch(torch.autograd.Function):
         return dx, dt, None, None, None, None, None, None
 
 
-def sparsemap_batch(x, kind, budget=0, t=None, max_iter=100, init_scores=None, only_positive=True):
+def sparsemap_batch(x, kind, budget=0, t=None, max_iter=100, init_scores=None, only_positive=True, static=False):
     """Returns (p [N], aset [N, n], aux) with aux = dict(sizes [rows] int64 CPU, idx [N] int32,
-    offsets, state)."""
-    aux = {}
+    offsets, state).  ``static``: N = rows * (n + 1) whatever the supports (zero padding behind the ragged
+    entries), ``aux["sizes"]`` stays on the device (int32) and nothing is read back -- graph-capturable."""
+    aux = {"static": bool(static)}
     p, aset = _SparseMAPBatch.apply(_f32c(x, "scores"), t, kind, int(budget), int(max_iter),
                                     init_scores, bool(only_positive), aux)
     return p, aset, aux

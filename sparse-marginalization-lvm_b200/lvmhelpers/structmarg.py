@@ -65,6 +65,30 @@ class _IdxList(list):
     tensor = None
 
 
+class _DeviceList:
+    """``idxs`` / ``support`` of the static-shape SparseMAP wrapper: the values live on the device (``tensor``, with
+    ``count`` valid entries when given); the Python list the reference returns (structmarg.py:195-202) is built on
+    first use -- that, and only that, synchronises."""
+
+    def __init__(self, tensor, count=None):
+        self.tensor, self.count, self._list = tensor, count, None
+
+    def tolist(self):
+        if self._list is None:
+            n = self.tensor.numel() if self.count is None else int(self.count.item())
+            self._list = self.tensor[:n].tolist()
+        return self._list
+
+    def __iter__(self):
+        return iter(self.tolist())
+
+    def __len__(self):
+        return len(self.tolist())
+
+    def __getitem__(self, i):
+        return self.tolist()[i]
+
+
 class PackedBitVectors:
     """The wrapper's first output when its consumer is ``TopKSparsemaxMarg``: the [B,k,n] {0,1}
     candidates as packed words [B,k,W].  ``dense()`` gives the reference's fp32 tensor,
@@ -193,12 +217,17 @@ class SparseMAPWrapper(nn.Module):
     """scores -> (vertices [N,n], distribution [N], entropy / B, idxs, support)
     (reference structmarg.py:156-202)."""
 
-    def __init__(self, agent, budget=0, init=False, max_iter=300):
+    def __init__(self, agent, budget=0, init=False, max_iter=300, static_shapes=False):
+        """``static_shapes`` (extension, default off = the reference's ragged outputs): N = B * (n + 1) entries
+        whatever the supports -- the reference's entries in sample order followed by zero rows with probability 0 --
+        and ``idxs`` / ``support`` as device-backed lists.  No host synchronisation: a training step over the wrapper
+        can be captured in a CUDA graph (the experiments' B = 64, n = 32 steps are launch- and sync-bound)."""
         super().__init__()
         self.agent = agent
         self.budget = budget
         self.init = init
         self.max_iter = max_iter
+        self.static_shapes = static_shapes
 
     def forward(self, *args, **kwargs):
         scores = self.agent(*args, **kwargs)
@@ -207,7 +236,11 @@ class SparseMAPWrapper(nn.Module):
         init_scores = draw_init_scores(batch_size, latent_size) if self.init else None
         distr, sample, aux = ops.sparsemap_batch(
             scores, kind, budget=self.budget, max_iter=self.max_iter,
-            init_scores=init_scores, only_positive=True)
+            init_scores=init_scores, only_positive=True, static=self.static_shapes)
+        self.last_solver_state = aux["state"]
+        if self.static_shapes:
+            entropy_distr = ops.ragged_entropy(distr, 1.0 / batch_size)
+            return sample, distr, entropy_distr, _DeviceList(aux["idx"], aux["offsets"][-1]), _DeviceList(aux["sizes"])
         support = aux["sizes"].tolist()
         assert all(s > 0 for s in support)  # structmarg.py:192
         idxs = _IdxList(aux["idx"].tolist())
@@ -255,7 +288,8 @@ class SparseMAPMarg(torch.nn.Module):
 
         logs['loss'] = loss.detach()
         logs['encoder_entropy'] = encoder_entropy.detach()
-        logs['support'] = torch.tensor(support).to(torch.float)
+        logs['support'] = support.tensor.to(torch.float) if isinstance(support, _DeviceList) \
+            else torch.tensor(support).to(torch.float)
         logs['distr'] = encoder_probs.detach()
         logs['loss_output'] = loss_components.detach()
         logs['idxs'] = idxs

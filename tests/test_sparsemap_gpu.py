@@ -300,3 +300,77 @@ def test_n128_flagged_samples_match_oracle(oracle, kind, budget, lo_hi_maxiter):
     assert int(st["kept"].min()) >= 1
     cnt = st["counts"].cpu().numpy()
     assert cnt.min() >= 1 and cnt.max() <= 129
+
+
+@pytest.mark.parametrize("budget", [0, 16])
+def test_static_shape_wrapper_equals_ragged_and_replays_as_graph(budget):
+    """SparseMAPWrapper(static_shapes=True): the reference's ragged outputs in sample order followed by zero padding
+    (N = B (n + 1)), device-backed idxs / support, no host synchronisation -- same loss, entropy and gradients as the
+    ragged wrapper through SparseMAPMarg, and the whole step replays as ONE CUDA graph."""
+    from lvmhelpers.structmarg import SparseMAPWrapper, SparseMAPMarg
+    B, n = 64, 32
+    torch.manual_seed(3)
+    enc = torch.nn.Linear(20, n).cuda()
+    dec = torch.nn.Linear(n, 12).cuda()
+    x = torch.randn(B, 20, device="cuda")
+    labels = torch.randn(B, 12, device="cuda")
+
+    def loss_fun(enc_in, z, dec_in, dec_out, lab):
+        return ((dec_out - lab) ** 2).sum(-1), {"acc": dec_out.mean(-1)}
+
+    params = list(enc.parameters()) + list(dec.parameters())
+    outs = {}
+    for static in (False, True):
+        for q in params:
+            q.grad = None
+        marg = SparseMAPMarg(SparseMAPWrapper(enc, budget=budget, max_iter=300, static_shapes=static), dec, loss_fun,
+                             encoder_entropy_coeff=0.7)
+        res = marg(x, x, labels)
+        res["loss"].backward()
+        outs[static] = (res, [q.grad.clone() for q in params])
+    (r0, g0), (r1, g1) = outs[False], outs[True]
+    N = len(r0["log"]["idxs"])
+    assert r1["log"]["distr"].numel() == B * (n + 1)
+    assert torch.equal(r1["log"]["distr"][:N], r0["log"]["distr"]) and bool((r1["log"]["distr"][N:] == 0).all())
+    assert list(r1["log"]["idxs"]) == list(r0["log"]["idxs"])
+    assert torch.equal(r1["log"]["support"].cpu(), r0["log"]["support"].cpu())
+    assert abs(r1["loss"].item() - r0["loss"].item()) <= 1e-5 * max(1.0, abs(r0["loss"].item()))
+    for a, b in zip(g0, g1):
+        assert (a - b).abs().max().item() <= 1e-5 * max(1.0, a.abs().max().item())
+
+    # one CUDA graph for forward + backward (fresh copies of the nets: autograd nodes of the eager passes above, made
+    # on the default stream and still referenced by their results, would pull that stream into the capture)
+    import copy
+    del outs, r0, r1, res
+    enc_e, dec_e = enc, dec
+    enc, dec = copy.deepcopy(enc_e), copy.deepcopy(dec_e)
+    params = list(enc.parameters()) + list(dec.parameters())
+    marg = SparseMAPMarg(SparseMAPWrapper(enc, budget=budget, max_iter=300, static_shapes=True), dec, loss_fun,
+                         encoder_entropy_coeff=0.7)
+    xs = x.clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            for q in params:
+                q.grad = None
+            marg(xs, xs, labels)["loss"].backward()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    for q in params:
+        q.grad = None
+    with torch.cuda.graph(graph):
+        out = marg(xs, xs, labels)
+        out["loss"].backward()
+    xs.copy_(torch.randn(B, 20, device="cuda"))
+    graph.replay()
+    torch.cuda.synchronize()
+    got_loss, got_grads = out["loss"].item(), [q.grad.clone() for q in params]
+    params_e = list(enc_e.parameters()) + list(dec_e.parameters())
+    for q in params_e:
+        q.grad = None
+    ref = SparseMAPMarg(SparseMAPWrapper(enc_e, budget=budget, max_iter=300), dec_e, loss_fun, encoder_entropy_coeff=0.7)(xs, xs, labels)
+    ref["loss"].backward()
+    assert abs(got_loss - ref["loss"].item()) <= 1e-5 * max(1.0, abs(ref["loss"].item()))
+    for a, q in zip(got_grads, params_e):
+        assert (a - q.grad).abs().max().item() <= 1e-5 * max(1.0, q.grad.abs().max().item())
