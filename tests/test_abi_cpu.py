@@ -141,7 +141,8 @@ def test_wrapper_api_surface_matches_reference():
     p = inspect.signature(structmarg.TopKSparsemaxWrapper.__init__).parameters
     assert list(p) == ["self", "agent", "k"] and p["k"].default == 10
     p = inspect.signature(structmarg.SparseMAPWrapper.__init__).parameters
-    assert [(k, v.default) for k, v in p.items()][2:] == [("budget", 0), ("init", False), ("max_iter", 300)]
+    assert [(k, v.default) for k, v in p.items()][2:5] == [("budget", 0), ("init", False), ("max_iter", 300)]
+    assert [(k, v.default) for k, v in p.items()][5:] == [("static_shapes", False)]   # opt-in extension, default off
     p = inspect.signature(sparsemap.budget_smap).parameters
     assert [(k, v.default) for k, v in p.items()][1:] == [("budget", 5), ("max_iter", 100), ("init", True)]
     p = inspect.signature(sparsemap.bernoulli_smap).parameters
