@@ -375,6 +375,10 @@ int topk_tile_launch(const float* x, float* configs, uint32_t* bits, float* dp_s
 
 // The thread-per-row kernel wins on throughput, the group-per-row kernel on latency (a row is a
 // chain of n dependent merges): small batches stay on the latter.  SMLVM_TOPK=reg|tile overrides.
+// (Round 2 measured a third variant -- configurations parked in a pool of k slots per row, list entries (score, slot
+// id), only the min(#A, #B) entries that survive on both sides of a merge copied: 1/8 of the shared-memory bytes, but
+// 394 -> 250 (unrolled) warp instructions per bit against 220, the copies run at the warp's worst row: 0.527 vs 0.490
+// ms at 262144 x 128, k = 10, 1.15 vs 0.94 ms at k = 16.  Dropped)
 static int topk_path_override()
 {
     static int cached = -1;
