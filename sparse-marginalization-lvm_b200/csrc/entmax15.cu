@@ -182,8 +182,12 @@ row_scale_kernel(const float* __restrict__ a, const float* __restrict__ scale, f
 }
 
 struct E15Shape { int E, G; };
-static E15Shape e15_shape(int K)
+// Large batches of rows wider than 32: 32 values per lane, K / 32 lanes per row (the layout of sparsemax_coop.cu) --
+// the Newton passes run in fp64 and their group reductions are 64-bit shuffles: 74 warp instructions per row and pass
+// with a warp per row (ncu r02: 1.70 ms at 1M x 128), 24 with 4 lanes per row.
+static E15Shape e15_shape(int K, int64_t rows)
 {
+    if (rows >= 4096 && K > 32 && K <= 512) return {32, K <= 64 ? 2 : (K <= 128 ? 4 : (K <= 256 ? 8 : 16))};
     if (K <= 4) return {4, 1};
     if (K <= 8) return {4, 2};
     if (K <= 16) return {4, 4};
@@ -204,7 +208,7 @@ static int e15_grid(int64_t rows, int G)
 
 #define SMLVM_E15_DISPATCH(KERNEL, vec, ...)                                                         \
     do {                                                                                             \
-        const E15Shape sh = e15_shape(cols);                                                         \
+        const E15Shape sh = e15_shape(cols, rows);                                                         \
         const int grid = e15_grid(rows, sh.G);                                                       \
         switch (sh.E * 100 + sh.G) {                                                                 \
             case 401: if (vec) KERNEL<4, 1, true><<<grid, kE15Threads, 0, st>>>(__VA_ARGS__); else KERNEL<4, 1, false><<<grid, kE15Threads, 0, st>>>(__VA_ARGS__); break; \
@@ -213,6 +217,10 @@ static int e15_grid(int64_t rows, int G)
             case 408: if (vec) KERNEL<4, 8, true><<<grid, kE15Threads, 0, st>>>(__VA_ARGS__); else KERNEL<4, 8, false><<<grid, kE15Threads, 0, st>>>(__VA_ARGS__); break; \
             case 416: if (vec) KERNEL<4, 16, true><<<grid, kE15Threads, 0, st>>>(__VA_ARGS__); else KERNEL<4, 16, false><<<grid, kE15Threads, 0, st>>>(__VA_ARGS__); break; \
             case 432: if (vec) KERNEL<4, 32, true><<<grid, kE15Threads, 0, st>>>(__VA_ARGS__); else KERNEL<4, 32, false><<<grid, kE15Threads, 0, st>>>(__VA_ARGS__); break; \
+            case 3202: if (vec) KERNEL<32, 2, true><<<grid, kE15Threads, 0, st>>>(__VA_ARGS__); else KERNEL<32, 2, false><<<grid, kE15Threads, 0, st>>>(__VA_ARGS__); break; \
+            case 3204: if (vec) KERNEL<32, 4, true><<<grid, kE15Threads, 0, st>>>(__VA_ARGS__); else KERNEL<32, 4, false><<<grid, kE15Threads, 0, st>>>(__VA_ARGS__); break; \
+            case 3208: if (vec) KERNEL<32, 8, true><<<grid, kE15Threads, 0, st>>>(__VA_ARGS__); else KERNEL<32, 8, false><<<grid, kE15Threads, 0, st>>>(__VA_ARGS__); break; \
+            case 3216: if (vec) KERNEL<32, 16, true><<<grid, kE15Threads, 0, st>>>(__VA_ARGS__); else KERNEL<32, 16, false><<<grid, kE15Threads, 0, st>>>(__VA_ARGS__); break; \
             case 832: if (vec) KERNEL<8, 32, true><<<grid, kE15Threads, 0, st>>>(__VA_ARGS__); else KERNEL<8, 32, false><<<grid, kE15Threads, 0, st>>>(__VA_ARGS__); break; \
             case 1632: if (vec) KERNEL<16, 32, true><<<grid, kE15Threads, 0, st>>>(__VA_ARGS__); else KERNEL<16, 32, false><<<grid, kE15Threads, 0, st>>>(__VA_ARGS__); break; \
             default: if (vec) KERNEL<32, 32, true><<<grid, kE15Threads, 0, st>>>(__VA_ARGS__); else KERNEL<32, 32, false><<<grid, kE15Threads, 0, st>>>(__VA_ARGS__); break; \

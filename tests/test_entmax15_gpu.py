@@ -8,7 +8,8 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("rows,K,scale", [(64, 10, 3.0), (64, 256, 0.1), (5000, 128, 1.0), (300, 128, 0.03), (7, 3, 1.0),
-                                          (40, 1000, 0.5), (33, 64, 10.0), (9, 1, 1.0), (100, 37, 2.0), (64, 500, 1.0)])
+                                          (40, 1000, 0.5), (33, 64, 10.0), (9, 1, 1.0), (100, 37, 2.0), (64, 500, 1.0),
+                                          (4096, 256, 0.1), (4100, 64, 1.0), (4096, 500, 0.3), (4097, 100, 1.0)])
 def test_entmax15_forward_backward(rows, K, scale):
     from lvmhelpers import ops
     from lvmhelpers.marg import _Entmax15, entropy
@@ -27,7 +28,9 @@ def test_entmax15_forward_backward(rows, K, scale):
     assert (p.detach().cpu().double() - p_ref.detach()).abs().max().item() <= 1e-6
     assert (p.detach().sum(-1) - 1).abs().max().item() <= 1e-5
     assert torch.equal(amax.cpu(), x.argmax(-1))
-    assert torch.allclose(ent.detach().cpu(), entropy(p_ref.detach().float()), rtol=1e-4, atol=2e-6)
+    # |d (p log p)| = |log p + 1| dp: an entry at the threshold (p ~ 1e-7 on one side, 0 on the other) moves the
+    # entropy by ~2e-5 for the 1e-6 the probabilities are allowed
+    assert torch.allclose(ent.detach().cpu(), entropy(p_ref.detach().float()), rtol=1e-4, atol=5e-5)
     (p * w.cuda()).sum().backward()
     tol = 2e-5 * max(1.0, xr.grad.abs().max().item())   # sqrt(p) amplifies 1e-6 on p near the threshold
     assert (xc.grad.cpu().double() - xr.grad).abs().max().item() <= tol
