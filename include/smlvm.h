@@ -48,6 +48,7 @@ extern "C" {
 #define SMLVM_FACTOR_BERNOULLI 0       /* lvmhelpers/bernoulli.h  (PFactorBernoulli)      */
 #define SMLVM_FACTOR_BUDGET 1          /* lvmhelpers/budget.h     (PFactorBudget)         */
 #define SMLVM_FACTOR_SEQUENCE_BINARY 2 /* lvmhelpers/sequence_binary.h (PFactorSequenceBinary) */
+#define SMLVM_FACTOR_SEQUENCE 3        /* lvmhelpers/sequence.h   (PFactorSequence: general chain; smlvm_sparsemap_seq_fwd) */
 
 /* per-sample solver status written by smlvm_sparsemap_fwd */
 #define SMLVM_SOLVE_CONVERGED 0
@@ -260,6 +261,27 @@ int smlvm_sparsemap_fwd(const float* x, const float* t, const double* init_score
                         uint32_t* aset_bits, int32_t* counts, int32_t* kept, int32_t* iters,
                         int32_t* status, double* S_arena, int64_t S_capacity, int64_t* S_offsets,
                         uint64_t* S_cursor, void* workspace, size_t workspace_bytes, void* stream);
+
+/* The general linear chain, FactorSequence of lvmhelpers/sequence.h:25-291 (bound as PFactorSequence.initialize(
+ * list[int]), lvmhelpers/psequence.pyx:10-22): `length` positions, position i with S_i <= 32 states, one variable per
+ * (position, state) -- n = sum S_i <= 128 -- and num_edges = S_0 + sum S_{i-1} S_i + S_{L-1} additional scores
+ * (start -> first, every transition row-major in (previous, current), last -> stop; sequence.h:264-291).
+ *   x[rows,n] node scores, edge_scores[rows,num_edges] (NULL: zeros),
+ *   layout[2 length + 3] int32 (device) = offsets of the states of position 0..length, then the first edge of
+ *   position 0..length+1.
+ * A vertex is the one-hot pattern of its state sequence: bit layout[i] + state_i set for every position i; the
+ * outputs have the layout of smlvm_sparsemap_fwd (aset_bits over the n variables).  MAP oracle = Viterbi with the
+ * reference's tie rule (lower predecessor wins, sequence.h:112,136); Gram entries = equal positions (:212-226).   */
+int smlvm_sparsemap_seq_fwd(const float* x, const float* edge_scores, const int32_t* layout, int32_t length,
+                            int32_t num_edges, int32_t max_iter, int64_t rows, int32_t n, float* p_pad,
+                            uint32_t* aset_bits, int32_t* counts, int32_t* kept, int32_t* iters, int32_t* status,
+                            double* S_arena, int64_t S_capacity, int64_t* S_offsets, uint64_t* S_cursor,
+                            void* workspace, size_t workspace_bytes, void* stream);
+/* its backward: dx[rows,n] = M (S dp), dedge[rows,num_edges] = N (S dp) (NULL to skip)                            */
+int smlvm_sparsemap_seq_bwd(const float* dp, const int64_t* offsets, int32_t only_positive, const float* p_pad,
+                            const uint32_t* aset_bits, const int32_t* counts, const double* S_arena,
+                            const int64_t* S_offsets, const int32_t* layout, int32_t length, int32_t num_edges,
+                            float* dx, float* dedge, int64_t rows, int32_t n, void* stream);
 
 /* Ragged expansion in sample order (structmarg.py:181-198): for every kept vertex
  * (all of them if only_positive == 0, those with p_pad > 0 otherwise) at

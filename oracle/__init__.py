@@ -64,6 +64,13 @@ def _bind_solver(lib):
     lib.smlvm_oracle_factor_map.restype = ctypes.c_int
     lib.smlvm_oracle_factor_map.argtypes = [
         ctypes.c_int, ctypes.c_int, ctypes.c_int, _f64p, _f64p, _i32p, _f64p]
+    lib.smlvm_oracle_seq_fwd.restype = ctypes.c_int
+    lib.smlvm_oracle_seq_fwd.argtypes = [ctypes.c_int, _i32p, _f64p, _f64p, ctypes.c_int, ctypes.c_int, _f64p, _i32p, _f64p,
+                                         _intp, _intp, _intp]
+    lib.smlvm_oracle_seq_fwd_bwd.restype = ctypes.c_int
+    lib.smlvm_oracle_seq_fwd_bwd.argtypes = [ctypes.c_int, _i32p, _f64p, _f64p, ctypes.c_int, _f64p, ctypes.c_int, _f64p, _f64p]
+    lib.smlvm_oracle_seq_map.restype = ctypes.c_int
+    lib.smlvm_oracle_seq_map.argtypes = [ctypes.c_int, _i32p, _f64p, _f64p, _i32p, _f64p]
     lib.smlvm_oracle_sparsemap_batch.restype = ctypes.c_long
     lib.smlvm_oracle_sparsemap_batch.argtypes = [
         ctypes.c_int, ctypes.c_int, ctypes.c_int, _f32p, ctypes.c_long,
@@ -267,6 +274,58 @@ def factor_map(eta2n, kind, budget=0, t=None, which="oracle"):
                                              _p(t_, _f64p), _p(y, _i32p), ctypes.byref(val))
     if rc != 0:
         raise RuntimeError("factor_map failed")
+    return y, val.value
+
+
+def seq_num_edges(num_states):
+    """Additional (edge) scores of the general chain: start, transitions, stop (sequence.h:264-291)."""
+    ns = list(num_states)
+    return ns[0] + sum(a * b for a, b in zip(ns[:-1], ns[1:])) + ns[-1]
+
+
+def seq_fwd(x, add, num_states, max_iter=100, which="oracle"):
+    """General linear chain, one sample.  x [sum num_states] node scores, add [seq_num_edges] edge scores ->
+    dict(p [|A|], aset [|A|, L] int32 state sequences, S, iters, status)."""
+    ns = np.ascontiguousarray(num_states, dtype=np.int32)
+    L, V = ns.shape[0], int(ns.sum())
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    add = np.ascontiguousarray(add, dtype=np.float64)
+    assert x.shape[0] == V and add.shape[0] == seq_num_edges(ns)
+    cap = V + 2
+    p = np.zeros(cap, dtype=np.float64)
+    aset = np.zeros((cap, L), dtype=np.int32)
+    S = np.zeros(cap * cap, dtype=np.float64)
+    cnt, it, st = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+    rc = _lib(which).smlvm_oracle_seq_fwd(L, _p(ns, _i32p), _p(x, _f64p), _p(add, _f64p), max_iter, cap, _p(p, _f64p),
+                                          _p(aset, _i32p), _p(S, _f64p), ctypes.byref(cnt), ctypes.byref(it), ctypes.byref(st))
+    if rc != 0:
+        raise RuntimeError("sequence oracle failed rc=%d" % rc)
+    m = cnt.value
+    return dict(p=p[:m].copy(), aset=aset[:m].copy(), S=S[:m * m].reshape(m, m).copy(), iters=it.value, status=st.value)
+
+
+def seq_bwd(x, add, num_states, dp, max_iter=100, which="oracle"):
+    """Re-solves, then dist_jacobian_vec: (dx [V], dadd [E])."""
+    ns = np.ascontiguousarray(num_states, dtype=np.int32)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    add = np.ascontiguousarray(add, dtype=np.float64)
+    dp = np.ascontiguousarray(dp, dtype=np.float64)
+    dx, dt = np.zeros(x.shape[0]), np.zeros(add.shape[0])
+    rc = _lib(which).smlvm_oracle_seq_fwd_bwd(ns.shape[0], _p(ns, _i32p), _p(x, _f64p), _p(add, _f64p), max_iter,
+                                              _p(dp, _f64p), dp.shape[0], _p(dx, _f64p), _p(dt, _f64p))
+    if rc != 0:
+        raise RuntimeError("sequence oracle bwd failed rc=%d" % rc)
+    return dx, dt
+
+
+def seq_map(x, add, num_states, which="oracle"):
+    """Viterbi of the general chain alone: (y [L] int32, value)."""
+    ns = np.ascontiguousarray(num_states, dtype=np.int32)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    add = np.ascontiguousarray(add, dtype=np.float64)
+    y = np.zeros(ns.shape[0], dtype=np.int32)
+    val = ctypes.c_double(0)
+    _lib(which).smlvm_oracle_seq_map(ns.shape[0], _p(ns, _i32p), _p(x, _f64p), _p(add, _f64p), _p(y, _i32p), ctypes.byref(val))
     return y, val.value
 
 

@@ -6,6 +6,9 @@
 //   RBudget          <- lvmhelpers/budget.h:18-85
 //   RSequenceBinary  <- lvmhelpers/sequence.h:74-243 specialised by
 //                       lvmhelpers/sequence_binary.h:10-73
+//   RSequence        <- lvmhelpers/sequence.h:25-291, the general chain: num_states[i] states at
+//                       position i, one variable per (position, state), one additional score per
+//                       edge (start -> first, every transition, last -> stop)
 // Written from the behaviour of those files (not copied): same tie rules
 // (strict '>'), same accumulation order, same sort key for the budget.
 // oracle/ref/Makefile builds the same driver against the reference's own
@@ -223,6 +226,120 @@ class RSequenceBinary : public RBernoulli
             prev = y[i];
         }
     }
+};
+
+// General linear chain (sequence.h).  Variables: offset[i] + state; additionals indexed as
+// Initialize builds them (sequence.h:264-291): position 0 has 1 x S_0 start edges, position i
+// S_{i-1} x S_i transitions (row-major in (previous, current)), position L has S_{L-1} x 1 stop edges.
+class RSequence : public GenericFactor
+{
+  public:
+    virtual ~RSequence() { ClearActiveSet(); }
+    void Initialize(const vector<int>& num_states)
+    {
+        ns_ = num_states;
+        const int L = static_cast<int>(ns_.size());
+        off_.assign(L, 0);
+        int o = 0;
+        for (int i = 0; i < L; ++i) { off_[i] = o; o += ns_[i]; }
+        ebase_.assign(L + 2, 0);
+        int e = 0;
+        for (int i = 0; i <= L; ++i) {
+            ebase_[i] = e;
+            e += ((i > 0) ? ns_[i - 1] : 1) * ((i < L) ? ns_[i] : 1);
+        }
+        ebase_[L + 1] = e;
+    }
+    size_t GetNumAdditionals() override { return ebase_.empty() ? 0 : ebase_.back(); }
+    inline double node(const vector<double>& eta, int pos, int s) const { return eta[off_[pos] + s]; }
+    inline int eidx(int pos, int prev, int s) const
+    {
+        const int cur = (pos < static_cast<int>(ns_.size())) ? ns_[pos] : 1;
+        return ebase_[pos] + prev * cur + s;
+    }
+
+    // sequence.h:74-151 -- Viterbi; among equal predecessors the lower state wins.
+    void Maximize(const vector<double>& eta, const vector<double>& add, Configuration& cfg, double* value) override
+    {
+        BitCfg& y = *static_cast<BitCfg*>(cfg);
+        const int L = static_cast<int>(ns_.size());
+        vector<vector<double>> val(L);
+        vector<vector<int>> path(L);
+        val[0].resize(ns_[0]);
+        path[0].assign(ns_[0], -1);
+        for (int l = 0; l < ns_[0]; ++l) val[0][l] = node(eta, 0, l) + add[eidx(0, 0, l)];
+        for (int i = 0; i + 1 < L; ++i) {
+            val[i + 1].resize(ns_[i + 1]);
+            path[i + 1].resize(ns_[i + 1]);
+            for (int k = 0; k < ns_[i + 1]; ++k) {
+                double best_value = -std::numeric_limits<double>::infinity();
+                int best = -1;
+                for (int l = 0; l < ns_[i]; ++l) {
+                    const double v = val[i][l] + add[eidx(i + 1, l, k)];
+                    if (best < 0 || v > best_value) { best_value = v; best = l; }
+                }
+                val[i + 1][k] = best_value + node(eta, i + 1, k);
+                path[i + 1][k] = best;
+            }
+        }
+        double best_value = -std::numeric_limits<double>::infinity();
+        int best = -1;
+        for (int l = 0; l < ns_[L - 1]; ++l) {
+            const double v = val[L - 1][l] + add[eidx(L, l, 0)];
+            if (best < 0 || v > best_value) { best_value = v; best = l; }
+        }
+        y[L - 1] = best;
+        for (int i = L - 1; i > 0; --i) y[i - 1] = path[i][y[i]];
+        *value = best_value;
+    }
+
+    // sequence.h:154-179: node then edge at every position, the stop edge last
+    void Evaluate(const vector<double>& eta, const vector<double>& add, const Configuration cfg, double* value) override
+    {
+        const BitCfg& y = *static_cast<const BitCfg*>(cfg);
+        double acc = 0.0;
+        int prev = 0;
+        for (size_t i = 0; i < y.size(); ++i) {
+            acc += node(eta, static_cast<int>(i), y[i]);
+            acc += add[eidx(static_cast<int>(i), prev, y[i])];
+            prev = y[i];
+        }
+        acc += add[eidx(static_cast<int>(y.size()), prev, 0)];
+        *value = acc;
+    }
+
+    // sequence.h:183-209
+    void UpdateMarginalsFromConfiguration(const Configuration& cfg, double w, vector<double>* post,
+                                          vector<double>* add_post) override
+    {
+        const BitCfg& y = *static_cast<const BitCfg*>(cfg);
+        int prev = 0;
+        for (size_t i = 0; i < y.size(); ++i) {
+            (*post)[off_[i] + y[i]] += w;
+            (*add_post)[eidx(static_cast<int>(i), prev, y[i])] += w;
+            prev = y[i];
+        }
+        (*add_post)[eidx(static_cast<int>(y.size()), prev, 0)] += w;
+    }
+
+    // sequence.h:212-243
+    int CountCommonValues(const Configuration& a, const Configuration& b) override
+    {
+        const BitCfg& ya = *static_cast<const BitCfg*>(a);
+        const BitCfg& yb = *static_cast<const BitCfg*>(b);
+        int c = 0;
+        for (size_t i = 0; i < ya.size(); ++i) c += (ya[i] == yb[i]);
+        return c;
+    }
+    bool SameConfiguration(const Configuration& a, const Configuration& b) override
+    {
+        return *static_cast<const BitCfg*>(a) == *static_cast<const BitCfg*>(b);
+    }
+    void DeleteConfiguration(Configuration cfg) override { delete static_cast<BitCfg*>(cfg); }
+    Configuration CreateConfiguration() override { return static_cast<Configuration>(new BitCfg(ns_.size(), -1)); }
+
+  protected:
+    vector<int> ns_, off_, ebase_;
 };
 
 } // namespace AD3

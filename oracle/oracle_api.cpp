@@ -24,6 +24,7 @@ namespace AD3 {
 typedef FactorBernoulli FBern;
 typedef FactorBudget FBudget;
 typedef FactorSequenceBinary FSeqBin;
+typedef FactorSequence FSeq;
 }
 #else
 #include "factors_restated.h"
@@ -31,6 +32,7 @@ namespace AD3 {
 typedef RBernoulli FBern;
 typedef RBudget FBudget;
 typedef RSequenceBinary FSeqBin;
+typedef RSequence FSeq;
 }
 #endif
 
@@ -161,6 +163,80 @@ int smlvm_oracle_factor_map(int kind, int n, int budget, const double* eta2n,
     f->Maximize(eta, add, cfg, value);
     const vector<int>& yy = *static_cast<const vector<int>*>(cfg);
     for (int i = 0; i < n; ++i) y[i] = yy[i];
+    f->DeleteConfiguration(cfg);
+    return 0;
+}
+
+// ---- general linear chain (lvmhelpers/sequence.h, bound as PFactorSequence.initialize(list[int])) ----
+// L positions with num_states[i] states; x[V] node scores (V = sum num_states), add[E] edge scores in the order of
+// FactorSequence::Initialize (sequence.h:264-291).  Vertices come back as state sequences, aset[cap * L].
+static FSeq* make_seq(int L, const int32_t* num_states)
+{
+    auto* f = new FSeq();
+    f->Initialize(vector<int>(num_states, num_states + L));
+    return f;
+}
+
+int smlvm_oracle_seq_fwd(int L, const int32_t* num_states, const double* x, const double* add_in, int max_iter, int cap,
+                         double* p, int32_t* aset, double* S, int* count, int* iters, int* status)
+{
+    std::unique_ptr<FSeq> f(make_seq(L, num_states));
+    int V = 0;
+    for (int i = 0; i < L; ++i) V += num_states[i];
+    f->SetVerbosity(1);
+    f->SetQPMaxIter(max_iter);
+    vector<double> eta(x, x + V), add(add_in, add_in + f->GetNumAdditionals());
+    vector<double> post_u, post_v;
+    f->SolveQP(eta, add, &post_u, &post_v);
+    const vector<Configuration>& A = f->GetQPActiveSet();
+    const vector<double>& dist = f->GetQPDistribution();
+    const vector<double>& invA = f->GetQPInvA();
+    const int m = static_cast<int>(A.size());
+    *count = m;
+    *iters = f->last_iterations();
+    *status = f->last_status();
+    if (m > cap) return -1;
+    for (int j = 0; j < m; ++j) {
+        p[j] = dist[j];
+        const vector<int>& y = *static_cast<const vector<int>*>(A[j]);
+        for (int i = 0; i < L; ++i) aset[j * L + i] = y[i];
+    }
+    if (S)
+        for (int i = 0; i < m; ++i)
+            for (int j = 0; j < m; ++j) S[i * m + j] = invA[(i + 1) * (m + 1) + (j + 1)];
+    return 0;
+}
+
+int smlvm_oracle_seq_fwd_bwd(int L, const int32_t* num_states, const double* x, const double* add_in, int max_iter,
+                             const double* dp, int dp_len, double* dx, double* dt)
+{
+    std::unique_ptr<FSeq> f(make_seq(L, num_states));
+    int V = 0;
+    for (int i = 0; i < L; ++i) V += num_states[i];
+    f->SetQPMaxIter(max_iter);
+    vector<double> eta(x, x + V), add(add_in, add_in + f->GetNumAdditionals());
+    vector<double> post_u, post_v;
+    f->SolveQP(eta, add, &post_u, &post_v);
+    const int m = static_cast<int>(f->GetQPActiveSet().size());
+    if (dp_len != m) return -2;
+    vector<double> v(dp, dp + m), out_u(V, 0.0), out_v(add.size(), 0.0);
+    f->DistJacobianVec(v, &out_u, &out_v);
+    for (int i = 0; i < V; ++i) dx[i] = out_u[i];
+    for (size_t i = 0; i < out_v.size(); ++i) dt[i] = out_v[i];
+    return 0;
+}
+
+int smlvm_oracle_seq_map(int L, const int32_t* num_states, const double* x, const double* add_in, int32_t* y,
+                         double* value)
+{
+    std::unique_ptr<FSeq> f(make_seq(L, num_states));
+    int V = 0;
+    for (int i = 0; i < L; ++i) V += num_states[i];
+    vector<double> eta(x, x + V), add(add_in, add_in + f->GetNumAdditionals());
+    Configuration cfg = f->CreateConfiguration();
+    f->Maximize(eta, add, cfg, value);
+    const vector<int>& yy = *static_cast<const vector<int>*>(cfg);
+    for (int i = 0; i < L; ++i) y[i] = yy[i];
     f->DeleteConfiguration(cfg);
     return 0;
 }

@@ -62,7 +62,24 @@ struct SolverSmem {
     uint32_t* ynew; // [W]
     unsigned char* bp;  // [2*n] Viterbi back-pointers
     int* misc;      // [8]
+    // general chain only (SMLVM_FACTOR_SEQUENCE), behind everything else:
+    double* te;     // [E]      edge scores in the order of FactorSequence::Initialize (sequence.h:264-291)
+    double* val;    // [2][32]  Viterbi values of the previous / current position
+    int* lay;       // [2L+3]   offset of the states of position i (L+1 entries), first edge of position i (L+2)
+    int* ys;        // [L]      state sequence of the vertex in ynew
 };
+
+// The general chain (lvmhelpers/sequence.h; PFactorSequence.initialize(list[int])): L positions, position i with
+// S_i states, one variable (bit) per (position, state) -- a vertex is a one-hot pattern per position, n = sum S_i bits
+// -- and E = S_0 + sum S_{i-1} S_i + S_{L-1} additional (edge) scores.  lay = [off_0..off_L | ebase_0..ebase_{L+1}].
+struct SeqArgs {
+    const int32_t* lay;  // device
+    int L, E;
+};
+__host__ __device__ inline size_t seq_extra_bytes(int L, int E)
+{
+    return L > 0 ? (((size_t)(E + 64) * 8 + (size_t)(3 * L + 3) * 4 + 15) & ~(size_t)15) : 0;
+}
 
 // The Schur terms of one insertion ((|A|+1)(|A|+2)/2 of them) are produced in rounds of whole matrix rows
 // into one half of a double buffer of kTermsChunk doubles per half while thread 0 folds the other half
@@ -76,7 +93,7 @@ __host__ __device__ inline int terms_doubles(int cap)
 }
 
 // `cap` = largest active set this launch can hold (a capacity tier, <= n + 1)
-__host__ __device__ inline size_t solver_smem_bytes(int n, int cap)
+__host__ __device__ inline size_t solver_smem_bytes(int n, int cap, size_t extra = 0)
 {
     const int LD = (cap + 1) | 1, W = (n + 31) / 32;
     const int LV = LD > n ? LD : n;  // d doubles as the budget oracle's gain vector [n]
@@ -86,10 +103,10 @@ __host__ __device__ inline size_t solver_smem_bytes(int n, int cap)
     b += (size_t)8 * sizeof(int);
     b += (size_t)(cap * W + W) * sizeof(uint32_t);
     b += (size_t)2 * n + 16;
-    return (b + 15) & ~(size_t)15;
+    return ((b + 15) & ~(size_t)15) + extra;
 }
 
-__device__ inline SolverSmem carve(unsigned char* raw, int n, int cap)
+__device__ inline SolverSmem carve(unsigned char* raw, int n, int cap, int L = 0, int E = 0)
 {
     const int LD = (cap + 1) | 1, W = (n + 31) / 32;
     const int ne = (n + 1) & ~1, ce = terms_doubles(cap);
@@ -115,6 +132,10 @@ __device__ inline SolverSmem carve(unsigned char* raw, int n, int cap)
     s.bits = up; up += cap * W;
     s.ynew = up; up += W;
     s.bp = reinterpret_cast<unsigned char*>(up);
+    s.te = reinterpret_cast<double*>(raw + solver_smem_bytes(n, cap));
+    s.val = s.te + E;
+    s.lay = reinterpret_cast<int*>(s.val + 64);
+    s.ys = s.lay + 2 * L + 3;
     return s;
 }
 
@@ -235,12 +256,69 @@ __device__ double map_sequence(const SolverSmem& sm, int n, const double* edge)
     return v;
 }
 
+// lvmhelpers/sequence.h:74-151, general chain.  Warp 0: lane k owns state k of the current position (S_i <= 32),
+// the values of the previous position sit in sm.val, back-pointers in sm.bp
+// (one per variable).  Additions in the reference's order: values[i][l] + edge, then + node; among equal
+// predecessors the lower state wins (`best < 0 || val > best_value`, sequence.h:112,136).
+__device__ double map_chain(const SolverSmem& sm, int n, int L)
+{
+    const int W = (n + 31) / 32;
+    const int* off = sm.lay;
+    const int* eb = sm.lay + L + 1;
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        double* val = sm.val;             // [2][32]
+        int S0 = off[1] - off[0];
+        if (lane < S0) val[lane] = __dadd_rn(sm.son[off[0] + lane], sm.te[eb[0] + lane]);
+        __syncwarp();
+        int cur = 0;
+        for (int i = 0; i + 1 < L; ++i) {
+            const int Sp = off[i + 1] - off[i], Sc = off[i + 2] - off[i + 1];
+            if (lane < Sc) {
+                double best_value = 0.0;
+                int best = -1;
+                for (int l = 0; l < Sp; ++l) {
+                    const double v = __dadd_rn(val[cur * 32 + l], sm.te[eb[i + 1] + l * Sc + lane]);
+                    if (best < 0 || v > best_value) { best_value = v; best = l; }
+                }
+                val[(cur ^ 1) * 32 + lane] = __dadd_rn(best_value, sm.son[off[i + 1] + lane]);
+                sm.bp[off[i + 1] + lane] = (unsigned char)best;
+            }
+            cur ^= 1;
+            __syncwarp();
+        }
+        if (lane == 0) {
+            const int Sl = off[L] - off[L - 1];
+            double best_value = 0.0;
+            int best = -1;
+            for (int l = 0; l < Sl; ++l) {
+                const double v = __dadd_rn(val[cur * 32 + l], sm.te[eb[L] + l]);
+                if (best < 0 || v > best_value) { best_value = v; best = l; }
+            }
+            sm.red[39] = best_value;
+            for (int q = 0; q < W; ++q) sm.ynew[q] = 0u;
+            int state = best;
+            for (int i = L - 1; i >= 0; --i) {
+                sm.ys[i] = state;
+                const int b = off[i] + state;
+                sm.ynew[b >> 5] |= 1u << (b & 31);
+                if (i > 0) state = sm.bp[off[i] + state];
+            }
+        }
+    }
+    __syncthreads();
+    const double v = sm.red[39];
+    __syncthreads();
+    return v;
+}
+
 template <int KIND>
 __device__ __forceinline__ double factor_map(const SolverSmem& sm, int n, int budget,
-                                             const double* edge)
+                                             const double* edge, int L = 0)
 {
     if (KIND == SMLVM_FACTOR_BERNOULLI) return map_bernoulli(sm, n);
     if (KIND == SMLVM_FACTOR_BUDGET) return map_budget(sm, n, budget);
+    if (KIND == SMLVM_FACTOR_SEQUENCE) return map_chain(sm, n, L);
     return map_sequence(sm, n, edge);
 }
 
@@ -282,9 +360,27 @@ __device__ __forceinline__ double fold_serial(const double* terms, int total, do
 // oracle calls; for the sequence every set bit is followed by its transition score or an exact 0.0),
 // then lane 0 folds the dense list.  Result valid in lane 0.
 template <int KIND>
-__device__ double evaluate_warp(const SolverSmem& sm, int n)
+__device__ double evaluate_warp(const SolverSmem& sm, int n, int L = 0)
 {
     const int lane = threadIdx.x & 31;
+    if (KIND == SMLVM_FACTOR_SEQUENCE) {
+        // sequence.h:154-179: node then edge at every position (sm.ys = the states of ynew, written by the oracle
+        // that produced it), the stop edge last -- one sequential fp64 sum
+        double acc = 0.0;
+        if (lane == 0) {
+            const int* off = sm.lay;
+            const int* eb = sm.lay + L + 1;
+            int prev = 0;
+            for (int i = 0; i < L; ++i) {
+                const int st = sm.ys[i], Sc = off[i + 1] - off[i];
+                acc = __dadd_rn(acc, sm.eta[off[i] + st]);
+                acc = __dadd_rn(acc, sm.te[eb[i] + prev * Sc + st]);
+                prev = st;
+            }
+            acc = __dadd_rn(acc, sm.te[eb[L] + prev]);
+        }
+        return acc;
+    }
     const int W = (n + 31) >> 5;
     double* list = sm.son;  // [2 * even(n)] with soff
     int base = 0;
@@ -354,11 +450,14 @@ __device__ __forceinline__ int schur_round_end(int m, int a0, int chunk, int& co
     return a1;
 }
 
+// CountCommonValues: equal positions of two vertices.  Independent bits (on / off per position): n - Hamming
+// distance; one-hot chain: the positions where both have the same state bit set.
+template <int KIND>
 __device__ __forceinline__ int common_values(const uint32_t* a, const uint32_t* b, int W, int n)
 {
-    int diff = 0;
-    for (int q = 0; q < W; ++q) diff += __popc(a[q] ^ b[q]);
-    return n - diff;
+    int c = 0;
+    for (int q = 0; q < W; ++q) c += (KIND == SMLVM_FACTOR_SEQUENCE) ? __popc(a[q] & b[q]) : __popc(a[q] ^ b[q]);
+    return (KIND == SMLVM_FACTOR_SEQUENCE) ? c : n - c;
 }
 
 template <int KIND>
@@ -372,13 +471,17 @@ __global__ void __launch_bounds__(256, 4) sparsemap_fwd_kernel(const float* __re
                                      int32_t* __restrict__ kept, int32_t* __restrict__ iters,
                                      int32_t* __restrict__ status, double* __restrict__ S_arena,
                                      long long S_capacity, long long* __restrict__ S_offsets,
-                                     unsigned long long* __restrict__ S_cursor)
+                                     unsigned long long* __restrict__ S_cursor, SeqArgs seq)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int cap_out = n + 1;                    // layout of the padded outputs (ABI)
     const int LD = (cap + 1) | 1, W = (n + 31) / 32;  // odd LD: row-wise reads spread over banks
-    const SolverSmem sm = carve(smem_raw, n, cap);
+    const SolverSmem sm = carve(smem_raw, n, cap, seq.L, seq.E);
     const int tid = threadIdx.x, T = blockDim.x;
+    // positions of a vertex = common(y, y): the n bits, or the L positions of the one-hot chain
+    const int npos = KIND == SMLVM_FACTOR_SEQUENCE ? seq.L : n;
+    if (KIND == SMLVM_FACTOR_SEQUENCE)
+        for (int i = tid; i < 2 * seq.L + 3; i += T) sm.lay[i] = __ldg(seq.lay + i);
 
     // the first capacity tier takes every sample; later tiers only the samples an earlier tier could not hold,
     // from the worklist that tier appended them to (a small persistent grid: no empty CTAs)
@@ -409,19 +512,21 @@ __global__ void __launch_bounds__(256, 4) sparsemap_fwd_kernel(const float* __re
                 sm.soff[i] = 0.0;
             }
         }
+        if (KIND == SMLVM_FACTOR_SEQUENCE)
+            for (int e = tid; e < seq.E; e += T) sm.te[e] = t != nullptr ? (double)t[row * (int64_t)seq.E + e] : 0.0;
         __syncthreads();
 
         // ---- seed: single MAP vertex, weight 1, inv = [[-n, 1], [1, 0]] ---------------------
         // (init_active_set_from_scores, sparsemap.py:25-27, or the LP solution under eta)
-        factor_map<KIND>(sm, n, budget, init_scores != nullptr ? nullptr : sm.t);
+        factor_map<KIND>(sm, n, budget, init_scores != nullptr ? nullptr : sm.t, seq.L);
         __syncthreads();
         if (tid < 32) {
-            const double sc0 = evaluate_warp<KIND>(sm, n);
+            const double sc0 = evaluate_warp<KIND>(sm, n, seq.L);
             if (tid == 0) {
                 sm.score[0] = sc0;
                 sm.p[0] = 1.0;
                 sm.z[0] = 1.0;
-                sm.inv[0] = -(double)n;
+                sm.inv[0] = -(double)npos;
                 sm.inv[1] = 1.0;
                 sm.inv[LD] = 1.0;
                 sm.inv[LD + 1] = 0.0;
@@ -570,12 +675,12 @@ __global__ void __launch_bounds__(256, 4) sparsemap_fwd_kernel(const float* __re
                         else uoff = __dadd_rn(uoff, zz);
                     }
                     sm.son[i] = __dsub_rn(sm.eta[i], uon);
-                    sm.soff[i] = __dsub_rn(0.0, uoff);
+                    if (KIND != SMLVM_FACTOR_SEQUENCE) sm.soff[i] = __dsub_rn(0.0, uoff);   // (the chain has no "off" half)
                 }
                 // Bernoulli / budget oracles read, per thread, the scores that thread wrote
-                if (KIND == SMLVM_FACTOR_SEQUENCE_BINARY) __syncthreads();
+                if (KIND == SMLVM_FACTOR_SEQUENCE_BINARY || KIND == SMLVM_FACTOR_SEQUENCE) __syncthreads();
                 PHASE(3);
-                const double value = factor_map<KIND>(sm, n, budget, sm.t);  // ends behind a barrier
+                const double value = factor_map<KIND>(sm, n, budget, sm.t, seq.L);  // ends behind a barrier
                 PHASE(4);
                 if (value <= tau + 1e-9) {
                     st = SMLVM_SOLVE_CONVERGED;
@@ -587,9 +692,9 @@ __global__ void __launch_bounds__(256, 4) sparsemap_fwd_kernel(const float* __re
                 int same = 0;
                 if (tid == 0) sm.r[0] = 1.0;
                 for (int a = tid; a < m; a += T) {
-                    const int c = common_values(sm.bits + a * W, sm.ynew, W, n);
+                    const int c = common_values<KIND>(sm.bits + a * W, sm.ynew, W, n);
                     sm.r[a + 1] = (double)c;
-                    same |= (c == n) ? 1 : 0;
+                    same |= (c == npos) ? 1 : 0;
                 }
                 same = __syncthreads_or(same);
                 PHASE(5);
@@ -607,7 +712,7 @@ __global__ void __launch_bounds__(256, 4) sparsemap_fwd_kernel(const float* __re
                 schur_terms_fill(sm, sm.terms, m, LD, 0, a_end, 0);
                 __syncthreads();
                 PHASE(6);
-                double sfold = (double)n;
+                double sfold = (double)npos;
                 const int fill_w0 = T > 32 ? 1 : 0;  // warp 0 folds: the others fill the next round meanwhile
                 for (int half = 0, first = 1;; half ^= 1, first = 0) {
                     int cnt_nxt = 0, a_nxt = a_end;
@@ -620,7 +725,7 @@ __global__ void __launch_bounds__(256, 4) sparsemap_fwd_kernel(const float* __re
                     PHASE(12);
                     if (first) {
                         if ((tid >> 5) == eval_warp) {
-                            const double scn = evaluate_warp<KIND>(sm, n);
+                            const double scn = evaluate_warp<KIND>(sm, n, seq.L);
                             if ((tid & 31) == 0) sm.red[35] = scn;
                         }
                         for (int j = T - 1 - tid; j <= m; j += T) {
@@ -770,13 +875,14 @@ sparsemap_bwd_kernel(const float* __restrict__ dp, const int64_t* __restrict__ o
                      int only_positive, const float* __restrict__ p_pad,
                      const uint32_t* __restrict__ aset_bits, const int32_t* __restrict__ counts,
                      const double* __restrict__ S_arena, const long long* __restrict__ S_offsets,
-                     float* __restrict__ dx, float* __restrict__ dt, int64_t rows, int n)
+                     float* __restrict__ dx, float* __restrict__ dt, int64_t rows, int n, SeqArgs seq)
 {
     extern __shared__ double sh[];
     const int cap = n + 1, W = (n + 31) / 32;
     double* g = sh;        // [cap] upstream gradient in solver order
     double* wv = sh + cap; // [cap]
     const int tid = threadIdx.x, T = blockDim.x;
+    const int dt_len = seq.L > 0 ? seq.E : n - 1;
     for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
         const int m = __ldg(counts + row);
         const int64_t base = __ldg(offsets + row);
@@ -792,10 +898,9 @@ sparsemap_bwd_kernel(const float* __restrict__ dp, const int64_t* __restrict__ o
         __syncthreads();
         const long long soff = __ldg(S_offsets + row);
         if (soff < 0) {  // this sample's inverse did not fit the arena of the forward call: fail loudly
-            for (int i = tid; i < n; i += T) {
-                dx[row * n + i] = __int_as_float(0x7fc00000);
-                if (dt != nullptr && i + 1 < n) dt[row * (int64_t)(n - 1) + i] = __int_as_float(0x7fc00000);
-            }
+            for (int i = tid; i < n; i += T) dx[row * n + i] = __int_as_float(0x7fc00000);
+            if (dt != nullptr)
+                for (int i = tid; i < dt_len; i += T) dt[row * (int64_t)dt_len + i] = __int_as_float(0x7fc00000);
             continue;
         }
         const double* S = S_arena + soff;
@@ -818,7 +923,28 @@ sparsemap_bwd_kernel(const float* __restrict__ dp, const int64_t* __restrict__ o
                 }
             }
             dx[row * n + i] = (float)on;
-            if (dt != nullptr && i + 1 < n) dt[row * (int64_t)(n - 1) + i] = (float)edge;
+            if (dt != nullptr && seq.L == 0 && i + 1 < n) dt[row * (int64_t)(n - 1) + i] = (float)edge;
+        }
+        if (dt != nullptr && seq.L > 0) {
+            // general chain: d eta_v[e] = sum_a w_a [vertex a runs over edge e].  A thread per edge of the layout
+            // (position i, previous state l, state k): both state bits set (start / stop edges: one of them).
+            const int* off = seq.lay;
+            const int* eb = seq.lay + seq.L + 1;
+            for (int e = tid; e < seq.E; e += T) {
+                int i = 0;
+                while (i < seq.L && __ldg(eb + i + 1) <= e) ++i;
+                const int Sc = i < seq.L ? __ldg(off + i + 1) - __ldg(off + i) : 1;
+                const int l = (e - __ldg(eb + i)) / Sc, k = (e - __ldg(eb + i)) - l * Sc;
+                const int bp = i > 0 ? __ldg(off + i - 1) + l : -1, bc = i < seq.L ? __ldg(off + i) + k : -1;
+                double acc = 0.0;
+                for (int a = 0; a < m; ++a) {
+                    const uint32_t* bw = aset_bits + (row * cap + a) * W;
+                    const bool hp = bp < 0 || ((__ldg(bw + (bp >> 5)) >> (bp & 31)) & 1u);
+                    const bool hc = bc < 0 || ((__ldg(bw + (bc >> 5)) >> (bc & 31)) & 1u);
+                    if (hp && hc) acc += wv[a];
+                }
+                dt[row * (int64_t)seq.E + e] = (float)acc;
+            }
         }
     }
 }
@@ -844,7 +970,7 @@ static int solver_threads(int n, int kind, int64_t rows = INT64_MAX)
 // First tier: the capacity that lets 5 samples share an SM (4 for the budget factor, whose active
 // sets run larger: measured at n = 128, bernoulli q99 = 57 vertices, budget-64 q99 = 83), second
 // tier 2 per SM, last tier n + 1.
-static int plan_tiers(int n, int kind, int (&tiers)[3])
+static int plan_tiers(int n, int kind, int (&tiers)[3], size_t extra = 0)
 {
     static int single = -1;
     static int forced[3] = {0, 0, 0};
@@ -858,7 +984,7 @@ static int plan_tiers(int n, int kind, int (&tiers)[3])
     auto cap_for = [&](int ctas) {
         const size_t budget_b = (size_t)(227 * 1024) / ctas - 1024;
         int c = n + 1;
-        while (c > 8 && solver_smem_bytes(n, c) > budget_b) --c;
+        while (c > 8 && solver_smem_bytes(n, c, extra) > budget_b) --c;
         return c;
     };
     int ntier = 0;
@@ -920,15 +1046,16 @@ extern "C" size_t smlvm_sparsemap_workspace_bytes(int64_t rows)
     return 2 * (64 + (size_t)rows * sizeof(int32_t)) + 64;
 }
 
-extern "C" int smlvm_sparsemap_fwd(const float* x, const float* t, const double* init_scores,
-                                   int32_t kind, int32_t budget, int32_t max_iter, int64_t rows,
-                                   int32_t n, float* p_pad, uint32_t* aset_bits, int32_t* counts,
-                                   int32_t* kept, int32_t* iters, int32_t* status, double* S_arena,
-                                   int64_t S_capacity, int64_t* S_offsets, uint64_t* S_cursor,
-                                   void* workspace, size_t workspace_bytes, void* stream)
+static int sparsemap_fwd_impl(const float* x, const float* t, const double* init_scores,
+                              int32_t kind, int32_t budget, int32_t max_iter, int64_t rows,
+                              int32_t n, float* p_pad, uint32_t* aset_bits, int32_t* counts,
+                              int32_t* kept, int32_t* iters, int32_t* status, double* S_arena,
+                              int64_t S_capacity, int64_t* S_offsets, uint64_t* S_cursor,
+                              void* workspace, size_t workspace_bytes, void* stream, SeqArgs seq)
 {
     if (rows < 0 || n < 1 || max_iter < 0 || budget < 0) return SMLVM_ERR_ARG;
-    if (kind < SMLVM_FACTOR_BERNOULLI || kind > SMLVM_FACTOR_SEQUENCE_BINARY) return SMLVM_ERR_ARG;
+    if (kind < SMLVM_FACTOR_BERNOULLI || kind > SMLVM_FACTOR_SEQUENCE) return SMLVM_ERR_ARG;
+    const size_t extra = seq_extra_bytes(seq.L, seq.E);
     if (n > SMLVM_SPARSEMAP_MAX_BITS) return SMLVM_ERR_UNSUPPORTED;
     if (rows == 0) return SMLVM_OK;
     if (x == nullptr || p_pad == nullptr || aset_bits == nullptr || counts == nullptr)
@@ -944,7 +1071,8 @@ extern "C" int smlvm_sparsemap_fwd(const float* x, const float* t, const double*
     // tier's worklist and re-solved from scratch there by a small persistent grid.  Same stream, no host
     // synchronisation; an empty tier costs one launch of CTAs that read a zero and exit.
     int tiers[3];
-    const int ntier = plan_tiers(n, kind, tiers);
+    const int ntier = plan_tiers(n, kind, tiers, extra);
+    if (solver_smem_bytes(n, tiers[0], extra) > (size_t)227 * 1024) return SMLVM_ERR_UNSUPPORTED;
     // first tier: one CTA per sample, the hardware scheduler evens out the data-dependent solve lengths
     // (measured best against persistent grids of 16/64/256 CTAs per SM at n = 32 and n = 128)
     int64_t cap_grid = 0x7fffffff;
@@ -980,14 +1108,16 @@ extern "C" int smlvm_sparsemap_fwd(const float* x, const float* t, const double*
     do {                                                                                           \
         cudaError_t e =                                                                            \
             cudaFuncSetAttribute(sparsemap_fwd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                 (int)solver_smem_bytes(n, n + 1));                                \
+                                 (int)(solver_smem_bytes(n, n + 1, extra) < (size_t)227 * 1024             \
+                                           ? solver_smem_bytes(n, n + 1, extra) : (size_t)227 * 1024));   \
         if (e != cudaSuccess) return (int)e;                                                       \
         e = cudaFuncSetAttribute(sparsemap_fwd_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, \
                                  (int)cudaSharedmemCarveoutMaxShared);                             \
         if (e != cudaSuccess) return (int)e;                                                       \
         for (int ti = 0; ti < ntier; ++ti) {                                                       \
             const int th = (ti == 0 || tail_threads == 0) ? threads : tail_threads;                \
-            const size_t smem = solver_smem_bytes(n, tiers[ti]);                                   \
+            const size_t smem = solver_smem_bytes(n, tiers[ti], extra);                            \
+            if (smem > (size_t)227 * 1024) return SMLVM_ERR_UNSUPPORTED;                           \
             int g = grid;                                                                          \
             if (ti > 0) {  /* persistent: as many CTAs as fit the device at this tier's footprint */ \
                 int per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));                          \
@@ -1000,15 +1130,42 @@ extern "C" int smlvm_sparsemap_fwd(const float* x, const float* t, const double*
                 wl_list[ti], wl_count[ti], ti + 1 < ntier ? wl_list[ti + 1] : nullptr,             \
                 ti + 1 < ntier ? wl_count[ti + 1] : nullptr, p_pad, aset_bits, counts, kept, iters, \
                 status, S_arena, (long long)S_capacity, reinterpret_cast<long long*>(S_offsets),   \
-                reinterpret_cast<unsigned long long*>(S_cursor));                                  \
+                reinterpret_cast<unsigned long long*>(S_cursor), seq);                             \
         }                                                                                          \
     } while (0)
     if (kind == SMLVM_FACTOR_BERNOULLI) SMLVM_SMAP_LAUNCH(SMLVM_FACTOR_BERNOULLI);
     else if (kind == SMLVM_FACTOR_BUDGET) SMLVM_SMAP_LAUNCH(SMLVM_FACTOR_BUDGET);
+    else if (kind == SMLVM_FACTOR_SEQUENCE) SMLVM_SMAP_LAUNCH(SMLVM_FACTOR_SEQUENCE);
     else SMLVM_SMAP_LAUNCH(SMLVM_FACTOR_SEQUENCE_BINARY);
 #undef SMLVM_SMAP_LAUNCH
     SMLVM_LAUNCH_CHECK();
     return SMLVM_OK;
+}
+
+extern "C" int smlvm_sparsemap_fwd(const float* x, const float* t, const double* init_scores,
+                                   int32_t kind, int32_t budget, int32_t max_iter, int64_t rows,
+                                   int32_t n, float* p_pad, uint32_t* aset_bits, int32_t* counts,
+                                   int32_t* kept, int32_t* iters, int32_t* status, double* S_arena,
+                                   int64_t S_capacity, int64_t* S_offsets, uint64_t* S_cursor,
+                                   void* workspace, size_t workspace_bytes, void* stream)
+{
+    if (kind == SMLVM_FACTOR_SEQUENCE) return SMLVM_ERR_ARG;   // the general chain has its own entry point
+    SeqArgs none = {nullptr, 0, 0};
+    return sparsemap_fwd_impl(x, t, init_scores, kind, budget, max_iter, rows, n, p_pad, aset_bits, counts, kept, iters,
+                              status, S_arena, S_capacity, S_offsets, S_cursor, workspace, workspace_bytes, stream, none);
+}
+
+extern "C" int smlvm_sparsemap_seq_fwd(const float* x, const float* edge_scores, const int32_t* layout, int32_t length,
+                                       int32_t num_edges, int32_t max_iter, int64_t rows, int32_t n, float* p_pad,
+                                       uint32_t* aset_bits, int32_t* counts, int32_t* kept, int32_t* iters,
+                                       int32_t* status, double* S_arena, int64_t S_capacity, int64_t* S_offsets,
+                                       uint64_t* S_cursor, void* workspace, size_t workspace_bytes, void* stream)
+{
+    if (layout == nullptr || length < 1 || num_edges < 2 || n < length) return SMLVM_ERR_ARG;
+    SeqArgs seq = {layout, length, num_edges};
+    return sparsemap_fwd_impl(x, edge_scores, nullptr, SMLVM_FACTOR_SEQUENCE, 0, max_iter, rows, n, p_pad, aset_bits, counts,
+                              kept, iters, status, S_arena, S_capacity, S_offsets, S_cursor, workspace, workspace_bytes,
+                              stream, seq);
 }
 
 extern "C" int smlvm_sparsemap_expand(const float* p_pad, const uint32_t* aset_bits,
@@ -1028,10 +1185,10 @@ extern "C" int smlvm_sparsemap_expand(const float* p_pad, const uint32_t* aset_b
     return SMLVM_OK;
 }
 
-extern "C" int smlvm_sparsemap_bwd(const float* dp, const int64_t* offsets, int32_t only_positive,
-                                   const float* p_pad, const uint32_t* aset_bits,
-                                   const int32_t* counts, const double* S_arena, const int64_t* S_offsets,
-                                   float* dx, float* dt, int64_t rows, int32_t n, void* stream)
+static int sparsemap_bwd_impl(const float* dp, const int64_t* offsets, int32_t only_positive,
+                              const float* p_pad, const uint32_t* aset_bits,
+                              const int32_t* counts, const double* S_arena, const int64_t* S_offsets,
+                              float* dx, float* dt, int64_t rows, int32_t n, void* stream, SeqArgs seq)
 {
     if (rows < 0 || n < 1) return SMLVM_ERR_ARG;
     if (rows == 0) return SMLVM_OK;
@@ -1043,7 +1200,29 @@ extern "C" int smlvm_sparsemap_bwd(const float* dp, const int64_t* offsets, int3
     int64_t cap = (int64_t)device_sm_count() * 32;
     sparsemap_bwd_kernel<<<(int)(rows < cap ? rows : cap), 128, smem, as_stream(stream)>>>(
         dp, offsets, only_positive, p_pad, aset_bits, counts, S_arena,
-        reinterpret_cast<const long long*>(S_offsets), dx, dt, rows, n);
+        reinterpret_cast<const long long*>(S_offsets), dx, dt, rows, n, seq);
     SMLVM_LAUNCH_CHECK();
     return SMLVM_OK;
+}
+
+extern "C" int smlvm_sparsemap_bwd(const float* dp, const int64_t* offsets, int32_t only_positive,
+                                   const float* p_pad, const uint32_t* aset_bits,
+                                   const int32_t* counts, const double* S_arena, const int64_t* S_offsets,
+                                   float* dx, float* dt, int64_t rows, int32_t n, void* stream)
+{
+    SeqArgs none = {nullptr, 0, 0};
+    return sparsemap_bwd_impl(dp, offsets, only_positive, p_pad, aset_bits, counts, S_arena, S_offsets, dx, dt, rows, n,
+                              stream, none);
+}
+
+extern "C" int smlvm_sparsemap_seq_bwd(const float* dp, const int64_t* offsets, int32_t only_positive,
+                                       const float* p_pad, const uint32_t* aset_bits, const int32_t* counts,
+                                       const double* S_arena, const int64_t* S_offsets, const int32_t* layout,
+                                       int32_t length, int32_t num_edges, float* dx, float* dedge, int64_t rows,
+                                       int32_t n, void* stream)
+{
+    if (layout == nullptr || length < 1 || num_edges < 2) return SMLVM_ERR_ARG;
+    SeqArgs seq = {layout, length, num_edges};
+    return sparsemap_bwd_impl(dp, offsets, only_positive, p_pad, aset_bits, counts, S_arena, S_offsets, dx, dedge, rows, n,
+                              stream, seq);
 }

@@ -56,6 +56,10 @@ _PROTOTYPES = {
     "smlvm_sparsemap_fwd": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i64, _i32,
                                            _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "smlvm_sparsemap_expand": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "smlvm_sparsemap_seq_fwd": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
+                                               _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "smlvm_sparsemap_seq_bwd": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i64,
+                                               _i32, _vp]),
     "smlvm_sparsemap_bwd": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "smlvm_reduce_workspace_bytes": (_sz, []),
     "smlvm_wloss_dense_fwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _i32, _vp, _sz, _vp]),

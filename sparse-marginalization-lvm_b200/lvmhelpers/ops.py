@@ -672,6 +672,83 @@ def sparsemap_solve(x, kind, budget=0, t=None, init_scores=None, max_iter=100, k
     return state
 
 
+def sequence_layout(num_states, device):
+    """int32 [2L+3] on ``device``: offsets of the states of position 0..L, then the first edge of position 0..L+1, in
+    the order FactorSequence::Initialize numbers them (sequence.h:264-291)."""
+    ns = [int(s) for s in num_states]
+    L = len(ns)
+    off, o = [], 0
+    for s_ in ns:
+        off.append(o)
+        o += s_
+    off.append(o)
+    eb, e = [], 0
+    for i in range(L + 1):
+        eb.append(e)
+        e += (ns[i - 1] if i > 0 else 1) * (ns[i] if i < L else 1)
+    eb.append(e)
+    return torch.tensor(off + eb, dtype=torch.int32, device=device), o, e
+
+
+def sparsemap_solve_sequence(x, edge_scores, num_states, max_iter=100):
+    """General linear chain (lvmhelpers/sequence.h; PFactorSequence): x [rows, sum num_states] node scores,
+    edge_scores [rows, E] (None: zeros) -> the padded solver state of ``sparsemap_solve`` (vertices as one-hot bits
+    over the (position, state) variables) + the layout.  The arena of the inverses is sized for the worst case."""
+    x = _f32c(x, "scores")
+    rows, n = x.shape
+    dev = x.device
+    lay, V, E = sequence_layout(num_states, dev)
+    if V != n:
+        raise ValueError("scores have %d columns, num_states sums to %d" % (n, V))
+    if max(num_states) > 32 or n > N.SPARSEMAP_MAX_BITS:
+        raise ValueError("the general chain holds at most 32 states per position and %d variables" % N.SPARSEMAP_MAX_BITS)
+    if edge_scores is not None:
+        edge_scores = _f32c(edge_scores, "edge scores")
+        if tuple(edge_scores.shape) != (rows, E):
+            raise ValueError("edge scores must be [%d, %d]" % (rows, E))
+    cap = lib.smlvm_sparsemap_capacity(n)
+    W = (n + 31) // 32
+    p_pad = torch.empty((rows, cap), dtype=torch.float32, device=dev)
+    bits = torch.empty((rows, cap, W), dtype=torch.int32, device=dev)
+    counts, kept, iters, status = (torch.empty(rows, dtype=torch.int32, device=dev) for _ in range(4))
+    capacity = max(rows * (n + 1) ** 2, 1)
+    S = torch.empty(capacity, dtype=torch.float64, device=dev)
+    S_off = torch.empty(rows, dtype=torch.int64, device=dev)
+    cursor = torch.zeros(1, dtype=torch.int64, device=dev)
+    state = dict(p_pad=p_pad, bits=bits, counts=counts, kept=kept, iters=iters, status=status, S=S, S_offsets=S_off,
+                 S_cursor=cursor, S_capacity=capacity, n=n, rows=rows, kind=N.FACTOR_SEQUENCE, budget=0,
+                 layout=lay, length=len(num_states), num_edges=E, num_states=[int(s) for s in num_states])
+    if rows == 0:
+        return state
+    ws = torch.empty(lib.smlvm_sparsemap_workspace_bytes(rows), dtype=torch.uint8, device=dev)
+    check(lib.smlvm_sparsemap_seq_fwd(ptr(x), ptr(edge_scores), ptr(lay), len(num_states), E, int(max_iter), rows, n,
+                                      ptr(p_pad), ptr(bits), ptr(counts), ptr(kept), ptr(iters), ptr(status), ptr(S),
+                                      capacity, ptr(S_off), ptr(cursor), ptr(ws), ws.numel(), stream()),
+          "smlvm_sparsemap_seq_fwd")
+    return state
+
+
+def sparsemap_bwd_sequence(state, dp, offsets, only_positive):
+    """(dx [rows, n], dedge [rows, E]) of the general chain."""
+    rows, n, E = state["rows"], state["n"], state["num_edges"]
+    dp = dp.contiguous().float()
+    dx = torch.empty((rows, n), dtype=torch.float32, device=dp.device)
+    de = torch.empty((rows, E), dtype=torch.float32, device=dp.device)
+    check(lib.smlvm_sparsemap_seq_bwd(ptr(dp), ptr(offsets), int(only_positive), ptr(state["p_pad"]), ptr(state["bits"]),
+                                      ptr(state["counts"]), ptr(state["S"]), ptr(state["S_offsets"]), ptr(state["layout"]),
+                                      state["length"], E, ptr(dx), ptr(de), rows, n, stream()), "smlvm_sparsemap_seq_bwd")
+    return dx, de
+
+
+def onehot_to_states(aset, num_states):
+    """[N, sum num_states] one-hot rows -> [N, L] fp32 state ids (the configurations get_sparse_solution returns)."""
+    cols, o = [], 0
+    for s_ in num_states:
+        cols.append(aset[:, o:o + s_].argmax(-1))
+        o += s_
+    return torch.stack(cols, dim=-1).to(torch.float32)
+
+
 def sparsemap_arena_overflow(state, needed=None):
     """Doubles the arena should have had if some inverse did not fit, else 0.  Reads the solver's cursor (a host
     synchronisation) unless the caller already has it (``needed``); remembers the per-sample need."""

@@ -21,7 +21,7 @@ import torch
 from . import ops
 from .pbernoulli import PFactorBernoulli
 from .pbudget import PFactorBudget
-from .psequence import PFactorSequenceBinary
+from .psequence import PFactorSequence, PFactorSequenceBinary
 
 
 def draw_init_scores(rows, n):
@@ -152,6 +152,49 @@ class SequenceBinarySparseMAP(SequenceSparseMAP):
     def backward(cls, ctx, dp, daset):
         d_eta_u, d_eta_v = cls.jv(ctx, dp)
         return d_eta_u, d_eta_v, None, None
+
+
+class GeneralSequenceSparseMAP(SequenceSparseMAP):
+    """SparseMAP over ``PFactorSequence`` (lvmhelpers/psequence.pyx:10-22, sequence.h:25-291): a chain whose position
+    i has ``num_states[i]`` states, node scores ``x [sum num_states]`` and one additional score per edge, ``t [E]``
+    (start, transitions, stop in the order of sequence.h:264-291).  The reference binds the factor but has no
+    autograd function over it; this one follows ``SequenceSparseMAP`` (sparsemap.py:47-87): returns ``(p [|A|],
+    aset [|A|, L])`` with the state sequences as the configurations ``get_sparse_solution`` returns, and the
+    backward gives ``(d x, d t)``.  ``init=False`` only (the reference's init path raises for sequences, :68)."""
+
+    @classmethod
+    def make_factor(cls, ctx):
+        f = PFactorSequence()
+        f.initialize(ctx.num_states)
+        return f
+
+    @classmethod
+    def forward(cls, ctx, x, t, num_states, max_iter):
+        ctx.num_states = [int(s) for s in num_states]
+        ctx.f = cls.make_factor(ctx)
+        if x.dim() != 1 or x.shape[0] != ctx.f.num_variables:
+            raise ValueError("expected %d node scores, got shape %s" % (ctx.f.num_variables, tuple(x.shape)))
+        if t.dim() != 1 or t.shape[0] != ctx.f.num_additionals:
+            raise ValueError("expected %d edge scores, got shape %s" % (ctx.f.num_additionals, tuple(t.shape)))
+        state = ops.sparsemap_solve_sequence(x.detach().reshape(1, -1), t.detach().reshape(1, -1), ctx.num_states,
+                                             max_iter=max_iter)
+        offsets = ops.scan_counts(state["counts"])
+        total = int(offsets[-1].item())
+        p, onehot, _ = ops.sparsemap_expand(state, False, offsets, total, want_idx=False)
+        aset = ops.onehot_to_states(onehot, ctx.num_states)
+        ctx.state, ctx.offsets = state, offsets
+        ctx.mark_non_differentiable(aset)
+        return p, aset
+
+    @classmethod
+    def backward(cls, ctx, dp, daset):
+        dx, dt = ops.sparsemap_bwd_sequence(ctx.state, dp, ctx.offsets, False)
+        return dx.reshape(-1), dt.reshape(-1), None, None
+
+
+def general_sequence_smap(x, t, num_states, max_iter=100):
+    """SparseMAP over the general chain factor (``PFactorSequence``): see ``GeneralSequenceSparseMAP``."""
+    return GeneralSequenceSparseMAP.apply(x, t, num_states, max_iter)
 
 
 def bernoulli_smap(x, max_iter=100, init=True):

@@ -230,3 +230,30 @@ def test_factor_maps_live_reference_when_present(oracle):
             y0, v0 = oracle.factor_map(eta, kind, budget, t=t)
             y1, v1 = oracle.factor_map(eta, kind, budget, t=t, which="ref_factors")
             assert np.array_equal(y0, y1) and abs(v0 - v1) < 1e-12
+
+
+def test_general_sequence_restatement_equals_reference_header():
+    """oracle RSequence (factors_restated.h) against the reference's own FactorSequence (sequence.h compiled into
+    oracle/_ref/libref_factors.so): Viterbi (ties included) and the whole solve, vertex for vertex."""
+    import numpy as np
+    import oracle
+    oracle.build(ref=True)
+    if not oracle.have_ref("ref_factors"):
+        import pytest
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    rng = np.random.default_rng(3)
+    for ns in ([3, 4, 2, 5, 3], [2] * 10, [4] * 6, [1, 3, 1, 2], [7]):
+        V, E = sum(ns), oracle.seq_num_edges(ns)
+        for trial in range(6):
+            x, add = rng.standard_normal(V), rng.standard_normal(E) * 0.5
+            if trial == 0:
+                x, add = np.round(x), np.zeros(E)
+            ya, va = oracle.seq_map(x, add, ns)
+            yb, vb = oracle.seq_map(x, add, ns, which="ref_factors")
+            assert np.array_equal(ya, yb) and va == vb
+            a = oracle.seq_fwd(x, add, ns, max_iter=200)
+            b = oracle.seq_fwd(x, add, ns, max_iter=200, which="ref_factors")
+            assert np.array_equal(a["aset"], b["aset"]) and np.array_equal(a["p"], b["p"])
+            assert a["iters"] == b["iters"] and a["status"] == b["status"]
+            # marginals are a distribution over state sequences: every position sums to one
+            assert abs(a["p"].sum() - 1) < 1e-9

@@ -374,3 +374,75 @@ def test_static_shape_wrapper_equals_ragged_and_replays_as_graph(budget):
     assert abs(got_loss - ref["loss"].item()) <= 1e-5 * max(1.0, abs(ref["loss"].item()))
     for a, q in zip(got_grads, params_e):
         assert (a - q.grad).abs().max().item() <= 1e-5 * max(1.0, q.grad.abs().max().item())
+
+
+SEQ_SHAPES = [[3, 4, 2, 5, 3], [2] * 12, [4] * 8, [1, 3, 1, 2], [32, 32, 32, 32], [5], [6, 2, 7, 3, 4, 4, 2, 8], [3] * 40]
+
+
+@pytest.mark.parametrize("num_states", SEQ_SHAPES)
+def test_general_sequence_factor_matches_oracle(oracle, num_states):
+    """The general chain factor (sequence.h:25-291, PFactorSequence): batched solve against the oracle's restatement
+    (pinned to the reference's own header compiled in oracle/_ref, tests/test_oracle_cpu.py): identical active sets in
+    the solver's order, p within 1e-5, iterations and status; backward (d x, d edge scores) against
+    dist_jacobian_vec of the oracle."""
+    from lvmhelpers import ops
+    V, E, L = sum(num_states), oracle.seq_num_edges(num_states), len(num_states)
+    rng = np.random.default_rng(V * 7 + L)
+    rows = 24
+    x = rng.standard_normal((rows, V)).astype(np.float32)
+    t = (rng.standard_normal((rows, E)) * 0.5).astype(np.float32)
+    x[3] = np.round(x[3] * 2) / 2          # ties in the Viterbi recursion
+    t[3] = 0.0
+    state = ops.sparsemap_solve_sequence(torch.from_numpy(x).cuda(), torch.from_numpy(t).cuda(), num_states, max_iter=200)
+    offsets = ops.scan_counts(state["counts"])
+    total = int(offsets[-1])
+    p, onehot, idx = ops.sparsemap_expand(state, False, offsets, total)
+    aset = ops.onehot_to_states(onehot, num_states).cpu().numpy().astype(np.int32)
+    assert bool((onehot.sum(-1) == L).all())
+    p, off = p.cpu().numpy(), offsets.cpu().numpy()
+    g = torch.Generator().manual_seed(1)
+    dp = torch.randn(total, generator=g)
+    dx, de = ops.sparsemap_bwd_sequence(state, dp.cuda(), offsets, False)
+    for r in range(rows):
+        ref = oracle.seq_fwd(x[r], t[r], num_states, max_iter=200)
+        sl = slice(off[r], off[r + 1])
+        assert state["counts"][r].item() == len(ref["p"])
+        assert np.array_equal(aset[sl], ref["aset"])
+        assert np.abs(p[sl] - ref["p"]).max() <= 1e-5
+        assert state["iters"][r].item() == ref["iters"] and state["status"][r].item() == ref["status"]
+        dx_ref, de_ref = oracle.seq_bwd(x[r], t[r], num_states, dp[sl].numpy(), max_iter=200)
+        scale = max(1.0, np.abs(dx_ref).max(), np.abs(de_ref).max())
+        assert np.abs(dx[r].cpu().numpy() - dx_ref).max() <= 1e-4 * scale
+        assert np.abs(de[r].cpu().numpy() - de_ref).max() <= 1e-4 * scale
+
+
+def test_general_sequence_autograd_function_and_binary_equivalence(oracle):
+    """general_sequence_smap: (p, state sequences) + gradients; with two states per position, zero start / stop edges
+    and a score on 1 -> 1 only it is the binary chain of sequence_smap (sparsemap.py:130-148)."""
+    from lvmhelpers.sparsemap import general_sequence_smap, sequence_smap
+    torch.manual_seed(5)
+    n = 9
+    x = torch.randn(n)
+    t = torch.randn(n - 1)
+    p_b, aset_b = sequence_smap(x.cuda(), t.cuda(), max_iter=200, init=False)
+    ns = [2] * n
+    xg = torch.zeros(2 * n)
+    xg[1::2] = x
+    add = torch.zeros(oracle.seq_num_edges(ns))
+    for i in range(1, n):
+        add[2 + 4 * (i - 1) + 3] = t[i - 1]       # edge (previous = 1, current = 1) of position i
+    xg = xg.cuda().requires_grad_(True)
+    add = add.cuda().requires_grad_(True)
+    p_g, aset_g = general_sequence_smap(xg, add, ns, max_iter=200)
+    assert torch.equal(aset_g, aset_b)
+    assert (p_g.detach() - p_b).abs().max().item() <= 1e-6
+    w = torch.randn(p_g.numel(), device="cuda")
+    (p_g * w).sum().backward()
+    xb = x.cuda().requires_grad_(True)
+    tb = t.cuda().requires_grad_(True)
+    p_b2, _ = sequence_smap(xb, tb, max_iter=200, init=False)
+    (p_b2 * w).sum().backward()
+    # the binary chain scores "off" states 0: its d x is the gradient of the "on" node scores
+    assert (xg.grad[1::2] - xb.grad).abs().max().item() <= 1e-5
+    got_t = torch.stack([add.grad[2 + 4 * (i - 1) + 3] for i in range(1, n)])
+    assert (got_t - tb.grad).abs().max().item() <= 1e-5
