@@ -593,8 +593,11 @@ def extra_paths(args, world, device, rank):
                                                value=rows * world / (res_marg["ms_per_step"] * 1e-3))
     del dec_in, lab
 
-    for name, kind, budget in (("sparsemap_bernoulli_n128", 0, 0), ("sparsemap_budget64_n128", 1, 64)):
-        rows = args.path_rows_smap
+    smap_cases = [("sparsemap_bernoulli_n128", 0, 0, args.path_rows_smap), ("sparsemap_budget64_n128", 1, 64, args.path_rows_smap)]
+    if world == 1 and args.rows >= (1 << 20):
+        # the sweep's largest point, one GPU: 1,048,576 samples (inverses bump-allocated from one arena, ~30 GB)
+        smap_cases += [("sparsemap_bernoulli_n128_1M", 0, 0, 1 << 20), ("sparsemap_budget64_n128_1M", 1, 64, 1 << 20)]
+    for name, kind, budget, rows in smap_cases:
         xs = torch.randn(rows, 128, generator=g).to(device).requires_grad_(True)
         stats = {}
 
@@ -607,7 +610,7 @@ def extra_paths(args, world, device, rank):
             stats["N"] = int(p.numel())
             stats["st"] = aux["state"]
 
-        ms, _, _ = timed(smap_step, 3, 3, world, device)
+        ms, _, _ = timed(smap_step, 3, 3 if rows <= (1 << 16) else 1, world, device)
         st = stats["st"]
         n_items = stats["N"]
         fwd_bytes = rows * 4 * 128 + n_items * (4 * 128 + 8) + 4 * rows
@@ -621,8 +624,12 @@ def extra_paths(args, world, device, rank):
                                          "samples_final_size_in_tier": int(((st["counts"] <= c) & (st["counts"] > lo)).sum())}
                                         for (c, b, o), lo in zip(ops.sparsemap_plan(128, kind),
                                                                  [0] + [t[0] for t in ops.sparsemap_plan(128, kind)][:-1])],
+                     "algorithmic_bytes": fwd_bytes + bwd_bytes,
                      "hbm_frac_of_algorithmic_bytes": (fwd_bytes + bwd_bytes) / (ms / 3 * 1e-3) / 1e9
                      / measured_hbm_peak()[0]}
+        del xs, st
+        stats.clear()
+        torch.cuda.empty_cache()
     if rank == 0 and world == 1 and not args.no_cpu:
         # the reference's CPU implementations of the same branches on the box's host cores, bounded
         # samples, single-threaded as in the reference (pbinary_topk.pyx:31-34 and the per-sample
@@ -694,6 +701,41 @@ def extra_paths(args, world, device, rank):
             par[name]["ok"] = bool(par[name]["active_set_sizes_equal"] and par[name]["iterations_equal"]
                                    and aset_ok and status_ok and worst_p <= 1e-5)
         out["_parity"] = par
+    return out
+
+
+def sparsemap_roofline(paths, peak):
+    """The SparseMAP branch of the same config (north star: "sparsemax and SparseMAP marginalization") in the terms
+    of the contract's `roofline` block: algorithmic bytes of SURVEY 8(d) over the measured step time, next to what
+    actually bounds the solver -- serial fp64 work per sample (warp instructions, issue utilisation and resident
+    CTAs of the first capacity tier; ncu, profiles/r02_ncu_kernels.md) -- and the measured DRAM bytes of one step."""
+    if not paths:
+        return None
+    tj = {}
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+    out = {}
+    for name, key in (("sparsemap_bernoulli_n128", "sparsemap_step_bernoulli_65536x128"),
+                      ("sparsemap_budget64_n128", "sparsemap_step_budget64_65536x128")):
+        pth = paths.get(name)
+        if not pth:
+            continue
+        meas = tj.get(key, {})
+        ab = pth["algorithmic_bytes"]
+        ach = ab / (pth["ms_per_step"] * 1e-3) / 1e9
+        out[name] = {"bound": "serial fp64 instruction issue per sample (not HBM): the pivoting of libad3 fixes the "
+                              "summation order of every sum that feeds z",
+                     "rows_per_gpu": pth["rows_per_gpu"], "ms_per_step": pth["ms_per_step"], "value": pth["value"],
+                     "unit": UNIT, "achieved": ach, "peak": peak, "achieved_unit": "GB/s", "frac": ach / peak,
+                     "algorithmic_bytes": ab, "traffic": meas.get("dram_bytes"),
+                     "mean_iterations": pth["mean_iterations"], "mean_support": pth["mean_support"],
+                     "status_hist": pth["status_hist"], "capacity_tiers": pth["capacity_tiers"],
+                     "ncu_first_tier": meas.get("tier1"), "ncu_kernels_ms": meas.get("kernels_ms")}
+        big = paths.get(name + "_1M")
+        if big:
+            out[name]["at_1048576_rows"] = {"ms_per_step": big["ms_per_step"], "value": big["value"],
+                                            "frac": big["hbm_frac_of_algorithmic_bytes"], "status_hist": big["status_hist"]}
     return out
 
 
@@ -837,6 +879,7 @@ def run_native(args, rank, local_rank, world):
                          "step": {"algorithmic_bytes": step_bytes,
                                   "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,
                                   "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak}},
+            "roofline_sparsemap": sparsemap_roofline(paths, peak),
             "kernels": kernels,
             "resident_uninstrumented": uninstrumented,
             "cpu_baseline": cpu,
