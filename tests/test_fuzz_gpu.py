@@ -43,3 +43,12 @@ def test_fuzz_sparsemap_sequence_factor():
     if not torch.cuda.is_available():
         pytest.skip("needs a GPU")
     assert _fuzz("fuzz_solver").run_sequence(seed=5, n_cases=4, rows=32, verbose=False) == 0
+
+
+@pytest.mark.parametrize("seed", [4, 12])
+def test_fuzz_wide_support_kernels(seed):
+    """Round-2 kernels (cooperative forward, dense fused step, k-sparsemax, entmax15) on random shapes / scales /
+    adversarial rows; the long form (tools/fuzz_wide.py, 150 cases) ran with 0 mismatches on the B200."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    assert _fuzz("fuzz_wide").run(seed=seed, n_cases=10, verbose=False) == 0
