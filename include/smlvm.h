@@ -254,7 +254,10 @@ int32_t smlvm_sparsemap_plan(int32_t n, int32_t kind, int32_t* caps, int32_t* sm
  *                                     arena; ends at the number of doubles all samples needed -- > S_capacity means
  *                                     some samples got offset -1 (re-solve with an arena of that size).  Padded to
  *                                     (n+1)^2 per sample the arena cannot overflow.
- * workspace: smlvm_sparsemap_workspace_bytes(rows) bytes (worklists of the capacity tiers); rows < 2^31.          */
+ * workspace: at least smlvm_sparsemap_workspace_bytes(rows) bytes (worklists of the capacity tiers); rows < 2^31.
+ *            Bytes beyond that are used as the pool of hand-off records: a sample whose active set outgrows a tier
+ *            is resumed by the next tier from its state (~8 (|A|+1)^2 bytes) when the pool has room, re-solved from
+ *            scratch otherwise -- same results either way.                                                          */
 size_t smlvm_sparsemap_workspace_bytes(int64_t rows);
 int smlvm_sparsemap_fwd(const float* x, const float* t, const double* init_scores, int32_t kind,
                         int32_t budget, int32_t max_iter, int64_t rows, int32_t n, float* p_pad,

@@ -460,6 +460,19 @@ __device__ __forceinline__ int common_values(const uint32_t* a, const uint32_t* 
     return (KIND == SMLVM_FACTOR_SEQUENCE) ? c : n - c;
 }
 
+// A sample that outgrows its capacity tier is handed to the next one WITH its solver state (active set, p, z, scores,
+// inverse, iteration count, tau): the next tier resumes at the insertion that did not fit instead of re-solving from
+// scratch (the samples that overflow are the long ones: before this, the second tier cost 5 of 33.5 ms for 2.7 % of
+// the Bernoulli samples at n = 128, 27 of 120 ms for 6.7 % of budget-64).  Records are bump-allocated from whatever
+// the caller's workspace holds beyond its mandatory part; a record that does not fit means "re-solve" (offset -1).
+struct TierHandoff {
+    unsigned char* pool;            // record storage (NULL: always re-solve)
+    long long pool_bytes;
+    unsigned long long* cursor;     // bytes handed out
+    const long long* rec_in;        // [work] record offset of the worklist entries of THIS tier (NULL: first tier)
+    long long* rec_out;             // [..]   record offsets for the next tier's worklist
+};
+
 template <int KIND>
 __global__ void __launch_bounds__(256, 4) sparsemap_fwd_kernel(const float* __restrict__ x, const float* __restrict__ t,
                                      const double* __restrict__ init_scores, int budget,
@@ -471,7 +484,7 @@ __global__ void __launch_bounds__(256, 4) sparsemap_fwd_kernel(const float* __re
                                      int32_t* __restrict__ kept, int32_t* __restrict__ iters,
                                      int32_t* __restrict__ status, double* __restrict__ S_arena,
                                      long long S_capacity, long long* __restrict__ S_offsets,
-                                     unsigned long long* __restrict__ S_cursor, SeqArgs seq)
+                                     unsigned long long* __restrict__ S_cursor, SeqArgs seq, TierHandoff ho)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int cap_out = n + 1;                    // layout of the padded outputs (ABI)
@@ -516,6 +529,34 @@ __global__ void __launch_bounds__(256, 4) sparsemap_fwd_kernel(const float* __re
             for (int e = tid; e < seq.E; e += T) sm.te[e] = t != nullptr ? (double)t[row * (int64_t)seq.E + e] : 0.0;
         __syncthreads();
 
+        int m = 1;          // |A|
+        bool changed = true;
+        double tau = 0.0;
+        int st = SMLVM_SOLVE_MAX_ITER;
+        int it = 0, it0 = 0;
+        const int eval_warp = T > 32 ? 1 : 0;  // folds the new vertex's score while thread 0 folds the Schur terms
+        const long long rec = (wl_in != nullptr && ho.rec_in != nullptr) ? __ldg(ho.rec_in + wi) : -1;
+        if (rec >= 0) {
+            // ---- resume: the state an earlier tier left when the active set outgrew it -----------------
+            const double* rd = reinterpret_cast<const double*>(ho.pool + rec);
+            m = (int)rd[0];
+            it0 = (int)rd[1];
+            tau = rd[2];
+            changed = false;
+            const double* rp = rd + 4;
+            for (int a = tid; a < m; a += T) {
+                sm.p[a] = rp[a];
+                sm.z[a] = rp[m + a];
+                sm.score[a] = rp[2 * m + a];
+            }
+            const double* ri = rp + 3 * m;
+            for (int e = tid; e < (m + 1) * (m + 1); e += T) {
+                const int a = e / (m + 1), c = e - a * (m + 1);
+                sm.inv[a * LD + c] = ri[e];
+            }
+            const uint32_t* rb = reinterpret_cast<const uint32_t*>(ri + (m + 1) * (m + 1));
+            for (int e = tid; e < m * W; e += T) sm.bits[e] = rb[e];
+        } else {
         // ---- seed: single MAP vertex, weight 1, inv = [[-n, 1], [1, 0]] ---------------------
         // (init_active_set_from_scores, sparsemap.py:25-27, or the LP solution under eta)
         factor_map<KIND>(sm, n, budget, init_scores != nullptr ? nullptr : sm.t, seq.L);
@@ -533,17 +574,12 @@ __global__ void __launch_bounds__(256, 4) sparsemap_fwd_kernel(const float* __re
             }
         }
         for (int q = tid; q < W; q += T) sm.bits[q] = sm.ynew[q];
-        int m = 1;          // |A|
-        bool changed = true;
-        double tau = 0.0;
-        int st = SMLVM_SOLVE_MAX_ITER;
-        int it = 0;
-        const int eval_warp = T > 32 ? 1 : 0;  // folds the new vertex's score while thread 0 folds the Schur terms
+        }
         __syncthreads();
 
         // Barrier discipline: every phase below ends with ONE barrier; what a phase reads was written
         // before the previous barrier, what it writes is not read by anyone inside the same phase.
-        for (it = 0; it < max_iter; ++it) {
+        for (it = it0; it < max_iter; ++it) {
             if (changed) {
                 // ---- [tau; z] = inv * [1; score]; a blocking constraint exists iff some z_a < p_a is negative:
                 //      the test rides on the barrier that publishes z, so the common pass (none) computes no
@@ -787,8 +823,44 @@ __global__ void __launch_bounds__(256, 4) sparsemap_fwd_kernel(const float* __re
 
         // ---- outputs (solver order) -----------------------------------------------------
         __syncthreads();
-        if (st == -1) {  // hand the sample to the next capacity tier
-            if (tid == 0) wl_out[atomicAdd(wl_out_count, 1)] = (int32_t)row;
+        if (st == -1) {  // hand the sample to the next capacity tier, with its state if the pool has room
+            const long long nd = 4 + 3 * (long long)m + (long long)(m + 1) * (m + 1);
+            const long long bytes = (nd * 8 + (long long)m * W * 4 + 15) & ~15LL;
+            if (tid == 0) {
+                const int idx = atomicAdd(wl_out_count, 1);
+                wl_out[idx] = (int32_t)row;
+                long long off = -1;
+                if (ho.pool != nullptr && ho.rec_out != nullptr) {
+                    const long long o = (long long)atomicAdd(ho.cursor, (unsigned long long)bytes);
+                    if (o + bytes <= ho.pool_bytes) off = o;
+                }
+                if (ho.rec_out != nullptr) ho.rec_out[idx] = off;
+                reinterpret_cast<long long*>(sm.red)[34] = off;
+            }
+            __syncthreads();
+            const long long off = reinterpret_cast<const long long*>(sm.red)[34];
+            if (off >= 0) {
+                double* rd = reinterpret_cast<double*>(ho.pool + off);
+                if (tid == 0) {
+                    rd[0] = (double)m;
+                    rd[1] = (double)(it - 1);   // the iteration whose insertion did not fit is run again
+                    rd[2] = tau;
+                    rd[3] = 0.0;
+                }
+                double* rp = rd + 4;
+                for (int a = tid; a < m; a += T) {
+                    rp[a] = sm.p[a];
+                    rp[m + a] = sm.z[a];
+                    rp[2 * m + a] = sm.score[a];
+                }
+                double* ri = rp + 3 * m;
+                for (int e = tid; e < (m + 1) * (m + 1); e += T) {
+                    const int a = e / (m + 1), c = e - a * (m + 1);
+                    ri[e] = sm.inv[a * LD + c];
+                }
+                uint32_t* rb = reinterpret_cast<uint32_t*>(ri + (m + 1) * (m + 1));
+                for (int e = tid; e < m * W; e += T) rb[e] = sm.bits[e];
+            }
             continue;
         }
         int kp = 0;
@@ -970,15 +1042,16 @@ static int solver_threads(int n, int kind, int64_t rows = INT64_MAX)
 // First tier: the capacity that lets 5 samples share an SM (4 for the budget factor, whose active
 // sets run larger: measured at n = 128, bernoulli q99 = 57 vertices, budget-64 q99 = 83), second
 // tier 2 per SM, last tier n + 1.
-static int plan_tiers(int n, int kind, int (&tiers)[3], size_t extra = 0)
+constexpr int kMaxTiers = 4;
+static int plan_tiers(int n, int kind, int (&tiers)[kMaxTiers], size_t extra = 0)
 {
     static int single = -1;
     static int forced[3] = {0, 0, 0};
     if (single < 0) {
         const char* e = getenv("SMLVM_SMAP_SINGLE_TIER");
         single = (e && atoi(e)) ? 1 : 0;
-        const char* t = getenv("SMLVM_SMAP_TIERS");  // experiments: "56,106"
-        if (t) sscanf(t, "%d,%d", &forced[0], &forced[1]);
+        const char* t = getenv("SMLVM_SMAP_TIERS");  // experiments: "56,106" or "54,72,110"
+        if (t) sscanf(t, "%d,%d,%d", &forced[0], &forced[1], &forced[2]);
     }
     // largest capacity that still lets `ctas` CTAs share the 227 KB (+1 KB reserved each) of an SM
     auto cap_for = [&](int ctas) {
@@ -994,6 +1067,7 @@ static int plan_tiers(int n, int kind, int (&tiers)[3], size_t extra = 0)
         if (forced[1] > 0) c2 = forced[1];
         if (c1 < n + 1 && (5 * c1 >= 2 * n || forced[0] > 0)) tiers[ntier++] = c1;  // useful only if >= 0.4 n
         if (c2 < n + 1 && (ntier == 0 || c2 > tiers[ntier - 1])) tiers[ntier++] = c2;
+        if (forced[2] > 0 && forced[2] < n + 1 && forced[2] > tiers[ntier - 1]) tiers[ntier++] = forced[2];
     }
     tiers[ntier++] = n + 1;
     return ntier;
@@ -1023,7 +1097,7 @@ extern "C" int32_t smlvm_sparsemap_plan(int32_t n, int32_t kind, int32_t* caps, 
 {
     if (n < 1 || n > SMLVM_SPARSEMAP_MAX_BITS) return 0;
     if (kind < SMLVM_FACTOR_BERNOULLI || kind > SMLVM_FACTOR_SEQUENCE_BINARY) return 0;
-    int tiers[3];
+    int tiers[kMaxTiers];
     const int nt = plan_tiers(n, kind, tiers);
     const int by_regs = 65536 / (64 * solver_threads(n, kind));  // __launch_bounds__(256, 4): <= 64 registers
     for (int i = 0; i < nt; ++i) {
@@ -1039,11 +1113,15 @@ extern "C" int32_t smlvm_sparsemap_plan(int32_t n, int32_t kind, int32_t* caps, 
     return nt;
 }
 
+static size_t ws_list_bytes(int64_t rows) { return ((size_t)rows * sizeof(int32_t) + 63) & ~(size_t)63; }
+static size_t ws_rec_bytes(int64_t rows) { return ((size_t)rows * sizeof(long long) + 63) & ~(size_t)63; }
+
 extern "C" size_t smlvm_sparsemap_workspace_bytes(int64_t rows)
 {
-    // per later tier (at most 2): one counter (64 B slot) + a worklist of sample ids
+    // per later tier (at most 3): one counter (64 B slot), a worklist of sample ids and of hand-off record offsets;
+    // then the cursor of the record pool.  Whatever the caller passes BEYOND this is the pool (smlvm.h).
     if (rows < 0) return 0;
-    return 2 * (64 + (size_t)rows * sizeof(int32_t)) + 64;
+    return 3 * (64 + ws_list_bytes(rows) + ws_rec_bytes(rows)) + 64;
 }
 
 static int sparsemap_fwd_impl(const float* x, const float* t, const double* init_scores,
@@ -1070,7 +1148,7 @@ static int sparsemap_fwd_impl(const float* x, const float* t, const double* init
     // (54 / 72 and 110 vertices at n = 128); a sample whose active set outgrows its tier is appended to the next
     // tier's worklist and re-solved from scratch there by a small persistent grid.  Same stream, no host
     // synchronisation; an empty tier costs one launch of CTAs that read a zero and exit.
-    int tiers[3];
+    int tiers[kMaxTiers];
     const int ntier = plan_tiers(n, kind, tiers, extra);
     if (solver_smem_bytes(n, tiers[0], extra) > (size_t)227 * 1024) return SMLVM_ERR_UNSUPPORTED;
     // first tier: one CTA per sample, the hardware scheduler evens out the data-dependent solve lengths
@@ -1096,12 +1174,30 @@ static int sparsemap_fwd_impl(const float* x, const float* t, const double* init
     }
     // workspace: [count_1 (64 B)] [list_1: rows x int32] [count_2 (64 B)] [list_2: rows x int32]
     unsigned char* ws = static_cast<unsigned char*>(workspace);
-    const size_t list_bytes = ((size_t)rows * sizeof(int32_t) + 63) & ~(size_t)63;
-    int32_t* wl_count[3] = {nullptr, reinterpret_cast<int32_t*>(ws), reinterpret_cast<int32_t*>(ws + 64 + list_bytes)};
-    int32_t* wl_list[3] = {nullptr, reinterpret_cast<int32_t*>(ws + 64), reinterpret_cast<int32_t*>(ws + 128 + list_bytes)};
-    if (ntier > 1) {
-        cudaError_t e = cudaMemsetAsync(wl_count[1], 0, 64, st);
-        if (e == cudaSuccess && ntier > 2) e = cudaMemsetAsync(wl_count[2], 0, 64, st);
+    const size_t list_bytes = ws_list_bytes(rows), rec_bytes = ws_rec_bytes(rows);
+    int32_t* wl_count[kMaxTiers] = {nullptr, nullptr, nullptr, nullptr};
+    int32_t* wl_list[kMaxTiers] = {nullptr, nullptr, nullptr, nullptr};
+    long long* wl_rec[kMaxTiers] = {nullptr, nullptr, nullptr, nullptr};
+    for (int ti = 1; ti < ntier; ++ti) {
+        unsigned char* base = ws + (size_t)(ti - 1) * (64 + list_bytes + rec_bytes);
+        wl_count[ti] = reinterpret_cast<int32_t*>(base);
+        wl_list[ti] = reinterpret_cast<int32_t*>(base + 64);
+        wl_rec[ti] = reinterpret_cast<long long*>(base + 64 + list_bytes);
+        cudaError_t e = cudaMemsetAsync(wl_count[ti], 0, 64, st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    // hand-off records: the pool is what the workspace holds beyond its mandatory part (none: samples are re-solved)
+    const size_t mandatory = smlvm_sparsemap_workspace_bytes(rows);
+    TierHandoff ho = {nullptr, 0, reinterpret_cast<unsigned long long*>(ws + mandatory - 64), nullptr, nullptr};
+    static int resume = -1;
+    if (resume < 0) {
+        const char* e = getenv("SMLVM_SMAP_RESUME");
+        resume = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    if (resume && ntier > 1 && workspace_bytes >= mandatory + 4096) {
+        ho.pool = ws + mandatory;
+        ho.pool_bytes = (long long)((workspace_bytes - mandatory) & ~(size_t)15);
+        cudaError_t e = cudaMemsetAsync(ho.cursor, 0, 64, st);
         if (e != cudaSuccess) return (int)e;
     }
 #define SMLVM_SMAP_LAUNCH(K)                                                                       \
@@ -1125,12 +1221,15 @@ static int sparsemap_fwd_impl(const float* x, const float* t, const double* init
                 const int64_t fit = (int64_t)device_sm_count() * per_sm;                           \
                 g = (int)(rows < fit ? rows : fit);                                                \
             }                                                                                      \
+            TierHandoff hot = ho;                                                                  \
+            hot.rec_in = wl_rec[ti];                                                               \
+            hot.rec_out = ti + 1 < ntier ? wl_rec[ti + 1] : nullptr;                               \
             sparsemap_fwd_kernel<K><<<g, th, smem, st>>>(                                          \
                 x, t, init_scores, budget, max_iter, rows, n, tiers[ti], ti == ntier - 1,          \
                 wl_list[ti], wl_count[ti], ti + 1 < ntier ? wl_list[ti + 1] : nullptr,             \
                 ti + 1 < ntier ? wl_count[ti + 1] : nullptr, p_pad, aset_bits, counts, kept, iters, \
                 status, S_arena, (long long)S_capacity, reinterpret_cast<long long*>(S_offsets),   \
-                reinterpret_cast<unsigned long long*>(S_cursor), seq);                             \
+                reinterpret_cast<unsigned long long*>(S_cursor), seq, hot);                        \
         }                                                                                          \
     } while (0)
     if (kind == SMLVM_FACTOR_BERNOULLI) SMLVM_SMAP_LAUNCH(SMLVM_FACTOR_BERNOULLI);

@@ -574,7 +574,7 @@ def bits_expand(bits, index, n):
 def sparsemap_plan(n, kind=0):
     """[(capacity, shared-memory bytes per CTA, CTAs per SM)] for each capacity tier of the solver."""
     import ctypes
-    caps, smem, ctas = ((ctypes.c_int32 * 3)() for _ in range(3))
+    caps, smem, ctas = ((ctypes.c_int32 * 4)() for _ in range(3))
     nt = lib.smlvm_sparsemap_plan(int(n), int(kind), caps, smem, ctas)
     return [(caps[i], smem[i], ctas[i]) for i in range(nt)]
 
@@ -600,6 +600,15 @@ def _side_stream(dev):
     if key not in _SIDE_STREAMS:
         _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
     return _SIDE_STREAMS[key]
+
+
+def _handoff_pool_bytes(rows, n):
+    """Room for the states of the samples that outgrow a capacity tier (resumed by the next tier instead of re-solved):
+    3-7 % of the samples at n = 128, ~8 (|A|+1)^2 bytes each; sized for 10 % at the second tier's entry size, capped."""
+    if n < 48:
+        return 0        # a single tier: nothing is handed over
+    per = 8 * (n * 3 // 4 + 1) ** 2
+    return int(min(max(rows // 10, 64) * per, 4 << 30))
 
 
 def sparsemap_arena_doubles(rows, n, kind, budget=0):
@@ -645,7 +654,8 @@ def sparsemap_solve(x, kind, budget=0, t=None, init_scores=None, max_iter=100, k
 
     def solve(r0, r1):
         sl = slice(r0, r1)
-        ws = torch.empty(lib.smlvm_sparsemap_workspace_bytes(r1 - r0), dtype=torch.uint8, device=dev)
+        ws = torch.empty(lib.smlvm_sparsemap_workspace_bytes(r1 - r0) + _handoff_pool_bytes(r1 - r0, n), dtype=torch.uint8,
+                         device=dev)
         check(lib.smlvm_sparsemap_fwd(ptr(x[sl]), ptr(None if t is None else t[sl]),
                                       ptr(None if init_scores is None else init_scores[sl]), kind, budget, max_iter,
                                       r1 - r0, n, ptr(p_pad[sl]), ptr(bits[sl]), ptr(counts[sl]), ptr(kept[sl]),
@@ -720,7 +730,7 @@ def sparsemap_solve_sequence(x, edge_scores, num_states, max_iter=100):
                  layout=lay, length=len(num_states), num_edges=E, num_states=[int(s) for s in num_states])
     if rows == 0:
         return state
-    ws = torch.empty(lib.smlvm_sparsemap_workspace_bytes(rows), dtype=torch.uint8, device=dev)
+    ws = torch.empty(lib.smlvm_sparsemap_workspace_bytes(rows) + _handoff_pool_bytes(rows, n), dtype=torch.uint8, device=dev)
     check(lib.smlvm_sparsemap_seq_fwd(ptr(x), ptr(edge_scores), ptr(lay), len(num_states), E, int(max_iter), rows, n,
                                       ptr(p_pad), ptr(bits), ptr(counts), ptr(kept), ptr(iters), ptr(status), ptr(S),
                                       capacity, ptr(S_off), ptr(cursor), ptr(ws), ws.numel(), stream()),
