@@ -81,7 +81,7 @@ class ClockSampler(threading.Thread):
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
                0x4: "sw_power_cap", 0x80: "hw_power_brake", 0x2: "applications_clocks_setting"}
 
-    def __init__(self, index, period=0.02):
+    def __init__(self, index, period=0.004):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.stop_flag, self.ok = [], False, False
