@@ -381,6 +381,26 @@ def small_config_latency(device):
             res[label] = e0.elapsed_time(e1) / 100 * 1e3
             if label == "eager_us":
                 res["host_wall_us"] = (time.perf_counter() - t0) / 100 * 1e6
+        if name.startswith("C4"):
+            # init=True (sparsemap.py:25-27): the 2n uniform draws per sample come from the CPU generator, as in the
+            # reference, and seed the active set -- one more H2D copy per step, eager launches only
+            from lvmhelpers.sparsemap import draw_init_scores
+            kind_b = (0, 0) if "bernoulli" in name else (1, 16)
+
+            def init_step():
+                xb.grad = None
+                p, _, _ = ops.sparsemap_batch(xb, kind_b[0], budget=kind_b[1], max_iter=300, only_positive=True,
+                                              init_scores=draw_init_scores(64, 32))
+                (ops.ragged_loss(p, torch.ones_like(p), 1.0 / 64) - ops.ragged_entropy(p, 1.0 / 64)).backward()
+
+            for _ in range(5):
+                init_step()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(50):
+                init_step()
+            torch.cuda.synchronize()
+            res["eager_init_true_host_wall_us"] = (time.perf_counter() - t0) / 50 * 1e6
         res["note"] = ("public wrapper API, forward + backward: eager launches (host-launch bound; the ragged SparseMAP "
                        "outputs read their sizes back) vs one CUDA-graph replay (SparseMAP: static-shape outputs, no host read)")
         out[name] = res
