@@ -106,6 +106,36 @@ class _Sparsemax(torch.autograd.Function):
         return sparsemax_bwd(p, supp, dp=dp)
 
 
+class _SlotPolicy:
+    """Whether the support slots pay, per (device, width), WITHOUT a host synchronisation: after every large forward the
+    number of rows whose support does not fit the 8 slots goes to pinned memory with an asynchronous copy; the NEXT
+    call reads whatever copy has completed (an event query, never a wait).  Slots stay on while at most 10 % of the
+    rows of the last observed batch overflowed them; flat score rows (the signal game at temperature 10: supports of
+    20+) switch to the cooperative forward and the dense-read consumers, which do not depend on the support size."""
+    _state = {}
+
+    @classmethod
+    def want(cls, dev, K):
+        st = cls._state.get((dev, K))
+        if st is None:
+            return True
+        if st["event"] is not None and st["event"].query():
+            st["frac"] = float(st["host"][0]) / max(st["rows"], 1)
+            st["event"] = None
+        return st["frac"] <= 0.10
+
+    @classmethod
+    def observe(cls, dev, K, nnz):
+        st = cls._state.setdefault((dev, K), {"host": torch.zeros(1, dtype=torch.int64).pin_memory(), "event": None,
+                                              "frac": 0.0, "rows": 1})
+        if st["event"] is not None:
+            return                      # a copy is still in flight: keep it
+        st["rows"] = nnz.numel()
+        st["host"].copy_((nnz > N.SUPPORT_SLOTS).sum().reshape(1), non_blocking=True)
+        st["event"] = torch.cuda.Event()
+        st["event"].record()
+
+
 class _SparsemaxStats(torch.autograd.Function):
     """(P, entropy, argmax, nnz) in one launch; backward fuses d entropy / d P."""
 
@@ -115,7 +145,11 @@ class _SparsemaxStats(torch.autograd.Function):
         # inside a warp); small batches are launch-bound and keep the plain kernels.  Rows of <= 16
         # columns are no longer than their 64 bytes of slots: the consumers read them directly
         big = x.shape[0] >= SLOTS_MIN_ROWS and x.shape[1] > SLOTS_MIN_COLS
+        observe = big and not torch.cuda.is_current_stream_capturing()
+        big = big and _SlotPolicy.want(x.device, x.shape[1])
         out = sparsemax_fwd(x, want_entropy=True, want_argmax=True, want_nnz=True, want_slots=big)
+        if observe:
+            _SlotPolicy.observe(x.device, x.shape[1], out["nnz"])
         ctx.save_for_backward(out["supp"], out["p"])
         slots = out["slots"] if big else torch.empty(0, device=x.device)
         ctx.mark_non_differentiable(out["argmax"], out["nnz"], out["supp"], slots)

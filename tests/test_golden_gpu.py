@@ -209,3 +209,37 @@ def test_marginalizer_compact_support_equals_reference_loop(wrap):
     _check(wrap, "marg", res, {"enc_w": enc.weight, "enc_b": enc.bias, "dec": dec.weight})
     n_support = int((wrap["marg_log_distr"] > 0).sum())
     assert res["log"]["decoder_rows"] == n_support < 64 * 10
+
+
+def test_slot_policy_follows_the_observed_supports_without_changing_results():
+    """ops.sparsemax_stats asks the forward for support slots on large batches until a batch shows that more than
+    10 % of its rows overflow them (observed through an asynchronous copy, never a wait); results are the same on
+    either path."""
+    from lvmhelpers import ops
+    from lvmhelpers.marg import ExplicitWrapper, Marginalizer
+    from lvmhelpers.utils import DeterministicWrapper
+    torch.manual_seed(0)
+    rows, K = 4096, 64
+    ops._SlotPolicy._state.clear()
+    dec = torch.nn.Embedding(K, 8).cuda()
+
+    def loss_fun(enc_in, z, dec_in, dec_out, labels):
+        return ((dec_out - labels) ** 2).sum(-1), {}
+
+    labels = torch.randn(rows, 8, device="cuda")
+    for scale in (0.05, 3.0):                 # flat rows (supports ~25), then peaked rows (supports ~2)
+        x = (torch.randn(rows, K) * scale).cuda()
+        res = []
+        for it in range(3):
+            xin = x.clone().requires_grad_(True)
+            m = Marginalizer(ExplicitWrapper(torch.nn.Identity(), normalizer="sparsemax"),
+                             DeterministicWrapper(lambda z, _inp: dec(z)), loss_fun, encoder_entropy_coeff=0.3)
+            out = m(xin, None, labels)
+            out["loss"].backward()
+            torch.cuda.synchronize()
+            res.append((out["loss"].item(), xin.grad.clone()))
+        wants = ops._SlotPolicy.want(x.device, K)
+        assert wants == (scale == 3.0)
+        for loss, g in res[1:]:
+            assert abs(loss - res[0][0]) <= 1e-5 * max(1.0, abs(res[0][0]))
+            assert (g - res[0][1]).abs().max().item() <= 1e-6 * max(1.0, res[0][1].abs().max().item())
