@@ -29,8 +29,8 @@ def entropy(p: torch.Tensor):
 class _Entmax15(torch.autograd.Function):
     """1.5-entmax (``entmax.entmax15``, the reference's DEFAULT normalizer argument at
     marg.py:39,46) restated with torch ops: exact sort-based threshold, closed-form backward.
-    The definition the kernel (``ops.entmax15``) is tested against, and the path of tensors the
-    kernel does not take (fp64, CPU, more than 1024 columns)."""
+    The definition the kernel (``ops.entmax15``) is tested against, and the path of CUDA tensors the
+    kernel does not take (fp64, more than 1024 columns)."""
 
     @staticmethod
     def forward(ctx, X):
@@ -60,12 +60,15 @@ class _Entmax15(torch.autograd.Function):
 
 def entmax15(X, dim=-1):
     """``entmax.entmax15``: the sm_100a kernel (``smlvm_entmax15_fwd/_bwd``) for fp32 CUDA scores with at most 1024
-    columns; other tensors (fp64 checks, CPU) take the torch-op restatement above."""
+    columns; fp64 or wider CUDA tensors take the torch-op restatement above; CPU tensors raise (no CPU path)."""
     if dim not in (-1, X.dim() - 1):
         return entmax15(X.transpose(dim, -1), -1).transpose(dim, -1)
-    if X.is_cuda and X.dtype == torch.float32 and X.shape[-1] <= ops.ENTMAX15_MAX_COLS:
+    if not X.is_cuda:
+        raise RuntimeError("entmax15: scores must live on a CUDA device: this package has no CPU implementation "
+                           "(got device=%s)" % X.device)
+    if X.dtype == torch.float32 and X.shape[-1] <= ops.ENTMAX15_MAX_COLS:
         return ops.entmax15(X)
-    return _Entmax15.apply(X)
+    return _Entmax15.apply(X)       # fp64 scores / more than 1024 columns, on the GPU
 
 
 class _FusedMarginalObjective(torch.autograd.Function):

@@ -1,6 +1,6 @@
-"""entmax15 (torch-op restatement kept for ExplicitWrapper's default normalizer): checked
-against its defining equations -- p = [(x/2 - tau)_+]^2 with sum p = 1 -- solved by bisection,
-and against finite differences.  Runs on CPU (pure torch ops)."""
+"""The sort-based definition of entmax15 (``lvmhelpers.marg._Entmax15``, the torch-op restatement the kernel is tested
+against in tests/test_entmax15_gpu.py): checked here against its defining equations -- p = [(x/2 - tau)_+]^2 with
+sum p = 1 -- solved by bisection, and against finite differences.  The product entry points have no CPU path."""
 import torch
 
 
@@ -17,7 +17,8 @@ def _bisect(x):
 
 
 def test_entmax15_matches_definition():
-    from lvmhelpers.marg import entmax15
+    from lvmhelpers.marg import _Entmax15
+    entmax15 = _Entmax15.apply
     g = torch.Generator().manual_seed(0)
     for K, scale in ((10, 3.0), (256, 0.1), (128, 1.0), (3, 1.0)):
         x = torch.randn(50, K, generator=g, dtype=torch.float64) * scale
@@ -28,15 +29,18 @@ def test_entmax15_matches_definition():
 
 
 def test_entmax15_backward_finite_differences():
-    from lvmhelpers.marg import entmax15
+    from lvmhelpers.marg import _Entmax15
+    entmax15 = _Entmax15.apply
     g = torch.Generator().manual_seed(1)
     x = torch.randn(4, 7, generator=g, dtype=torch.float64, requires_grad=True)
     assert torch.autograd.gradcheck(entmax15, (x,), eps=1e-6, atol=1e-5)
 
 
-def test_explicit_wrapper_default_normalizer_runs():
-    from lvmhelpers.marg import ExplicitWrapper
+def test_explicit_wrapper_default_normalizer_has_no_cpu_path():
+    import pytest
+    from lvmhelpers.marg import ExplicitWrapper, entmax15
     w = ExplicitWrapper(torch.nn.Linear(5, 6))          # normalizer='entmax', the reference's default
-    sample, distr, ent = w(torch.randn(9, 5))
-    assert sample.shape == (9,) and distr.shape == (9, 6) and ent.shape == (9,)
-    assert torch.allclose(distr.sum(-1), torch.ones(9), atol=1e-5)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        w(torch.randn(9, 5))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        entmax15(torch.randn(3, 4))
