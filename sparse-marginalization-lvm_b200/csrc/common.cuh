@@ -38,6 +38,17 @@ __device__ __forceinline__ float ldg_stream(const float* p)
     asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
     return r;
 }
+// A 4-byte gather (one loss entry per non-zero of P): ask L2 for the smallest fill it offers, keep the line out of L1.
+__device__ __forceinline__ float ldg_gather(const float* p)
+{
+    float r;
+#if defined(SMLVM_GATHER_PLAIN)
+    r = __ldg(p);
+#else
+    asm volatile("ld.global.nc.L1::no_allocate.L2::64B.f32 %0, [%1];" : "=f"(r) : "l"(p));
+#endif
+    return r;
+}
 __device__ __forceinline__ void stg_stream4(float* p, float4 v)
 {
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x),

@@ -283,8 +283,8 @@ bwd_slots_tma_kernel(const float* __restrict__ p, const int32_t* __restrict__ su
         for (int j = 0; j < NS; ++j) {
             const bool on = live && !scan && c[j] >= 0;
             if (loss_slots == nullptr || loss == nullptr)
-                lv[j] = (on && loss != nullptr) ? __ldg(loss + row * K + c[j]) : 0.f;
-            gv[j] = (on && dp != nullptr) ? __ldg(dp + row * K + c[j]) : 0.f;
+                lv[j] = (on && loss != nullptr) ? ldg_gather(loss + row * K + c[j]) : 0.f;
+            gv[j] = (on && dp != nullptr) ? ldg_gather(dp + row * K + c[j]) : 0.f;
         }
         float vhat = 0.f;
         if (live && !scan) {

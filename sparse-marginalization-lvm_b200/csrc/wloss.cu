@@ -149,7 +149,7 @@ wloss_slots_kernel(const float* __restrict__ p, const float* __restrict__ loss, 
         const bool scan = live && c[0] == -2;
         float lv[NS];
 #pragma unroll
-        for (int j = 0; j < NS; ++j) lv[j] = (live && !scan && c[j] >= 0) ? __ldg(loss + r * K + c[j]) : 0.f;
+        for (int j = 0; j < NS; ++j) lv[j] = (live && !scan && c[j] >= 0) ? ldg_gather(loss + r * K + c[j]) : 0.f;
         float s = 0.f;
 #pragma unroll
         for (int j = 0; j < NS; ++j) s = fmaf(v[j], lv[j], s);  // empty slots carry v = 0
