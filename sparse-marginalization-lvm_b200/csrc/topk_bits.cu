@@ -398,30 +398,28 @@ __global__ void __launch_bounds__(256)
 bits_expand_vec_kernel(const uint32_t* __restrict__ bits, const int64_t* __restrict__ index, float* __restrict__ out,
                        int64_t n_out, int n)
 {
+    // a warp per output row, four rows in flight; lane l writes the float4s l, l + 32, ... of the row (no 64-bit
+    // division per 16 bytes as in the first version: 324 -> see DESIGN.md 4.4); {0,1} as bit * 0x3F800000
     const int W = (n + 31) >> 5, q4 = n >> 2;  // float4s per row (n % 4 == 0)
-    const int64_t total = n_out * q4, stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t c0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c0 < total; c0 += 4 * stride) {
-        uint32_t word[4];
-        int col[4];
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t e0 = warp * 4; e0 < n_out; e0 += nwarps * 4) {
+        int64_t src[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int64_t c = c0 + u * stride;
-            word[u] = 0u;
-            col[u] = 0;
-            if (c < total) {
-                const int64_t e = c / q4;
-                col[u] = (int)(c - e * q4) * 4;
-                const int64_t src = index != nullptr ? __ldg(index + e) : e;
-                word[u] = __ldg(bits + src * W + (col[u] >> 5));
-            }
-        }
+        for (int u = 0; u < 4; ++u) src[u] = (e0 + u < n_out) ? (index != nullptr ? __ldg(index + e0 + u) : e0 + u) : -1;
+        for (int q = lane; q < q4; q += 32) {
+            uint32_t word[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int64_t c = c0 + u * stride;
-            if (c < total) {
-                const uint32_t nib = word[u] >> (col[u] & 31);
-                stg_stream4(out + c * 4, make_float4((float)(nib & 1u), (float)((nib >> 1) & 1u),
-                                                     (float)((nib >> 2) & 1u), (float)((nib >> 3) & 1u)));
+            for (int u = 0; u < 4; ++u) word[u] = src[u] >= 0 ? __ldg(bits + src[u] * W + (q >> 3)) : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (src[u] >= 0) {
+                    const uint32_t nib = word[u] >> ((q & 7) * 4);
+                    stg_stream4(out + (e0 + u) * n + q * 4,
+                                make_float4(__uint_as_float((nib & 1u) * 0x3F800000u), __uint_as_float(((nib >> 1) & 1u) * 0x3F800000u),
+                                            __uint_as_float(((nib >> 2) & 1u) * 0x3F800000u),
+                                            __uint_as_float(((nib >> 3) & 1u) * 0x3F800000u)));
+                }
             }
         }
     }
@@ -446,24 +444,36 @@ bits_expand_kernel(const uint32_t* __restrict__ bits, const int64_t* __restrict_
 // chunk, four in flight, consecutive threads on consecutive chunks of the output.
 template <typename T>
 __global__ void __launch_bounds__(256)
+gather_rows_small_kernel(const T* __restrict__ src, const int32_t* __restrict__ idx, T* __restrict__ out, int64_t n_out,
+                         int64_t row_chunks)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_out; e += stride) {
+        const int64_t from = (int64_t)__ldg(idx + e) * row_chunks;
+        for (int64_t c = 0; c < row_chunks; ++c) out[e * row_chunks + c] = __ldg(src + from + c);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
 gather_rows_kernel(const T* __restrict__ src, const int32_t* __restrict__ idx, T* __restrict__ out, int64_t n_out,
                    int64_t row_chunks)
 {
-    const int64_t total = n_out * row_chunks, stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t c0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c0 < total; c0 += 4 * stride) {
-        T v[4];
+    // a warp per output row, four rows in flight; lane l copies the chunks l, l + 32, ... of the row
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t e0 = warp * 4; e0 < n_out; e0 += nwarps * 4) {
+        int64_t from[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int64_t c = c0 + u * stride;
-            if (c < total) {
-                const int64_t e = c / row_chunks;
-                v[u] = __ldg(src + (int64_t)__ldg(idx + e) * row_chunks + (c - e * row_chunks));
-            }
-        }
+        for (int u = 0; u < 4; ++u) from[u] = (e0 + u < n_out) ? (int64_t)__ldg(idx + e0 + u) * row_chunks : -1;
+        for (int64_t c = lane; c < row_chunks; c += 32) {
+            T v[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int64_t c = c0 + u * stride;
-            if (c < total) out[c] = v[u];
+            for (int u = 0; u < 4; ++u)
+                if (from[u] >= 0) v[u] = __ldg(src + from[u] + c);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (from[u] >= 0) out[(e0 + u) * row_chunks + c] = v[u];
         }
     }
 }
@@ -573,7 +583,7 @@ extern "C" int smlvm_bits_expand(const uint32_t* bits, const int64_t* index, flo
     if (bits == nullptr || out == nullptr) return SMLVM_ERR_ARG;
     const int64_t cap = (int64_t)device_sm_count() * 16;
     if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
-        const int64_t need = (n_out * (n >> 2) + 1023) / 1024;
+        const int64_t need = (n_out + 31) / 32;   // 8 warps x 4 rows per CTA and pass
         bits_expand_vec_kernel<<<(int)(need < cap ? need : cap), 256, 0, as_stream(stream)>>>(bits, index, out, n_out, n);
     } else {
         const int64_t need = (n_out + 7) / 8;
@@ -594,9 +604,18 @@ extern "C" int smlvm_gather_rows(const void* src, const int32_t* idx, void* out,
     if (chunk == 0) return SMLVM_ERR_UNSUPPORTED;
     const int64_t row_chunks = row_bytes / chunk;
     const int64_t cap = (int64_t)device_sm_count() * 16;
-    const int64_t need = (n_out * row_chunks + 1023) / 1024;
+    // rows of at least 8 chunks: a warp per row; shorter rows (labels, scalars): a thread per row
+    const bool small = row_chunks < 8;
+    const int64_t need = small ? (n_out + 255) / 256 : (n_out + 31) / 32;
     const int grid = (int)(need < cap ? need : cap);
     cudaStream_t st = as_stream(stream);
+    if (small) {
+        if (chunk == 16) gather_rows_small_kernel<uint4><<<grid, 256, 0, st>>>((const uint4*)src, idx, (uint4*)out, n_out, row_chunks);
+        else if (chunk == 8) gather_rows_small_kernel<uint2><<<grid, 256, 0, st>>>((const uint2*)src, idx, (uint2*)out, n_out, row_chunks);
+        else gather_rows_small_kernel<uint32_t><<<grid, 256, 0, st>>>((const uint32_t*)src, idx, (uint32_t*)out, n_out, row_chunks);
+        SMLVM_LAUNCH_CHECK();
+        return SMLVM_OK;
+    }
     if (chunk == 16)
         gather_rows_kernel<uint4><<<grid, 256, 0, st>>>((const uint4*)src, idx, (uint4*)out, n_out, row_chunks);
     else if (chunk == 8)
