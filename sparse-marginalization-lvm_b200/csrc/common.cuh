@@ -60,6 +60,12 @@ __device__ __forceinline__ void stg_stream(float* p, float v)
     asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
+// t / d for a grid-stride index: 32-bit when it fits (a 64-bit division by a run-time divisor is a ~70-instruction call)
+__device__ __forceinline__ int64_t div_idx(int64_t t, int d)
+{
+    return ((unsigned long long)t >> 31) == 0 ? (int64_t)((unsigned)t / (unsigned)d) : t / d;
+}
+
 // Butterfly reductions over the G (power of two) lanes of a sub-warp group.
 template <int G, typename T, typename Op>
 __device__ __forceinline__ T group_reduce(T v, Op op)

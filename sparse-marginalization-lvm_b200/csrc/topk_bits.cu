@@ -125,7 +125,7 @@ bits_score_fwd_kernel(const uint32_t* __restrict__ bits, const float* __restrict
     const int64_t total = rows * k;
     for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total;
          t += (int64_t)gridDim.x * kThreads) {
-        const int64_t r = t / k;
+        const int64_t r = div_idx(t, k);
         const uint32_t* b = bits + t * words_n;
         const float* xr = x + r * (int64_t)n;
         double acc = 0.0;
@@ -152,7 +152,7 @@ bits_score_fwd_vec_kernel(const uint32_t* __restrict__ bits, const float* __rest
     const int64_t total = rows * k;
     for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < total;
          t += (int64_t)gridDim.x * kThreads) {
-        const int64_t r = t / k;
+        const int64_t r = div_idx(t, k);
         const uint32_t* b = bits + t * words_n;
         const float4* xr = reinterpret_cast<const float4*>(x + r * (int64_t)n);
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
@@ -325,7 +325,7 @@ bits_score_bwd_vec_kernel(const uint32_t* __restrict__ bits, const float* __rest
     const int words_n = (n + 31) >> 5, qn = n / CPT;
     const int64_t total = rows * qn, stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
-        const int64_t r = t / qn;
+        const int64_t r = div_idx(t, qn);
         const int c = (int)(t - r * qn) * CPT;
         const uint32_t* b = bits + r * (int64_t)k * words_n + (c >> 5);
         const float* d = ds + r * k;

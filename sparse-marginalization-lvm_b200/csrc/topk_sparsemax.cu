@@ -83,7 +83,7 @@ topk_sparsemax_bwd_kernel(const uint32_t* __restrict__ bits, const float* __rest
     const float ge = gent != nullptr ? __ldg(gent) * ent_scale : 0.f;
     const int64_t total = rows * qn, stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
-        const int64_t r = t / qn;
+        const int64_t r = div_idx(t, qn);
         const int c = (int)(t - r * qn) * CPT;
         float ds[kKsMax];
         unsigned on = 0u;
@@ -110,9 +110,12 @@ topk_sparsemax_bwd_kernel(const uint32_t* __restrict__ bits, const float* __rest
         float a[CPT];
 #pragma unroll
         for (int e = 0; e < CPT; ++e) a[e] = 0.f;
+        // candidates outside the k-sparsemax support have ds = 0 (typically all but the first three or four of a row):
+        // a candidate rank that is zero in every row of the warp is skipped
+        const unsigned act = __activemask();
 #pragma unroll
         for (int j = 0; j < kKsMax; ++j) {
-            if (j < k) {
+            if (j < k && __any_sync(act, ds[j] != 0.f)) {
                 const uint32_t w = __ldg(b + j * words_n) >> sh;
                 const float dj = ds[j];
 #pragma unroll
