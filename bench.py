@@ -833,7 +833,7 @@ def run_native(args, rank, local_rank, world):
     uninstrumented = {"ms_per_step": ms_plain / args.steps, "ms_per_step_cuda_graph": ms_graph / args.steps,
                       "value": rows * world / (ms_plain / args.steps * 1e-3),
                       "value_cuda_graph": rows * world / (ms_graph / args.steps * 1e-3), "unit": UNIT,
-                      "note": "no per-kernel events; scan + fill on a side stream (hotpath.SparsemaxMargStep.run)"}
+                      "note": "no per-kernel events between the launches (hotpath.SparsemaxMargStep.run: forward -> scan -> fused step)"}
     del graph
 
     # end to end through host buffers: H2D of X and L, the step, D2H of gradient + loss, every
