@@ -844,6 +844,8 @@ def run_native(args, rank, local_rank, world):
                                  entropy_coeff=1.0, chunks=args.e2e_chunks)
     ms_e2e, _, _ = timed(lambda: pipe.run(x_pin, l_pin, dx_pin), e2e_steps, 3, world, device)
     loss_value = pipe.loss()
+    # the same with the gradient left on the device (the encoder that consumes it runs there): only the loss is read back
+    ms_e2e_lo, _, _ = timed(lambda: pipe.run(x_pin, l_pin, None), e2e_steps, 3, world, device)
     # the ceiling of an upload-bound step: a plain pinned-memory H2D copy of the same two inputs, nothing else
     ms_copy, _, _ = timed(lambda: (x.copy_(x_pin, non_blocking=True), losses.copy_(l_pin, non_blocking=True)), 5, 2,
                           world, device)
@@ -859,6 +861,10 @@ def run_native(args, rank, local_rank, world):
            "check_dx_vs_resident": float((dx_pin[:4096].to(device) - step.dx[:4096]).abs().max()),
            "d2h_contents": "dX [rows, K] + one partial loss per micro-batch; P, dL and the compacted (value, row, col) "
                            "lists stay on the device (the decoder that consumes them runs there)",
+           "loss_only_readback": {"value": rows * world / (ms_e2e_lo / e2e_steps * 1e-3), "unit": UNIT,
+                                  "ms_per_step": ms_e2e_lo / e2e_steps, "d2h_bytes_per_step": 4 * args.e2e_chunks,
+                                  "note": "informational: the same call with dX left on the device; `value` above "
+                                          "also returns the dense gradient to the host every step"},
            "host_cpus_bound_per_rank": numa_cpus}
 
     paths = extra_paths(args, world, device, rank) if not args.no_paths else None

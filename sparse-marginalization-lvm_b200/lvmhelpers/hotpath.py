@@ -243,7 +243,8 @@ class HostPipelinedMargStep:
     (rows x K x 4 B) overlap; PCIe is full duplex, the step time tends to the upload time alone.
 
     ``run(x_host, l_host, dx_host)`` returns the loss as a 0-d pinned host tensor valid after
-    the CURRENT stream has been synchronised (the call itself does not block).
+    the CURRENT stream has been synchronised (the call itself does not block).  ``dx_host=None``: the gradient stays
+    on the device (``steps[b].dx`` of the last micro-batches), only the partial losses come back.
     """
 
     def __init__(self, rows, cols, device, capacity_per_row, entropy_coeff=0.0, chunks=8, nbuf=3):
@@ -287,7 +288,8 @@ class HostPipelinedMargStep:
                 done.record(self.s_cmp)
             with torch.cuda.stream(self.s_d2h):
                 self.s_d2h.wait_event(done)
-                dx_host[lo:hi].copy_(self.steps[b].dx, non_blocking=True)
+                if dx_host is not None:
+                    dx_host[lo:hi].copy_(self.steps[b].dx, non_blocking=True)
                 self.tot_host[c:c + 1].copy_(self.steps[b].total.reshape(1), non_blocking=True)
                 last = torch.cuda.Event()
                 last.record(self.s_d2h)
