@@ -373,8 +373,14 @@ bool topk_tile_supported(int n, int k);
 int topk_tile_launch(const float* x, float* configs, uint32_t* bits, float* dp_scores, int64_t rows, int n,
                      int k, cudaStream_t st);
 
-// The thread-per-row kernel wins on throughput, the group-per-row kernel on latency (a row is a
-// chain of n dependent merges): small batches stay on the latter.  SMLVM_TOPK=reg|tile overrides.
+// topk_blk.cu
+bool topk_blk_supported(int n, int k);
+int topk_blk_launch(const float* x, float* configs, uint32_t* bits, float* dp_scores, int64_t rows, int n,
+                    int k, cudaStream_t st);
+
+// The thread-per-row kernels win on throughput (topk_blk.cu: 64-bit list entries, configurations materialised every
+// 28 bits; topk_tile.cu: configurations riding along), the group-per-row kernel on latency (a row is a
+// chain of n dependent merges): small batches stay on the latter.  SMLVM_TOPK=reg|tile|blk overrides.
 // (Round 2 measured a third variant -- configurations parked in a pool of k slots per row, list entries (score, slot
 // id), only the min(#A, #B) entries that survive on both sides of a merge copied: 1/8 of the shared-memory bytes, but
 // 394 -> 250 (unrolled) warp instructions per bit against 220, the copies run at the warp's worst row: 0.527 vs 0.490
@@ -384,7 +390,7 @@ static int topk_path_override()
     static int cached = -1;
     if (cached < 0) {
         const char* e = getenv("SMLVM_TOPK");
-        cached = (e == nullptr) ? 0 : (strcmp(e, "reg") == 0 ? 1 : (strcmp(e, "tile") == 0 ? 2 : 0));
+        cached = (e == nullptr) ? 0 : (strcmp(e, "reg") == 0 ? 1 : (strcmp(e, "tile") == 0 ? 2 : (strcmp(e, "blk") == 0 ? 3 : 0)));
     }
     return cached;
 }
@@ -492,6 +498,10 @@ extern "C" int smlvm_topk_bits(const float* x, float* configs, uint32_t* bits, f
     if (x == nullptr) return SMLVM_ERR_ARG;
     {
         const int ovr = topk_path_override();
+        // block-local configurations pay when a configuration is wide (3-4 words) and the lists are long
+        const bool blk_wins = n > 64 && k >= 8;
+        if (topk_blk_supported(n, k) && ovr != 1 && ovr != 2 && ((rows >= kTopkTileMinRows && blk_wins) || ovr == 3))
+            return topk_blk_launch(x, configs, bits, dp_scores, rows, n, k, as_stream(stream));
         if (topk_tile_supported(n, k) && ovr != 1 && (rows >= kTopkTileMinRows || ovr == 2))
             return topk_tile_launch(x, configs, bits, dp_scores, rows, n, k, as_stream(stream));
     }

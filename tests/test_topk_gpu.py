@@ -295,3 +295,47 @@ def test_topk_sparsemax_fused_equals_composed(rows, n, k):
     gd = torch.where(on, -(1.0 / rows) * (P.clamp(min=1e-300).log() + 1.0), torch.zeros_like(P))
     ds = torch.where(on, gd - gd.sum(-1, keepdim=True) / on.sum(-1, keepdim=True), torch.zeros_like(gd))
     assert (x3.grad.double() - torch.einsum("bk,bkj->bj", ds, cfg2.double())).abs().max().item() <= 1e-6
+
+
+_TOPK_PATH_SCRIPT = r"""
+import sys, numpy as np, torch
+sys.path[:0] = [%r, %r]
+import oracle
+from lvmhelpers import ops
+bad = []
+for rows, n, k in [(16384 + 37, 128, 10), (16400, 128, 16), (16384, 100, 8), (16390, 96, 9), (16384, 64, 8), (16400, 33, 16),
+                   (16384, 29, 10), (16384, 57, 12), (16390, 7, 5), (300, 128, 10), (16384, 128, 2)]:
+    rng = np.random.default_rng(n * 131 + k)
+    s = rng.standard_normal((rows, n)).astype(np.float32)
+    s[::7] = np.round(s[::7] * 2) / 2
+    s[5] = 0.0
+    s[6, ::2] = 0.0
+    chk = min(rows, 3000)
+    ref, ref_sc = oracle.topk(s[:chk], k, return_scores=True)
+    cfg, bits, sc = ops.topk_bits(torch.from_numpy(s).cuda(), k, want_scores=True)
+    b = bits[:chk].cpu().numpy().astype(np.uint32)
+    idx = np.arange(n)
+    ok = np.array_equal(cfg[:chk].cpu().numpy(), ref) and np.array_equal(sc[:chk].cpu().numpy(), ref_sc) \
+        and np.array_equal(((b[:, :, idx // 32] >> (idx %% 32)) & 1).astype(np.float32), ref)
+    _, bits2, _ = ops.topk_bits(torch.from_numpy(s).cuda(), k, want_configs=False)
+    ok = ok and torch.equal(bits2, bits)
+    if not ok:
+        bad.append((rows, n, k))
+print("BAD", bad) if bad else print("ALL-OK")
+"""
+
+
+@pytest.mark.parametrize("path", ["reg", "tile", "blk"])
+def test_every_topk_path_in_a_subprocess(path):
+    """SMLVM_TOPK pins the k-best search to ONE of its three kernels (group-per-row, thread-per-row with the
+    configurations riding along, thread-per-row with block-local configurations materialised every 28 bits): each must
+    be bit-exact against the oracle, block boundaries (n = 29, 57, 96, 100, 128) and partial tiles included."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SMLVM_TOPK=path)
+    script = _TOPK_PATH_SCRIPT % (root, os.path.join(root, "sparse-marginalization-lvm_b200"))
+    res = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert "ALL-OK" in res.stdout, res.stdout[-2000:]
