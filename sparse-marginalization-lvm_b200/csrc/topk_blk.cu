@@ -129,7 +129,7 @@ __device__ __forceinline__ void blk_materialise(uint2* SLcur, CfgB<W>* pool, int
 }
 
 template <int W, int STAGE, int KT>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(640, 1)
 topk_blk_kernel(const float* __restrict__ x, float* __restrict__ configs, uint32_t* __restrict__ bits,
                 float* __restrict__ dp_scores, int64_t rows, int n, int k)
 {
@@ -268,18 +268,18 @@ int topk_blk_launch(const float* x, float* configs, uint32_t* bits, float* dp_sc
     const int words_n = (n + 31) >> 5;
     const int W = words_n <= 1 ? 1 : (words_n <= 2 ? 2 : 4);
     auto per_warp_bytes = [&](int stage) { return ((size_t)k * W * 32 + (2 * k + 1) * 64 + stage * 33) * 4; };
-    // resident warps per SM: 200 KB of lists, at most 32 (two CTAs of <= 16 warps)
+    // one CTA per SM with as many warps as 224 KB of lists hold, at most 20 (640 threads x <= 102 registers): the kernel
+    // is bound by the latency of its merge chain, and the number of resident warps also sets how many rounds of tiles a
+    // batch needs (262144 rows = 8192 tiles: 3 rounds with 19 warps per SM, 4 with 16)
     auto warps_per_sm = [&](int stage) {
-        const int w = (int)((200 * 1024) / per_warp_bytes(stage));
-        return w > 32 ? 32 : (w < 1 ? 1 : w);
+        const int w = (int)((224 * 1024) / per_warp_bytes(stage));
+        return w > 20 ? 20 : (w < 1 ? 1 : w);
     };
-    const int stage = 8;   // 8 staged bits: more resident warps (the kernel is bound by the latency of its merge chain)
+    const int stage = 8;   // 8 staged bits: more resident warps
     const size_t per_warp = per_warp_bytes(stage);
-    const int wsm = warps_per_sm(stage);
-    const int ctas_per_sm = wsm > 16 ? 2 : 1;
-    int warps = wsm / ctas_per_sm;
+    int warps = warps_per_sm(stage);
     const int64_t ntiles = (rows + 31) / 32;
-    const int64_t slots = (int64_t)device_sm_count() * ctas_per_sm;
+    const int64_t slots = (int64_t)device_sm_count();
     if (ntiles < (int64_t)warps * slots) {  // small batches: spread the tiles over the SMs
         const int w2 = (int)((ntiles + slots - 1) / slots);
         warps = w2 < 1 ? 1 : (w2 < warps ? w2 : warps);
@@ -290,7 +290,7 @@ int topk_blk_launch(const float* x, float* configs, uint32_t* bits, float* dp_sc
 #define SMLVM_TOPK_BLK_LAUNCH(WW, SS, KK)                                                                     \
     do {                                                                                                      \
         cudaError_t e = cudaFuncSetAttribute(topk_blk_kernel<WW, SS, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                             200 * 1024);                                                     \
+                                             224 * 1024);                                                     \
         if (e != cudaSuccess) return (int)e;                                                                  \
         topk_blk_kernel<WW, SS, KK><<<grid, warps * 32, smem, st>>>(x, configs, bits, dp_scores, rows, n, k); \
     } while (0)
@@ -303,8 +303,7 @@ int topk_blk_launch(const float* x, float* configs, uint32_t* bits, float* dp_sc
     } while (0)
 #define SMLVM_TOPK_BLK_CASE(WW)                                                                               \
     case WW:                                                                                                  \
-        if (stage == 8) SMLVM_TOPK_BLK_K(WW, 8);                                                              \
-        else SMLVM_TOPK_BLK_K(WW, 32);                                                                        \
+        SMLVM_TOPK_BLK_K(WW, 8);                                                                              \
         break;
     switch (W) {
         SMLVM_TOPK_BLK_CASE(1)
