@@ -840,25 +840,45 @@ def run_native(args, rank, local_rank, world):
     # step, through the host-buffer entry point of the package (micro-batched over 3 streams)
     from lvmhelpers.hotpath import HostPipelinedMargStep
     e2e_steps = max(3, min(args.steps, 20))
+    # (the loss matrix stays in its pinned host buffer: the fused step kernel reads it over PCIe on the support only --
+    # one read per non-zero of P instead of an upload of all rows x K losses; scores up, dense gradient + loss down)
+    zero_copy = step.fused and step.use_slots
     pipe = HostPipelinedMargStep(rows, K, device, capacity_per_row=total_nnz / rows * 1.05 + 0.5,
-                                 entropy_coeff=1.0, chunks=args.e2e_chunks)
+                                 entropy_coeff=1.0, chunks=args.e2e_chunks, zero_copy_losses=zero_copy)
     ms_e2e, _, _ = timed(lambda: pipe.run(x_pin, l_pin, dx_pin), e2e_steps, 3, world, device)
     loss_value = pipe.loss()
+    e2e_dx_err = float((dx_pin[:4096].to(device) - step.dx[:4096]).abs().max())
+    # round 1 / early round 2 form, for comparison: both inputs uploaded in full
+    pipe_up = HostPipelinedMargStep(rows, K, device, capacity_per_row=total_nnz / rows * 1.05 + 0.5,
+                                    entropy_coeff=1.0, chunks=8) if zero_copy else pipe
+    ms_e2e_up, _, _ = timed(lambda: pipe_up.run(x_pin, l_pin, dx_pin), e2e_steps, 3, world, device) if zero_copy \
+        else (ms_e2e, None, None)
+    loss_value_up = pipe_up.loss()
     # the same with the gradient left on the device (the encoder that consumes it runs there): only the loss is read back
     ms_e2e_lo, _, _ = timed(lambda: pipe.run(x_pin, l_pin, None), e2e_steps, 3, world, device)
     # the ceiling of an upload-bound step: a plain pinned-memory H2D copy of the same two inputs, nothing else
     ms_copy, _, _ = timed(lambda: (x.copy_(x_pin, non_blocking=True), losses.copy_(l_pin, non_blocking=True)), 5, 2,
                           world, device)
+    gather_wire = 64 * total_nnz if zero_copy else 0    # one PCIe read per non-zero; 64 B each is what the step time implies
     e2e = {"value": rows * world / (ms_e2e / e2e_steps * 1e-3), "unit": UNIT,
-           "h2d_gbs_achieved_per_rank": pipe.h2d_bytes / (ms_e2e / e2e_steps * 1e-3) / 1e9,
-           "h2d_gbs_plain_pinned_copy_per_rank": pipe.h2d_bytes / (ms_copy / 5 * 1e-3) / 1e9,
-           "bound": "PCIe / host memory: every rank uploads 2 x rows x K x 4 B per step; all ranks of a box share "
-                    "the host's DRAM and PCIe root complexes, so e2e scales with host bandwidth, not with GPUs",
-           "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
+           "h2d_gbs_achieved_per_rank": (pipe.h2d_bytes + gather_wire) / (ms_e2e / e2e_steps * 1e-3) / 1e9,
+           "h2d_gbs_plain_pinned_copy_per_rank": 2 * rows * K * 4 / (ms_copy / 5 * 1e-3) / 1e9,
+           "bound": "PCIe / host memory: every rank uploads rows x K x 4 B of scores per step and reads one loss per "
+                    "non-zero of P in place; all ranks of a box share the host's DRAM and PCIe root complexes, so e2e "
+                    "scales with host bandwidth, not with GPUs",
+           "h2d_bytes_per_step": pipe.h2d_bytes + gather_wire, "d2h_bytes_per_step": pipe.d2h_bytes,
+           "h2d_bytes_copied": pipe.h2d_bytes, "h2d_zero_copy_reads": total_nnz if zero_copy else 0,
+           "h2d_zero_copy_bytes_useful": 4 * total_nnz if zero_copy else 0,
+           "losses_read_in_place": bool(zero_copy),
            "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
-           "api": "lvmhelpers.hotpath.HostPipelinedMargStep.run over pinned host buffers, "
-                  "%d micro-batches, H2D / kernels / D2H on three streams" % args.e2e_chunks,
-           "check_dx_vs_resident": float((dx_pin[:4096].to(device) - step.dx[:4096]).abs().max()),
+           "api": "lvmhelpers.hotpath.HostPipelinedMargStep.run over pinned host buffers (zero_copy_losses=%s), "
+                  "%d micro-batches, H2D / kernels / D2H on three streams" % (zero_copy, args.e2e_chunks),
+           "check_dx_vs_resident": e2e_dx_err,
+           "both_inputs_uploaded": {"value": rows * world / (ms_e2e_up / e2e_steps * 1e-3), "unit": UNIT,
+                                    "ms_per_step": ms_e2e_up / e2e_steps, "h2d_bytes_per_step": 2 * rows * K * 4,
+                                    "loss": loss_value_up,
+                                    "note": "the round-1 form of the same call (zero_copy_losses=False, its best setting of "
+                                            "8 micro-batches): the loss matrix uploaded in full before the step"},
            "d2h_contents": "dX [rows, K] + one partial loss per micro-batch; P, dL and the compacted (value, row, col) "
                            "lists stay on the device (the decoder that consumes them runs there)",
            "loss_only_readback": {"value": rows * world / (ms_e2e_lo / e2e_steps * 1e-3), "unit": UNIT,
@@ -927,7 +947,7 @@ def main():
     ap.add_argument("--cols", type=int, default=128)
     ap.add_argument("--path-rows-topk", type=int, default=1 << 18)
     ap.add_argument("--path-rows-smap", type=int, default=1 << 16)
-    ap.add_argument("--e2e-chunks", type=int, default=8)
+    ap.add_argument("--e2e-chunks", type=int, default=32)
     ap.add_argument("--no-paths", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -49,6 +49,14 @@ __device__ __forceinline__ float ldg_gather(const float* p)
 #endif
     return r;
 }
+// The same from PINNED HOST memory (the loss matrix left in place, hotpath.HostPipelinedMargStep(zero_copy_losses=True)):
+// every gather is a PCIe read, so no L2 prefetch hint -- the smallest request the memory system makes.
+__device__ __forceinline__ float ldg_gather_host(const float* p)
+{
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
 __device__ __forceinline__ void stg_stream4(float* p, float4 v)
 {
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x),

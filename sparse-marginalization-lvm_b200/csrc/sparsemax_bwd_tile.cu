@@ -241,7 +241,7 @@ bwd_slots_tma_kernel(const float* __restrict__ p, const int32_t* __restrict__ su
                      const float* __restrict__ loss, const float* __restrict__ loss_scale_dev,
                      float loss_scale_host, const float* __restrict__ dent, const float* __restrict__ slots,
                      const float* __restrict__ loss_slots, float* __restrict__ dx, float* __restrict__ dloss,
-                     int64_t rows, int K, FusedExtras fx)
+                     int64_t rows, int K, FusedExtras fx, bool loss_host)
 {
     __shared__ double red[20];
     double acc_total = 0.0;
@@ -283,7 +283,7 @@ bwd_slots_tma_kernel(const float* __restrict__ p, const int32_t* __restrict__ su
         for (int j = 0; j < NS; ++j) {
             const bool on = live && !scan && c[j] >= 0;
             if (loss_slots == nullptr || loss == nullptr)
-                lv[j] = (on && loss != nullptr) ? ldg_gather(loss + row * K + c[j]) : 0.f;
+                lv[j] = (on && loss != nullptr) ? (loss_host ? ldg_gather_host(loss + row * K + c[j]) : ldg_gather(loss + row * K + c[j])) : 0.f;
             gv[j] = (on && dp != nullptr) ? ldg_gather(dp + row * K + c[j]) : 0.f;
         }
         float vhat = 0.f;
@@ -444,8 +444,20 @@ static int bwd_slots_launch_t(const float* p, const int32_t* supp, const float* 
     const int64_t nt = (rows + kTileRows - 1) / kTileRows;
     const int64_t nd = (nt + warps - 1) / warps;
     const int64_t cp = (int64_t)device_sm_count();
+    // the loss matrix may be pinned host memory read in place (include/smlvm.h, smlvm_marg_step_fused): plain gathers then
+    bool loss_host = false;
+    if (loss != nullptr) {
+        static int hint = -1;
+        if (hint < 0) {
+            const char* ev = getenv("SMLVM_GATHER_HOST_HINT");     // development: 1 keeps the 64-byte L2 hint on host memory
+            hint = (ev && atoi(ev)) ? 1 : 0;
+        }
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, loss) == cudaSuccess) loss_host = at.type == cudaMemoryTypeHost && hint == 0;
+        else cudaGetLastError();
+    }
     bwd_slots_tma_kernel<FUSED><<<(int)(nd < cp ? nd : cp), warps * 32, smem, st>>>(p, supp, dp, loss, lsd, lsh, dent, slots,
-                                                                                     loss_slots, dx, dloss, rows, K, fx);
+                                                                                     loss_slots, dx, dloss, rows, K, fx, loss_host);
     cudaError_t e2 = cudaGetLastError();
     return e2 == cudaSuccess ? SMLVM_OK : (int)e2;
 }

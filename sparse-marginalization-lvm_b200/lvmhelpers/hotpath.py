@@ -95,7 +95,11 @@ class SparsemaxMargStep:
         caller can bracket the kernels with CUDA events; the launches are then serial on the current
         stream."""
         N.require_cuda(x, "scores")      # also: on the current device (the launches go to its stream)
-        if x.device != self.p.device or losses.device != self.p.device:
+        # ``losses`` may also be a PINNED HOST tensor when the step is slot-driven and fused: the kernel then reads the
+        # loss matrix only on the support (one PCIe read per non-zero, through the unified address space) instead of
+        # having all of it uploaded first -- the host-buffer pipeline's ``zero_copy_losses``
+        mapped = (not losses.is_cuda) and losses.is_pinned() and self.fused and self.use_slots
+        if x.device != self.p.device or (losses.device != self.p.device and not mapped):
             raise RuntimeError("SparsemaxMargStep was built for %s, got inputs on %s / %s" % (self.p.device, x.device, losses.device))
         fork = rec is None and self.side is not None and not self.fused
         cur = torch.cuda.current_stream() if fork else None
@@ -247,8 +251,12 @@ class HostPipelinedMargStep:
     on the device (``steps[b].dx`` of the last micro-batches), only the partial losses come back.
     """
 
-    def __init__(self, rows, cols, device, capacity_per_row, entropy_coeff=0.0, chunks=8, nbuf=3):
+    def __init__(self, rows, cols, device, capacity_per_row, entropy_coeff=0.0, chunks=8, nbuf=3, zero_copy_losses=False):
+        """``zero_copy_losses``: do not upload the loss matrix; the fused step kernel reads it from the pinned host
+        buffer, and only where the support is (the loss of a latent assignment with probability zero never enters the
+        objective or a gradient: marg.py:125-126).  Needs the slot-driven fused step (peaked rows); the upload halves."""
         assert rows % chunks == 0, "rows must divide into equal micro-batches"
+        self.zero_copy_losses = bool(zero_copy_losses)
         self.rows, self.cols, self.device = rows, cols, device
         self.chunks, self.nbuf = chunks, min(nbuf, chunks)
         self.crow = rows // chunks
@@ -261,7 +269,9 @@ class HostPipelinedMargStep:
         self.tot_host = torch.zeros(chunks).pin_memory()
         self.loss_host = torch.zeros(()).pin_memory()
         self.ev_free = [None] * self.nbuf   # D2H of the chunk that last used buffer b
-        self.h2d_bytes = 2 * rows * cols * 4
+        if self.zero_copy_losses and not all(st.fused and st.use_slots for st in self.steps):
+            raise RuntimeError("zero_copy_losses needs the slot-driven fused step (supports of at most ~6 entries per row)")
+        self.h2d_bytes = (1 if self.zero_copy_losses else 2) * rows * cols * 4   # copies; + one PCIe read per non-zero
         self.d2h_bytes = rows * cols * 4 + 4 * chunks
 
     def run(self, x_host, l_host, dx_host):
@@ -278,12 +288,13 @@ class HostPipelinedMargStep:
                 if self.ev_free[b] is not None:
                     self.s_h2d.wait_event(self.ev_free[b])
                 self.xd[b].copy_(x_host[lo:hi], non_blocking=True)
-                self.ld[b].copy_(l_host[lo:hi], non_blocking=True)
+                if not self.zero_copy_losses:
+                    self.ld[b].copy_(l_host[lo:hi], non_blocking=True)
                 up = torch.cuda.Event()
                 up.record(self.s_h2d)
             with torch.cuda.stream(self.s_cmp):
                 self.s_cmp.wait_event(up)
-                self.steps[b].run(self.xd[b], self.ld[b])
+                self.steps[b].run(self.xd[b], l_host[lo:hi] if self.zero_copy_losses else self.ld[b])
                 done = torch.cuda.Event()
                 done.record(self.s_cmp)
             with torch.cuda.stream(self.s_d2h):

@@ -76,8 +76,10 @@ def test_wide_support_step_matches_oracle(oracle, rows, K, scale, fused):
     assert torch.equal(small.ri.cpu().long(), nz[: n // 2, 0])
 
 
+@pytest.mark.parametrize("zero_copy", [False, True])
 @pytest.mark.parametrize("chunks", [1, 4, 8])
-def test_host_pipelined_step_equals_resident(chunks):
+def test_host_pipelined_step_equals_resident(chunks, zero_copy):
+    """zero_copy: the loss matrix is not uploaded, the fused kernel gathers it from the pinned host buffer."""
     from lvmhelpers.hotpath import SparsemaxMargStep, HostPipelinedMargStep
     rows, K = 8192 * 4, 128
     x, L = _inputs(rows, K, 9)
@@ -88,13 +90,43 @@ def test_host_pipelined_step_equals_resident(chunks):
     step = SparsemaxMargStep(rows, K, dev, nnz + 16, entropy_coeff=1.0)
     total = step.run(xd, Ld)
     pipe = HostPipelinedMargStep(rows, K, dev, capacity_per_row=nnz / rows * 1.2 + 1, entropy_coeff=1.0,
-                                 chunks=chunks)
+                                 chunks=chunks, zero_copy_losses=zero_copy)
     dx_host = torch.empty(rows, K).pin_memory()
     for _ in range(3):   # buffer rotation across calls
         pipe.run(xp, Lp, dx_host)
     torch.cuda.synchronize()
     assert torch.equal(dx_host, step.dx.cpu())
     assert abs(pipe.loss() - total.item()) <= 1e-5
+    assert pipe.h2d_bytes == (1 if zero_copy else 2) * rows * K * 4
+
+
+def test_losses_read_in_place_from_pinned_host_memory():
+    """smlvm_marg_step_fused with `loss` in pinned host memory (include/smlvm.h): same loss, lists and gradients as with
+    the matrix on the device, rows beyond the 8 support slots included (they read their loss row densely); pageable host
+    memory and the paths that read the loss matrix densely refuse."""
+    from lvmhelpers.hotpath import SparsemaxMargStep, HostPipelinedMargStep
+    rows, K = 8192, 128
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(rows, K, generator=g)
+    x[::97] *= 0.05                       # flat rows: supports far beyond the slots
+    L = torch.rand(rows, K, generator=g) * 3
+    xd, Ld, Lp = x.to(dev), L.to(dev), L.pin_memory()
+    nnz = SparsemaxMargStep.size_capacity(xd)
+    a = SparsemaxMargStep(rows, K, dev, nnz + 16, entropy_coeff=1.0, use_slots=True)
+    b = SparsemaxMargStep(rows, K, dev, nnz + 16, entropy_coeff=1.0, use_slots=True)
+    ta, tb = a.run(xd, Ld), b.run(xd, Lp)
+    torch.cuda.synchronize()
+    assert int((a.nnz > 8).sum()) > 0
+    assert ta.item() == tb.item() and torch.equal(a.dx, b.dx) and torch.equal(a.dloss, b.dloss)
+    assert torch.equal(a.vals[:nnz], b.vals[:nnz]) and torch.equal(a.ri[:nnz], b.ri[:nnz]) and torch.equal(a.ci[:nnz], b.ci[:nnz])
+    with pytest.raises(RuntimeError):
+        b.run(xd, L)                      # pageable host memory is not device-readable
+    dense = SparsemaxMargStep(rows, K, dev, nnz + 16, entropy_coeff=1.0, use_slots=False)
+    with pytest.raises(RuntimeError):
+        dense.run(xd, Lp)                 # the dense-read step would stream the whole matrix over PCIe
+    with pytest.raises(RuntimeError):
+        HostPipelinedMargStep(rows, K, dev, capacity_per_row=40.0, zero_copy_losses=True)   # wide supports: no slots
 
 
 @pytest.mark.parametrize("rows,K", [(64, 10), (64, 256), (8192, 128)])
