@@ -100,7 +100,11 @@ class SparsemaxMargStep:
         # having all of it uploaded first -- the host-buffer pipeline's ``zero_copy_losses``
         mapped = (not losses.is_cuda) and losses.is_pinned() and self.fused and self.use_slots
         if x.device != self.p.device or (losses.device != self.p.device and not mapped):
-            raise RuntimeError("SparsemaxMargStep was built for %s, got inputs on %s / %s" % (self.p.device, x.device, losses.device))
+            raise RuntimeError("SparsemaxMargStep was built for %s, got inputs on %s / %s%s" % (
+                self.p.device, x.device, losses.device,
+                "" if losses.is_cuda else " (host losses are read in place only from PINNED memory and only by the "
+                                          "slot-driven fused step: pinned=%s, fused=%s, slots=%s)"
+                                          % (losses.is_pinned(), self.fused, self.use_slots)))
         fork = rec is None and self.side is not None and not self.fused
         cur = torch.cuda.current_stream() if fork else None
         st = cur.cuda_stream if fork else N.stream()
