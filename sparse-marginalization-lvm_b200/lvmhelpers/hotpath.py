@@ -250,6 +250,8 @@ class HostPipelinedMargStep:
     device buffer sets, so that the uploads (2 x rows x K x 4 B), the kernels and the downloads
     (rows x K x 4 B) overlap; PCIe is full duplex, the step time tends to the upload time alone.
 
+    The call is asynchronous: ``x_host`` / ``l_host`` (pinned; with ``zero_copy_losses`` the kernels read ``l_host`` itself)
+    must not be modified, and ``dx_host`` not read, before the current stream has been synchronised.
     ``run(x_host, l_host, dx_host)`` returns the loss as a 0-d pinned host tensor valid after
     the CURRENT stream has been synchronised (the call itself does not block).  ``dx_host=None``: the gradient stays
     on the device (``steps[b].dx`` of the last micro-batches), only the partial losses come back.
