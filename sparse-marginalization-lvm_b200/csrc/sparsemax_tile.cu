@@ -533,6 +533,8 @@ int sparsemax_fwd_tile_launch(const float* x, float* p, int32_t* supp, int32_t* 
             return launch_tile<64, 2, 8>(x, p, supp, nnz, ent, amax, slots, rows, st);
         case 128:
             if (variant == 1) return launch_tile<128, 2, 6>(x, p, supp, nnz, ent, amax, slots, rows, st);
+            // (fewer warp pipelines, measured at 1M x 128, N(0,1): 9 warps 0.2066, 8 warps 0.2089, 7 warps 0.2240 ms
+            // against 0.2054 ms for 10 -- the forward wants them all)
             return launch_tile<128, 1, 10>(x, p, supp, nnz, ent, amax, slots, rows, st);
         default: return SMLVM_ERR_UNSUPPORTED;
     }
