@@ -169,7 +169,12 @@ static int launch_dense(const float* p, const int32_t* supp, const float* loss, 
 {
     const int rows_per_cta = (kDenseThreads / kWarp) * (kWarp / G);
     const int64_t need = (rows + rows_per_cta - 1) / rows_per_cta;
-    int64_t cap = (int64_t)device_sm_count() * 2;
+    static int per_sm = -1;
+    if (per_sm < 0) { const char* ev = getenv("SMLVM_DENSE_CTAS_PER_SM"); per_sm = ev ? atoi(ev) : 13; if (per_sm < 1) per_sm = 13; }
+    // 13 CTAs per SM in the grid (2 resident; grid-stride beyond): measured at 1M x 128 against one resident wave of 2 per
+    // SM -- 0.4219 -> 0.3932 ms (support 8.5), 0.4506 -> 0.4219 (20), 0.5263 -> 0.4834 (49); 4 / 8 per SM 0.412 / 0.401, 16 the
+    // same as 13, 24+ slower again.  The per-CTA totals still fit the reduction workspace (kMaxCtas).
+    int64_t cap = (int64_t)device_sm_count() * per_sm;
     if (cap > kMaxCtas) cap = kMaxCtas;
     const int grid = (int)(need < cap ? need : cap);
     const size_t smem = (size_t)(kDenseThreads / kWarp) * 2 * kWarp * 32 * sizeof(float);   // 64 KB

@@ -449,9 +449,11 @@ static int bwd_slots_launch_t(const float* p, const int32_t* supp, const float* 
         if (ea != cudaSuccess) return (int)ea;
         configured_dev[dev & 63] = true;
     }
+    static int gmul = -1;
+    if (gmul < 0) { const char* ev = getenv("SMLVM_BWD_SLOTS_GRID"); gmul = ev ? atoi(ev) : 1; if (gmul < 1) gmul = 1; }
     const int64_t nt = (rows + kTileRows - 1) / kTileRows;
     const int64_t nd = (nt + warps - 1) / warps;
-    const int64_t cp = (int64_t)device_sm_count();
+    const int64_t cp = (int64_t)device_sm_count() * gmul;
     // the loss matrix may be pinned host memory read in place (include/smlvm.h, smlvm_marg_step_fused): plain gathers then
     bool loss_host = false;
     if (loss != nullptr) {

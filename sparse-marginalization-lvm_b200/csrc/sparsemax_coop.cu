@@ -24,6 +24,7 @@
 // The cost no longer depends on the support size: ~140 instructions per row at K = 128 whatever the score scale.
 #include <math_constants.h>
 
+#include <stdlib.h>
 #include "common.cuh"
 #include "sparsemax_exact.cuh"
 
@@ -265,7 +266,12 @@ static int launch_coop(const float* x, float* p, int32_t* supp, int32_t* nnz, fl
 {
     const int rows_per_cta = (kCoopThreads / kWarp) * (kWarp / G);
     const int64_t need = (rows + rows_per_cta - 1) / rows_per_cta;
-    const int64_t cap = (int64_t)device_sm_count() * 3;   // one resident wave of 3 CTAs per SM, grid-stride beyond
+    static int per_sm = -1;
+    if (per_sm < 0) { const char* ev = getenv("SMLVM_COOP_CTAS_PER_SM"); per_sm = ev ? atoi(ev) : 8; if (per_sm < 1) per_sm = 8; }
+    // 8 CTAs per SM in the grid (3-4 resident, grid-stride beyond): measured at 1M x 128 against exactly one resident wave
+    // of 3 per SM -- 0.2252 -> 0.2140 ms (support 8.5), 0.2353 -> 0.2265 (20), 0.2518 -> 0.2417 (49); 12 and 16 the same,
+    // 24+ slower again.  The hardware scheduler evens out what a fixed share per CTA leaves as a tail.
+    const int64_t cap = (int64_t)device_sm_count() * per_sm;
     const int grid = (int)(need < cap ? need : cap);
 #define SMLVM_COOP_LAUNCH(V, A, H) \
     sparsemax_fwd_coop<G, V, A, H><<<grid, kCoopThreads, 0, st>>>(x, p, supp, nnz, ent, amax, rows, K)

@@ -508,7 +508,9 @@ static int launch_tile(const float* x, float* p, int32_t* supp, int32_t* nnz, fl
     }
     const int64_t ntiles = (rows + kTileRows - 1) / kTileRows;
     const int64_t need = (ntiles + W - 1) / W;
-    const int64_t cap = (int64_t)device_sm_count() * ctas_per_sm;
+    static int gmul = -1;
+    if (gmul < 0) { const char* ev = getenv("SMLVM_TILE_GRID"); gmul = ev ? atoi(ev) : 1; if (gmul < 1) gmul = 1; }
+    const int64_t cap = (int64_t)device_sm_count() * ctas_per_sm * gmul;
     const int grid = (int)(need < cap ? need : cap);
     kern<<<grid, W * 32, smem, st>>>(x, p, supp, nnz, ent, amax, slots, rows);
     cudaError_t e = cudaGetLastError();
