@@ -1,6 +1,6 @@
-"""k-best kernel (topk_blk.cu) under the current SMLVM_TOPK_STAGGER: exactness of the first 4096 rows against the oracle, bits vs
-fp32 configurations on every row, then timing with and without the fp32 configurations (development aid; the sweep over the
-stagger settings is tools/topk_stagger_sweep.sh)."""
+"""k-best kernel (topk_blk.cu): exactness of the first 4096 rows against the oracle, bits vs fp32 configurations on every row,
+then timing with and without the fp32 configurations (development aid).  It produced profiles/r02_topk_stagger.log when the
+kernel had a phase-stagger knob (SMLVM_TOPK_STAGGER, measured and removed: DESIGN.md 4.4)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "sparse-marginalization-lvm_b200"))
