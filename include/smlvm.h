@@ -129,8 +129,9 @@ int smlvm_sparsemax_bwd_ragged(const int64_t* offsets, const int32_t* col_idx, c
  * One read of the 64 B of slots and one gather of loss per non-zero serve all three.  SMLVM_ERR_UNSUPPORTED when the
  * slot-driven tile kernel does not cover the shape (cols % 4, cols <= 512, 16-byte aligned dx / dloss): use the
  * separate entry points.
- * With support_slots != NULL, `loss` may also point to PINNED HOST memory (cudaHostAlloc / cudaHostRegister, reachable
- * through the unified address space): the kernel reads it only on the support, one PCIe read per non-zero, so a caller
+ * With support_slots != NULL, `loss` may also point to PINNED HOST memory (cudaHostAlloc, or registered memory on systems
+ * where the host pointer is usable on the device: cudaDevAttrCanUseHostPointerForRegisteredMem), reachable through the
+ * unified address space: the kernel reads it only on the support, one PCIe read per non-zero, so a caller
  * whose loss matrix lives on the host need not upload it (hotpath.HostPipelinedMargStep(zero_copy_losses=True)).
  * replaces: marg.py:125-126 forward + autograd backward, entropy() backward marg.py:6-28, and the mask indexing of
  *           structmarg.py:116-126.                                                                              */
